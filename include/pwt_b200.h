@@ -1,0 +1,147 @@
+/*
+ * pwt_b200.h -- C ABI of the B200-native wavelet hot path (libpwt_b200.so).
+ *
+ * This is the drop-in boundary: every entry point replaces one method of the
+ * reference's C++ `class Wavelets` (pdwt/src/wt.h:20-76, implemented in
+ * pdwt/src/wt.cu) that the Cython wrapper binds in src/pypwt.pyx:29-61.
+ * Plain pointers and sizes only; no C++ / torch types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns an int: PWT_OK (0) or a negative PWT_ERR_* code,
+ *     except the *_ptr accessors (address or 0) and the two `get_*` copies that
+ *     keep the reference's "number of elements copied, 0 on refusal" convention.
+ *   - images are row-major float32 `Nr x Nc`; bands are dense row-major float32.
+ *   - band numbering (wt.cu:435-506): 2D  0:A  1:H1 2:V1 3:D1 4:H2 ...   1D  0:A 1:D1 2:D2 ...
+ *     level 1 = finest.  Band shapes: div2^l (ceil halving, utils.cu:24) for the DWT, Nr x Nc for the SWT.
+ *   - all work is enqueued on the plan's stream; like the reference (wt.cu:236-305, no sync)
+ *     forward/inverse/threshold calls return without synchronising.  Copies to host synchronise.
+ *   - a plan may hold a STACK of `batch` independent images (extension used for multi-GPU
+ *     sharding of 3D stacks; the reference handles one image per object).  With batch == 1
+ *     the layout is exactly the reference's.
+ */
+#ifndef PWT_B200_H
+#define PWT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pwt_plan pwt_plan; /* opaque; replaces `Wavelets*` (wt.h:20) */
+
+/* error codes */
+#define PWT_OK 0
+#define PWT_ERR_ARG (-1)            /* bad argument / too-long filter (wt.cu:560-563)     */
+#define PWT_ERR_UNKNOWN_WAVELET (-2)/* reference: prints + hangs in w_ilog2 (separable.cu:44, utils.cu:14) */
+#define PWT_ERR_CUDA (-3)           /* a CUDA runtime call failed (reference ignores all of them) */
+#define PWT_ERR_STATE (-4)          /* creation error state (wt.cu:237)                    */
+#define PWT_ERR_NOMEM (-5)
+#define PWT_ERR_UNSUPPORTED (-6)    /* e.g. cycle spinning in 1D (wt.cu:179-183), ndim > 2 */
+#define PWT_ERR_TOO_SMALL (-7)      /* image smaller than the filter: no valid level       */
+#define PWT_ERR_COMM (-8)           /* NCCL communicator problem                           */
+
+/* plan states -- same meaning and values as `w_state` (wt.h:8-17) */
+enum { PWT_INIT = 0, PWT_FORWARD = 1, PWT_INVERSE = 2, PWT_THRESHOLD = 3, PWT_CREATION_ERROR = 4 };
+
+/* read-only description of a plan; replaces direct reads of `winfos`, `do_separable`, `state`
+ * (pypwt.pyx:181-183) */
+typedef struct pwt_info {
+    int batch;             /* number of stacked images (1 for the reference API)  */
+    int Nr, Nc;            /* per-image rows / columns (1D: Nr = 1 or batch rows) */
+    int ndims;             /* 1 or 2 after the reference's coercions (wt.cu:133)  */
+    int nlevels;           /* after clipping (wt.cu:156-165)                      */
+    int hlen;              /* filter length                                       */
+    int do_swt, do_separable, do_cycle_spinning;
+    int state;             /* PWT_INIT ...                                        */
+    int shift_r, shift_c;  /* current cycle-spinning shift (wt.h:31-32)           */
+    int nbands;            /* 3*nlevels+1 (2D) or nlevels+1 (1D)                  */
+    int device;            /* CUDA device ordinal the plan lives on               */
+} pwt_info;
+
+/* ---- life cycle ---------------------------------------------------------------------- */
+/* Wavelets::Wavelets(img,Nr,Nc,wname,levels,memisonhost,do_separable,do_cycle_spinning,do_swt,ndim)
+ * wt.cu:84-185.  img may be NULL (zero image).  Unknown wavelet -> PWT_ERR_UNKNOWN_WAVELET. */
+int pwt_create(pwt_plan** out, const float* img, int Nr, int Nc, const char* wname, int levels,
+               int memisonhost, int do_separable, int do_cycle_spinning, int do_swt, int ndim);
+/* same, for a stack of `batch` images laid out [batch][Nr][Nc] (extension) */
+int pwt_create_batch(pwt_plan** out, const float* img, int batch, int Nr, int Nc, const char* wname,
+                     int levels, int memisonhost, int do_separable, int do_cycle_spinning,
+                     int do_swt, int ndim);
+/* Wavelets::Wavelets(const Wavelets&) wt.cu:191-222 (deep copy of device state) */
+int pwt_clone(pwt_plan** out, const pwt_plan* src);
+/* Wavelets::~Wavelets wt.cu:226-233 */
+void pwt_destroy(pwt_plan* p);
+int pwt_get_info(const pwt_plan* p, pwt_info* info);
+/* shape of band `num` (what wt.cu:478-502 recomputes on every get_coeff) */
+int pwt_band_shape(const pwt_plan* p, int num, int* nr, int* nc);
+
+/* ---- transforms ---------------------------------------------------------------------- */
+int pwt_forward(pwt_plan* p);   /* Wavelets::forward wt.cu:236-269 */
+int pwt_inverse(pwt_plan* p);   /* Wavelets::inverse wt.cu:271-305; returns 1 if refused (already inverted) */
+
+/* ---- coefficient operators ------------------------------------------------------------ */
+int pwt_soft_threshold(pwt_plan* p, float beta, int do_thresh_appcoeffs, int normalize); /* wt.cu:308 */
+int pwt_hard_threshold(pwt_plan* p, float beta, int do_thresh_appcoeffs, int normalize); /* wt.cu:318 */
+int pwt_group_soft_threshold(pwt_plan* p, float beta, int do_thresh_appcoeffs, int normalize); /* wt.cu:329 */
+int pwt_shrink(pwt_plan* p, float beta, int do_thresh_appcoeffs);                        /* wt.cu:340 */
+int pwt_proj_linf(pwt_plan* p, float beta, int do_thresh_appcoeffs);                     /* wt.cu:349 */
+int pwt_circshift(pwt_plan* p, int sr, int sc, int inplace);                             /* wt.cu:364 */
+int pwt_norm1(pwt_plan* p, float* out);      /* Wavelets::norm1   wt.cu:396-416 */
+int pwt_norm2sq(pwt_plan* p, float* out);    /* Wavelets::norm2sq wt.cu:368-393 (1D: true sum of squares) */
+/* both norms in one pass, double precision, per plan (local to this GPU) */
+int pwt_norms(pwt_plan* p, double* norm1, double* norm2sq);
+int pwt_add_wavelet(pwt_plan* dst, const pwt_plan* src, float alpha); /* wt.cu:622-655; same return codes */
+
+/* ---- data in / out -------------------------------------------------------------------- */
+int pwt_get_image(pwt_plan* p, float* dst);                              /* wt.cu:419 -> batch*Nr*Nc */
+int pwt_set_image(pwt_plan* p, const float* img, int mem_is_on_device);  /* wt.cu:425 */
+int pwt_get_coeff(pwt_plan* p, float* dst, int num);                     /* wt.cu:473 -> count or 0 */
+int pwt_set_coeff(pwt_plan* p, const float* src, int num, int mem_is_on_device); /* wt.cu:435 */
+intptr_t pwt_image_ptr(pwt_plan* p);                                     /* wt.cu:658 */
+intptr_t pwt_coeff_ptr(pwt_plan* p, int num);                            /* wt.cu:663 */
+
+/* ---- custom filter banks --------------------------------------------------------------- */
+/* wt.cu:558-581.  separable: f1=L, f2=H (f3,f4 ignored).  non-separable: LL, LH, HL, HH (len x len). */
+int pwt_set_filters_forward(pwt_plan* p, const char* name, unsigned len, const float* f1,
+                            const float* f2, const float* f3, const float* f4);
+/* wt.cu:586-600 */
+int pwt_set_filters_inverse(pwt_plan* p, const float* f1, const float* f2, const float* f3,
+                            const float* f4);
+
+/* ---- misc ------------------------------------------------------------------------------ */
+int pwt_print_informations(pwt_plan* p);   /* wt.cu:511-550 */
+int pwt_sync(pwt_plan* p);                 /* cudaStreamSynchronize on the plan's stream */
+const char* pwt_last_error(void);          /* thread-local message of the last failure */
+const char* pwt_version(void);             /* "1.0.3" -- pypwt.pyx:608-615 */
+int pwt_device_count(void);                /* 0 if no usable CUDA device */
+
+/* look up a built-in bank (filters.cpp:5919-6002): writes hlen taps into each non-NULL array
+ * (capacity >= 40) and returns hlen, or PWT_ERR_UNKNOWN_WAVELET.  Host-only, no CUDA call. */
+int pwt_lookup_filters(const char* wname, float* L, float* H, float* IL, float* IH);
+
+/* pinned host memory for fast H<->D transfers of numpy buffers */
+int pwt_host_alloc(void** ptr, size_t bytes);
+int pwt_host_free(void* ptr);
+
+/* ---- measurement helpers (CUDA events on the plan's own stream) ------------------------ */
+int pwt_timer_start(pwt_plan* p);
+int pwt_timer_stop(pwt_plan* p, float* ms);      /* records, synchronises, returns elapsed ms */
+int pwt_flush_l2(pwt_plan* p);                   /* overwrites a >L2-sized scratch buffer on the stream */
+long long pwt_launch_count(const pwt_plan* p);   /* kernels launched by this plan so far */
+/* choose kernel family: 0 = auto (default), 1 = force the generic tiled kernels */
+int pwt_set_kernel_mode(pwt_plan* p, int mode);
+
+/* ---- multi-GPU: one process per GPU, NCCL only for the scalar all-reduce --------------- */
+/* 128-byte NCCL unique id, created by rank 0 and distributed by the host (torch.distributed / files) */
+int pwt_comm_unique_id(unsigned char id[128]);
+int pwt_comm_init(pwt_plan* p, int nranks, int rank, const unsigned char id[128]);
+int pwt_comm_destroy(pwt_plan* p);
+/* global norms over all ranks' shards: fused local reduction + ncclAllReduce on the plan's stream */
+int pwt_norms_allreduce(pwt_plan* p, double* norm1, double* norm2sq);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PWT_B200_H */

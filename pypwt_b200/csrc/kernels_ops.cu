@@ -1,0 +1,231 @@
+// Coefficient operators: thresholds, shrink, norms, axpy, circular shift.
+// All are streaming (HBM-bound) kernels: one launch covers every band of the pyramid through a
+// small segment table, 128-bit accesses on the 16-byte aligned body of each band, scalar head/tail,
+// persistent grid sized from the SM count.
+// Reference semantics: pdwt/src/common.cu:13-211 (kernels), :219-396 (callers), wt.cu:368-416 (norms).
+#include "pwt_internal.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float apply_op(float v, float beta, int op) {
+    switch (op) {
+        case PWT_OP_SOFT:   // common.cu:19  copysignf(max(|v|-beta,0), v)
+            return copysignf(fmaxf(fabsf(v) - beta, 0.0f), v);
+        case PWT_OP_HARD:   // common.cu:63  max(W_SIGN(|v|-beta),0)*v  (strict >)
+            return (fabsf(v) - beta > 0.0f) ? v : 0.0f * v;
+        case PWT_OP_PROJ:   // common.cu:107 copysignf(min(|v|,beta), v)
+            return copysignf(fminf(fabsf(v), beta), v);
+        default:            // PWT_OP_SCALE: cublasSscal(alpha = beta), common.cu:355
+            return v * beta;
+    }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kThreads)
+k_eltwise(const __grid_constant__ PwtSegTable t) {
+    const long long gtid = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const long long gsz = (long long)gridDim.x * kThreads;
+    for (int s = 0; s < t.nseg; s++) {
+        float* p = t.seg[s].ptr;
+        const long long n = t.seg[s].n;
+        const float beta = t.seg[s].beta;
+        // head up to 16-byte alignment
+        long long head = ((16 - ((uintptr_t)p & 15)) & 15) / 4;
+        if (head > n) head = n;
+        const long long nvec = (n - head) / 4;
+        float4* pv = reinterpret_cast<float4*>(p + head);
+        for (long long i = gtid; i < nvec; i += gsz) {
+            float4 v = pv[i];
+            v.x = apply_op(v.x, beta, OP);
+            v.y = apply_op(v.y, beta, OP);
+            v.z = apply_op(v.z, beta, OP);
+            v.w = apply_op(v.w, beta, OP);
+            pv[i] = v;
+        }
+        const long long tail0 = head + nvec * 4;
+        const long long nscal = head + (n - tail0);
+        for (long long i = gtid; i < nscal; i += gsz) {
+            const long long j = i < head ? i : tail0 + (i - head);
+            p[j] = apply_op(p[j], beta, OP);
+        }
+    }
+}
+
+// common.cu:145-198: joint shrink of (h, v, d [, a]) by max(1 - beta/||.||_2, 0)
+__global__ void __launch_bounds__(kThreads)
+k_group_soft(float* __restrict__ h, float* __restrict__ v, float* __restrict__ d,
+             float* __restrict__ a, long long n, float beta) {
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n;
+         i += (long long)gridDim.x * kThreads) {
+        const float vh = h ? h[i] : 0.f, vv = v ? v[i] : 0.f, vd = d[i], va = a ? a[i] : 0.f;
+        float nrm = vh * vh + vv * vv + vd * vd;
+        if (a) nrm += va * va;
+        nrm = sqrtf(nrm);
+        const float res = (nrm == 0.f) ? 0.f : fmaxf(1.0f - beta / nrm, 0.0f);
+        if (h) h[i] = vh * res;
+        if (v) v[i] = vv * res;
+        d[i] = vd * res;
+        if (a) a[i] = va * res;
+    }
+}
+
+// sum |c| and sum c^2 over all segments: fp32 loads, fp64 accumulation per thread, warp shuffle,
+// one atomicAdd(double) pair per block.
+__global__ void __launch_bounds__(kThreads)
+k_norms(const __grid_constant__ PwtSegTable t, double* __restrict__ acc) {
+    const long long gtid = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const long long gsz = (long long)gridDim.x * kThreads;
+    double l1 = 0.0, l2 = 0.0;
+    for (int s = 0; s < t.nseg; s++) {
+        const float* p = t.seg[s].ptr;
+        const long long n = t.seg[s].n;
+        long long head = ((16 - ((uintptr_t)p & 15)) & 15) / 4;
+        if (head > n) head = n;
+        const long long nvec = (n - head) / 4;
+        const float4* pv = reinterpret_cast<const float4*>(p + head);
+        float f1 = 0.f, f2 = 0.f;   // short fp32 partials, flushed to fp64 every iteration
+        for (long long i = gtid; i < nvec; i += gsz) {
+            const float4 v = pv[i];
+            f1 = (fabsf(v.x) + fabsf(v.y)) + (fabsf(v.z) + fabsf(v.w));
+            f2 = fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
+            l1 += (double)f1;
+            l2 += (double)f2;
+        }
+        const long long tail0 = head + nvec * 4;
+        const long long nscal = head + (n - tail0);
+        for (long long i = gtid; i < nscal; i += gsz) {
+            const long long j = i < head ? i : tail0 + (i - head);
+            const float v = p[j];
+            l1 += (double)fabsf(v);
+            l2 += (double)v * (double)v;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+        l2 += __shfl_xor_sync(0xffffffffu, l2, o);
+    }
+    __shared__ double s1[kThreads / 32], s2[kThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        s1[warp] = l1;
+        s2[warp] = l2;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        l1 = lane < kThreads / 32 ? s1[lane] : 0.0;
+        l2 = lane < kThreads / 32 ? s2[lane] : 0.0;
+        for (int o = 4; o > 0; o >>= 1) {
+            l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+            l2 += __shfl_xor_sync(0xffffffffu, l2, o);
+        }
+        if (lane == 0) {
+            atomicAdd(acc, l1);
+            atomicAdd(acc + 1, l2);
+        }
+    }
+}
+
+// dst += alpha * src (cublasSaxpy, common.cu:499-526)
+__global__ void __launch_bounds__(kThreads)
+k_axpy(const __grid_constant__ PwtSegTable dst, const __grid_constant__ PwtSegTable src, float alpha) {
+    const long long gtid = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const long long gsz = (long long)gridDim.x * kThreads;
+    for (int s = 0; s < dst.nseg; s++) {
+        float* d = dst.seg[s].ptr;
+        const float* q = src.seg[s].ptr;
+        const long long n = dst.seg[s].n;
+        for (long long i = gtid; i < n; i += gsz) d[i] = fmaf(alpha, q[i], d[i]);
+    }
+}
+
+// out[y,x] = in[(y-sr) mod Nr, (x-sc) mod Nc]  (common.cu:202-211); sr, sc already in [0,N)
+__global__ void __launch_bounds__(kThreads)
+k_circshift(const float* __restrict__ in, float* __restrict__ out, int Nr, int Nc, int sr, int sc) {
+    const int x = blockIdx.x * kThreads + threadIdx.x;
+    const long long pb = (long long)blockIdx.z * Nr * Nc;
+    if (x >= Nc) return;
+    int cx = x - sc;
+    if (cx < 0) cx += Nc;
+    for (int y = blockIdx.y; y < Nr; y += gridDim.y) {
+        int r = y - sr;
+        if (r < 0) r += Nr;
+        out[pb + (long long)y * Nc + x] = __ldg(in + pb + (long long)r * Nc + cx);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_fill(float* p, long long n, float v) {
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n;
+         i += (long long)gridDim.x * kThreads)
+        p[i] = v;
+}
+
+int persistent_grid() {
+    static int blocks = 0;
+    if (!blocks) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        blocks = sms * 8;   // 8 x 256 threads = full occupancy, grid = multiple of the SM count
+    }
+    return blocks;
+}
+
+long long total_elems(const PwtSegTable& t) {
+    long long n = 0;
+    for (int i = 0; i < t.nseg; i++) n += t.seg[i].n;
+    return n;
+}
+
+int grid_for(long long n) {
+    long long need = (n / 4 + kThreads - 1) / kThreads;
+    if (need < 1) need = 1;
+    const int cap = persistent_grid();
+    return (int)(need < cap ? need : cap);
+}
+
+}  // namespace
+
+int pwt_launch_eltwise(const PwtSegTable& t, int op, cudaStream_t st) {
+    if (t.nseg == 0) return 0;
+    const int grid = grid_for(total_elems(t));
+    switch (op) {
+        case PWT_OP_SOFT: k_eltwise<PWT_OP_SOFT><<<grid, kThreads, 0, st>>>(t); break;
+        case PWT_OP_HARD: k_eltwise<PWT_OP_HARD><<<grid, kThreads, 0, st>>>(t); break;
+        case PWT_OP_PROJ: k_eltwise<PWT_OP_PROJ><<<grid, kThreads, 0, st>>>(t); break;
+        default: k_eltwise<PWT_OP_SCALE><<<grid, kThreads, 0, st>>>(t); break;
+    }
+    return 1;
+}
+
+int pwt_launch_group_soft(float* h, float* v, float* d, float* a, long long n, float beta,
+                          cudaStream_t st) {
+    k_group_soft<<<grid_for(n * 4), kThreads, 0, st>>>(h, v, d, a, n, beta);
+    return 1;
+}
+
+int pwt_launch_norms(const PwtSegTable& t, double* d_acc, cudaStream_t st) {
+    cudaMemsetAsync(d_acc, 0, 2 * sizeof(double), st);
+    if (t.nseg == 0) return 0;
+    k_norms<<<grid_for(total_elems(t)), kThreads, 0, st>>>(t, d_acc);
+    return 1;
+}
+
+int pwt_launch_axpy(const PwtSegTable& dst, const PwtSegTable& src, float alpha, cudaStream_t st) {
+    if (dst.nseg == 0) return 0;
+    k_axpy<<<grid_for(total_elems(dst) * 4), kThreads, 0, st>>>(dst, src, alpha);
+    return 1;
+}
+
+int pwt_launch_circshift(const float* in, float* out, int batch, int Nr, int Nc, int sr, int sc,
+                         cudaStream_t st) {
+    dim3 grid((Nc + kThreads - 1) / kThreads, Nr < 65535 ? Nr : 65535, batch);
+    k_circshift<<<grid, kThreads, 0, st>>>(in, out, Nr, Nc, sr, sc);
+    return 1;
+}
+
+int pwt_launch_fill(float* p, long long n, float v, cudaStream_t st) {
+    k_fill<<<grid_for(n * 4), kThreads, 0, st>>>(p, n, v);
+    return 1;
+}

@@ -1,0 +1,95 @@
+// Internal declarations shared by the plan/dispatch code and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#define PWT_MAX_TAPS 40      // same cap as the reference (common.h:15)
+#define PWT_MAX_LEVELS 31
+#define PWT_MAX_BANDS (3 * PWT_MAX_LEVELS + 1)
+
+// 1D filter bank, passed BY VALUE to kernels (lands in the constant bank as kernel
+// parameters, so every instance has its own filters -- fixes reference quirk Q4).
+struct PwtFilters {
+    float L[PWT_MAX_TAPS];    // analysis low-pass   (dec_lo)
+    float H[PWT_MAX_TAPS];    // analysis high-pass  (dec_hi)
+    float IL[PWT_MAX_TAPS];   // synthesis low-pass  (rec_lo)
+    float IH[PWT_MAX_TAPS];   // synthesis high-pass (rec_hi)
+    int hlen;
+};
+
+// Geometry of one 2D plane set processed by a launch (all strides in elements).
+struct PwtPlane {
+    int nr, nc;               // rows, cols of ONE image of the stack
+    long long bstride;        // distance between consecutive images of the stack
+};
+
+// element-wise operator codes (kernels_ops.cu)
+enum { PWT_OP_SOFT = 0, PWT_OP_HARD = 1, PWT_OP_PROJ = 2, PWT_OP_SCALE = 3 };
+
+struct PwtSeg {               // one contiguous run of coefficients + its parameter
+    float* ptr;
+    long long n;
+    float beta;
+    int pad;
+};
+#define PWT_MAX_SEGS PWT_MAX_BANDS
+struct PwtSegTable {
+    PwtSeg seg[PWT_MAX_SEGS];
+    int nseg;
+};
+
+// ---- kernel launchers (each returns the number of kernels it launched) ----------------
+// kernels_generic.cu : tiled kernels valid for every size / filter length
+int pwt_launch_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr,
+                         int Nc, long long in_bs, long long out_bs, const PwtFilters& f, bool haar,
+                         cudaStream_t st);
+int pwt_launch_dwt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out,
+                         int batch, int nr, int nc, int Nr_out, int Nc_out, long long in_bs,
+                         long long out_bs, const PwtFilters& f, bool haar, cudaStream_t st);
+// batched 1D over `rows` rows (rows = batch*Nr)
+int pwt_launch_dwt_fwd1d(const float* in, float* A, float* D, int rows, int Nc, const PwtFilters& f,
+                         bool haar, cudaStream_t st);
+int pwt_launch_dwt_inv1d(const float* A, const float* D, float* out, int rows, int nc, int Nc_out,
+                         const PwtFilters& f, bool haar, cudaStream_t st);
+// SWT (a trous), level >= 1.  tmp must hold 2*batch*Nr*Nc floats (2D only).
+int pwt_launch_swt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, float* tmp,
+                         int batch, int Nr, int Nc, int level, const PwtFilters& f, cudaStream_t st);
+int pwt_launch_swt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out,
+                         float* tmp, int batch, int Nr, int Nc, int level, const PwtFilters& f,
+                         cudaStream_t st);
+int pwt_launch_swt_fwd1d(const float* in, float* A, float* D, int rows, int Nc, int level,
+                         const PwtFilters& f, cudaStream_t st);
+int pwt_launch_swt_inv1d(const float* A, const float* D, float* out, int rows, int Nc, int level,
+                         const PwtFilters& f, cudaStream_t st);
+// non-separable (true 2D stencils).  k2d = device array of 4*hlen*hlen taps: LL, LH, HL, HH.
+int pwt_launch_ns_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr,
+                        int Nc, long long in_bs, long long out_bs, const float* k2d, int hlen,
+                        cudaStream_t st);
+int pwt_launch_ns_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out,
+                        int batch, int nr, int nc, int Nr_out, int Nc_out, long long in_bs,
+                        long long out_bs, const float* k2d, int hlen, cudaStream_t st);
+int pwt_launch_ns_swt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch,
+                            int Nr, int Nc, int level, const float* k2d, int hlen, cudaStream_t st);
+int pwt_launch_ns_swt_inv2d(const float* A, const float* Hb, const float* V, const float* D,
+                            float* out, int batch, int Nr, int Nc, int level, const float* k2d,
+                            int hlen, cudaStream_t st);
+
+// kernels_ops.cu
+int pwt_launch_eltwise(const PwtSegTable& t, int op, cudaStream_t st);
+int pwt_launch_group_soft(float* h, float* v, float* d, float* a, long long n, float beta,
+                          cudaStream_t st);
+int pwt_launch_norms(const PwtSegTable& t, double* d_acc /* [2]: l1, l2sq */, cudaStream_t st);
+int pwt_launch_axpy(const PwtSegTable& dst, const PwtSegTable& src, float alpha, cudaStream_t st);
+int pwt_launch_circshift(const float* in, float* out, int batch, int Nr, int Nc, int sr, int sc,
+                         cudaStream_t st);
+int pwt_launch_fill(float* p, long long n, float v, cudaStream_t st);
+
+// kernels_fast.cu : register/shuffle-blocked kernels for short filters on the headline path.
+// Return 0 when the configuration is not covered (caller falls back to the generic kernels).
+int pwt_fast_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr,
+                       int Nc, long long in_bs, long long out_bs, const PwtFilters& f, bool haar,
+                       cudaStream_t st);
+int pwt_fast_dwt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out,
+                       int batch, int nr, int nc, int Nr_out, int Nc_out, long long in_bs,
+                       long long out_bs, const PwtFilters& f, bool haar, cudaStream_t st);

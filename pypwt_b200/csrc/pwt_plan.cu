@@ -1,0 +1,999 @@
+// Plan object + C ABI (include/pwt_b200.h).  Host-side driver of the hot path: owns the device
+// slab, the per-instance filters, the stream, and the reference's state machine and dispatch
+// (pdwt/src/wt.cu:84-665), re-designed around fused single-launch-per-level kernels.
+//
+// Device memory layout (one cudaMalloc per plan, 256-byte aligned sub-buffers):
+//   [ image  B*Nr*Nc ][ image2 (cycle spinning only) ][ band 0 = A ][ band 1 ] ... [ tmp ]
+// band 0 is allocated at level-1 size like the reference (common.cu:421-423) because it doubles as
+// the ping-pong buffer of the intermediate approximations; every band is a dense row-major array
+// (per image of the stack), so pwt_coeff_ptr() exposes the same layout as the reference.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <strings.h>
+
+#include "../../include/pwt_b200.h"
+#include "pwt_internal.h"
+
+int pwt_is_haar_alias(const char* wname);
+int pwt_fill_filters(const char* wname, PwtFilters* out);
+
+// ---- error plumbing --------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(PWT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),      \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+#define CK_LAUNCH()                                                                                \
+    do {                                                                                           \
+        cudaError_t e_ = cudaGetLastError();                                                       \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(PWT_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_),  \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+// ---- minimal NCCL binding (dlopen: the product has no link-time dependency on NCCL) -----------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId_t;
+struct NcclApi {
+    void* lib;
+    int (*GetUniqueId)(ncclUniqueId_t*);
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId_t, int);
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+    int (*CommDestroy)(ncclComm_t);
+    const char* (*GetErrorString)(int);
+};
+static NcclApi g_nccl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+static int load_nccl() {
+    if (g_nccl.lib) return PWT_OK;
+    const char* cands[] = {getenv("PWT_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* c : cands) {
+        if (!c || !*c) continue;
+        lib = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) return fail(PWT_ERR_COMM, "cannot dlopen libnccl.so.2 (set PWT_NCCL_LIB): %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(ncclUniqueId_t*))dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId_t, int))dlsym(lib, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(
+        lib, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail(PWT_ERR_COMM, "libnccl is missing required symbols");
+    g_nccl.lib = lib;
+    return PWT_OK;
+}
+enum { kNcclFloat64 = 8, kNcclSum = 0 };
+
+// ---- the plan --------------------------------------------------------------------------------
+struct pwt_plan {
+    int device;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    int batch, Nr, Nc, ndims, nlevels, hlen, do_swt, do_separable, do_cs;
+    int state, shift_r, shift_c;
+    char wname[128];
+    PwtFilters filt;
+    float* d_k2d_fwd;   // non-separable analysis filters  [LL, LH, HL, HH], hlen*hlen each
+    float* d_k2d_inv;   // non-separable synthesis filters
+    int lvNr[PWT_MAX_LEVELS + 1], lvNc[PWT_MAX_LEVELS + 1];
+    float* slab;
+    size_t slab_floats;
+    float* d_image;
+    float* d_image2;    // second image plane (cycle spinning): shifts are a kernel + pointer swap
+    float* d_tmp;
+    size_t tmp_floats;
+    int nbands;
+    float* d_band[PWT_MAX_BANDS];
+    int band_nr[PWT_MAX_BANDS], band_nc[PWT_MAX_BANDS];
+    double* d_acc;      // device accumulators for the norms
+    double* h_acc;      // pinned mirror
+    void* d_flush;
+    size_t flush_bytes;
+    long long launches;
+    int kernel_mode;
+    unsigned custom_len;   // taps given to set_filters_forward (0: built-in bank)
+    ncclComm_t comm;
+    int comm_nranks;
+};
+
+static inline int div2i(int n) { return (n + 1) >> 1; }            // utils.cu:24-27
+static inline int ilog2i(int i) {                                   // utils.cu:14-20 (guarded)
+    int l = 0;
+    while (i > 1) {
+        i >>= 1;
+        ++l;
+    }
+    return l;
+}
+static inline size_t align64(size_t nfloats) { return (nfloats + 63) & ~(size_t)63; }
+static inline bool is_haar(const pwt_plan* p) { return p->hlen == 2 && !p->do_swt; }  // wt.cu:248,255
+static inline long long img_elems(const pwt_plan* p) { return (long long)p->Nr * p->Nc; }
+static inline long long band_elems(const pwt_plan* p, int b) {
+    return (long long)p->band_nr[b] * p->band_nc[b];
+}
+static inline long long lvl_elems(const pwt_plan* p, int l) { return (long long)p->lvNr[l] * p->lvNc[l]; }
+
+static int build_k2d(pwt_plan* p) {
+    // nonseparable.cu:70-74: LL = lo(x)lo, LH = lo(x)hi, HL = hi(x)lo, HH = hi(x)hi with
+    // res[i*len+j] = a[i]*b[j]  (i = y tap, j = x tap)
+    const int F = p->hlen;
+    const size_t n = (size_t)4 * F * F;
+    float* h = (float*)malloc(2 * n * sizeof(float));
+    if (!h) return fail(PWT_ERR_NOMEM, "out of host memory");
+    for (int dir = 0; dir < 2; dir++) {
+        const float* lo = dir ? p->filt.IL : p->filt.L;
+        const float* hi = dir ? p->filt.IH : p->filt.H;
+        float* o = h + dir * n;
+        for (int i = 0; i < F; i++)
+            for (int j = 0; j < F; j++) {
+                o[0 * F * F + i * F + j] = lo[i] * lo[j];
+                o[1 * F * F + i * F + j] = lo[i] * hi[j];
+                o[2 * F * F + i * F + j] = hi[i] * lo[j];
+                o[3 * F * F + i * F + j] = hi[i] * hi[j];
+            }
+    }
+    cudaError_t e = cudaMemcpyAsync(p->d_k2d_fwd, h, n * sizeof(float), cudaMemcpyHostToDevice, p->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(p->d_k2d_inv, h + n, n * sizeof(float), cudaMemcpyHostToDevice, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    free(h);
+    if (e != cudaSuccess) return fail(PWT_ERR_CUDA, "2D filter upload failed: %s", cudaGetErrorString(e));
+    return PWT_OK;
+}
+
+static void compute_geometry(pwt_plan* p) {
+    p->lvNr[0] = p->Nr;
+    p->lvNc[0] = p->Nc;
+    for (int l = 1; l <= p->nlevels; l++) {
+        if (p->do_swt) {
+            p->lvNr[l] = p->Nr;
+            p->lvNc[l] = p->Nc;
+        } else {
+            p->lvNr[l] = p->ndims == 2 ? div2i(p->lvNr[l - 1]) : p->Nr;
+            p->lvNc[l] = div2i(p->lvNc[l - 1]);
+        }
+    }
+    const int L = p->nlevels;
+    if (p->ndims == 2) {
+        p->nbands = 3 * L + 1;
+        for (int i = 0; i < L; i++)
+            for (int j = 1; j <= 3; j++) {
+                p->band_nr[3 * i + j] = p->lvNr[i + 1];
+                p->band_nc[3 * i + j] = p->lvNc[i + 1];
+            }
+    } else {
+        p->nbands = L + 1;
+        for (int i = 0; i < L; i++) {
+            p->band_nr[i + 1] = p->lvNr[i + 1];
+            p->band_nc[i + 1] = p->lvNc[i + 1];
+        }
+    }
+    p->band_nr[0] = p->lvNr[L];
+    p->band_nc[0] = p->lvNc[L];
+}
+
+static int alloc_plan(pwt_plan* p) {
+    const size_t B = (size_t)p->batch;
+    const size_t img = align64(B * img_elems(p));
+    size_t total = img + (p->do_cs ? img : 0);
+    size_t off[PWT_MAX_BANDS];
+    for (int b = 0; b < p->nbands; b++) {
+        off[b] = total;
+        const size_t n = b == 0 ? B * (size_t)lvl_elems(p, 1) : B * (size_t)band_elems(p, b);
+        total += align64(n);
+    }
+    // scratch: DWT needs one approximation plane (we keep a full image so circshift can use it);
+    // the unfused SWT path needs two full planes for (lo, hi)/(t1, t2) plus the A ping-pong plane.
+    p->tmp_floats = (p->do_swt && p->ndims == 2) ? 3 * img : img;
+    const size_t tmp_off = total;
+    total += p->tmp_floats;
+    p->slab_floats = total;
+    CK(cudaMalloc((void**)&p->slab, total * sizeof(float)));
+    CK(cudaMemsetAsync(p->slab, 0, total * sizeof(float), p->stream));
+    p->d_image = p->slab;
+    p->d_image2 = p->do_cs ? p->slab + img : nullptr;
+    for (int b = 0; b < p->nbands; b++) p->d_band[b] = p->slab + off[b];
+    p->d_tmp = p->slab + tmp_off;
+    const size_t k2d = (size_t)4 * PWT_MAX_TAPS * PWT_MAX_TAPS * sizeof(float);
+    CK(cudaMalloc((void**)&p->d_k2d_fwd, k2d));
+    CK(cudaMalloc((void**)&p->d_k2d_inv, k2d));
+    CK(cudaMalloc((void**)&p->d_acc, 2 * sizeof(double)));
+    CK(cudaMallocHost((void**)&p->h_acc, 2 * sizeof(double)));
+    return PWT_OK;
+}
+
+extern "C" void pwt_destroy(pwt_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->slab) cudaFree(p->slab);
+    if (p->d_k2d_fwd) cudaFree(p->d_k2d_fwd);
+    if (p->d_k2d_inv) cudaFree(p->d_k2d_inv);
+    if (p->d_acc) cudaFree(p->d_acc);
+    if (p->h_acc) cudaFreeHost(p->h_acc);
+    if (p->d_flush) cudaFree(p->d_flush);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    free(p);
+}
+
+extern "C" int pwt_create_batch(pwt_plan** out, const float* img, int batch, int Nr, int Nc,
+                                const char* wname, int levels, int memisonhost, int do_separable,
+                                int do_cycle_spinning, int do_swt, int ndim) {
+    if (!out) return fail(PWT_ERR_ARG, "null output handle");
+    *out = nullptr;
+    if (!wname || Nr < 1 || Nc < 1 || batch < 1) return fail(PWT_ERR_ARG, "invalid geometry %dx%dx%d", batch, Nr, Nc);
+    if ((long long)Nr * Nc >= (1LL << 31)) return fail(PWT_ERR_ARG, "one image must hold < 2^31 samples");
+    if (ndim > 2) return fail(PWT_ERR_UNSUPPORTED, "ndim=%d is not implemented", ndim);   // wt.cu:171-175
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(PWT_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+
+    pwt_plan* p = (pwt_plan*)calloc(1, sizeof(pwt_plan));
+    if (!p) return fail(PWT_ERR_NOMEM, "out of host memory");
+    cudaGetDevice(&p->device);
+    p->batch = batch;
+    p->Nr = Nr;
+    p->Nc = Nc;
+    p->do_swt = do_swt ? 1 : 0;
+    p->do_cs = do_cycle_spinning ? 1 : 0;
+    p->state = PWT_INIT;
+    p->ndims = (ndim < 2 || Nr == 1) ? 1 : 2;                       // wt.cu:133-136
+    p->do_separable = (p->ndims == 1) ? 1 : (do_separable ? 1 : 0); // wt.cu:138-142
+    strncpy(p->wname, wname, sizeof(p->wname) - 1);
+    if (levels < 1) levels = 1;                                     // wt.cu:111-114
+
+    // filters (separable.cu:19-54).  With do_swt only the table names are known (separable.cu:24-28).
+    if (p->do_swt && pwt_is_haar_alias(wname) && strcasecmp(wname, "haar")) {
+        free(p);
+        return fail(PWT_ERR_UNKNOWN_WAVELET, "unknown wavelet '%s' for the stationary transform", wname);
+    }
+    const int hlen = pwt_fill_filters(wname, &p->filt);
+    if (hlen < 0) {
+        free(p);
+        return fail(PWT_ERR_UNKNOWN_WAVELET, "unknown wavelet name '%s'", wname);
+    }
+    p->hlen = hlen;
+    // level clipping (wt.cu:156-165)
+    const int N = p->ndims == 2 ? (Nr < Nc ? Nr : Nc) : Nc;
+    const int wmaxlev = ilog2i(N / (hlen - 1));
+    if (wmaxlev < 1) {
+        free(p);
+        return fail(PWT_ERR_TOO_SMALL, "a %dx%d image is too small for wavelet %s (%d taps)", Nr, Nc, wname, hlen);
+    }
+    if (levels > wmaxlev) {
+        printf("Warning: required level (%d) is greater than the maximum possible level for %s (%d) on a %dx%d image.\n",
+               levels, wname, wmaxlev, Nc, Nr);
+        printf("Forcing nlevels = %d\n", wmaxlev);
+        levels = wmaxlev;
+    }
+    if (levels > PWT_MAX_LEVELS) levels = PWT_MAX_LEVELS;
+    p->nlevels = levels;
+    if (p->do_cs && p->ndims == 1) {                                // wt.cu:179-183
+        free(p);
+        return fail(PWT_ERR_UNSUPPORTED, "cycle spinning is not implemented for 1D. Use SWT instead.");
+    }
+    if (p->do_cs && p->do_swt)
+        puts("Warning: makes little sense to use Cycle spinning with stationary Wavelet transform");
+    compute_geometry(p);
+
+    int rc = PWT_OK;
+    cudaError_t e = cudaStreamCreate(&p->stream);
+    if (e == cudaSuccess) e = cudaEventCreate(&p->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&p->ev1);
+    if (e != cudaSuccess) rc = fail(PWT_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
+    if (rc == PWT_OK) rc = alloc_plan(p);
+    if (rc == PWT_OK && img) {
+        e = cudaMemcpyAsync(p->d_image, img, (size_t)batch * img_elems(p) * sizeof(float),
+                            memisonhost ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, p->stream);
+        if (e != cudaSuccess) rc = fail(PWT_ERR_CUDA, "image upload failed: %s", cudaGetErrorString(e));
+    }
+    if (rc == PWT_OK && !p->do_separable) rc = build_k2d(p);
+    if (rc == PWT_OK) {
+        e = cudaStreamSynchronize(p->stream);
+        if (e != cudaSuccess) rc = fail(PWT_ERR_CUDA, "plan initialisation failed: %s", cudaGetErrorString(e));
+    }
+    if (rc != PWT_OK) {
+        pwt_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return PWT_OK;
+}
+
+extern "C" int pwt_create(pwt_plan** out, const float* img, int Nr, int Nc, const char* wname,
+                          int levels, int memisonhost, int do_separable, int do_cycle_spinning,
+                          int do_swt, int ndim) {
+    return pwt_create_batch(out, img, 1, Nr, Nc, wname, levels, memisonhost, do_separable,
+                            do_cycle_spinning, do_swt, ndim);
+}
+
+extern "C" int pwt_clone(pwt_plan** out, const pwt_plan* src) {
+    if (!out || !src) return fail(PWT_ERR_ARG, "null argument");
+    pwt_plan* p = (pwt_plan*)malloc(sizeof(pwt_plan));
+    if (!p) return fail(PWT_ERR_NOMEM, "out of host memory");
+    memcpy(p, src, sizeof(pwt_plan));
+    p->stream = nullptr;
+    p->ev0 = p->ev1 = nullptr;
+    p->slab = nullptr;
+    p->d_k2d_fwd = p->d_k2d_inv = nullptr;
+    p->d_acc = nullptr;
+    p->h_acc = nullptr;
+    p->d_flush = nullptr;
+    p->flush_bytes = 0;
+    p->comm = nullptr;
+    p->comm_nranks = 0;
+    p->launches = 0;
+    *out = nullptr;
+    cudaSetDevice(src->device);
+    cudaStreamSynchronize(src->stream);
+    int rc = PWT_OK;
+    cudaError_t e = cudaStreamCreate(&p->stream);
+    if (e == cudaSuccess) e = cudaEventCreate(&p->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&p->ev1);
+    if (e != cudaSuccess) rc = fail(PWT_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
+    if (rc == PWT_OK) rc = alloc_plan(p);
+    if (rc == PWT_OK) {
+        // alloc_plan placed image/image2 in canonical order; keep the source's current roles
+        if (src->d_image2 && src->d_image != src->slab) {
+            float* t = p->d_image;
+            p->d_image = p->d_image2;
+            p->d_image2 = t;
+        }
+        const size_t k2d = (size_t)4 * PWT_MAX_TAPS * PWT_MAX_TAPS * sizeof(float);
+        e = cudaMemcpyAsync(p->slab, src->slab, src->slab_floats * sizeof(float), cudaMemcpyDeviceToDevice, p->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_k2d_fwd, src->d_k2d_fwd, k2d, cudaMemcpyDeviceToDevice, p->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_k2d_inv, src->d_k2d_inv, k2d, cudaMemcpyDeviceToDevice, p->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+        if (e != cudaSuccess) rc = fail(PWT_ERR_CUDA, "plan copy failed: %s", cudaGetErrorString(e));
+    }
+    if (rc != PWT_OK) {
+        pwt_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return PWT_OK;
+}
+
+extern "C" int pwt_get_info(const pwt_plan* p, pwt_info* info) {
+    if (!p || !info) return fail(PWT_ERR_ARG, "null argument");
+    info->batch = p->batch;
+    info->Nr = p->Nr;
+    info->Nc = p->Nc;
+    info->ndims = p->ndims;
+    info->nlevels = p->nlevels;
+    info->hlen = p->hlen;
+    info->do_swt = p->do_swt;
+    info->do_separable = p->do_separable;
+    info->do_cycle_spinning = p->do_cs;
+    info->state = p->state;
+    info->shift_r = p->shift_r;
+    info->shift_c = p->shift_c;
+    info->nbands = p->nbands;
+    info->device = p->device;
+    return PWT_OK;
+}
+
+extern "C" int pwt_band_shape(const pwt_plan* p, int num, int* nr, int* nc) {
+    if (!p || num < 0 || num >= p->nbands) return fail(PWT_ERR_ARG, "band %d out of range", num);
+    if (nr) *nr = p->band_nr[num];
+    if (nc) *nc = p->band_nc[num];
+    return PWT_OK;
+}
+
+// ---- circular shift ---------------------------------------------------------------------------
+static int do_circshift(pwt_plan* p, int sr, int sc, int inplace) {
+    // common.cu:378-396
+    const int Nr = p->Nr, Nc = p->Nc;
+    if (sr < 0) sr += Nr;
+    if (sc < 0) sc += Nc;
+    sr %= Nr;
+    sc %= Nc;
+    if (sr < 0) sr += Nr;
+    if (sc < 0) sc += Nc;
+    if (p->ndims == 1) sr = 0;
+    if (!inplace) {
+        p->launches += pwt_launch_circshift(p->d_image, p->d_tmp, p->batch, Nr, Nc, sr, sc, p->stream);
+    } else if (p->d_image2) {
+        // one gather pass into the spare plane, then swap roles (8 B/px instead of the
+        // reference's memcpy + kernel = 16 B/px)
+        p->launches += pwt_launch_circshift(p->d_image, p->d_image2, p->batch, Nr, Nc, sr, sc, p->stream);
+        float* t = p->d_image;
+        p->d_image = p->d_image2;
+        p->d_image2 = t;
+    } else {
+        p->launches += pwt_launch_circshift(p->d_image, p->d_tmp, p->batch, Nr, Nc, sr, sc, p->stream);
+        CK(cudaMemcpyAsync(p->d_image, p->d_tmp, (size_t)p->batch * img_elems(p) * sizeof(float),
+                           cudaMemcpyDeviceToDevice, p->stream));
+    }
+    CK_LAUNCH();
+    return PWT_OK;
+}
+
+extern "C" int pwt_circshift(pwt_plan* p, int sr, int sc, int inplace) {
+    if (!p) return fail(PWT_ERR_ARG, "null plan");
+    cudaSetDevice(p->device);
+    return do_circshift(p, sr, sc, inplace);
+}
+
+// ---- forward ----------------------------------------------------------------------------------
+// Destination of the level-l approximation so that A_L ends in band 0 without a fix-up copy
+// (the reference ping-pongs and memcpy's back for even level counts, e.g. haar.cu:83).
+static inline float* approx_dst(pwt_plan* p, int l, float* alt) {
+    return ((p->nlevels - l) & 1) ? alt : p->d_band[0];
+}
+
+extern "C" int pwt_forward(pwt_plan* p) {
+    if (!p) return fail(PWT_ERR_ARG, "null plan");
+    if (p->state == PWT_CREATION_ERROR) return fail(PWT_ERR_STATE, "plan is in creation-error state");
+    cudaSetDevice(p->device);
+    if (p->do_cs) {                                                 // wt.cu:242-246
+        p->shift_r = rand() % p->Nr;
+        p->shift_c = rand() % p->Nc;
+        int rc = do_circshift(p, p->shift_r, p->shift_c, 1);
+        if (rc != PWT_OK) return rc;
+    }
+    const int L = p->nlevels, B = p->batch;
+    const bool haar = is_haar(p);
+    cudaStream_t st = p->stream;
+    const float* src = p->d_image;
+    if (p->ndims == 1) {
+        const int rows = B * p->Nr;
+        for (int l = 1; l <= L; l++) {
+            float* dstA = approx_dst(p, l, p->d_tmp);
+            if (p->do_swt)
+                p->launches += pwt_launch_swt_fwd1d(src, dstA, p->d_band[l], rows, p->Nc, l, p->filt, st);
+            else
+                p->launches += pwt_launch_dwt_fwd1d(src, dstA, p->d_band[l], rows, p->lvNc[l - 1], p->filt, haar, st);
+            src = dstA;
+        }
+    } else {
+        const long long plane = (long long)B * img_elems(p);
+        for (int l = 1; l <= L; l++) {
+            float* Hb = p->d_band[3 * (l - 1) + 1];
+            float* V = p->d_band[3 * (l - 1) + 2];
+            float* D = p->d_band[3 * (l - 1) + 3];
+            if (p->do_swt) {
+                float* dstA = approx_dst(p, l, p->d_tmp + 2 * plane);
+                if (p->do_separable)
+                    p->launches += pwt_launch_swt_fwd2d(src, dstA, Hb, V, D, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
+                else
+                    p->launches += pwt_launch_ns_swt_fwd2d(src, dstA, Hb, V, D, B, p->Nr, p->Nc, l, p->d_k2d_fwd, p->hlen, st);
+                src = dstA;
+            } else {
+                float* dstA = approx_dst(p, l, p->d_tmp);
+                const long long in_bs = lvl_elems(p, l - 1), out_bs = lvl_elems(p, l);
+                const int nr = p->lvNr[l - 1], nc = p->lvNc[l - 1];
+                if (haar || p->do_separable) {
+                    int n = 0;
+                    if (p->kernel_mode == 0)
+                        n = pwt_fast_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, st);
+                    if (!n) n = pwt_launch_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, st);
+                    p->launches += n;
+                } else {
+                    p->launches += pwt_launch_ns_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->d_k2d_fwd, p->hlen, st);
+                }
+                src = dstA;
+            }
+        }
+    }
+    CK_LAUNCH();
+    p->state = PWT_FORWARD;
+    return PWT_OK;
+}
+
+// ---- inverse ----------------------------------------------------------------------------------
+extern "C" int pwt_inverse(pwt_plan* p) {
+    if (!p) return fail(PWT_ERR_ARG, "null plan");
+    if (p->state == PWT_INVERSE) {                                  // wt.cu:272-275
+        puts("Warning: W.inverse() has already been run. Inverse is available in W.get_image()");
+        return 1;
+    }
+    if (p->state == PWT_CREATION_ERROR) return fail(PWT_ERR_STATE, "plan is in creation-error state");
+    cudaSetDevice(p->device);
+    const int L = p->nlevels, B = p->batch;
+    const bool haar = is_haar(p);
+    cudaStream_t st = p->stream;
+    const float* cur = p->d_band[0];
+    if (p->ndims == 1) {
+        const int rows = B * p->Nr;
+        for (int l = L; l >= 1; l--) {
+            float* dst = (l == 1) ? p->d_image : (cur == p->d_band[0] ? p->d_tmp : p->d_band[0]);
+            if (p->do_swt)
+                p->launches += pwt_launch_swt_inv1d(cur, p->d_band[l], dst, rows, p->Nc, l, p->filt, st);
+            else
+                p->launches += pwt_launch_dwt_inv1d(cur, p->d_band[l], dst, rows, p->lvNc[l], p->lvNc[l - 1], p->filt, haar, st);
+            cur = dst;
+        }
+    } else {
+        const long long plane = (long long)B * img_elems(p);
+        for (int l = L; l >= 1; l--) {
+            const float* Hb = p->d_band[3 * (l - 1) + 1];
+            const float* V = p->d_band[3 * (l - 1) + 2];
+            const float* D = p->d_band[3 * (l - 1) + 3];
+            if (p->do_swt) {
+                float* alt = p->d_tmp + 2 * plane;
+                float* dst = (l == 1) ? p->d_image : (cur == p->d_band[0] ? alt : p->d_band[0]);
+                if (p->do_separable)
+                    p->launches += pwt_launch_swt_inv2d(cur, Hb, V, D, dst, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
+                else
+                    p->launches += pwt_launch_ns_swt_inv2d(cur, Hb, V, D, dst, B, p->Nr, p->Nc, l, p->d_k2d_inv, p->hlen, st);
+                cur = dst;
+            } else {
+                float* dst = (l == 1) ? p->d_image : (cur == p->d_band[0] ? p->d_tmp : p->d_band[0]);
+                const long long in_bs = lvl_elems(p, l), out_bs = lvl_elems(p, l - 1);
+                const int nr = p->lvNr[l], nc = p->lvNc[l], Nro = p->lvNr[l - 1], Nco = p->lvNc[l - 1];
+                if (haar || p->do_separable) {
+                    int n = 0;
+                    if (p->kernel_mode == 0)
+                        n = pwt_fast_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, st);
+                    if (!n) n = pwt_launch_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, st);
+                    p->launches += n;
+                } else {
+                    p->launches += pwt_launch_ns_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->d_k2d_inv, p->hlen, st);
+                }
+                cur = dst;
+            }
+        }
+    }
+    CK_LAUNCH();
+    if (p->do_cs) {                                                 // wt.cu:303
+        int rc = do_circshift(p, -p->shift_r, -p->shift_c, 1);
+        if (rc != PWT_OK) return rc;
+    }
+    p->state = PWT_INVERSE;
+    return PWT_OK;
+}
+
+// ---- thresholds / shrink ----------------------------------------------------------------------
+static const double kSqrt2 = 1.4142135623730951;   // common.cu:8
+
+static void add_seg(PwtSegTable* t, float* ptr, long long n, float beta) {
+    if (n <= 0 || t->nseg >= PWT_MAX_SEGS) return;
+    t->seg[t->nseg].ptr = ptr;
+    t->seg[t->nseg].n = n;
+    t->seg[t->nseg].beta = beta;
+    t->seg[t->nseg].pad = 0;
+    t->nseg++;
+}
+
+// Per-band parameter schedule of the reference callers (common.cu:219-282, 347-371):
+//  - details of level i+1 use beta / sqrt(2)^(i+1), computed by cumulative fp32 division by the
+//    double constant SQRT_2 when normalize > 0;
+//  - the approximation uses beta / sqrt(2)^L for the soft threshold, but the UNscaled beta for the
+//    hard threshold (common.cu:264-270 computes beta2 and then passes beta) -- replicated.
+static void build_thresh_table(pwt_plan* p, PwtSegTable* t, float beta, int app, int normalize,
+                               bool app_scaled, bool const_param, float cparam) {
+    t->nseg = 0;
+    const long long B = p->batch;
+    const int L = p->nlevels;
+    if (app) {
+        float beta2 = beta;
+        if (normalize > 0 && app_scaled) {
+            const int n2 = L / 2;
+            beta2 /= (float)(1 << n2);
+            if (n2 * 2 != L) beta2 = (float)(beta2 / kSqrt2);
+        }
+        add_seg(t, p->d_band[0], B * band_elems(p, 0), const_param ? cparam : beta2);
+    }
+    for (int i = 0; i < L; i++) {
+        if (normalize > 0) beta = (float)(beta / kSqrt2);
+        const float b = const_param ? cparam : beta;
+        if (p->ndims == 2) {
+            for (int j = 1; j <= 3; j++) add_seg(t, p->d_band[3 * i + j], B * band_elems(p, 3 * i + j), b);
+        } else {
+            add_seg(t, p->d_band[i + 1], B * band_elems(p, i + 1), b);
+        }
+    }
+}
+
+static int run_thresh(pwt_plan* p, int op, float beta, int app, int normalize, bool app_scaled,
+                      const char* what) {
+    if (!p) return fail(PWT_ERR_ARG, "null plan");
+    if (p->state == PWT_INVERSE) {                                  // wt.cu:309-312
+        printf("Warning: Wavelets(): cannot %s coefficients, as they were modified by W.inverse()\n", what);
+        return 1;
+    }
+    cudaSetDevice(p->device);
+    PwtSegTable t;
+    if (op == PWT_OP_SCALE)
+        build_thresh_table(p, &t, beta, app, 0, false, true, 1.0f / (1.0f + beta));   // common.cu:355
+    else
+        build_thresh_table(p, &t, beta, app, normalize, app_scaled, false, 0.f);
+    p->launches += pwt_launch_eltwise(t, op, p->stream);
+    CK_LAUNCH();
+    return PWT_OK;
+}
+
+extern "C" int pwt_soft_threshold(pwt_plan* p, float beta, int app, int normalize) {
+    return run_thresh(p, PWT_OP_SOFT, beta, app, normalize, true, "threshold");
+}
+extern "C" int pwt_hard_threshold(pwt_plan* p, float beta, int app, int normalize) {
+    return run_thresh(p, PWT_OP_HARD, beta, app, normalize, false, "threshold");
+}
+extern "C" int pwt_proj_linf(pwt_plan* p, float beta, int app) {
+    return run_thresh(p, PWT_OP_PROJ, beta, app, 0, false, "project");
+}
+extern "C" int pwt_shrink(pwt_plan* p, float beta, int app) {
+    return run_thresh(p, PWT_OP_SCALE, beta, app, 0, false, "shrink");
+}
+
+extern "C" int pwt_group_soft_threshold(pwt_plan* p, float beta, int app, int normalize) {
+    // common.cu:311-341: A joins the group of the LAST level only
+    if (!p) return fail(PWT_ERR_ARG, "null plan");
+    if (p->state == PWT_INVERSE) {
+        puts("Warning: Wavelets(): cannot threshold coefficients, as they were modified by W.inverse()");
+        return 1;
+    }
+    cudaSetDevice(p->device);
+    const int L = p->nlevels;
+    for (int i = 0; i < L; i++) {
+        if (normalize > 0) beta = (float)(beta / kSqrt2);
+        float* a = (app && i == L - 1) ? p->d_band[0] : nullptr;
+        if (p->ndims == 2) {
+            const long long n = (long long)p->batch * band_elems(p, 3 * i + 1);
+            p->launches += pwt_launch_group_soft(p->d_band[3 * i + 1], p->d_band[3 * i + 2], p->d_band[3 * i + 3], a, n, beta, p->stream);
+        } else {
+            const long long n = (long long)p->batch * band_elems(p, i + 1);
+            p->launches += pwt_launch_group_soft(nullptr, nullptr, p->d_band[i + 1], a, n, beta, p->stream);
+        }
+    }
+    CK_LAUNCH();
+    return PWT_OK;
+}
+
+// ---- norms ------------------------------------------------------------------------------------
+static int local_norms_async(pwt_plan* p) {
+    PwtSegTable t;
+    t.nseg = 0;
+    for (int b = 0; b < p->nbands; b++) add_seg(&t, p->d_band[b], (long long)p->batch * band_elems(p, b), 0.f);
+    p->launches += pwt_launch_norms(t, p->d_acc, p->stream);
+    CK_LAUNCH();
+    return PWT_OK;
+}
+
+extern "C" int pwt_norms(pwt_plan* p, double* n1, double* n2) {
+    if (!p) return fail(PWT_ERR_ARG, "null plan");
+    cudaSetDevice(p->device);
+    int rc = local_norms_async(p);
+    if (rc != PWT_OK) return rc;
+    CK(cudaMemcpyAsync(p->h_acc, p->d_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    if (n1) *n1 = p->h_acc[0];
+    if (n2) *n2 = p->h_acc[1];
+    return PWT_OK;
+}
+extern "C" int pwt_norm1(pwt_plan* p, float* out) {
+    double a = 0, b = 0;
+    int rc = pwt_norms(p, &a, &b);
+    if (rc == PWT_OK && out) *out = (float)a;
+    return rc;
+}
+extern "C" int pwt_norm2sq(pwt_plan* p, float* out) {
+    double a = 0, b = 0;
+    int rc = pwt_norms(p, &a, &b);
+    if (rc == PWT_OK && out) *out = (float)b;
+    return rc;
+}
+
+// ---- add_wavelet ------------------------------------------------------------------------------
+extern "C" int pwt_add_wavelet(pwt_plan* d, const pwt_plan* s, float alpha) {
+    if (!d || !s) return fail(PWT_ERR_ARG, "null plan");
+    // wt.cu:625-650
+    if (d->nlevels != s->nlevels || strcasecmp(d->wname, s->wname)) {
+        puts("ERROR: add_wavelet(): right operand is not the same transform (wname, level)");
+        return -1;
+    }
+    if (d->state == PWT_INVERSE || s->state == PWT_INVERSE) {
+        puts("WARNING: add_wavelet(): this operation makes no sense when wavelet has just been inverted");
+        return 1;
+    }
+    if (d->Nr != s->Nr || d->Nc != s->Nc || d->ndims != s->ndims || d->batch != s->batch) {
+        puts("ERROR: add_wavelet(): operands do not have the same geometry");
+        return -2;
+    }
+    if ((d->do_swt != 0) != (s->do_swt != 0)) {
+        puts("ERROR: add_wavelet(): operands should both use SWT or DWT");
+        return -3;
+    }
+    if (d->do_cs && s->do_cs && (d->shift_r != s->shift_r || d->shift_c != s->shift_c)) {
+        puts("ERROR: add_wavelet(): operands do not have the same current shift");
+        return -4;
+    }
+    cudaSetDevice(d->device);
+    cudaStreamSynchronize(s->stream);   // the source's pending work must be visible
+    PwtSegTable td, ts;
+    td.nseg = ts.nseg = 0;
+    for (int b = 0; b < d->nbands; b++) {
+        const long long n = (long long)d->batch * band_elems(d, b);
+        add_seg(&td, d->d_band[b], n, 0.f);
+        add_seg(&ts, s->d_band[b], n, 0.f);
+    }
+    d->launches += pwt_launch_axpy(td, ts, alpha, d->stream);
+    CK_LAUNCH();
+    return 0;
+}
+
+// ---- data in / out ----------------------------------------------------------------------------
+extern "C" int pwt_get_image(pwt_plan* p, float* dst) {
+    if (!p || !dst) return 0;
+    cudaSetDevice(p->device);
+    const size_t n = (size_t)p->batch * img_elems(p);
+    if (cudaMemcpyAsync(dst, p->d_image, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream) != cudaSuccess ||
+        cudaStreamSynchronize(p->stream) != cudaSuccess) {
+        fail(PWT_ERR_CUDA, "get_image failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
+    return n > 0x7fffffff ? 0x7fffffff : (int)n;
+}
+
+extern "C" int pwt_set_image(pwt_plan* p, const float* img, int on_device) {
+    if (!p || !img) return fail(PWT_ERR_ARG, "null argument");
+    cudaSetDevice(p->device);
+    const size_t n = (size_t)p->batch * img_elems(p);
+    CK(cudaMemcpyAsync(p->d_image, img, n * sizeof(float),
+                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, p->stream));
+    if (!on_device) CK(cudaStreamSynchronize(p->stream));   // the host buffer may be reused by the caller
+    p->state = PWT_INIT;                                            // wt.cu:430
+    return PWT_OK;
+}
+
+extern "C" int pwt_get_coeff(pwt_plan* p, float* dst, int num) {
+    if (!p || !dst || num < 0 || num >= p->nbands) return 0;
+    if (p->state == PWT_INVERSE) {                                  // wt.cu:474-477
+        puts("Warning: get_coeff(): inverse() has been performed, the coefficients has been modified and do not make sense anymore.");
+        return 0;
+    }
+    cudaSetDevice(p->device);
+    const size_t n = (size_t)p->batch * band_elems(p, num);
+    if (cudaMemcpyAsync(dst, p->d_band[num], n * sizeof(float), cudaMemcpyDeviceToHost, p->stream) != cudaSuccess ||
+        cudaStreamSynchronize(p->stream) != cudaSuccess) {
+        fail(PWT_ERR_CUDA, "get_coeff failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
+    return n > 0x7fffffff ? 0x7fffffff : (int)n;
+}
+
+extern "C" int pwt_set_coeff(pwt_plan* p, const float* src, int num, int on_device) {
+    if (!p || !src || num < 0 || num >= p->nbands) return fail(PWT_ERR_ARG, "bad argument");
+    cudaSetDevice(p->device);
+    const size_t n = (size_t)p->batch * band_elems(p, num);
+    CK(cudaMemcpyAsync(p->d_band[num], src, n * sizeof(float),
+                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, p->stream));
+    if (!on_device) CK(cudaStreamSynchronize(p->stream));
+    return PWT_OK;                                                  // state untouched (wt.cu:465)
+}
+
+extern "C" intptr_t pwt_image_ptr(pwt_plan* p) { return p ? (intptr_t)p->d_image : 0; }
+extern "C" intptr_t pwt_coeff_ptr(pwt_plan* p, int num) {
+    return (p && num >= 0 && num < p->nbands) ? (intptr_t)p->d_band[num] : 0;
+}
+
+// ---- custom filters ---------------------------------------------------------------------------
+// Odd lengths are zero-padded at the front to the next even length: for the analysis side this
+// reproduces the reference's odd-length window exactly (separable.cu:98-102: centre hlen/2).
+static void load_taps(float* dst, const float* src, unsigned len, unsigned padded) {
+    memset(dst, 0, PWT_MAX_TAPS * sizeof(float));
+    const unsigned o = padded - len;
+    for (unsigned k = 0; k < len; k++) dst[o + k] = src[k];
+}
+
+static int upload_k2d(pwt_plan* p, float* d_dst, const float* f[4], unsigned len, unsigned padded) {
+    const size_t n = (size_t)padded * padded;
+    float* h = (float*)calloc(4 * n, sizeof(float));
+    if (!h) return -3;
+    const unsigned o = padded - len;
+    for (int b = 0; b < 4; b++)
+        for (unsigned i = 0; i < len; i++)
+            for (unsigned j = 0; j < len; j++) h[b * n + (o + i) * padded + (o + j)] = f[b][i * len + j];
+    cudaError_t e = cudaMemcpyAsync(d_dst, h, 4 * n * sizeof(float), cudaMemcpyHostToDevice, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    free(h);
+    return e == cudaSuccess ? 0 : -3;
+}
+
+extern "C" int pwt_set_filters_forward(pwt_plan* p, const char* name, unsigned len, const float* f1,
+                                       const float* f2, const float* f3, const float* f4) {
+    if (!p || !f1 || !f2 || len < 2) return fail(PWT_ERR_ARG, "bad argument");
+    const unsigned padded = len + (len & 1);
+    if (padded > PWT_MAX_TAPS) {                                    // wt.cu:560-563
+        printf("ERROR: Wavelets.set_filters_forward(): filter length (%d) exceeds the maximum size (%d)\n", len, PWT_MAX_TAPS);
+        return -1;
+    }
+    cudaSetDevice(p->device);
+    int res = 0;
+    if (p->do_separable) {
+        load_taps(p->filt.L, f1, len, padded);
+        load_taps(p->filt.H, f2, len, padded);
+    } else {
+        if (!f3 || !f4) {
+            puts("ERROR: Wavelets.set_filters_forward(): expected argument 4 and 5 for non-separable filtering");
+            return -2;
+        }
+        const float* f[4] = {f1, f2, f3, f4};
+        res = upload_k2d(p, p->d_k2d_fwd, f, len, padded);
+    }
+    p->hlen = (int)padded;
+    p->filt.hlen = (int)padded;
+    p->custom_len = len;
+    if (name) {
+        memset(p->wname, 0, sizeof(p->wname));
+        strncpy(p->wname, name, sizeof(p->wname) - 1);
+    }
+    return res;
+}
+
+extern "C" int pwt_set_filters_inverse(pwt_plan* p, const float* f1, const float* f2, const float* f3,
+                                       const float* f4) {
+    if (!p || !f1 || !f2) return fail(PWT_ERR_ARG, "bad argument");
+    cudaSetDevice(p->device);
+    // the reference assumes the length given to set_filters_forward (wt.cu:587); odd lengths were
+    // padded there, the caller still passes the original number of taps
+    const unsigned padded = (unsigned)p->hlen;
+    const unsigned len = p->custom_len ? p->custom_len : padded;
+    if (p->do_separable) {
+        load_taps(p->filt.IL, f1, len, padded);
+        load_taps(p->filt.IH, f2, len, padded);
+        return 0;
+    }
+    if (!f3 || !f4) {
+        puts("ERROR: Wavelets.set_filters_inverse(): expected argument 4 and 5 for non-separable filtering");
+        return -2;
+    }
+    const float* f[4] = {f1, f2, f3, f4};
+    return upload_k2d(p, p->d_k2d_inv, f, len, padded);
+}
+
+// ---- misc -------------------------------------------------------------------------------------
+extern "C" int pwt_print_informations(pwt_plan* p) {
+    if (!p) return fail(PWT_ERR_ARG, "null plan");
+    // wt.cu:511-550
+    const char* yn[2] = {"no", "yes"};
+    puts("------------- Wavelet transform infos ------------");
+    printf("Data dimensions : ");
+    if (p->ndims == 2) printf("(%d, %d)\n", p->Nr, p->Nc);
+    else if (p->Nr == 1) printf("%d\n", p->Nc);
+    else printf("(%d, %d) [batched 1D transform]\n", p->Nr, p->Nc);
+    if (p->batch > 1) printf("Stack size : %d\n", p->batch);
+    printf("Wavelet name : %s\n", p->wname);
+    printf("Number of levels : %d\n", p->nlevels);
+    printf("Stationary WT : %s\n", yn[p->do_swt]);
+    printf("Cycle spinning : %s\n", yn[p->do_cs]);
+    printf("Separable transform : %s\n", yn[p->do_separable]);
+    printf("Estimated memory footprint : %.2f MB\n", p->slab_floats * sizeof(float) / 1e6);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, p->device) == cudaSuccess) printf("Running on device : %s\n", prop.name);
+    puts("--------------------------------------------------");
+    fflush(stdout);
+    return PWT_OK;
+}
+
+extern "C" int pwt_sync(pwt_plan* p) {
+    if (!p) return fail(PWT_ERR_ARG, "null plan");
+    cudaSetDevice(p->device);
+    CK(cudaStreamSynchronize(p->stream));
+    return PWT_OK;
+}
+
+extern "C" const char* pwt_last_error(void) { return g_err; }
+extern "C" const char* pwt_version(void) { return "1.0.3"; }
+extern "C" int pwt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int pwt_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(PWT_ERR_ARG, "null argument");
+    CK(cudaMallocHost(ptr, bytes ? bytes : 1));
+    return PWT_OK;
+}
+extern "C" int pwt_host_free(void* ptr) {
+    if (ptr) CK(cudaFreeHost(ptr));
+    return PWT_OK;
+}
+
+extern "C" int pwt_timer_start(pwt_plan* p) {
+    if (!p) return fail(PWT_ERR_ARG, "null plan");
+    cudaSetDevice(p->device);
+    CK(cudaEventRecord(p->ev0, p->stream));
+    return PWT_OK;
+}
+extern "C" int pwt_timer_stop(pwt_plan* p, float* ms) {
+    if (!p) return fail(PWT_ERR_ARG, "null plan");
+    cudaSetDevice(p->device);
+    CK(cudaEventRecord(p->ev1, p->stream));
+    CK(cudaEventSynchronize(p->ev1));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, p->ev0, p->ev1));
+    if (ms) *ms = t;
+    return PWT_OK;
+}
+extern "C" int pwt_flush_l2(pwt_plan* p) {
+    if (!p) return fail(PWT_ERR_ARG, "null plan");
+    cudaSetDevice(p->device);
+    if (!p->d_flush) {
+        p->flush_bytes = (size_t)256 << 20;   // > 126 MB L2
+        CK(cudaMalloc(&p->d_flush, p->flush_bytes));
+    }
+    CK(cudaMemsetAsync(p->d_flush, 0, p->flush_bytes, p->stream));
+    return PWT_OK;
+}
+extern "C" long long pwt_launch_count(const pwt_plan* p) { return p ? p->launches : 0; }
+extern "C" int pwt_set_kernel_mode(pwt_plan* p, int mode) {
+    if (!p) return fail(PWT_ERR_ARG, "null plan");
+    p->kernel_mode = mode;
+    return PWT_OK;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------------
+extern "C" int pwt_comm_unique_id(unsigned char id[128]) {
+    int rc = load_nccl();
+    if (rc != PWT_OK) return rc;
+    ncclUniqueId_t u;
+    const int r = g_nccl.GetUniqueId(&u);
+    if (r != 0) return fail(PWT_ERR_COMM, "ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    memcpy(id, u.internal, 128);
+    return PWT_OK;
+}
+
+extern "C" int pwt_comm_init(pwt_plan* p, int nranks, int rank, const unsigned char id[128]) {
+    if (!p || !id) return fail(PWT_ERR_ARG, "null argument");
+    int rc = load_nccl();
+    if (rc != PWT_OK) return rc;
+    cudaSetDevice(p->device);
+    ncclUniqueId_t u;
+    memcpy(u.internal, id, 128);
+    const int r = g_nccl.CommInitRank(&p->comm, nranks, u, rank);
+    if (r != 0) return fail(PWT_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    p->comm_nranks = nranks;
+    return PWT_OK;
+}
+
+extern "C" int pwt_comm_destroy(pwt_plan* p) {
+    if (p && p->comm && g_nccl.CommDestroy) {
+        cudaSetDevice(p->device);
+        cudaStreamSynchronize(p->stream);
+        g_nccl.CommDestroy(p->comm);
+        p->comm = nullptr;
+        p->comm_nranks = 0;
+    }
+    return PWT_OK;
+}
+
+extern "C" int pwt_norms_allreduce(pwt_plan* p, double* n1, double* n2) {
+    if (!p) return fail(PWT_ERR_ARG, "null plan");
+    if (!p->comm) return fail(PWT_ERR_COMM, "no communicator: call pwt_comm_init first");
+    cudaSetDevice(p->device);
+    int rc = local_norms_async(p);
+    if (rc != PWT_OK) return rc;
+    // the all-reduce is enqueued on the same stream right behind the reduction kernel: no host sync
+    const int r = g_nccl.AllReduce(p->d_acc, p->d_acc, 2, kNcclFloat64, kNcclSum, p->comm, p->stream);
+    if (r != 0) return fail(PWT_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    CK(cudaMemcpyAsync(p->h_acc, p->d_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    if (n1) *n1 = p->h_acc[0];
+    if (n2) *n2 = p->h_acc[1];
+    return PWT_OK;
+}

@@ -1,0 +1,588 @@
+# cython: language_level=3
+"""pycudwt -- drop-in `Wavelets` class over the B200-native C ABI (include/pwt_b200.h).
+
+Mirrors the reference's Cython wrapper (src/pypwt.pyx:64-616): same constructor signature,
+attributes, coefficient list layout, shape / dtype coercions, state rules and exceptions.
+All numerics run in libpwt_b200.so on the GPU; there is no CPU fallback.
+
+Extensions (not in the reference): 3D input with ndim=2 is treated as a stack of independent
+images (the reference raises NotImplementedError, pypwt.pyx:155-156); `norms()`, `sync()`,
+`image_into()`, pinned host buffers and the measurement helpers used by bench.py.
+"""
+import os
+import numpy as np
+from cython cimport view
+from libc.stdint cimport intptr_t
+
+cdef extern from "pwt_b200.h":
+    ctypedef struct pwt_plan:
+        pass
+    ctypedef struct pwt_info:
+        int batch
+        int Nr
+        int Nc
+        int ndims
+        int nlevels
+        int hlen
+        int do_swt
+        int do_separable
+        int do_cycle_spinning
+        int state
+        int shift_r
+        int shift_c
+        int nbands
+        int device
+    int pwt_create_batch(pwt_plan** out, const float* img, int batch, int Nr, int Nc, const char* wname,
+                         int levels, int memisonhost, int do_separable, int do_cycle_spinning,
+                         int do_swt, int ndim) nogil
+    int pwt_clone(pwt_plan** out, const pwt_plan* src) nogil
+    void pwt_destroy(pwt_plan* p) nogil
+    int pwt_get_info(const pwt_plan* p, pwt_info* info) nogil
+    int pwt_band_shape(const pwt_plan* p, int num, int* nr, int* nc) nogil
+    int pwt_forward(pwt_plan* p) nogil
+    int pwt_inverse(pwt_plan* p) nogil
+    int pwt_soft_threshold(pwt_plan* p, float beta, int app, int normalize) nogil
+    int pwt_hard_threshold(pwt_plan* p, float beta, int app, int normalize) nogil
+    int pwt_group_soft_threshold(pwt_plan* p, float beta, int app, int normalize) nogil
+    int pwt_shrink(pwt_plan* p, float beta, int app) nogil
+    int pwt_proj_linf(pwt_plan* p, float beta, int app) nogil
+    int pwt_circshift(pwt_plan* p, int sr, int sc, int inplace) nogil
+    int pwt_norm1(pwt_plan* p, float* out) nogil
+    int pwt_norm2sq(pwt_plan* p, float* out) nogil
+    int pwt_norms(pwt_plan* p, double* n1, double* n2) nogil
+    int pwt_add_wavelet(pwt_plan* dst, const pwt_plan* src, float alpha) nogil
+    int pwt_get_image(pwt_plan* p, float* dst) nogil
+    int pwt_set_image(pwt_plan* p, const float* img, int on_device) nogil
+    int pwt_get_coeff(pwt_plan* p, float* dst, int num) nogil
+    int pwt_set_coeff(pwt_plan* p, const float* src, int num, int on_device) nogil
+    intptr_t pwt_image_ptr(pwt_plan* p) nogil
+    intptr_t pwt_coeff_ptr(pwt_plan* p, int num) nogil
+    int pwt_set_filters_forward(pwt_plan* p, const char* name, unsigned int len, const float* f1,
+                                const float* f2, const float* f3, const float* f4) nogil
+    int pwt_set_filters_inverse(pwt_plan* p, const float* f1, const float* f2, const float* f3,
+                                const float* f4) nogil
+    int pwt_print_informations(pwt_plan* p) nogil
+    int pwt_sync(pwt_plan* p) nogil
+    const char* pwt_last_error() nogil
+    const char* pwt_version() nogil
+    int pwt_device_count() nogil
+    int pwt_lookup_filters(const char* wname, float* L, float* H, float* IL, float* IH) nogil
+    int pwt_host_alloc(void** ptr, size_t nbytes) nogil
+    int pwt_host_free(void* ptr) nogil
+    int pwt_timer_start(pwt_plan* p) nogil
+    int pwt_timer_stop(pwt_plan* p, float* ms) nogil
+    int pwt_flush_l2(pwt_plan* p) nogil
+    long long pwt_launch_count(const pwt_plan* p) nogil
+    int pwt_set_kernel_mode(pwt_plan* p, int mode) nogil
+    int pwt_comm_unique_id(unsigned char* id) nogil
+    int pwt_comm_init(pwt_plan* p, int nranks, int rank, const unsigned char* id) nogil
+    int pwt_comm_destroy(pwt_plan* p) nogil
+    int pwt_norms_allreduce(pwt_plan* p, double* n1, double* n2) nogil
+
+PWT_ERR_UNKNOWN_WAVELET = -2
+PWT_ERR_UNSUPPORTED = -6
+PWT_ERR_TOO_SMALL = -7
+
+
+cdef str _errmsg():
+    return pwt_last_error().decode("utf-8", "replace")
+
+
+cdef void _free_pinned(void* ptr) noexcept:
+    pwt_host_free(ptr)
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """numpy array backed by page-locked host memory (fast, truly asynchronous H<->D copies).
+    Falls back to a regular array if pinning fails or PYCUDWT_PINNED=0."""
+    shape = tuple(int(s) for s in (shape if hasattr(shape, "__len__") else (shape,)))
+    cdef size_t n = 1
+    for s in shape:
+        n *= <size_t> s
+    dt = np.dtype(dtype)
+    if n == 0 or os.environ.get("PYCUDWT_PINNED", "1") == "0":
+        return np.empty(shape, dtype=dt)
+    cdef void* ptr = NULL
+    if pwt_host_alloc(&ptr, n * dt.itemsize) != 0 or ptr == NULL:
+        return np.empty(shape, dtype=dt)
+    cdef view.array arr = view.array(shape=(n * dt.itemsize,), itemsize=1, format="B", mode="c",
+                                     allocate_buffer=False)
+    arr.data = <char*> ptr
+    arr.callback_free_data = _free_pinned
+    return np.asarray(arr).view(dt).reshape(shape)
+
+
+def pinned_zeros(shape, dtype=np.float32):
+    a = pinned_empty(shape, dtype)
+    a[...] = 0
+    return a
+
+
+def device_count():
+    """Number of usable CUDA devices (0 on a CPU-only box)."""
+    return pwt_device_count()
+
+
+def lookup_filters(str wname):
+    """(dec_lo, dec_hi, rec_lo, rec_hi) of a built-in bank, float32 -- the table of filters.cpp."""
+    cdef float L[40]
+    cdef float H[40]
+    cdef float IL[40]
+    cdef float IH[40]
+    b = wname.encode("ASCII")
+    cdef int hlen = pwt_lookup_filters(b, L, H, IL, IH)
+    if hlen < 0:
+        raise ValueError("unknown wavelet name %r" % wname)
+    return tuple(np.array([arr[i] for i in range(hlen)], dtype=np.float32)
+                 for arr in (<float[:40]> L, <float[:40]> H, <float[:40]> IL, <float[:40]> IH))
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (create on rank 0, broadcast to the other ranks)."""
+    cdef unsigned char buf[128]
+    if pwt_comm_unique_id(buf) != 0:
+        raise RuntimeError(_errmsg())
+    return bytes(buf[:128])
+
+
+cdef class Wavelets:
+    """
+    Initializes the Wavelet transform from an image and given parameters.
+
+    img: numpy.ndarray (float32 after coercion)
+        2D image, 1D signal, or (extension) 3D stack of images
+    wname: string
+        Name of the wavelet
+    levels: int
+        Number of decomposition levels
+    do_separable: int
+        if not 0, perform a separable transform
+    do_cycle_spinning: int
+        if not 0, perform a random shift on the image (useful for iterative algorithms)
+    do_swt: int
+        if not 0, perform a Stationary (non-decimated) wavelet transform
+    ndim: int
+        1 on 2D input = batched 1D transform of the rows
+    """
+    cdef pwt_plan* w
+    cdef readonly int Nr
+    cdef readonly int Nc
+    cdef readonly list sizes
+    cdef readonly str wname
+    cdef readonly int levels
+    cdef readonly int do_cycle_spinning
+    cdef readonly int hlen
+    cdef readonly int do_swt
+    cdef readonly int do_separable
+    cdef readonly int ndim
+    cdef readonly int batched1d
+    cdef readonly int batch
+    cdef list _coeffs
+    cdef tuple shape
+    cdef int _is1d
+
+    def __cinit__(self, img, str wname, int levels, int do_separable=1, int do_cycle_spinning=0,
+                  int do_swt=0, int ndim=2, Wavelets copy=None):
+        self.w = NULL
+        img = self._checkarray(img)
+        ndim = min(ndim, 2)                                       # pypwt.pyx:145
+        self.batched1d = 0
+        self.batch = 1
+        if img.ndim == 2:
+            self.Nr = img.shape[0]
+            self.Nc = img.shape[1]
+            if img.ndim != ndim:
+                self.batched1d = 1
+        elif img.ndim == 1:
+            self.Nr = 1
+            self.Nc = img.shape[0]
+        elif img.ndim == 3 and ndim == 2:
+            # extension: stack of independent 2D images (SURVEY 8e)
+            self.batch = img.shape[0]
+            self.Nr = img.shape[1]
+            self.Nc = img.shape[2]
+        else:
+            raise NotImplementedError("Wavelets(): Only 1D and 2D transforms are supported for now")
+        self.shape = tuple(int(s) for s in img.shape)
+        self.wname = wname
+        py_wname = wname.encode("ASCII")
+        self.do_cycle_spinning = do_cycle_spinning
+        self.do_swt = do_swt
+        self.ndim = img.ndim
+
+        if pwt_device_count() < 1:
+            raise RuntimeError("pycudwt: no CUDA device available (there is no CPU fallback)")
+        cdef const float* src = <const float*> <size_t> img.ctypes.data
+        cdef const char* c_wname = py_wname
+        cdef int rc, c_ndim = ndim, c_levels = levels, c_sep = do_separable
+        with nogil:
+            rc = pwt_create_batch(&self.w, src, self.batch, self.Nr, self.Nc, c_wname, c_levels, 1,
+                                  c_sep, self.do_cycle_spinning, self.do_swt, c_ndim)
+        if rc != 0:
+            self.w = NULL
+            msg = _errmsg()
+            if rc in (PWT_ERR_UNKNOWN_WAVELET, PWT_ERR_TOO_SMALL, PWT_ERR_UNSUPPORTED, -1):
+                raise ValueError(msg)
+            raise RuntimeError(msg)
+        # Retrieve the possibly updated attributes (pypwt.pyx:181-183)
+        cdef pwt_info info
+        pwt_get_info(self.w, &info)
+        self.levels = info.nlevels
+        self.hlen = info.hlen
+        self.do_separable = info.do_separable
+        self._is1d = 1 if info.ndims == 1 else 0
+        self.sizes = self._compute_sizes()
+
+        # persistent host buffers: [A, [H1, V1, D1], ...] or [A, D1, ...]  (pypwt.pyx:191-205)
+        lead = (self.batch,) if self.batch > 1 else ()
+        self._coeffs = [pinned_zeros(lead + tuple(self.sizes[-1]))]
+        for i in range(self.levels):
+            if self._is1d:
+                self._coeffs.append(pinned_zeros(lead + tuple(self.sizes[i])))
+            else:
+                self._coeffs.append([pinned_zeros(lead + tuple(self.sizes[i])) for _ in range(3)])
+
+    def info(self):
+        """Print some information on the current ``Wavelets`` instance."""
+        pwt_print_informations(self.w)
+
+    def __repr__(self):
+        self.info()
+        return ""
+
+    def __str__(self):
+        self.info()
+        return ""
+
+    @staticmethod
+    def _checkarray(arr, shp=None):
+        arr = np.asarray(arr)
+        res = arr
+        if arr.dtype != np.float32 or not arr.flags["C_CONTIGUOUS"]:
+            res = np.ascontiguousarray(arr, dtype=np.float32)
+        if shp is not None:
+            if arr.ndim != len(shp):
+                raise ValueError("Invalid number of dimensions (expected %d, got %d)" % (len(shp), arr.ndim))
+            for i in range(arr.ndim):
+                if arr.shape[i] != shp[i]:
+                    raise ValueError("The image does not have the correct shape (expected %s, got %s)"
+                                     % (str(shp), str(arr.shape)))
+        return res
+
+    @staticmethod
+    def div2(n):
+        """Returns (N + (N%2))/2: image size at the next scale."""
+        return (n + (n & 1)) // 2
+
+    def _compute_sizes(self):
+        cdef int nr = 0, nc = 0
+        res = []
+        for i in range(self.levels):
+            num = (3 * i + 1) if not self._is1d else (i + 1)
+            pwt_band_shape(self.w, num, &nr, &nc)
+            res.append((nr, nc))
+        return res
+
+    cdef object _coeff_ref(self, int num):
+        if num == 0:
+            return self._coeffs[0]
+        if not self._is1d:
+            return self._coeffs[(num - 1) // 3 + 1][(num - 1) % 3]
+        return self._coeffs[num]
+
+    def coeff_only(self, int num):
+        """
+        Get only the coeff "num".  2D : [0: A, 1: H1, 2: V1, 3: D1, 4: H2, ...] ; 1D : [0: A, 1: D1, ...]
+        The returned array is the persistent host buffer of that band, refreshed in place.
+        """
+        nb = (3 * self.levels + 1) if not self._is1d else (self.levels + 1)
+        if num < 0 or num >= nb:
+            raise IndexError("coefficient number %d out of range" % num)
+        coeff_ref = self._coeff_ref(num)
+        cdef float* dst = <float*> <size_t> coeff_ref.ctypes.data
+        cdef int numc
+        with nogil:
+            numc = pwt_get_coeff(self.w, dst, num)
+        if numc != min(coeff_ref.size, 0x7fffffff):
+            raise RuntimeError("Wavelets.coeff_only(): something went wrong when retrieving coefficients numbef %d, expected %d coeffs, got %d"
+                               % (num, coeff_ref.size, numc))
+        return coeff_ref
+
+    @property
+    def coeffs(self):
+        """[A, [H1, V1, D1], [H2, V2, D2], ...] (2D) or [A, D1, ...] (1D); copies every band from the device."""
+        self.coeff_only(0)
+        i_end = 3 * self.levels if not self._is1d else self.levels
+        for cnt in range(1, i_end + 1):
+            self.coeff_only(cnt)
+        return self._coeffs
+
+    def _img_shape(self):
+        return ((self.batch,) if self.batch > 1 else ()) + (self.Nr, self.Nc)
+
+    @property
+    def image(self):
+        res = np.empty(self._img_shape(), dtype=np.float32)
+        return self.image_into(res)
+
+    def image_into(self, out):
+        """Copy the device image into `out` (float32, C-contiguous, e.g. from `pinned_empty`)."""
+        if out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"] or out.size != self.batch * self.Nr * self.Nc:
+            raise ValueError("image_into(): expected a C-contiguous float32 array of %d elements" % (self.batch * self.Nr * self.Nc))
+        cdef float* dst = <float*> <size_t> out.ctypes.data
+        cdef int numc
+        with nogil:
+            numc = pwt_get_image(self.w, dst)
+        if numc != min(out.size, 0x7fffffff):
+            raise RuntimeError("Wavelets.image(): something went wrong when retrieving image, expected %d coeffs, got %d" % (out.size, numc))
+        return out
+
+    def set_image(self, img):
+        """Replace the device image (does not update the coefficients)."""
+        img = self._checkarray(img, self._img_shape())
+        cdef const float* src = <const float*> <size_t> img.ctypes.data
+        cdef int rc
+        with nogil:
+            rc = pwt_set_image(self.w, src, 0)
+        if rc != 0:
+            raise RuntimeError(_errmsg())
+
+    def forward(self, img=None):
+        """Forward transform of `img` (if given, checked against the original shape) or of the current image."""
+        cdef const float* src
+        cdef int rc
+        if img is not None:
+            img = self._checkarray(img, self.shape)
+            src = <const float*> <size_t> img.ctypes.data
+            with nogil:
+                rc = pwt_set_image(self.w, src, 0)
+            if rc != 0:
+                raise RuntimeError(_errmsg())
+        with nogil:
+            rc = pwt_forward(self.w)
+        if rc < 0:
+            raise RuntimeError(_errmsg())
+
+    def inverse(self):
+        """Inverse transform; consumes the coefficients (a second call is refused until forward())."""
+        cdef int rc
+        with nogil:
+            rc = pwt_inverse(self.w)
+        if rc < 0:
+            raise RuntimeError(_errmsg())
+
+    def soft_threshold(self, float beta, int do_threshold_appcoeffs=0, int normalize=0):
+        """ST(x, t) = (|x| - t)_+ . sign(x) on the detail (and optionally approximation) coefficients."""
+        if pwt_soft_threshold(self.w, beta, do_threshold_appcoeffs, normalize) < 0:
+            raise RuntimeError(_errmsg())
+
+    def hard_threshold(self, float beta, int do_threshold_appcoeffs=0, int normalize=0):
+        """HT(x, t) = x . 1_{|x| > t}."""
+        if pwt_hard_threshold(self.w, beta, do_threshold_appcoeffs, normalize) < 0:
+            raise RuntimeError(_errmsg())
+
+    def group_soft_threshold(self, float beta, int do_threshold_appcoeffs=0, int normalize=0):
+        """Joint (h, v, d[, a]) shrinkage (C++ only in the reference, wt.h:58)."""
+        if pwt_group_soft_threshold(self.w, beta, do_threshold_appcoeffs, normalize) < 0:
+            raise RuntimeError(_errmsg())
+
+    def shrink(self, float beta, int do_threshold_appcoeffs=1):
+        """shrink(x, t) = x / (1 + t)."""
+        if pwt_shrink(self.w, beta, do_threshold_appcoeffs) < 0:
+            raise RuntimeError(_errmsg())
+
+    def proj_linf(self, float beta, int do_threshold_appcoeffs=1):
+        """Projection onto the L-infinity ball of radius beta (C++ only in the reference, wt.h:60)."""
+        if pwt_proj_linf(self.w, beta, do_threshold_appcoeffs) < 0:
+            raise RuntimeError(_errmsg())
+
+    def circshift(self, int sr, int sc):
+        """In-place circular shift of the device image (np.roll(img, (sr, sc)))."""
+        if pwt_circshift(self.w, sr, sc, 1) < 0:
+            raise RuntimeError(_errmsg())
+
+    def norm1(self):
+        """L1 norm of all coefficients."""
+        cdef float r = 0
+        if pwt_norm1(self.w, &r) != 0:
+            raise RuntimeError(_errmsg())
+        return r
+
+    def norm2sq(self):
+        """Squared L2 norm of all coefficients."""
+        cdef float r = 0
+        if pwt_norm2sq(self.w, &r) != 0:
+            raise RuntimeError(_errmsg())
+        return r
+
+    def norms(self):
+        """(norm1, norm2sq) in one pass, double precision (local to this GPU)."""
+        cdef double a = 0, b = 0
+        cdef int rc
+        with nogil:
+            rc = pwt_norms(self.w, &a, &b)
+        if rc != 0:
+            raise RuntimeError(_errmsg())
+        return a, b
+
+    def add_wavelet(self, Wavelets W, alpha=1.0):
+        """coeffs += alpha * W.coeffs."""
+        cdef float c_alpha = alpha
+        return pwt_add_wavelet(self.w, W.w, c_alpha)
+
+    def copy(self):
+        """Deep copy (device state included), the equivalent of the reference's C++ copy constructor."""
+        cdef Wavelets other = Wavelets.__new__(Wavelets, np.zeros(self.shape, np.float32), self.wname,
+                                               self.levels, self.do_separable, self.do_cycle_spinning,
+                                               self.do_swt, 1 if self.batched1d else 2)
+        cdef pwt_plan* fresh = NULL
+        if pwt_clone(&fresh, self.w) != 0:
+            raise RuntimeError(_errmsg())
+        pwt_destroy(other.w)
+        other.w = fresh
+        return other
+
+    def set_coeff(self, coeff, int num, check=False):
+        """Overwrite coefficient `num` on the device."""
+        coeff = self._checkarray(coeff)
+        ref = self._coeff_ref(num)
+        if check:
+            dcoeff = self.coeff_only(num)
+            if dcoeff.shape != coeff.shape:
+                raise ValueError("set_coefInvalid coefficient shape : expected %s, got %s" % (str(dcoeff.shape), str(coeff.shape)))
+        if coeff.size != ref.size:
+            raise ValueError("set_coeff(): expected %d elements, got %d" % (ref.size, coeff.size))
+        cdef const float* src = <const float*> <size_t> coeff.ctypes.data
+        cdef int rc
+        with nogil:
+            rc = pwt_set_coeff(self.w, src, num, 0)
+        if rc != 0:
+            raise RuntimeError(_errmsg())
+
+    def set_wavelets_filters(self, filter_name, lowpass, highpass, i_lowpass, i_highpass,
+                             LH=None, HL=None, i_LH=None, i_HL=None):
+        """Custom filter bank (re-defines the transform).  Non-separable mode takes the four 2D
+        filters LL=lowpass, LH, HL, HH=highpass (and their inverse counterparts)."""
+        if any(len(arr) != len(lowpass) for arr in [lowpass, highpass, i_lowpass, i_highpass, LH, HL, i_LH, i_HL] if arr is not None):
+            raise ValueError("All filters must have the same length")
+        lp = self._checkarray(lowpass); hp = self._checkarray(highpass)
+        ilp = self._checkarray(i_lowpass); ihp = self._checkarray(i_highpass)
+        name = filter_name.encode("ASCII")
+        cdef unsigned int flen = len(lowpass)
+        cdef int rc
+        if self.do_separable:
+            rc = pwt_set_filters_forward(self.w, name, flen, <const float*> <size_t> lp.ctypes.data,
+                                         <const float*> <size_t> hp.ctypes.data, NULL, NULL)
+            if rc == 0:
+                rc = pwt_set_filters_inverse(self.w, <const float*> <size_t> ilp.ctypes.data,
+                                             <const float*> <size_t> ihp.ctypes.data, NULL, NULL)
+        else:
+            if LH is None or HL is None or i_LH is None or i_HL is None:
+                raise ValueError("Expected LH and HL filters for non-separable transform")
+            lh = self._checkarray(LH); hl = self._checkarray(HL)
+            ilh = self._checkarray(i_LH); ihl = self._checkarray(i_HL)
+            rc = pwt_set_filters_forward(self.w, name, flen, <const float*> <size_t> lp.ctypes.data,
+                                         <const float*> <size_t> lh.ctypes.data,
+                                         <const float*> <size_t> hl.ctypes.data,
+                                         <const float*> <size_t> hp.ctypes.data)
+            if rc == 0:
+                rc = pwt_set_filters_inverse(self.w, <const float*> <size_t> ilp.ctypes.data,
+                                             <const float*> <size_t> ilh.ctypes.data,
+                                             <const float*> <size_t> ihl.ctypes.data,
+                                             <const float*> <size_t> ihp.ctypes.data)
+        if rc != 0:
+            raise ValueError("set_wavelets_filters() failed with code %d" % rc)
+        cdef pwt_info info
+        pwt_get_info(self.w, &info)
+        self.hlen = info.hlen
+        self.wname = filter_name
+
+    def image_int_ptr(self):
+        """Address of the device image."""
+        return pwt_image_ptr(self.w)
+
+    def coeff_int_ptr(self, int num):
+        """Address of a device coefficient band."""
+        return pwt_coeff_ptr(self.w, num)
+
+    # ---- extensions ------------------------------------------------------------------------
+    def sync(self):
+        """Block until all work queued by this instance has finished (forward/inverse are asynchronous)."""
+        cdef int rc
+        with nogil:
+            rc = pwt_sync(self.w)
+        if rc != 0:
+            raise RuntimeError(_errmsg())
+
+    @property
+    def state(self):
+        cdef pwt_info info
+        pwt_get_info(self.w, &info)
+        return info.state
+
+    @property
+    def current_shift(self):
+        cdef pwt_info info
+        pwt_get_info(self.w, &info)
+        return (info.shift_r, info.shift_c)
+
+    @property
+    def launch_count(self):
+        return pwt_launch_count(self.w)
+
+    def set_kernel_mode(self, int mode):
+        """0 = auto, 1 = force the generic tiled kernels (used by the parity tests)."""
+        pwt_set_kernel_mode(self.w, mode)
+
+    def timer_start(self):
+        if pwt_timer_start(self.w) != 0:
+            raise RuntimeError(_errmsg())
+
+    def timer_stop(self):
+        cdef float ms = 0
+        cdef int rc
+        with nogil:
+            rc = pwt_timer_stop(self.w, &ms)
+        if rc != 0:
+            raise RuntimeError(_errmsg())
+        return ms
+
+    def flush_l2(self):
+        if pwt_flush_l2(self.w) != 0:
+            raise RuntimeError(_errmsg())
+
+    def comm_init(self, int nranks, int rank, bytes unique_id):
+        if len(unique_id) != 128:
+            raise ValueError("unique_id must be 128 bytes")
+        cdef const unsigned char* idp = unique_id
+        cdef int rc
+        with nogil:
+            rc = pwt_comm_init(self.w, nranks, rank, idp)
+        if rc != 0:
+            raise RuntimeError(_errmsg())
+
+    def comm_destroy(self):
+        pwt_comm_destroy(self.w)
+
+    def norms_allreduce(self):
+        """Global (norm1, norm2sq) over all ranks of the communicator (fused reduction + NCCL all-reduce)."""
+        cdef double a = 0, b = 0
+        cdef int rc
+        with nogil:
+            rc = pwt_norms_allreduce(self.w, &a, &b)
+        if rc != 0:
+            raise RuntimeError(_errmsg())
+        return a, b
+
+    def __dealloc__(self):
+        self.cleanup()
+
+    def cleanup(self):  # should not be called manually
+        if self.w is not NULL:
+            pwt_destroy(self.w)
+            self.w = NULL
+
+    @classmethod
+    def version(cls):
+        """Version string of the library this is a drop-in for."""
+        return pwt_version().decode("ASCII")
