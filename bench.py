@@ -1,0 +1,349 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the wavelet hot path.
+
+Metric (BASELINE.json): Mpixel/s of forward + inverse separable 2D DWT, db2, 3 levels, 8192x8192 fp32.
+A "step" = one forward() + inverse() over the per-GPU batch (one 8192^2 image per GPU; weak scaling:
+every rank owns its own image(s), no data-path collective).  Mpixel/s = pixels transformed / time.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Keys of the JSON line (one line, rank 0):
+  value        device-resident throughput: inputs already in HBM, CUDA events on the plan's stream,
+               barrier + synchronize on both sides, max over ranks
+  e2e          same metric through the public pycudwt.Wavelets API with HOST buffers: every step does
+               forward(img_host) [H2D of the image from pinned memory] + inverse() + image_into(pinned) [D2H]
+  roofline     dominant kernel (level-1 forward), algorithmic bytes (8 B per level-1 pixel) / its
+               CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth
+  roofline_step  whole step at 16 B/px (the BASELINE.md headline fraction)
+  cpu_baseline the numpy oracle port of the same transform timed on the host (bounded sample)
+  pdwt_cuda    the reference's own CUDA kernels (oracle/_ref, recompiled for sm_100a) on the same GPU,
+               same workload, device-resident -- reported beside, not part of `value`
+--impl reference: the CPU path of the reference workflow (pywt-equivalent numpy restatement; pywt itself
+is not installable here) on the host cores, same metric/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Mpixel/s fwd+inv 2D DWT (db2, 3 lvl, 8192^2 fp32)"
+WNAME, LEVELS, SIDE = "db2", 3, 8192
+
+
+def synth(shape, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(shape, dtype=np.float32) * 50 + 128
+    i = np.arange(shape[-2], dtype=np.float32)[:, None]
+    j = np.arange(shape[-1], dtype=np.float32)[None, :]
+    x += 64 * np.sin(2 * np.pi * i / shape[-2] * 3) * np.cos(2 * np.pi * j / shape[-1] * 5)
+    return x
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_fwd_inv(img):
+    """The CPU restatement of the reference path (oracle port): 3-level db2 forward + inverse, fp32."""
+    from oracle import pdwt_oracle as O
+    W = O.OracleWavelets(img, WNAME, LEVELS, dtype=np.float32)
+    W.forward()
+    W.inverse()
+    return W.image
+
+
+def time_cpu_port(budget_s=10.0, side=2048):
+    img = synth((side, side), 99)
+    cpu_port_fwd_inv(img[:256, :256])      # warm numpy
+    n, t0 = 0, time.perf_counter()
+    while True:
+        cpu_port_fwd_inv(img)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt >= budget_s or n >= 50:
+            break
+    return n * side * side / dt / 1e6, "%d x (%dx%d db2 3-level fwd+inv), numpy fp32, %.1f s" % (n, side, side, dt)
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    side = 2048     # bounded sample of the workload (one step = one 2048^2 fwd+inv on the host)
+    img = synth((side, side), 99)
+    for _ in range(max(args.warmup, 1)):
+        cpu_port_fwd_inv(img)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_fwd_inv(img)
+    dt = time.perf_counter() - t0
+    val = args.steps * side * side / dt / 1e6
+    cores = 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mpixel/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "gpu_launches": 0,
+        "config": {"workload": "8192x8192 fp32 db2 3-level separable DWT forward+inverse",
+                   "sample": "each step = one %dx%d image (bounded sample of the 8192^2 workload)" % (side, side),
+                   "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": cores, "kind": "port",
+                         "sample": "%d steps x %dx%d, numpy fp32 restatement of pywt mode=periodization "
+                                   "(pywt not installable here); host has %d cores" % (args.steps, side, side, os.cpu_count() or 0)},
+        "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def time_pdwt(img, steps, warmup):
+    """PDWT's own CUDA build on the same image (device-resident, explicit sync through a tiny D2H)."""
+    p = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(p):
+        return None
+    sys.path.insert(0, p)
+    try:
+        import pycudwt_ref
+    except Exception as e:      # noqa: BLE001
+        return {"unavailable": str(e)[:200]}
+    try:
+        R = pycudwt_ref.Wavelets(img, WNAME, LEVELS)
+
+        def sync():
+            R.norm1()   # blocking cuBLAS call: the only sync point the reference API offers
+
+        for _ in range(max(warmup, 1)):
+            R.forward(); R.inverse()
+        sync()
+        t_sync0 = time.perf_counter(); sync(); t_sync = time.perf_counter() - t_sync0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            R.forward(); R.inverse()
+        sync()
+        dt = time.perf_counter() - t0 - t_sync
+        rec_err = float(np.abs(R.image - img).max())
+        del R
+        return {"value": steps * img.size / dt / 1e6, "unit": "Mpixel/s", "ms_per_step": dt / steps * 1e3,
+                "how": "oracle/_ref (unmodified PDWT, sm_100a), wall clock around %d fwd+inv, sync via norm1()" % steps,
+                "reconstruction_max_err": rec_err}
+    except Exception as e:      # noqa: BLE001
+        return {"unavailable": str(e)[:200]}
+
+
+def run_ours(args):
+    rank, world, local = dist_env()
+    import pypwt_b200
+    import pycudwt
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if pypwt_b200.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    pypwt_b200.set_device(local)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    B = args.batch
+    shape = (SIDE, SIDE) if B == 1 else (B, SIDE, SIDE)
+    pix = B * SIDE * SIDE
+    img = pypwt_b200.pinned_empty(shape)
+    img[...] = synth(shape, 1234 + rank)
+    out = pypwt_b200.pinned_empty(shape)
+    W = pycudwt.Wavelets(img, WNAME, LEVELS)
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        W.forward(); W.inverse()
+    W.sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = W.launch_count
+    barrier(); W.sync()
+    W.timer_start()
+    for _ in range(args.steps):
+        W.forward(); W.inverse()
+    ms = W.timer_stop()
+    W.sync(); barrier()
+    launches = W.launch_count - l0
+    ms = max_over_ranks(ms)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * pix * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- per-kernel durations (same loop, every launch bracketed by events) --------------------
+    W.profile_enable(1)
+    for _ in range(args.steps):
+        W.forward(); W.inverse()
+    recs = W.profile_read()
+    W.profile_enable(0)
+    by_tag = {}
+    for tag, t in recs:
+        by_tag.setdefault(tag, []).append(t)
+    avg = {tag: float(np.mean(v)) for tag, v in by_tag.items()}
+    peak, peak_src = measured_peak()
+    k_ms = avg.get(101)
+    alg_bytes = 8.0 * pix                      # level-1 forward: read 4 B/px + write 4 B/px of coefficients
+    roof = {"bound": "hbm", "kernel": "level-1 forward (fused row+column analysis)",
+            "achieved": alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None, "peak": peak, "unit": "GB/s",
+            "frac": (alg_bytes / (k_ms * 1e-3) / 1e9 / peak) if k_ms else None, "traffic": None,
+            "peak_source": peak_src, "kernel_ms": k_ms,
+            "kernel_ms_by_level": {("fwd" if t % 100 == 1 else "inv") + str(t // 100): round(v, 5) for t, v in sorted(avg.items())},
+            "share_of_step": (k_ms / sum(avg.values())) if k_ms else None}
+    step_gbs = 16.0 * pix / (ms / args.steps * 1e-3) / 1e9
+    roof_step = {"bytes_per_px": 16, "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak}
+
+    # ---- end to end through the public API with host buffers -----------------------------------
+    for _ in range(2):
+        W.forward(img); W.inverse(); W.image_into(out)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        W.forward(img)          # H2D (pinned -> device) + forward
+        W.inverse()
+        W.image_into(out)       # D2H of the reconstructed image (synchronises)
+    dt = time.perf_counter() - t0
+    barrier()
+    dt = max_over_ranks(dt)
+    e2e = {"value": world * pix * e2e_steps / dt / 1e6, "unit": "Mpixel/s",
+           "h2d_bytes_per_step": int(img.nbytes), "d2h_bytes_per_step": int(out.nbytes),
+           "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
+           "max_abs_reconstruction_err": float(np.abs(out - img).max())}
+
+    # ---- multi-GPU: global norms through the fused reduction + NCCL all-reduce ------------------
+    extra = {}
+    if world > 1:
+        uid = [pypwt_b200.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        W.forward()
+        W.comm_init(world, rank, uid[0])
+        g1, g2 = W.norms_allreduce()
+        W.sync(); barrier()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            g1, g2 = W.norms_allreduce()
+        extra["global_norms"] = {"norm1": g1, "norm2sq": g2,
+                                 "us_per_call": (time.perf_counter() - t0) / 20 * 1e6,
+                                 "how": "fused |c|,c^2 reduction kernel + ncclAllReduce(2 x f64) on the plan's stream"}
+        l1, l2 = W.norms()
+        extra["global_norms"]["local_norm1_rank0"] = l1
+        W.comm_destroy()
+
+    if rank == 0:
+        cpu_v, cpu_s = time_cpu_port()
+        pd = time_pdwt(np.asarray(img if B == 1 else img[0]), min(args.steps, 10), 2) if not args.no_pdwt else None
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "8192x8192 fp32 db2 3-level separable DWT forward+inverse",
+                       "per_gpu_batch": B, "l2": "inputs larger than L2 (256 MiB image + 256 MiB coefficients per image vs 126 MB L2); no flush",
+                       "parallelism": "independent images per GPU, no data-path collective"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roof, "roofline_step": roof_step,
+            "cpu_baseline": {"value": cpu_v, "unit": "Mpixel/s", "cores": 1, "kind": "port", "sample": cpu_s},
+            "pdwt_cuda": pd,
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="8192^2 images per GPU per step")
+    ap.add_argument("--no-pdwt", action="store_true", help="skip the side-by-side timing of the reference's CUDA build")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

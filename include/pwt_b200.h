@@ -116,6 +116,7 @@ int pwt_sync(pwt_plan* p);                 /* cudaStreamSynchronize on the plan'
 const char* pwt_last_error(void);          /* thread-local message of the last failure */
 const char* pwt_version(void);             /* "1.0.3" -- pypwt.pyx:608-615 */
 int pwt_device_count(void);                /* 0 if no usable CUDA device */
+int pwt_set_device(int device);            /* device used by subsequently created plans (cudaSetDevice) */
 
 /* look up a built-in bank (filters.cpp:5919-6002): writes hlen taps into each non-NULL array
  * (capacity >= 40) and returns hlen, or PWT_ERR_UNKNOWN_WAVELET.  Host-only, no CUDA call. */
@@ -130,6 +131,13 @@ int pwt_timer_start(pwt_plan* p);
 int pwt_timer_stop(pwt_plan* p, float* ms);      /* records, synchronises, returns elapsed ms */
 int pwt_flush_l2(pwt_plan* p);                   /* overwrites a >L2-sized scratch buffer on the stream */
 long long pwt_launch_count(const pwt_plan* p);   /* kernels launched by this plan so far */
+/* per-launch device timing: when enabled every transform kernel launched by forward/inverse is
+ * bracketed by CUDA events on the plan's stream.  pwt_profile_read synchronises and returns, in launch
+ * order since the last call to pwt_profile_enable, the duration (ms) and a tag of each launch:
+ * tag = 100*level + kind, kind 1 = forward (analysis) kernel, 2 = inverse (synthesis) kernel,
+ * 3 = other.  Returns the number of records written (<= cap). */
+int pwt_profile_enable(pwt_plan* p, int on);
+int pwt_profile_read(pwt_plan* p, float* ms, int* tags, int cap);
 /* choose kernel family: 0 = auto (default), 1 = force the generic tiled kernels */
 int pwt_set_kernel_mode(pwt_plan* p, int mode);
 

@@ -30,9 +30,10 @@ Wavelets = _ext.Wavelets
 pinned_empty = _ext.pinned_empty
 pinned_zeros = _ext.pinned_zeros
 device_count = _ext.device_count
+set_device = _ext.set_device
 lookup_filters = _ext.lookup_filters
 comm_unique_id = _ext.comm_unique_id
 LIBRARY_PATH = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "libpwt_b200.so")
 __version__ = "1.0.3"
-__all__ = ["Wavelets", "pinned_empty", "pinned_zeros", "device_count", "lookup_filters",
+__all__ = ["Wavelets", "pinned_empty", "pinned_zeros", "device_count", "set_device", "lookup_filters",
            "comm_unique_id", "LIBRARY_PATH"]

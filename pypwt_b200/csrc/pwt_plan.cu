@@ -80,6 +80,7 @@ static int load_nccl() {
 }
 enum { kNcclFloat64 = 8, kNcclSum = 0 };
 
+#define PWT_PROF_CAP 512
 // ---- the plan --------------------------------------------------------------------------------
 struct pwt_plan {
     int device;
@@ -108,6 +109,9 @@ struct pwt_plan {
     long long launches;
     int kernel_mode;
     unsigned custom_len;   // taps given to set_filters_forward (0: built-in bank)
+    int prof_on, prof_n;
+    cudaEvent_t* prof_ev;  // 2 events per record
+    int prof_tag[PWT_PROF_CAP];
     ncclComm_t comm;
     int comm_nranks;
 };
@@ -229,6 +233,11 @@ extern "C" void pwt_destroy(pwt_plan* p) {
     if (p->d_acc) cudaFree(p->d_acc);
     if (p->h_acc) cudaFreeHost(p->h_acc);
     if (p->d_flush) cudaFree(p->d_flush);
+    if (p->prof_ev) {
+        for (int i = 0; i < 2 * PWT_PROF_CAP; i++)
+            if (p->prof_ev[i]) cudaEventDestroy(p->prof_ev[i]);
+        free(p->prof_ev);
+    }
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -342,6 +351,8 @@ extern "C" int pwt_clone(pwt_plan** out, const pwt_plan* src) {
     p->comm = nullptr;
     p->comm_nranks = 0;
     p->launches = 0;
+    p->prof_ev = nullptr;
+    p->prof_on = p->prof_n = 0;
     *out = nullptr;
     cudaSetDevice(src->device);
     cudaStreamSynchronize(src->stream);
@@ -434,6 +445,44 @@ extern "C" int pwt_circshift(pwt_plan* p, int sr, int sc, int inplace) {
     return do_circshift(p, sr, sc, inplace);
 }
 
+// ---- per-launch profiling --------------------------------------------------------------------
+static inline void prof_begin(pwt_plan* p, int tag) {
+    if (!p->prof_on || p->prof_n >= PWT_PROF_CAP) return;
+    p->prof_tag[p->prof_n] = tag;
+    cudaEventRecord(p->prof_ev[2 * p->prof_n], p->stream);
+}
+static inline void prof_end(pwt_plan* p) {
+    if (!p->prof_on || p->prof_n >= PWT_PROF_CAP) return;
+    cudaEventRecord(p->prof_ev[2 * p->prof_n + 1], p->stream);
+    p->prof_n++;
+}
+
+extern "C" int pwt_profile_enable(pwt_plan* p, int on) {
+    if (!p) return fail(PWT_ERR_ARG, "null plan");
+    cudaSetDevice(p->device);
+    if (on && !p->prof_ev) {
+        p->prof_ev = (cudaEvent_t*)calloc(2 * PWT_PROF_CAP, sizeof(cudaEvent_t));
+        if (!p->prof_ev) return fail(PWT_ERR_NOMEM, "out of host memory");
+        for (int i = 0; i < 2 * PWT_PROF_CAP; i++) CK(cudaEventCreate(&p->prof_ev[i]));
+    }
+    p->prof_on = on ? 1 : 0;
+    p->prof_n = 0;
+    return PWT_OK;
+}
+
+extern "C" int pwt_profile_read(pwt_plan* p, float* ms, int* tags, int cap) {
+    if (!p || !ms || !tags) return fail(PWT_ERR_ARG, "null argument");
+    cudaSetDevice(p->device);
+    CK(cudaStreamSynchronize(p->stream));
+    int n = p->prof_n < cap ? p->prof_n : cap;
+    for (int i = 0; i < n; i++) {
+        CK(cudaEventElapsedTime(&ms[i], p->prof_ev[2 * i], p->prof_ev[2 * i + 1]));
+        tags[i] = p->prof_tag[i];
+    }
+    p->prof_n = 0;
+    return n;
+}
+
 // ---- forward ----------------------------------------------------------------------------------
 // Destination of the level-l approximation so that A_L ends in band 0 without a fix-up copy
 // (the reference ping-pongs and memcpy's back for even level counts, e.g. haar.cu:83).
@@ -459,10 +508,12 @@ extern "C" int pwt_forward(pwt_plan* p) {
         const int rows = B * p->Nr;
         for (int l = 1; l <= L; l++) {
             float* dstA = approx_dst(p, l, p->d_tmp);
+            prof_begin(p, 100 * l + 1);
             if (p->do_swt)
                 p->launches += pwt_launch_swt_fwd1d(src, dstA, p->d_band[l], rows, p->Nc, l, p->filt, st);
             else
                 p->launches += pwt_launch_dwt_fwd1d(src, dstA, p->d_band[l], rows, p->lvNc[l - 1], p->filt, haar, st);
+            prof_end(p);
             src = dstA;
         }
     } else {
@@ -471,6 +522,7 @@ extern "C" int pwt_forward(pwt_plan* p) {
             float* Hb = p->d_band[3 * (l - 1) + 1];
             float* V = p->d_band[3 * (l - 1) + 2];
             float* D = p->d_band[3 * (l - 1) + 3];
+            prof_begin(p, 100 * l + 1);
             if (p->do_swt) {
                 float* dstA = approx_dst(p, l, p->d_tmp + 2 * plane);
                 if (p->do_separable)
@@ -493,6 +545,7 @@ extern "C" int pwt_forward(pwt_plan* p) {
                 }
                 src = dstA;
             }
+            prof_end(p);
         }
     }
     CK_LAUNCH();
@@ -517,10 +570,12 @@ extern "C" int pwt_inverse(pwt_plan* p) {
         const int rows = B * p->Nr;
         for (int l = L; l >= 1; l--) {
             float* dst = (l == 1) ? p->d_image : (cur == p->d_band[0] ? p->d_tmp : p->d_band[0]);
+            prof_begin(p, 100 * l + 2);
             if (p->do_swt)
                 p->launches += pwt_launch_swt_inv1d(cur, p->d_band[l], dst, rows, p->Nc, l, p->filt, st);
             else
                 p->launches += pwt_launch_dwt_inv1d(cur, p->d_band[l], dst, rows, p->lvNc[l], p->lvNc[l - 1], p->filt, haar, st);
+            prof_end(p);
             cur = dst;
         }
     } else {
@@ -529,6 +584,7 @@ extern "C" int pwt_inverse(pwt_plan* p) {
             const float* Hb = p->d_band[3 * (l - 1) + 1];
             const float* V = p->d_band[3 * (l - 1) + 2];
             const float* D = p->d_band[3 * (l - 1) + 3];
+            prof_begin(p, 100 * l + 2);
             if (p->do_swt) {
                 float* alt = p->d_tmp + 2 * plane;
                 float* dst = (l == 1) ? p->d_image : (cur == p->d_band[0] ? alt : p->d_band[0]);
@@ -552,6 +608,7 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                 }
                 cur = dst;
             }
+            prof_end(p);
         }
     }
     CK_LAUNCH();
@@ -902,6 +959,11 @@ extern "C" int pwt_device_count(void) {
         return 0;
     }
     return n;
+}
+
+extern "C" int pwt_set_device(int device) {
+    CK(cudaSetDevice(device));
+    return PWT_OK;
 }
 
 extern "C" int pwt_host_alloc(void** ptr, size_t bytes) {

@@ -74,6 +74,9 @@ cdef extern from "pwt_b200.h":
     int pwt_flush_l2(pwt_plan* p) nogil
     long long pwt_launch_count(const pwt_plan* p) nogil
     int pwt_set_kernel_mode(pwt_plan* p, int mode) nogil
+    int pwt_set_device(int device) nogil
+    int pwt_profile_enable(pwt_plan* p, int on) nogil
+    int pwt_profile_read(pwt_plan* p, float* ms, int* tags, int cap) nogil
     int pwt_comm_unique_id(unsigned char* id) nogil
     int pwt_comm_init(pwt_plan* p, int nranks, int rank, const unsigned char* id) nogil
     int pwt_comm_destroy(pwt_plan* p) nogil
@@ -121,6 +124,12 @@ def pinned_zeros(shape, dtype=np.float32):
 def device_count():
     """Number of usable CUDA devices (0 on a CPU-only box)."""
     return pwt_device_count()
+
+
+def set_device(int device):
+    """Select the CUDA device used by Wavelets objects created afterwards (one process per GPU)."""
+    if pwt_set_device(device) != 0:
+        raise RuntimeError(_errmsg())
 
 
 def lookup_filters(str wname):
@@ -533,6 +542,22 @@ cdef class Wavelets:
     def set_kernel_mode(self, int mode):
         """0 = auto, 1 = force the generic tiled kernels (used by the parity tests)."""
         pwt_set_kernel_mode(self.w, mode)
+
+    def profile_enable(self, int on=1):
+        """Bracket every transform kernel with CUDA events (see pwt_profile_enable)."""
+        if pwt_profile_enable(self.w, on) != 0:
+            raise RuntimeError(_errmsg())
+
+    def profile_read(self):
+        """[(tag, ms), ...] in launch order; tag = 100*level + (1 forward | 2 inverse)."""
+        cdef float ms[512]
+        cdef int tags[512]
+        cdef int n
+        with nogil:
+            n = pwt_profile_read(self.w, ms, tags, 512)
+        if n < 0:
+            raise RuntimeError(_errmsg())
+        return [(tags[i], ms[i]) for i in range(n)]
 
     def timer_start(self):
         if pwt_timer_start(self.w) != 0:

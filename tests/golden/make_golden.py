@@ -60,10 +60,17 @@ def main(path):
         store["in/" + iname] = img
         for wname in WAVELETS:
             for tag, kw, lev in MODES:
-                if iname == "smooth" and tag not in ("dwt2", "swt2"):
+                if iname == "smooth" and (tag not in ("dwt2", "swt2", "dwt1") or wname not in ("haar", "db2", "sym4", "bior2.2")):
+                    continue
+                if iname == "odd" and tag in ("swt1", "ns_swt2") and wname not in ("haar", "db2", "db3", "bior2.2"):
                     continue
                 key = "%s/%s/%s" % (iname, wname, tag)
-                W = ref.Wavelets(img, wname, lev, **kw)
+                try:
+                    W = ref.Wavelets(img, wname, lev, **kw)
+                except IndexError:
+                    # image too small for this filter: the reference clips the level count to 0
+                    # and its wrapper trips over the empty size list (pypwt.pyx:193)
+                    continue
                 store[key + "/levels"] = np.array([W.levels], np.int32)
                 W.forward()
                 for i, b in enumerate(flat_coeffs(W.coeffs)):

@@ -1,0 +1,13 @@
+# usage: bash tools/gpu_round.sh [tests|bench|ncu ...]   (run on the GPU box through gpurun)
+set -x
+mkdir -p gpurun_out
+for what in "$@"; do
+case $what in
+golden) python tests/golden/make_golden.py gpurun_out/pdwt_golden.npz 2>&1 | tail -2 ;;
+tests) python -m pytest tests -m gpu -q --maxfail=30 --timeout=900 -p no:cacheprovider 2>&1 | grep -v "^Warning\|^Forcing" | tail -40 ;;
+smoke) python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ;;
+bench) python bench.py --steps 20 --warmup 3 2>&1 | grep -v "^Warning\|^Forcing" | tee gpurun_out/bench.json | tail -3 ;;
+launches) ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-pdwt > gpurun_out/ncu_bench.log 2>&1; tail -2 gpurun_out/ncu_bench.log; grep -c . gpurun_out/launches.csv ;;
+ncufull) ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNEL:-k_dwt}" -s ${NCU_SKIP:-12} -c ${NCU_COUNT:-6} -f -o gpurun_out/prof python bench.py --steps 2 --warmup 1 --no-pdwt > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log; ls -la gpurun_out/ ;;
+esac
+done
