@@ -87,9 +87,13 @@ int pwt_launch_fill(float* p, long long n, float v, cudaStream_t st);
 
 // kernels_fast.cu : register/shuffle-blocked kernels for short filters on the headline path.
 // Return 0 when the configuration is not covered (caller falls back to the generic kernels).
+// hint_flags: PWT_HINT_OUT_FEEDS_NEXT = the approximation / image written by this launch is the input
+// of the next launch (keep it L2-resident), PWT_HINT_IN_FROM_PREV = the input came from the previous one.
+#define PWT_HINT_OUT_FEEDS_NEXT 4
+#define PWT_HINT_IN_FROM_PREV 8
 int pwt_fast_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr,
                        int Nc, long long in_bs, long long out_bs, const PwtFilters& f, bool haar,
-                       cudaStream_t st);
+                       int hint_flags, cudaStream_t st);
 int pwt_fast_dwt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out,
                        int batch, int nr, int nc, int Nr_out, int Nc_out, long long in_bs,
-                       long long out_bs, const PwtFilters& f, bool haar, cudaStream_t st);
+                       long long out_bs, const PwtFilters& f, bool haar, int hint_flags, cudaStream_t st);

@@ -537,7 +537,8 @@ extern "C" int pwt_forward(pwt_plan* p) {
                 if (haar || p->do_separable) {
                     int n = 0;
                     if (p->kernel_mode == 0)
-                        n = pwt_fast_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, st);
+                        n = pwt_fast_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar,
+                                               (l < L ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l > 1 ? PWT_HINT_IN_FROM_PREV : 0), st);
                     if (!n) n = pwt_launch_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, st);
                     p->launches += n;
                 } else {
@@ -600,7 +601,8 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                 if (haar || p->do_separable) {
                     int n = 0;
                     if (p->kernel_mode == 0)
-                        n = pwt_fast_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, st);
+                        n = pwt_fast_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar,
+                                               (l > 1 ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l < L ? PWT_HINT_IN_FROM_PREV : 0), st);
                     if (!n) n = pwt_launch_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, st);
                     p->launches += n;
                 } else {
