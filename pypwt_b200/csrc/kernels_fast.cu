@@ -33,6 +33,19 @@ __device__ __forceinline__ int wrap_per(int i, int N) {
     return i < 0 ? i + N : i;
 }
 
+// single-step versions, valid for -N <= i < 2N (the dispatcher only uses these kernels for N >= 64)
+__device__ __forceinline__ int wrap1_dwt(int i, int N) {
+    const int Ne = N + (N & 1);
+    if (i < 0) i += Ne;
+    if (i >= Ne) i -= Ne;
+    return i >= N ? N - 1 : i;
+}
+__device__ __forceinline__ int wrap1_per(int i, int N) {
+    if (i < 0) i += N;
+    if (i >= N) i -= N;
+    return i;
+}
+
 // ---- cache-policy helpers ---------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long policy_evict_last() {
     unsigned long long p;
@@ -111,7 +124,7 @@ k_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ H
     auto load_row = [&](int grow) -> float4 {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (col_active) {
-            const float* row = in + (long long)wrap_dwt(grow, Nr) * Nc;
+            const float* row = in + (long long)wrap1_dwt(grow, Nr) * Nc;
             if (vec) {
                 v = ldg4(row + xcol, pol_in);
             } else {
@@ -130,14 +143,20 @@ k_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ H
 
     const int npairs = (txe + 1) >> 1;
     const bool vec_out = (flags & FLAG_VEC_OUT) != 0;
+    const int ky_end = min(ky0 + TYT, Nr2);
+    // software pipeline: the 2R rows of chunk n+1 are in flight while chunk n is computed
+    float4 nw[2 * R], nx[2 * R];
+#pragma unroll
+    for (int i = 0; i < 2 * R; i++) nw[i] = load_row(2 * ky0 - C + F - 2 + i);
     int buf = 0;
-    for (int kyc = ky0; kyc < ky0 + TYT && kyc < Nr2; kyc += R, buf ^= 1) {
+    for (int kyc = ky0; kyc < ky_end; kyc += R, buf ^= 1) {
         float* s_lo = sm + buf * (2 * R * SW);
         float* s_hi = s_lo + R * SW;
-        // ---- pass 1: column analysis, 2R new rows, R output rows ----
-        float4 nw[2 * R];
+        if (kyc + R < ky_end) {
 #pragma unroll
-        for (int i = 0; i < 2 * R; i++) nw[i] = load_row(2 * kyc - C + F - 2 + i);
+            for (int i = 0; i < 2 * R; i++) nx[i] = load_row(2 * (kyc + R) - C + F - 2 + i);
+        }
+        // ---- pass 1: column analysis, 2R new rows, R output rows ----
 #pragma unroll
         for (int i = 0; i < R; i++) {
             w[F - 2] = nw[2 * i];
@@ -213,37 +232,45 @@ k_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ H
                 }
             }
         }
+#pragma unroll
+        for (int i = 0; i < 2 * R; i++) nw[i] = nx[i];
     }
 }
 
 // =========================================================================================
 // inverse
 // =========================================================================================
+// NT threads = two roles of NT/2 threads: role 0 synthesises t1 = syn_y(A, H), role 1 synthesises
+// t2 = syn_y(V, D) (halves the register footprint of the sliding windows); both roles share the
+// row-synthesis pass.
 template <int F, bool HAAR, int NT, int R>
 __global__ void __launch_bounds__(NT)
 k_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float* __restrict__ V,
       const float* __restrict__ D, float* __restrict__ out, int nr, int nc, int Nr_out, int Nc_out, int TXH,
       int TYH, long long in_bs, long long out_bs, int flags, const __grid_constant__ PwtFilters f) {
+    constexpr int NC = NT / 2;                           // column groups (threads per role)
     constexpr int P = F / 2 - 1, HALF = F / 2;
     constexpr int S0 = P >> 1, E0 = P & 1;               // output parity 0: row shift / first tap
     constexpr int S1 = (P + 1) >> 1, E1 = (P + 1) & 1;   // output parity 1
     constexpr int WIN = HALF + (S1 - S0);                // band rows alive per output pair
     constexpr int HL = S1;                               // horizontal reach on both sides
     constexpr int HLr = (HL + 3) & ~3;
-    constexpr int SW = 4 * NT + 4;
+    constexpr int SW = 4 * NC + 4;
     constexpr int NV = (4 + 2 * HLr) / 4;
     extern __shared__ __align__(16) float sm[];          // [2 bufs][2 planes][2R][SW]
 
     const int tid = threadIdx.x;
+    const int role = tid / NC, t = tid - role * NC;
     const int x0h = blockIdx.x * TXH, y0h = blockIdx.y * TYH;       // tile origin in band coordinates
     const long long ib = blockIdx.z * in_bs;
-    A += ib; Hb += ib; V += ib; D += ib;
+    const float* __restrict__ ba = (role ? V : A) + ib;              // low-pass partner of this role
+    const float* __restrict__ bd = (role ? D : Hb) + ib;             // high-pass partner
     out += blockIdx.z * out_bs;
     const unsigned long long pol_in = policy_evict_first();
     const unsigned long long pol_out = (flags & FLAG_A_KEEP) ? policy_evict_last() : policy_evict_first();
 
     const int txe = min(TXH, nc - x0h);
-    const int kcol = x0h - HLr + 4 * tid;
+    const int kcol = x0h - HLr + 4 * t;
     const bool col_active = kcol <= x0h + txe - 1 + HL;
     const bool vec = (flags & FLAG_VEC_IN) && kcol >= 0 && kcol + 3 < nc;
     int cx[4];
@@ -253,7 +280,7 @@ k_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float* __
     auto load_row = [&](const float* band, int grow) -> float4 {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (col_active) {
-            const float* row = band + (long long)wrap_per(grow, nr) * nc;
+            const float* row = band + (long long)wrap1_per(grow, nr) * nc;
             if (vec) {
                 v = ldg4(row + kcol, pol_in);
             } else {
@@ -267,108 +294,111 @@ k_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float* __
     };
 
     // window row j <-> band row q + S0 - (HALF-1) + j for the current q
-    float4 wa[WIN], wh[WIN], wv[WIN], wd[WIN];
+    float4 wa[WIN], wd[WIN];
 #pragma unroll
     for (int j = 0; j < WIN - 1; j++) {
         const int r = y0h + S0 - (HALF - 1) + j;
-        wa[j] = load_row(A, r);
-        wh[j] = load_row(Hb, r);
-        wv[j] = load_row(V, r);
-        wd[j] = load_row(D, r);
+        wa[j] = load_row(ba, r);
+        wd[j] = load_row(bd, r);
     }
 
     const int ngroups = (txe + 3) >> 2;
     const bool vec_out = (flags & FLAG_VEC_OUT) != 0;
-    int buf = 0;
-    for (int qc = y0h; qc < y0h + TYH && qc < nr; qc += R, buf ^= 1) {
-        float* s_1 = sm + buf * (4 * R * SW);
-        float* s_2 = s_1 + 2 * R * SW;
-        float4 na[R], nh[R], nv[R], nd[R];
+    const int q_end = min(y0h + TYH, nr);
+    float4 na[R], nd[R], xa[R], xd[R];
 #pragma unroll
-        for (int i = 0; i < R; i++) {
-            const int r = qc + i + S1;
-            na[i] = load_row(A, r);
-            nh[i] = load_row(Hb, r);
-            nv[i] = load_row(V, r);
-            nd[i] = load_row(D, r);
+    for (int i = 0; i < R; i++) {
+        na[i] = load_row(ba, y0h + i + S1);
+        nd[i] = load_row(bd, y0h + i + S1);
+    }
+    int buf = 0;
+    for (int qc = y0h; qc < q_end; qc += R, buf ^= 1) {
+        float* s_mine = sm + buf * (4 * R * SW) + role * (2 * R * SW);
+        if (qc + R < q_end) {
+#pragma unroll
+            for (int i = 0; i < R; i++) {
+                xa[i] = load_row(ba, qc + R + i + S1);
+                xd[i] = load_row(bd, qc + R + i + S1);
+            }
         }
 #pragma unroll
         for (int i = 0; i < R; i++) {
-            wa[WIN - 1] = na[i]; wh[WIN - 1] = nh[i]; wv[WIN - 1] = nv[i]; wd[WIN - 1] = nd[i];
-            float4 t1e, t1o, t2e, t2o;
+            wa[WIN - 1] = na[i];
+            wd[WIN - 1] = nd[i];
+            float4 te, to;
             if (HAAR) {
-                t1e = make_float4(wa[0].x + wh[0].x, wa[0].y + wh[0].y, wa[0].z + wh[0].z, wa[0].w + wh[0].w);
-                t1o = make_float4(wa[0].x - wh[0].x, wa[0].y - wh[0].y, wa[0].z - wh[0].z, wa[0].w - wh[0].w);
-                t2e = make_float4(wv[0].x + wd[0].x, wv[0].y + wd[0].y, wv[0].z + wd[0].z, wv[0].w + wd[0].w);
-                t2o = make_float4(wv[0].x - wd[0].x, wv[0].y - wd[0].y, wv[0].z - wd[0].z, wv[0].w - wd[0].w);
+                te = make_float4(wa[0].x + wd[0].x, wa[0].y + wd[0].y, wa[0].z + wd[0].z, wa[0].w + wd[0].w);
+                to = make_float4(wa[0].x - wd[0].x, wa[0].y - wd[0].y, wa[0].z - wd[0].z, wa[0].w - wd[0].w);
             } else {
-                t1e = make_float4(0.f, 0.f, 0.f, 0.f);
-                t1o = t1e; t2e = t1e; t2o = t1e;
+                te = make_float4(0.f, 0.f, 0.f, 0.f);
+                to = te;
 #pragma unroll
                 for (int jj = 0; jj < HALF; jj++) {
-                    const float le = f.IL[2 * jj + E0], he = f.IH[2 * jj + E0];
-                    const float lo = f.IL[2 * jj + E1], ho = f.IH[2 * jj + E1];
                     const int je = HALF - 1 - jj, jo = HALF - 1 - jj + (S1 - S0);
-                    fma4(t1e, wa[je], le); fma4(t1e, wh[je], he);
-                    fma4(t2e, wv[je], le); fma4(t2e, wd[je], he);
-                    fma4(t1o, wa[jo], lo); fma4(t1o, wh[jo], ho);
-                    fma4(t2o, wv[jo], lo); fma4(t2o, wd[jo], ho);
+                    fma4(te, wa[je], f.IL[2 * jj + E0]);
+                    fma4(te, wd[je], f.IH[2 * jj + E0]);
+                    fma4(to, wa[jo], f.IL[2 * jj + E1]);
+                    fma4(to, wd[jo], f.IH[2 * jj + E1]);
                 }
             }
-            *reinterpret_cast<float4*>(s_1 + (2 * i) * SW + 4 * tid) = t1e;
-            *reinterpret_cast<float4*>(s_1 + (2 * i + 1) * SW + 4 * tid) = t1o;
-            *reinterpret_cast<float4*>(s_2 + (2 * i) * SW + 4 * tid) = t2e;
-            *reinterpret_cast<float4*>(s_2 + (2 * i + 1) * SW + 4 * tid) = t2o;
+            *reinterpret_cast<float4*>(s_mine + (2 * i) * SW + 4 * t) = te;
+            *reinterpret_cast<float4*>(s_mine + (2 * i + 1) * SW + 4 * t) = to;
 #pragma unroll
             for (int j = 0; j < WIN - 1; j++) {
-                wa[j] = wa[j + 1]; wh[j] = wh[j + 1]; wv[j] = wv[j + 1]; wd[j] = wd[j + 1];
+                wa[j] = wa[j + 1];
+                wd[j] = wd[j + 1];
             }
         }
         __syncthreads();
-        // ---- row synthesis: 4 band columns -> 8 output columns per item ----
+        // ---- row synthesis: 4 band columns -> 8 output columns per item; items = 2R rows x ngroups ----
+        const float* s_1 = sm + buf * (4 * R * SW);
+        const float* s_2 = s_1 + 2 * R * SW;
+        const int rows_here = min(2 * R, min(Nr_out - 2 * qc, 2 * (nr - qc)));
+        for (int it = tid; it < rows_here * ngroups; it += NT) {
+            const int i = it / ngroups, u = it - i * ngroups;
+            float v1[4 * NV], v2[4 * NV];
 #pragma unroll
-        for (int i = 0; i < 2 * R; i++) {
-            const int gy = 2 * qc + i;
-            if (gy >= Nr_out || (qc + (i >> 1)) >= nr) break;
-            for (int u = tid; u < ngroups; u += NT) {
-                float v1[4 * NV], v2[4 * NV];
+            for (int k = 0; k < NV; k++) {
+                const float4 a = *reinterpret_cast<const float4*>(s_1 + i * SW + 4 * u + 4 * k);
+                const float4 b = *reinterpret_cast<const float4*>(s_2 + i * SW + 4 * u + 4 * k);
+                v1[4 * k] = a.x; v1[4 * k + 1] = a.y; v1[4 * k + 2] = a.z; v1[4 * k + 3] = a.w;
+                v2[4 * k] = b.x; v2[4 * k + 1] = b.y; v2[4 * k + 2] = b.z; v2[4 * k + 3] = b.w;
+            }
+            float o[8];
 #pragma unroll
-                for (int k = 0; k < NV; k++) {
-                    const float4 a = *reinterpret_cast<const float4*>(s_1 + i * SW + 4 * u + 4 * k);
-                    const float4 b = *reinterpret_cast<const float4*>(s_2 + i * SW + 4 * u + 4 * k);
-                    v1[4 * k] = a.x; v1[4 * k + 1] = a.y; v1[4 * k + 2] = a.z; v1[4 * k + 3] = a.w;
-                    v2[4 * k] = b.x; v2[4 * k + 1] = b.y; v2[4 * k + 2] = b.z; v2[4 * k + 3] = b.w;
-                }
-                float o[8];
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    if (HAAR) {
-                        o[2 * c] = 0.5f * (v1[HLr + c] + v2[HLr + c]);
-                        o[2 * c + 1] = 0.5f * (v1[HLr + c] - v2[HLr + c]);
-                    } else {
-                        float e = 0.f, od = 0.f;
-#pragma unroll
-                        for (int jj = 0; jj < HALF; jj++) {
-                            e = fmaf(v1[HLr + c + S0 - jj], f.IL[2 * jj + E0], e);
-                            e = fmaf(v2[HLr + c + S0 - jj], f.IH[2 * jj + E0], e);
-                            od = fmaf(v1[HLr + c + S1 - jj], f.IL[2 * jj + E1], od);
-                            od = fmaf(v2[HLr + c + S1 - jj], f.IH[2 * jj + E1], od);
-                        }
-                        o[2 * c] = e;
-                        o[2 * c + 1] = od;
-                    }
-                }
-                const int gx = 2 * (x0h + 4 * u);
-                float* dst = out + (long long)gy * Nc_out + gx;
-                if (vec_out && gx + 7 < Nc_out) {
-                    stg4(dst, make_float4(o[0], o[1], o[2], o[3]), pol_out);
-                    stg4(dst + 4, make_float4(o[4], o[5], o[6], o[7]), pol_out);
+            for (int c = 0; c < 4; c++) {
+                if (HAAR) {
+                    o[2 * c] = 0.5f * (v1[HLr + c] + v2[HLr + c]);
+                    o[2 * c + 1] = 0.5f * (v1[HLr + c] - v2[HLr + c]);
                 } else {
+                    float e = 0.f, od = 0.f;
 #pragma unroll
-                    for (int c = 0; c < 8; c++)
-                        if (gx + c < Nc_out) stg1(dst + c, o[c], pol_out);
+                    for (int jj = 0; jj < HALF; jj++) {
+                        e = fmaf(v1[HLr + c + S0 - jj], f.IL[2 * jj + E0], e);
+                        e = fmaf(v2[HLr + c + S0 - jj], f.IH[2 * jj + E0], e);
+                        od = fmaf(v1[HLr + c + S1 - jj], f.IL[2 * jj + E1], od);
+                        od = fmaf(v2[HLr + c + S1 - jj], f.IH[2 * jj + E1], od);
+                    }
+                    o[2 * c] = e;
+                    o[2 * c + 1] = od;
                 }
             }
+            const int gy = 2 * qc + i;
+            const int gx = 2 * (x0h + 4 * u);
+            float* dst = out + (long long)gy * Nc_out + gx;
+            if (vec_out && gx + 7 < Nc_out) {
+                stg4(dst, make_float4(o[0], o[1], o[2], o[3]), pol_out);
+                stg4(dst + 4, make_float4(o[4], o[5], o[6], o[7]), pol_out);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; c++)
+                    if (gx + c < Nc_out) stg1(dst + c, o[c], pol_out);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+            na[i] = xa[i];
+            nd[i] = xd[i];
         }
     }
 }
@@ -434,8 +464,9 @@ int launch_inv(const float* A, const float* Hb, const float* V, const float* D, 
                int nr, int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs, int flags,
                const PwtFilters& f, cudaStream_t st) {
     constexpr int P = F / 2 - 1, HL = (P + 1) >> 1, HLr = (HL + 3) & ~3;
-    constexpr int SW = 4 * NT + 4;
-    int txmax = (4 * NT - HL - HLr) & ~3;
+    constexpr int NC = NT / 2;
+    constexpr int SW = 4 * NC + 4;
+    int txmax = (4 * NC - HL - HLr) & ~3;
     const int nx = cdiv(nc, txmax);
     const int TXH = min(txmax, (cdiv(nc, nx) + 3) & ~3);
     const size_t smem = sizeof(float) * 2 * 2 * 2 * R * SW;
@@ -460,7 +491,7 @@ int pwt_fast_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D,
                        int Nc, long long in_bs, long long out_bs, const PwtFilters& f, bool haar,
                        int hint_flags, cudaStream_t st) {
     const int F = haar ? 2 : f.hlen;
-    if (Nr < 2 * F || Nc < 2 * F) return 0;          // tiny levels: the generic kernel handles them
+    if (Nr < 64 || Nc < 64) return 0;                // tiny levels: the generic kernel handles them
     const int Nc2 = (Nc + 1) / 2;
     int flags = hint_flags & (FLAG_A_KEEP | FLAG_IN_LAST);
     if (Nc % 4 == 0 && in_bs % 4 == 0 && ((uintptr_t)in & 15) == 0) flags |= FLAG_VEC_IN;
@@ -488,18 +519,24 @@ int pwt_fast_dwt_inv2d(const float* A, const float* Hb, const float* V, const fl
                        int batch, int nr, int nc, int Nr_out, int Nc_out, long long in_bs,
                        long long out_bs, const PwtFilters& f, bool haar, int hint_flags, cudaStream_t st) {
     const int F = haar ? 2 : f.hlen;
-    if (nr < F || nc < F) return 0;
+    if (nr < 64 || nc < 64) return 0;
     int flags = hint_flags & (FLAG_A_KEEP | FLAG_IN_LAST);
     if (nc % 4 == 0 && in_bs % 4 == 0 && (((uintptr_t)A | (uintptr_t)Hb | (uintptr_t)V | (uintptr_t)D) & 15) == 0)
         flags |= FLAG_VEC_IN;
     if (Nc_out % 4 == 0 && out_bs % 4 == 0 && ((uintptr_t)out & 15) == 0) flags |= FLAG_VEC_OUT;
-#define INV(FF, HH, RR) return launch_inv<FF, HH, 128, RR>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, flags, f, st)
+#define INV(FF, HH, RR) return launch_inv<FF, HH, 256, RR>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, flags, f, st)
     if (haar) INV(2, true, 4);
     switch (F) {
         case 2: INV(2, false, 4);
         case 4: INV(4, false, 4);
-        case 6: INV(6, false, 2);
-        case 8: INV(8, false, 2);
+        case 6: INV(6, false, 4);
+        case 8: INV(8, false, 4);
+        case 10: INV(10, false, 2);
+        case 12: INV(12, false, 2);
+        case 14: INV(14, false, 2);
+        case 16: INV(16, false, 2);
+        case 18: INV(18, false, 2);
+        case 20: INV(20, false, 2);
         default: return 0;
     }
 #undef INV

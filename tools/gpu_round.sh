@@ -4,6 +4,7 @@ mkdir -p gpurun_out
 for what in "$@"; do
 case $what in
 golden) python tests/golden/make_golden.py gpurun_out/pdwt_golden.npz 2>&1 | tail -2 ;;
+quick) python -m pytest tests -m gpu -q -x --timeout=900 -p no:cacheprovider -k "agree or odd_sizes or idwt2 or full_size or stack or vs_pdwt" 2>&1 | grep -v "^Warning\|^Forcing" | tail -15 ;;
 tests) python -m pytest tests -m gpu -q --maxfail=30 --timeout=900 -p no:cacheprovider 2>&1 | grep -v "^Warning\|^Forcing" | tail -40 ;;
 smoke) python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ;;
 bench) python bench.py --steps 20 --warmup 3 2>&1 | grep -v "^Warning\|^Forcing" | tee gpurun_out/bench.json | tail -3 ;;
