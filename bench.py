@@ -112,7 +112,7 @@ def cpu_port_fwd_inv(img):
     return W.image
 
 
-def time_cpu_port(budget_s=10.0, side=2048):
+def time_cpu_port(budget_s=float(os.environ.get("PWT_BENCH_CPU_BUDGET", "10")), side=2048):
     img = synth((side, side), 99)
     cpu_port_fwd_inv(img[:256, :256])      # warm numpy
     n, t0 = 0, time.perf_counter()

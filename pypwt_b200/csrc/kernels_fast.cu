@@ -18,6 +18,10 @@
 // The analysis runs columns-then-rows (the reference does rows-then-columns, separable.cu:196-197);
 // the two orders differ only in fp32 rounding (~1e-7 relative, tolerance is 1e-5).  For Haar the
 // butterfly order is exactly the reference's (haar.cu:27-35).
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "pwt_internal.h"
 
 namespace {
@@ -91,8 +95,11 @@ constexpr int FLAG_IN_LAST = 8;   // the input was produced by the previous laun
 // =========================================================================================
 // forward
 // =========================================================================================
-template <int F, bool HAAR, int NT, int R>
-__global__ void __launch_bounds__(NT)
+// Border handling stays out of the hot path: a thread whose 4 columns are interior and 16-byte aligned
+// (`vec`) and a chunk whose rows do not wrap (`rows_plain`, CTA-uniform) load with plain 128-bit loads
+// at `row * Nc + xcol`; only the few border threads / chunks take the gather path.
+template <int F, bool HAAR, int NT, int R, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 k_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ Hb, float* __restrict__ V,
       float* __restrict__ D, int Nr, int Nc, int TX, int TYT, long long in_bs, long long out_bs, int flags,
       const __grid_constant__ PwtFilters f) {
@@ -107,21 +114,26 @@ k_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ H
     const int Nr2 = (Nr + 1) >> 1, Nc2 = (Nc + 1) >> 1;
     const int kx0 = blockIdx.x * TX, ky0 = blockIdx.y * TYT;
     in += blockIdx.z * in_bs;
-    const long long ob = blockIdx.z * out_bs;
-    const unsigned long long pol_in = (flags & FLAG_IN_LAST) ? policy_evict_first() : policy_evict_first();
+    A += blockIdx.z * out_bs;
+    Hb += blockIdx.z * out_bs;
+    V += blockIdx.z * out_bs;
+    D += blockIdx.z * out_bs;
+    const unsigned long long pol_in = policy_evict_first();
     const unsigned long long pol_det = policy_evict_first();
     const unsigned long long pol_a = (flags & FLAG_A_KEEP) ? policy_evict_last() : policy_evict_first();
 
-    // ---- this thread's 4 columns ----
-    const int xcol = 2 * kx0 - CL + 4 * tid;
-    const int txe = min(TX, Nc2 - kx0);                           // valid output columns of the tile
+    const int xcol = 2 * kx0 - CL + 4 * tid;                       // this thread's 4 columns
+    const int txe = min(TX, Nc2 - kx0);                            // valid output columns of the tile
     const bool col_active = xcol <= 2 * kx0 + 2 * txe + F / 2 - 2;
     const bool vec = (flags & FLAG_VEC_IN) && xcol >= 0 && xcol + 3 < Nc;
+    const float* in_t = in + xcol;
+    const int ky_end = min(ky0 + TYT, Nr2);
     int cx[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) cx[i] = wrap_dwt(xcol + i, Nc);
 
-    auto load_row = [&](int grow) -> float4 {
+    // any row, any thread (border path)
+    auto load_any = [&](int grow) -> float4 {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (col_active) {
             const float* row = in + (long long)wrap1_dwt(grow, Nr) * Nc;
@@ -137,30 +149,39 @@ k_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ H
         return v;
     };
 
-    float4 w[F];
+    float4 w[F];        // sliding window: w[j] = input row 2*ky - C + j
+    float4 q[2 * R];    // prefetch queue: the 2R new rows of the NEXT chunk are in flight during this one
+    {
+        const int r0 = 2 * ky0 - C;
+        if (vec && r0 >= 0 && r0 + F - 2 + 2 * R <= Nr) {
+            const float* p = in_t + (long long)r0 * Nc;
 #pragma unroll
-    for (int j = 0; j < F - 2; j++) w[j] = load_row(2 * ky0 - C + j);
-
-    const int npairs = (txe + 1) >> 1;
-    const bool vec_out = (flags & FLAG_VEC_OUT) != 0;
-    const int ky_end = min(ky0 + TYT, Nr2);
-    // software pipeline: the 2R rows of chunk n+1 are in flight while chunk n is computed
-    float4 nw[2 * R], nx[2 * R];
+            for (int j = 0; j < F - 2; j++) w[j] = ldg4(p + (long long)j * Nc, pol_in);
 #pragma unroll
-    for (int i = 0; i < 2 * R; i++) nw[i] = load_row(2 * ky0 - C + F - 2 + i);
-    int buf = 0;
-    for (int kyc = ky0; kyc < ky_end; kyc += R, buf ^= 1) {
-        float* s_lo = sm + buf * (2 * R * SW);
-        float* s_hi = s_lo + R * SW;
-        if (kyc + R < ky_end) {
+            for (int i = 0; i < 2 * R; i++) q[i] = ldg4(p + (long long)(F - 2 + i) * Nc, pol_in);
+        } else {
 #pragma unroll
-            for (int i = 0; i < 2 * R; i++) nx[i] = load_row(2 * (kyc + R) - C + F - 2 + i);
+            for (int j = 0; j < F - 2; j++) w[j] = load_any(r0 + j);
+#pragma unroll
+            for (int i = 0; i < 2 * R; i++) q[i] = load_any(r0 + F - 2 + i);
         }
-        // ---- pass 1: column analysis, 2R new rows, R output rows ----
+    }
+
+    // pass 1 of one chunk: consume 2 queued rows per output row, refill the queue, column analysis
+    auto pass1 = [&](auto mode, float* s_lo, float* s_hi, int rn0) {
+        constexpr int MODE = decltype(mode)::value;     // 0: no next chunk, 1: plain loads, 2: border loads
+        const float* pn = in_t + (long long)rn0 * Nc;
 #pragma unroll
         for (int i = 0; i < R; i++) {
-            w[F - 2] = nw[2 * i];
-            w[F - 1] = nw[2 * i + 1];
+            w[F - 2] = q[2 * i];
+            w[F - 1] = q[2 * i + 1];
+            if (MODE == 1) {
+                q[2 * i] = ldg4(pn + (long long)(2 * i) * Nc, pol_in);
+                q[2 * i + 1] = ldg4(pn + (long long)(2 * i + 1) * Nc, pol_in);
+            } else if (MODE == 2) {
+                q[2 * i] = load_any(rn0 + 2 * i);
+                q[2 * i + 1] = load_any(rn0 + 2 * i + 1);
+            }
             float4 lo, hi;
             if (HAAR) {
                 lo = make_float4(w[0].x + w[1].x, w[0].y + w[1].y, w[0].z + w[1].z, w[0].w + w[1].w);
@@ -179,18 +200,35 @@ k_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ H
 #pragma unroll
             for (int j = 0; j < F - 2; j++) w[j] = w[j + 2];
         }
+    };
+
+    const int npairs = (txe + 1) >> 1;
+    const bool vec_out = (flags & FLAG_VEC_OUT) != 0;
+    int buf = 0;
+    for (int kyc = ky0; kyc < ky_end; kyc += R, buf ^= 1) {
+        float* s_lo = sm + buf * (2 * R * SW);
+        float* s_hi = s_lo + R * SW;
+        const int rn0 = 2 * (kyc + R) - C + F - 2;                 // first new row of the next chunk
+        if (kyc + R >= ky_end)
+            pass1(std::integral_constant<int, 0>{}, s_lo, s_hi, rn0);
+        else if (vec && rn0 >= 0 && rn0 + 2 * R <= Nr)
+            pass1(std::integral_constant<int, 1>{}, s_lo, s_hi, rn0);
+        else
+            pass1(std::integral_constant<int, 2>{}, s_lo, s_hi, rn0);
         __syncthreads();
-        // ---- pass 2: row analysis from the ring, two output columns per item ----
+        // ---- pass 2: row analysis from the ring, two output columns per thread ----
+        if (tid < npairs) {
+            int o = kyc * Nc2 + kx0 + 2 * tid;       // < 2^31: one image holds < 2^31 samples
+            const bool pair_ok = vec_out && (kx0 + 2 * tid + 1 < Nc2);
+            const bool second = kx0 + 2 * tid + 1 < Nc2;
 #pragma unroll
-        for (int i = 0; i < R; i++) {
-            const int ky = kyc + i;
-            if (ky >= Nr2) break;
-            for (int q = tid; q < npairs; q += NT) {
+            for (int i = 0; i < R; i++, o += Nc2) {
+                if (kyc + i >= Nr2) break;
                 float vl[4 * NV], vh[4 * NV];
 #pragma unroll
                 for (int k = 0; k < NV; k++) {
-                    const float4 a = *reinterpret_cast<const float4*>(s_lo + i * SW + 4 * q + 4 * k);
-                    const float4 b = *reinterpret_cast<const float4*>(s_hi + i * SW + 4 * q + 4 * k);
+                    const float4 a = *reinterpret_cast<const float4*>(s_lo + i * SW + 4 * tid + 4 * k);
+                    const float4 b = *reinterpret_cast<const float4*>(s_hi + i * SW + 4 * tid + 4 * k);
                     vl[4 * k] = a.x; vl[4 * k + 1] = a.y; vl[4 * k + 2] = a.z; vl[4 * k + 3] = a.w;
                     vh[4 * k] = b.x; vh[4 * k + 1] = b.y; vh[4 * k + 2] = b.z; vh[4 * k + 3] = b.w;
                 }
@@ -211,9 +249,7 @@ k_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ H
                         d0 = fmaf(vh[DELTA + j], th, d0);     d1 = fmaf(vh[DELTA + 2 + j], th, d1);
                     }
                 }
-                const int kx = kx0 + 2 * q;
-                const long long o = ob + (long long)ky * Nc2 + kx;
-                if (vec_out && kx + 1 < Nc2) {
+                if (pair_ok) {
                     stg2(A + o, a0, a1, pol_a);
                     stg2(Hb + o, h0, h1, pol_det);
                     stg2(V + o, v0, v1, pol_det);
@@ -223,7 +259,7 @@ k_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ H
                     stg1(Hb + o, h0, pol_det);
                     stg1(V + o, v0, pol_det);
                     stg1(D + o, d0, pol_det);
-                    if (kx + 1 < Nc2) {
+                    if (second) {
                         stg1(A + o + 1, a1, pol_a);
                         stg1(Hb + o + 1, h1, pol_det);
                         stg1(V + o + 1, v1, pol_det);
@@ -232,8 +268,6 @@ k_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ H
                 }
             }
         }
-#pragma unroll
-        for (int i = 0; i < 2 * R; i++) nw[i] = nx[i];
     }
 }
 
@@ -243,8 +277,8 @@ k_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ H
 // NT threads = two roles of NT/2 threads: role 0 synthesises t1 = syn_y(A, H), role 1 synthesises
 // t2 = syn_y(V, D) (halves the register footprint of the sliding windows); both roles share the
 // row-synthesis pass.
-template <int F, bool HAAR, int NT, int R>
-__global__ void __launch_bounds__(NT)
+template <int F, bool HAAR, int NT, int R, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 k_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float* __restrict__ V,
       const float* __restrict__ D, float* __restrict__ out, int nr, int nc, int Nr_out, int Nc_out, int TXH,
       int TYH, long long in_bs, long long out_bs, int flags, const __grid_constant__ PwtFilters f) {
@@ -295,36 +329,55 @@ k_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float* __
 
     // window row j <-> band row q + S0 - (HALF-1) + j for the current q
     float4 wa[WIN], wd[WIN];
+    float4 qa[R], qd[R];      // prefetch queue: the R new band rows of the NEXT chunk
+    const float* ba_t = ba + kcol;
+    const float* bd_t = bd + kcol;
+    {
+        const int r0 = y0h + S0 - (HALF - 1);
+        if (vec && r0 >= 0 && r0 + WIN - 1 + R <= nr) {
 #pragma unroll
-    for (int j = 0; j < WIN - 1; j++) {
-        const int r = y0h + S0 - (HALF - 1) + j;
-        wa[j] = load_row(ba, r);
-        wd[j] = load_row(bd, r);
+            for (int j = 0; j < WIN - 1; j++) {
+                wa[j] = ldg4(ba_t + (long long)(r0 + j) * nc, pol_in);
+                wd[j] = ldg4(bd_t + (long long)(r0 + j) * nc, pol_in);
+            }
+#pragma unroll
+            for (int i = 0; i < R; i++) {
+                qa[i] = ldg4(ba_t + (long long)(r0 + WIN - 1 + i) * nc, pol_in);
+                qd[i] = ldg4(bd_t + (long long)(r0 + WIN - 1 + i) * nc, pol_in);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < WIN - 1; j++) {
+                wa[j] = load_row(ba, r0 + j);
+                wd[j] = load_row(bd, r0 + j);
+            }
+#pragma unroll
+            for (int i = 0; i < R; i++) {
+                qa[i] = load_row(ba, r0 + WIN - 1 + i);
+                qd[i] = load_row(bd, r0 + WIN - 1 + i);
+            }
+        }
     }
 
     const int ngroups = (txe + 3) >> 2;
     const bool vec_out = (flags & FLAG_VEC_OUT) != 0;
     const int q_end = min(y0h + TYH, nr);
-    float4 na[R], nd[R], xa[R], xd[R];
-#pragma unroll
-    for (int i = 0; i < R; i++) {
-        na[i] = load_row(ba, y0h + i + S1);
-        nd[i] = load_row(bd, y0h + i + S1);
-    }
-    int buf = 0;
-    for (int qc = y0h; qc < q_end; qc += R, buf ^= 1) {
-        float* s_mine = sm + buf * (4 * R * SW) + role * (2 * R * SW);
-        if (qc + R < q_end) {
-#pragma unroll
-            for (int i = 0; i < R; i++) {
-                xa[i] = load_row(ba, qc + R + i + S1);
-                xd[i] = load_row(bd, qc + R + i + S1);
-            }
-        }
+
+    auto pass1 = [&](auto mode, float* s_mine, int rn0) {
+        constexpr int MODE = decltype(mode)::value;     // 0: no next chunk, 1: plain loads, 2: border loads
+        const float* pa = ba_t + (long long)rn0 * nc;
+        const float* pd = bd_t + (long long)rn0 * nc;
 #pragma unroll
         for (int i = 0; i < R; i++) {
-            wa[WIN - 1] = na[i];
-            wd[WIN - 1] = nd[i];
+            wa[WIN - 1] = qa[i];
+            wd[WIN - 1] = qd[i];
+            if (MODE == 1) {
+                qa[i] = ldg4(pa + (long long)i * nc, pol_in);
+                qd[i] = ldg4(pd + (long long)i * nc, pol_in);
+            } else if (MODE == 2) {
+                qa[i] = load_row(ba, rn0 + i);
+                qd[i] = load_row(bd, rn0 + i);
+            }
             float4 te, to;
             if (HAAR) {
                 te = make_float4(wa[0].x + wd[0].x, wa[0].y + wd[0].y, wa[0].z + wd[0].z, wa[0].w + wd[0].w);
@@ -349,6 +402,18 @@ k_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float* __
                 wd[j] = wd[j + 1];
             }
         }
+    };
+
+    int buf = 0;
+    for (int qc = y0h; qc < q_end; qc += R, buf ^= 1) {
+        float* s_mine = sm + buf * (4 * R * SW) + role * (2 * R * SW);
+        const int rn0 = qc + R + S1;                                // first new band row of the next chunk
+        if (qc + R >= q_end)
+            pass1(std::integral_constant<int, 0>{}, s_mine, rn0);
+        else if (vec && rn0 + R <= nr)
+            pass1(std::integral_constant<int, 1>{}, s_mine, rn0);
+        else
+            pass1(std::integral_constant<int, 2>{}, s_mine, rn0);
         __syncthreads();
         // ---- row synthesis: 4 band columns -> 8 output columns per item; items = 2R rows x ngroups ----
         const float* s_1 = sm + buf * (4 * R * SW);
@@ -395,11 +460,6 @@ k_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float* __
                     if (gx + c < Nc_out) stg1(dst + c, o[c], pol_out);
             }
         }
-#pragma unroll
-        for (int i = 0; i < R; i++) {
-            na[i] = xa[i];
-            nd[i] = xd[i];
-        }
     }
 }
 
@@ -418,6 +478,10 @@ int num_sms() {
 // Pick the tile height (multiple of `quantum` rows) so that the grid is a whole number of waves when
 // possible: total CTAs close below a multiple of (#SM x resident CTAs).
 int pick_tile_rows(int rows, int nx, int batch, int quantum, int resident) {
+    if (const char* e = getenv("PWT_FAST_TILE_ROWS")) {      // tuning override (multiple of the chunk size)
+        const int v = atoi(e);
+        if (v > 0) return ((v + quantum - 1) / quantum) * quantum;
+    }
     const int slots = num_sms() * resident;
     int best = quantum * 8, best_waste = 1 << 30;
     for (int t = 4; t <= 64; t++) {                 // tile heights 4..64 quanta
@@ -435,7 +499,7 @@ int pick_tile_rows(int rows, int nx, int batch, int quantum, int resident) {
     return best;
 }
 
-template <int F, bool HAAR, int NT, int R>
+template <int F, bool HAAR, int NT, int R, int MINB>
 int launch_fwd(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
                long long in_bs, long long out_bs, int flags, const PwtFilters& f, cudaStream_t st) {
     constexpr int C = F / 2 - 1, CL = (C + 3) & ~3;
@@ -447,19 +511,19 @@ int launch_fwd(const float* in, float* A, float* Hb, float* V, float* D, int bat
     const size_t smem = sizeof(float) * 2 * 2 * R * SW;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_fwd<F, HAAR, NT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_fwd<F, HAAR, NT, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done = true;
     }
     int resident = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fwd<F, HAAR, NT, R>, NT, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fwd<F, HAAR, NT, R, MINB>, NT, smem);
     if (resident < 1) resident = 1;
     const int TYT = pick_tile_rows(Nr2, cdiv(Nc2, TX), batch, R, resident);
     dim3 grid(cdiv(Nc2, TX), cdiv(Nr2, TYT), batch);
-    k_fwd<F, HAAR, NT, R><<<grid, NT, smem, st>>>(in, A, Hb, V, D, Nr, Nc, TX, TYT, in_bs, out_bs, flags, f);
+    k_fwd<F, HAAR, NT, R, MINB><<<grid, NT, smem, st>>>(in, A, Hb, V, D, Nr, Nc, TX, TYT, in_bs, out_bs, flags, f);
     return 1;
 }
 
-template <int F, bool HAAR, int NT, int R>
+template <int F, bool HAAR, int NT, int R, int MINB>
 int launch_inv(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
                int nr, int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs, int flags,
                const PwtFilters& f, cudaStream_t st) {
@@ -472,15 +536,15 @@ int launch_inv(const float* A, const float* Hb, const float* V, const float* D, 
     const size_t smem = sizeof(float) * 2 * 2 * 2 * R * SW;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_inv<F, HAAR, NT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_inv<F, HAAR, NT, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done = true;
     }
     int resident = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_inv<F, HAAR, NT, R>, NT, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_inv<F, HAAR, NT, R, MINB>, NT, smem);
     if (resident < 1) resident = 1;
     const int TYH = pick_tile_rows(nr, cdiv(nc, TXH), batch, R, resident);
     dim3 grid(cdiv(nc, TXH), cdiv(nr, TYH), batch);
-    k_inv<F, HAAR, NT, R><<<grid, NT, smem, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out, TXH, TYH, in_bs,
+    k_inv<F, HAAR, NT, R, MINB><<<grid, NT, smem, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out, TXH, TYH, in_bs,
                                                   out_bs, flags, f);
     return 1;
 }
@@ -497,19 +561,25 @@ int pwt_fast_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D,
     if (Nc % 4 == 0 && in_bs % 4 == 0 && ((uintptr_t)in & 15) == 0) flags |= FLAG_VEC_IN;
     if (Nc2 % 2 == 0 && out_bs % 2 == 0 && (((uintptr_t)A | (uintptr_t)Hb | (uintptr_t)V | (uintptr_t)D) & 7) == 0)
         flags |= FLAG_VEC_OUT;
-#define FWD(FF, HH, RR) return launch_fwd<FF, HH, 128, RR>(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, flags, f, st)
-    if (haar) FWD(2, true, 4);
+#define FWD(FF, HH, RR, MB) return launch_fwd<FF, HH, 128, RR, MB>(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, flags, f, st)
+    if (haar) FWD(2, true, 4, 6);
     switch (F) {
-        case 2: FWD(2, false, 4);
-        case 4: FWD(4, false, 4);
-        case 6: FWD(6, false, 4);
-        case 8: FWD(8, false, 4);
-        case 10: FWD(10, false, 2);
-        case 12: FWD(12, false, 2);
-        case 14: FWD(14, false, 2);
-        case 16: FWD(16, false, 2);
-        case 18: FWD(18, false, 2);
-        case 20: FWD(20, false, 2);
+        case 2: FWD(2, false, 4, 6);
+        case 4:
+            if (const char* e = getenv("PWT_FWD_VARIANT")) {
+                if (atoi(e) == 1) FWD(4, false, 2, 8);
+                if (atoi(e) == 2) FWD(4, false, 2, 6);
+                if (atoi(e) == 3) FWD(4, false, 8, 3);
+            }
+            FWD(4, false, 4, 5);
+        case 6: FWD(6, false, 4, 4);
+        case 8: FWD(8, false, 4, 4);
+        case 10: FWD(10, false, 2, 4);
+        case 12: FWD(12, false, 2, 4);
+        case 14: FWD(14, false, 2, 3);
+        case 16: FWD(16, false, 2, 3);
+        case 18: FWD(18, false, 2, 3);
+        case 20: FWD(20, false, 2, 3);
         default: return 0;
     }
 #undef FWD
@@ -524,19 +594,19 @@ int pwt_fast_dwt_inv2d(const float* A, const float* Hb, const float* V, const fl
     if (nc % 4 == 0 && in_bs % 4 == 0 && (((uintptr_t)A | (uintptr_t)Hb | (uintptr_t)V | (uintptr_t)D) & 15) == 0)
         flags |= FLAG_VEC_IN;
     if (Nc_out % 4 == 0 && out_bs % 4 == 0 && ((uintptr_t)out & 15) == 0) flags |= FLAG_VEC_OUT;
-#define INV(FF, HH, RR) return launch_inv<FF, HH, 256, RR>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, flags, f, st)
-    if (haar) INV(2, true, 4);
+#define INV(FF, HH, RR, MB) return launch_inv<FF, HH, 256, RR, MB>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, flags, f, st)
+    if (haar) INV(2, true, 4, 3);
     switch (F) {
-        case 2: INV(2, false, 4);
-        case 4: INV(4, false, 4);
-        case 6: INV(6, false, 4);
-        case 8: INV(8, false, 4);
-        case 10: INV(10, false, 2);
-        case 12: INV(12, false, 2);
-        case 14: INV(14, false, 2);
-        case 16: INV(16, false, 2);
-        case 18: INV(18, false, 2);
-        case 20: INV(20, false, 2);
+        case 2: INV(2, false, 4, 3);
+        case 4: INV(4, false, 4, 3);
+        case 6: INV(6, false, 4, 2);
+        case 8: INV(8, false, 4, 2);
+        case 10: INV(10, false, 2, 2);
+        case 12: INV(12, false, 2, 2);
+        case 14: INV(14, false, 2, 1);
+        case 16: INV(16, false, 2, 1);
+        case 18: INV(18, false, 2, 1);
+        case 20: INV(20, false, 2, 1);
         default: return 0;
     }
 #undef INV

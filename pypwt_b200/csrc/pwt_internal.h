@@ -97,3 +97,12 @@ int pwt_fast_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D,
 int pwt_fast_dwt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out,
                        int batch, int nr, int nc, int Nr_out, int Nc_out, long long in_bs,
                        long long out_bs, const PwtFilters& f, bool haar, int hint_flags, cudaStream_t st);
+
+// kernels_reg.cu : register-resident kernels (warp shuffles, no shared memory) for F <= 10 on
+// 128-column-aligned planes.  Return 0 when the configuration is not covered.
+int pwt_reg_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr,
+                      int Nc, long long in_bs, long long out_bs, const PwtFilters& f, bool haar,
+                      int hint_flags, cudaStream_t st);
+int pwt_reg_dwt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out,
+                      int batch, int nr, int nc, int Nr_out, int Nc_out, long long in_bs,
+                      long long out_bs, const PwtFilters& f, bool haar, int hint_flags, cudaStream_t st);

@@ -304,6 +304,24 @@ extern "C" int pwt_create_batch(pwt_plan** out, const float* img, int batch, int
         puts("Warning: makes little sense to use Cycle spinning with stationary Wavelet transform");
     compute_geometry(p);
 
+    // L2 residency of the ping-pong approximation planes: the kernels store them with an
+    // L2::evict_last policy, which only has an effect when a persisting-L2 carve-out exists.
+    {
+        static bool l2_done = false;
+        if (!l2_done) {
+            l2_done = true;
+            int max_persist = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, p->device);
+            // measured on B200 (profiles/r01_notes.md): a carve-out SLOWS the level-1 kernels (0.10 -> 0.15-0.18 ms)
+            // and does not speed up level 2, so it is off unless PWT_L2_PERSIST_MB asks for it.
+            const char* env = getenv("PWT_L2_PERSIST_MB");
+            size_t want = env ? (size_t)atoi(env) << 20 : 0;
+            if (want > (size_t)max_persist) want = (size_t)max_persist;
+            if (want > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            if (getenv("PWT_VERBOSE")) printf("pwt: persisting L2 carve-out %zu MB (max %d MB)\n", want >> 20, max_persist >> 20);
+        }
+    }
+
     int rc = PWT_OK;
     cudaError_t e = cudaStreamCreate(&p->stream);
     if (e == cudaSuccess) e = cudaEventCreate(&p->ev0);
@@ -536,7 +554,10 @@ extern "C" int pwt_forward(pwt_plan* p) {
                 const int nr = p->lvNr[l - 1], nc = p->lvNc[l - 1];
                 if (haar || p->do_separable) {
                     int n = 0;
+                    const int hints = (l < L ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l > 1 ? PWT_HINT_IN_FROM_PREV : 0);
                     if (p->kernel_mode == 0)
+                        n = pwt_reg_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, hints, st);
+                    if (!n && (p->kernel_mode == 0 || p->kernel_mode == 2))
                         n = pwt_fast_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar,
                                                (l < L ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l > 1 ? PWT_HINT_IN_FROM_PREV : 0), st);
                     if (!n) n = pwt_launch_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, st);
@@ -600,7 +621,10 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                 const int nr = p->lvNr[l], nc = p->lvNc[l], Nro = p->lvNr[l - 1], Nco = p->lvNc[l - 1];
                 if (haar || p->do_separable) {
                     int n = 0;
+                    const int hints = (l > 1 ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l < L ? PWT_HINT_IN_FROM_PREV : 0);
                     if (p->kernel_mode == 0)
+                        n = pwt_reg_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, hints, st);
+                    if (!n && (p->kernel_mode == 0 || p->kernel_mode == 2))
                         n = pwt_fast_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar,
                                                (l > 1 ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l < L ? PWT_HINT_IN_FROM_PREV : 0), st);
                     if (!n) n = pwt_launch_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, st);
