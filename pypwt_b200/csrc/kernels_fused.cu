@@ -1,0 +1,384 @@
+// Three decomposition levels in ONE launch, entirely in registers (forward and inverse).
+//
+// With one launch per level the intermediate approximations A1 and A2 make a round trip through
+// memory (10.5 B per pixel and per direction instead of the compulsory 8).  Here a warp streams down
+// a strip of the image and runs the three levels as a cascade:
+//
+//   forward   input row pair -> A1 row (2 columns per lane)  -> level-1 details stored
+//             A1 row pair    -> A2 row (1 column per lane)   -> level-2 details stored
+//             A2 row pair    -> A3 row (every other lane)    -> level-3 details + A3 stored
+//   inverse   the mirror image: A3 + details3 -> A2 rows -> (+ details2) A1 rows -> (+ details1) image
+//
+// Horizontal neighbours come from warp shuffles; what a warp cannot get from its own lanes (the
+// cascade of the neighbouring strip) is recomputed: strips overlap, and a warp OWNS (stores) fewer
+// columns than it loads (forward db2: 112 of 128).  The same holds vertically: a task warms its
+// sliding windows up on 8+6 extra input rows.  The arithmetic order inside each level is the same as
+// in the single-level kernels of kernels_reg.cu, so results are bit-identical to three launches.
+//
+// Requirements (checked by the dispatcher): even filter length <= 8, rows and columns multiples of 8
+// (every level then has an even size: pure periodic wrap, no odd-size extension), >= 3 levels.
+#include <stdlib.h>
+
+#include "pwt_internal.h"
+
+namespace {
+
+__device__ __forceinline__ int wrap1_per(int i, int N) {   // -N <= i < 2N
+    if (i < 0) i += N;
+    if (i >= N) i -= N;
+    return i;
+}
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void stg2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int kWarps = 4;
+
+__device__ __forceinline__ float comp(const float4& v, int c) {
+    return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w));
+}
+
+struct Fwd3Args {
+    const float* in;
+    float* A3;
+    float* H[3];
+    float* V[3];
+    float* D[3];
+    int Nr, Nc;            // level-0 size
+    int n3;                // level-3 columns owned by one warp
+    int T3;                // level-3 rows per task
+    long long in_bs;       // batch strides (elements) of the input and of the level-1/2/3 planes
+    long long bs[3];
+    unsigned* counter;     // dynamic task queue: task = atomicAdd(counter, 1) - base
+    unsigned base;
+    int ntasks;            // tasks per image (strips * bands); total = ntasks * batch
+    int batch;
+};
+
+// geometry shared by host and device
+template <int F>
+struct Geo {
+    static constexpr int C = F / 2 - 1;                 // left reach of an analysis window
+    static constexpr int O1 = (3 * C + 1) & ~1;         // level-1 columns loaded left of the owned region (even)
+    static constexpr int D2 = O1 / 2;                   // level-2 lane offset of the owned region
+    // owned level-3 columns per warp: 64 level-1 columns must cover [4c3 - 3C, 4c3 + 4n - 4 + 3F/2]
+    static constexpr int N3 = (63 - O1 - 3 * F / 2 + 4) / 4;
+};
+
+template <int F, bool HAAR, int MINB, bool PF>
+__global__ void __launch_bounds__(32 * kWarps, MINB)
+k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ PwtFilters f) {
+    using G = Geo<F>;
+    constexpr int C = G::C;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Nr = a.Nr, Nc = a.Nc;
+    const int W1 = Nc >> 1, W2 = Nc >> 2, W3 = Nc >> 3;
+    const int R3 = Nr >> 3;
+    const int strips = (W3 + a.n3 - 1) / a.n3;
+  for (;;) {
+    // persistent warp: pull the next (image, band, strip) task from the queue
+    unsigned t_ = 0;
+    if (lane == 0) t_ = atomicAdd(a.counter, 1u) - a.base;
+    t_ = __shfl_sync(FULL, t_, 0);
+    if (t_ >= (unsigned)a.ntasks * (unsigned)a.batch) return;
+    const int img = t_ / a.ntasks, task = t_ - img * a.ntasks;
+    const int strip = task % strips, band = task / strips;
+    const int n0 = band * a.T3;
+    const int n1 = min(n0 + a.T3, R3);
+    const int c3 = strip * a.n3;                         // first owned level-3 column
+    const int n3e = min(a.n3, W3 - c3);                  // owned level-3 columns (last strip may be short)
+    const int K1 = 4 * c3 - G::O1;                       // level-1 column of lane 0 (may be negative: wraps)
+    const int X0 = 2 * K1;                               // input column of lane 0
+
+    const float* in = a.in + img * a.in_bs;
+    const int xcol = wrap1_per(X0 + 4 * lane, Nc);       // Nc % 4 == 0: a lane's 4 samples never straddle the wrap
+    // halo samples of the warp's strip: lane 0 fetches the C samples left of it, lane 31 the C samples
+    // right of it; every other lane re-reads its own first sample (same sector as its 128-bit load), so
+    // the extra load is branch-free.
+    int ecol[C > 0 ? C : 1];
+#pragma unroll
+    for (int i = 0; i < C; i++)
+        ecol[i] = lane == 0 ? wrap1_per(X0 - C + i, Nc) : (lane == 31 ? wrap1_per(wrap1_per(X0 + 128, Nc) + i, Nc) : xcol);
+    // ownership of this lane's columns
+    const int k1 = K1 + 2 * lane;                        // level-1 columns k1, k1+1
+    const bool own1 = k1 >= 4 * c3 && k1 < 4 * (c3 + n3e);
+    const int k2 = (K1 >> 1) + lane;                     // level-2 column (K1 is even)
+    const bool own2 = k2 >= 2 * c3 && k2 < 2 * (c3 + n3e);
+    const int i3 = lane - G::D2;                         // level-3: column c3 + i3/2 lives on lane D2 + 2*i
+    const int k3 = c3 + (i3 >> 1);
+    const bool own3 = i3 >= 0 && !(i3 & 1) && (i3 >> 1) < n3e;
+    float* H1 = a.H[0] + img * a.bs[0]; float* V1 = a.V[0] + img * a.bs[0]; float* D1 = a.D[0] + img * a.bs[0];
+    float* H2 = a.H[1] + img * a.bs[1]; float* V2 = a.V[1] + img * a.bs[1]; float* D2p = a.D[1] + img * a.bs[1];
+    float* H3 = a.H[2] + img * a.bs[2]; float* V3 = a.V[2] + img * a.bs[2]; float* D3 = a.D[2] + img * a.bs[2];
+    float* A3 = a.A3 + img * a.bs[2];
+
+    // ---- level 1: horizontal pass of one input row (same arithmetic as k_fwd_reg) ----
+    // eight consecutive rows starting at rb; the wrap test is hoisted out (uniform)
+    auto load_rows8 = [&](int rb, float4* v, float (*e)[C > 0 ? C : 1]) {
+        if (rb >= 0 && rb + 8 <= Nr) {
+            const float* p = in + (long long)rb * Nc;
+#pragma unroll
+            for (int i = 0; i < 8; i++, p += Nc) {
+                v[i] = ldg4(p + xcol);
+#pragma unroll
+                for (int c = 0; c < C; c++) e[i][c] = __ldg(p + ecol[c]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float* p = in + (long long)wrap1_per(rb + i, Nr) * Nc;
+                v[i] = ldg4(p + xcol);
+#pragma unroll
+                for (int c = 0; c < C; c++) e[i][c] = __ldg(p + ecol[c]);
+            }
+        }
+    };
+    const bool first_lane = lane == 0, last_lane = lane == 31;
+    auto hpass1 = [&](const float4& v, const float* e) -> float4 {
+        if (HAAR) return v;      // raw samples: the Haar butterfly combines rows first (haar.cu:27-35)
+        float ext[F + 2];
+#pragma unroll
+        for (int c = 0; c < 4; c++) ext[C + c] = comp(v, c);
+#pragma unroll
+        for (int i = 0; i < C; i++) {
+            const float l = __shfl_up_sync(FULL, comp(v, 4 - C + i), 1);
+            const float r = __shfl_down_sync(FULL, comp(v, i), 1);
+            ext[i] = first_lane ? e[i] : l;
+            ext[C + 4 + i] = last_lane ? e[i] : r;
+        }
+        float lo0 = 0.f, lo1 = 0.f, hi0 = 0.f, hi1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < F; j++) {
+            const float tl = f.L[F - 1 - j], th = f.H[F - 1 - j];
+            lo0 = fmaf(ext[j], tl, lo0);
+            lo1 = fmaf(ext[j + 2], tl, lo1);
+            hi0 = fmaf(ext[j], th, hi0);
+            hi1 = fmaf(ext[j + 2], th, hi1);
+        }
+        return make_float4(lo0, lo1, hi0, hi1);
+    };
+    // ---- levels 2 and 3: horizontal pass of an approximation row held one/two columns per lane ----
+    // level 2: this lane's output column is 2*k2 = its own pair (a0, a1); offset d lives in lane + floor(d/2)
+    auto hpass2 = [&](float a0, float a1) -> float2 {
+        if (HAAR) return make_float2(a0, a1);
+        float lo = 0.f, hi = 0.f;
+#pragma unroll
+        for (int j = 0; j < F; j++) {
+            const int d = j - C;                         // column offset relative to a0
+            const int dl = d >= 0 ? d / 2 : -((1 - d) / 2);   // floor(d / 2)
+            const float src = (d & 1) ? a1 : a0;
+            const float val = dl == 0 ? src : __shfl_sync(FULL, src, lane + dl);
+            lo = fmaf(val, f.L[F - 1 - j], lo);
+            hi = fmaf(val, f.H[F - 1 - j], hi);
+        }
+        return make_float2(lo, hi);
+    };
+    // level 3: one column per lane; column offset d lives in lane + d
+    auto hpass3 = [&](float a2) -> float2 {
+        if (HAAR) {
+            const float nb = __shfl_down_sync(FULL, a2, 1);
+            return make_float2(a2, nb);
+        }
+        float lo = 0.f, hi = 0.f;
+#pragma unroll
+        for (int j = 0; j < F; j++) {
+            const int d = j - C;
+            const float val = d == 0 ? a2 : __shfl_sync(FULL, a2, lane + d);
+            lo = fmaf(val, f.L[F - 1 - j], lo);
+            hi = fmaf(val, f.H[F - 1 - j], hi);
+        }
+        return make_float2(lo, hi);
+    };
+
+    constexpr int FW = HAAR ? 2 : F;
+    float4 w1[FW];     // level-1 window of horizontally filtered rows: (lo0, lo1, hi0, hi1)
+    float2 w2[FW];     // level-2 window: (lo, hi)
+    float2 w3[FW];     // level-3 window
+#pragma unroll
+    for (int j = 0; j < FW; j++) {
+        w1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w2[j] = make_float2(0.f, 0.f);
+        w3[j] = make_float2(0.f, 0.f);
+    }
+
+    // vertical steps: combine the window into one output row (Haar: exact 1/2 butterfly, haar.cu:27-35 order
+    // differs from the single-level kernel only in that rows are combined after columns)
+    auto vstep1 = [&](int krow, bool row_owned, float& a0, float& a1) {
+        float h0, h1, v0, v1, d0, d1;
+        if (HAAR) {
+            const float sx = w1[0].x + w1[1].x, sy = w1[0].y + w1[1].y, sz = w1[0].z + w1[1].z, sw = w1[0].w + w1[1].w;
+            const float dx = w1[0].x - w1[1].x, dy = w1[0].y - w1[1].y, dz = w1[0].z - w1[1].z, dw = w1[0].w - w1[1].w;
+            a0 = 0.5f * (sx + sy); a1 = 0.5f * (sz + sw);
+            v0 = 0.5f * (sx - sy); v1 = 0.5f * (sz - sw);
+            h0 = 0.5f * (dx + dy); h1 = 0.5f * (dz + dw);
+            d0 = 0.5f * (dx - dy); d1 = 0.5f * (dz - dw);
+        } else {
+            a0 = a1 = h0 = h1 = v0 = v1 = d0 = d1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < F; j++) {
+                const float tl = f.L[F - 1 - j], th = f.H[F - 1 - j];
+                a0 = fmaf(w1[j].x, tl, a0); a1 = fmaf(w1[j].y, tl, a1);
+                h0 = fmaf(w1[j].x, th, h0); h1 = fmaf(w1[j].y, th, h1);
+                v0 = fmaf(w1[j].z, tl, v0); v1 = fmaf(w1[j].w, tl, v1);
+                d0 = fmaf(w1[j].z, th, d0); d1 = fmaf(w1[j].w, th, d1);
+            }
+        }
+        if (row_owned && own1) {
+            const int o = krow * W1 + k1;
+            stg2(H1 + o, h0, h1);
+            stg2(V1 + o, v0, v1);
+            stg2(D1 + o, d0, d1);
+        }
+#pragma unroll
+        for (int j = 0; j < FW - 2; j++) w1[j] = w1[j + 2];
+    };
+    auto vstep23 = [&](float2* w, float& av, float& hv, float& vv, float& dv) {
+        if (HAAR) {
+            const float sp = w[0].x + w[1].x, sq = w[0].y + w[1].y, dp = w[0].x - w[1].x, dq = w[0].y - w[1].y;
+            av = 0.5f * (sp + sq); vv = 0.5f * (sp - sq);
+            hv = 0.5f * (dp + dq); dv = 0.5f * (dp - dq);
+        } else {
+            av = hv = vv = dv = 0.f;
+#pragma unroll
+            for (int j = 0; j < F; j++) {
+                const float tl = f.L[F - 1 - j], th = f.H[F - 1 - j];
+                av = fmaf(w[j].x, tl, av);
+                hv = fmaf(w[j].x, th, hv);
+                vv = fmaf(w[j].y, tl, vv);
+                dv = fmaf(w[j].y, th, dv);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < FW - 2; j++) w[j] = w[j + 2];
+    };
+
+    // ---- warm-up: the F-2 input rows that precede the first full iteration, then (for F > 2) enough
+    // level-1 rows to fill the level-2 window.  Input rows are numbered so that level-1 row k uses
+    // rows 2k - C .. 2k - C + F - 1, level-2 row m uses level-1 rows 2m - C .., and so on.
+    // Steady state, iteration n (level-3 row n): consumes input rows r0(n) .. r0(n)+7 with
+    //   r0(n) = 8n + 7*(F/2) - 7*C ... derived below from the newest rows each window needs.
+    // newest level-2 rows for level-3 row n : 2n - C + F - 2, 2n - C + F - 1           =: m_a, m_b
+    // newest level-1 rows for level-2 row m : 2m - C + F - 2, 2m - C + F - 1
+    // newest input   rows for level-1 row k : 2k - C + F - 2, 2k - C + F - 1
+    constexpr int E = F - 1 - C;                 // newest row offset: level row k needs source rows up to 2k + E
+    // level-1 rows consumed by iteration n: k = 4n + 3E - 2 - 1 ... explicit list below
+    // input rows of iteration n start at rbase(n); PREFETCH: the 8 rows of iteration n+1 are requested
+    // before iteration n is computed (template parameter PF), so a warp always has loads in flight.
+    auto rbase_of = [&](int n) { return 2 * (2 * (2 * n + E - 1) + E - 1) + E - 1; };
+    auto iteration = [&](int n, bool store_ok) {
+        // level-2 rows produced here: m0 = 2n + E - 1, m1 = 2n + E ; level-1 rows: k = 2*m0 + E - 1 .. 2*m1 + E
+        const int m0 = 2 * n + E - 1;
+        const int kbase = 2 * m0 + E - 1;                 // four level-1 rows kbase .. kbase+3
+        float4 v[8];
+        float e[8][C > 0 ? C : 1];
+        load_rows8(rbase_of(n), v, e);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            w1[FW - 2] = hpass1(v[2 * t], e[2 * t]);
+            w1[FW - 1] = hpass1(v[2 * t + 1], e[2 * t + 1]);
+            const int k = kbase + t;
+            float a0, a1;
+            vstep1(k, store_ok && k >= 4 * n0 && k < 4 * n1, a0, a1);
+            w2[FW - 2 + (t & 1)] = hpass2(a0, a1);
+            if (t & 1) {
+                const int m = m0 + (t >> 1);
+                float a2, h2, v2, d2;
+                vstep23(w2, a2, h2, v2, d2);
+                if (store_ok && own2 && m >= 2 * n0 && m < 2 * n1) {
+                    const int o = m * W2 + k2;
+                    H2[o] = h2;
+                    V2[o] = v2;
+                    D2p[o] = d2;
+                }
+                w3[FW - 2 + (t >> 1)] = hpass3(a2);
+            }
+        }
+        float a3, h3, v3, d3;
+        vstep23(w3, a3, h3, v3, d3);
+        if (store_ok && own3 && n >= n0 && n < n1) {
+            const int o = n * W3 + k3;
+            A3[o] = a3;
+            H3[o] = h3;
+            V3[o] = v3;
+            D3[o] = d3;
+        }
+    };
+
+    // Warm-up: J extra iterations fill the three sliding windows; whatever they compute from a still
+    // incomplete window belongs to rows this task does not own, and the ownership tests inside
+    // iteration() keep it from being stored.  J = ceil((3E + 4C - 3) / 4): 0 (haar), 2 (F=4), 4 (F=6), 6 (F=8).
+    constexpr int J = HAAR ? 0 : (3 * E + 4 * C - 3 + 3) / 4;
+    for (int n = n0 - J; n < n1; n++) iteration(n, true);
+  }
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
+template <int F, bool HAAR, int MINB, bool PF>
+int launch_fwd3(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cudaStream_t st) {
+    a.n3 = HAAR ? 16 : Geo<F>::N3;
+    a.T3 = env_int("PWT_FUSED_T3", 16);
+    const int W3 = a.Nc / 8, R3 = a.Nr / 8;
+    a.ntasks = cdiv(W3, a.n3) * cdiv(R3, a.T3);
+    a.batch = batch;
+    static int resident = 0;
+    if (!resident) {
+        int dev = 0, sms = 148, per_sm = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fwd3<F, HAAR, MINB, PF>, 32 * kWarps, 0);
+        resident = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    long long total = (long long)a.ntasks * batch;
+    int grid = (int)(total < (long long)resident * kWarps ? (total + kWarps - 1) / kWarps : resident);
+    a.counter = q->counter;
+    a.base = q->base;
+    q->base += (unsigned)total + (unsigned)grid * kWarps;      // every warp makes exactly one failing pull
+    k_fwd3<F, HAAR, MINB, PF><<<grid, 32 * kWarps, 0, st>>>(a, f);
+    return 1;
+}
+
+}  // namespace
+
+// Levels 1..3 of the forward transform in one launch.  band pointers: H/V/D of levels 1, 2, 3; A3.
+int pwt_fused_dwt_fwd3(const float* in, float* A3, float* const* H, float* const* V, float* const* D,
+                       int batch, int Nr, int Nc, const PwtFilters& f, bool haar, PwtTaskQueue* q,
+                       cudaStream_t st) {
+    const int F = haar ? 2 : f.hlen;
+    if (env_int("PWT_NO_FUSED", 0)) return 0;
+    if (F > 8 || (F & 1) || Nr % 8 != 0 || Nc % 8 != 0 || Nc < 512 || Nr < 64 || batch > 65535) return 0;
+    if (((uintptr_t)in & 15) != 0) return 0;
+    Fwd3Args a;
+    a.in = in;
+    a.A3 = A3;
+    for (int l = 0; l < 3; l++) {
+        a.H[l] = H[l];
+        a.V[l] = V[l];
+        a.D[l] = D[l];
+        a.bs[l] = (long long)(Nr >> (l + 1)) * (Nc >> (l + 1));
+        if (((uintptr_t)H[l] | (uintptr_t)V[l] | (uintptr_t)D[l]) & 7) return 0;
+    }
+    a.Nr = Nr;
+    a.Nc = Nc;
+    a.in_bs = (long long)Nr * Nc;
+    const int variant = env_int("PWT_FUSED_VARIANT", 0);
+    if (haar) return launch_fwd3<2, true, 6, false>(a, batch, f, q, st);
+    switch (F) {
+        case 4:
+            if (variant == 2) return launch_fwd3<4, false, 5, false>(a, batch, f, q, st);
+            if (variant == 3) return launch_fwd3<4, false, 6, false>(a, batch, f, q, st);
+            return launch_fwd3<4, false, 4, false>(a, batch, f, q, st);
+        case 6: return launch_fwd3<6, false, 3, false>(a, batch, f, q, st);
+        case 8: return launch_fwd3<8, false, 3, false>(a, batch, f, q, st);
+        default: return 0;
+    }
+}
+
+int pwt_fused_dwt_inv3(const float*, const float* const*, const float* const*, const float* const*, float*,
+                       int, int, int, const PwtFilters&, bool, PwtTaskQueue*, cudaStream_t) {
+    return 0;
+}

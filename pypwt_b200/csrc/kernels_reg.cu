@@ -18,6 +18,8 @@
 //           result differs only by fp32 rounding.  Haar uses the reference's exact butterfly order.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "pwt_internal.h"
 
 namespace {
@@ -73,17 +75,69 @@ __device__ __forceinline__ float comp(const float4& v, int c) {
 
 // Horizontal neighbourhood of a lane's 4 samples: ext[HW + c] = sample (4*lane + c), c in [-HW, 4+HW).
 // Interior lanes get the halo from lanes +-1 by shuffle, lane 0 / 31 from eL / eR (own scalar loads).
+// e[i]: on lane 0 the i-th sample LEFT of the strip, on lane 31 the i-th sample RIGHT of it (other lanes:
+// unused).  It is fetched by one branch-free scalar load per row (see the ecol[] set-up in the kernels).
 template <int HW>
-__device__ __forceinline__ void build_ext(const float4& v, const float* eL, const float* eR, int lane,
-                                          float* ext) {
+__device__ __forceinline__ void build_ext(const float4& v, const float* e, int lane, float* ext) {
+    const bool first = lane == 0, last = lane == 31;
 #pragma unroll
     for (int c = 0; c < 4; c++) ext[HW + c] = comp(v, c);
 #pragma unroll
     for (int i = 0; i < HW; i++) {
         const float l = __shfl_up_sync(FULL, comp(v, 4 - HW + i), 1);      // lane-1's last HW samples
         const float r = __shfl_down_sync(FULL, comp(v, i), 1);             // lane+1's first HW samples
-        ext[i] = lane == 0 ? eL[i] : l;
-        ext[HW + 4 + i] = lane == 31 ? eR[i] : r;
+        ext[i] = first ? e[i] : l;
+        ext[HW + 4 + i] = last ? e[i] : r;
+    }
+}
+
+
+// N consecutive input rows starting at row rb: one 128-bit load + HW halo scalars per lane and row.
+// The wrap test is uniform and hoisted out of the row loop.
+template <int N, int HW>
+__device__ __forceinline__ void load_rows_fwd(const float* __restrict__ in, int rb, int Nr, int Nc, int px0,
+                                              const int* ecol, unsigned long long pol, float4* v,
+                                              float (*e)[HW > 0 ? HW : 1]) {
+    if (rb >= 0 && rb + N <= Nr) {
+        const float* p = in + (long long)rb * Nc;
+#pragma unroll
+        for (int i = 0; i < N; i++, p += Nc) {
+            v[i] = ldg4(p + px0, pol);
+#pragma unroll
+            for (int c = 0; c < HW; c++) e[i][c] = __ldg(p + ecol[c]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const float* p = in + (long long)wrap1_dwt(rb + i, Nr) * Nc;
+            v[i] = ldg4(p + px0, pol);
+#pragma unroll
+            for (int c = 0; c < HW; c++) e[i][c] = __ldg(p + ecol[c]);
+        }
+    }
+}
+
+// N consecutive band rows of the four bands
+template <int N, int HW>
+__device__ __forceinline__ void load_rows_inv(const float* __restrict__ A, const float* __restrict__ Hb,
+                                              const float* __restrict__ V, const float* __restrict__ D, int rb,
+                                              int nr, int nc, int x0, const int* ecol, unsigned long long pol,
+                                              float4 (*b)[4], float (*e)[4][HW > 0 ? HW : 1]) {
+    const bool plain = rb >= 0 && rb + N <= nr;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const long long ro = (long long)(plain ? rb + i : wrap1_per(rb + i, nr)) * nc;
+        b[i][0] = ldg4(A + ro + x0, pol);
+        b[i][1] = ldg4(Hb + ro + x0, pol);
+        b[i][2] = ldg4(V + ro + x0, pol);
+        b[i][3] = ldg4(D + ro + x0, pol);
+#pragma unroll
+        for (int c = 0; c < HW; c++) {
+            e[i][0][c] = __ldg(A + ro + ecol[c]);
+            e[i][1][c] = __ldg(Hb + ro + ecol[c]);
+            e[i][2][c] = __ldg(V + ro + ecol[c]);
+            e[i][3][c] = __ldg(D + ro + ecol[c]);
+        }
     }
 }
 
@@ -114,13 +168,13 @@ k_fwd_reg(const float* __restrict__ in, float* __restrict__ A, float* __restrict
 
     const int px0 = (strip << 7) + 4 * lane;
     const float* in_t = in + px0;
-    // wrapped columns of the halo samples fetched by lane 0 (left) and lane 31 (right)
-    int cL[HW > 0 ? HW : 1], cR[HW > 0 ? HW : 1];
+    // halo samples: lane 0 fetches the HW samples left of the strip, lane 31 the HW samples right of it;
+    // the other lanes re-read their own first sample so that the extra load needs no branch
+    int ecol[HW > 0 ? HW : 1];
 #pragma unroll
-    for (int i = 0; i < HW; i++) {
-        cL[i] = wrap1_per((strip << 7) - HW + i, Nc);
-        cR[i] = wrap1_per((strip << 7) + 128 + i, Nc);
-    }
+    for (int i = 0; i < HW; i++)
+        ecol[i] = lane == 0 ? wrap1_per((strip << 7) - HW + i, Nc)
+                            : (lane == 31 ? wrap1_per((strip << 7) + 128 + i, Nc) : px0);
     int o = ky0 * Nc2 + (strip << 6) + 2 * lane;      // output offset (elements, < 2^31)
     A += ob; Hb += ob; V += ob; D += ob;
 
@@ -150,9 +204,9 @@ k_fwd_reg(const float* __restrict__ in, float* __restrict__ A, float* __restrict
     }
 
     // horizontal analysis of one input row -> (lo0, lo1, hi0, hi1) of this lane's two output columns
-    auto hpass = [&](const float4& v, const float* eL, const float* eR) -> float4 {
+    auto hpass = [&](const float4& v, const float* e) -> float4 {
         float ext[F + 2];
-        build_ext<HW>(v, eL, eR, lane, ext);
+        build_ext<HW>(v, e, lane, ext);
         float lo0 = 0.f, lo1 = 0.f, hi0 = 0.f, hi1 = 0.f;
 #pragma unroll
         for (int j = 0; j < F; j++) {
@@ -164,38 +218,24 @@ k_fwd_reg(const float* __restrict__ in, float* __restrict__ A, float* __restrict
         }
         return make_float4(lo0, lo1, hi0, hi1);
     };
-    auto load_row = [&](int grow, float4& v, float* eL, float* eR) {
-        const long long ro = (long long)wrap1_dwt(grow, Nr) * Nc;
-        v = ldg4(in_t + ro, pol_in);
-#pragma unroll
-        for (int i = 0; i < HW; i++) {
-            eL[i] = 0.f;
-            eR[i] = 0.f;
-            if (lane == 0) eL[i] = __ldg(in + ro + cL[i]);
-            if (lane == 31) eR[i] = __ldg(in + ro + cR[i]);
-        }
-    };
-
     // vertical sliding window: hw[j] = horizontally filtered row (2*ky - C + j)
     float4 hw[F];
     {
         constexpr int NPRE = F > 2 ? F - 2 : 1;
         float4 v[NPRE];
-        float eL[NPRE][HW > 0 ? HW : 1], eR[NPRE][HW > 0 ? HW : 1];
+        float e[NPRE][HW > 0 ? HW : 1];
+        load_rows_fwd<F - 2, HW>(in, 2 * ky0 - C, Nr, Nc, px0, ecol, pol_in, v, e);
 #pragma unroll
-        for (int j = 0; j < F - 2; j++) load_row(2 * ky0 - C + j, v[j], eL[j], eR[j]);
-#pragma unroll
-        for (int j = 0; j < F - 2; j++) hw[j] = hpass(v[j], eL[j], eR[j]);
+        for (int j = 0; j < F - 2; j++) hw[j] = hpass(v[j], e[j]);
     }
     for (int ky = ky0; ky < ky1; ky += U) {
         float4 v[2 * U];
-        float eL[2 * U][HW > 0 ? HW : 1], eR[2 * U][HW > 0 ? HW : 1];
-#pragma unroll
-        for (int i = 0; i < 2 * U; i++) load_row(2 * ky - C + F - 2 + i, v[i], eL[i], eR[i]);
+        float e[2 * U][HW > 0 ? HW : 1];
+        load_rows_fwd<2 * U, HW>(in, 2 * ky - C + F - 2, Nr, Nc, px0, ecol, pol_in, v, e);
 #pragma unroll
         for (int u = 0; u < U; u++, o += Nc2) {
-            hw[F - 2] = hpass(v[2 * u], eL[2 * u], eR[2 * u]);
-            hw[F - 1] = hpass(v[2 * u + 1], eL[2 * u + 1], eR[2 * u + 1]);
+            hw[F - 2] = hpass(v[2 * u], e[2 * u]);
+            hw[F - 1] = hpass(v[2 * u + 1], e[2 * u + 1]);
             float a0 = 0.f, a1 = 0.f, h0 = 0.f, h1 = 0.f, v0 = 0.f, v1 = 0.f, d0 = 0.f, d1 = 0.f;
 #pragma unroll
             for (int j = 0; j < F; j++) {
@@ -249,12 +289,11 @@ k_inv_reg(const float* __restrict__ A, const float* __restrict__ Hb, const float
     const unsigned long long pol_out = nohint ? 0ull : ((flags & FLAG_OUT_KEEP) ? policy_evict_last() : policy_evict_first());
 
     const int x0 = (strip << 7) + 4 * lane;
-    int cL[HW > 0 ? HW : 1], cR[HW > 0 ? HW : 1];
+    int ecol[HW > 0 ? HW : 1];
 #pragma unroll
-    for (int i = 0; i < HW; i++) {
-        cL[i] = wrap1_per((strip << 7) - HW + i, nc);
-        cR[i] = wrap1_per((strip << 7) + 128 + i, nc);
-    }
+    for (int i = 0; i < HW; i++)
+        ecol[i] = lane == 0 ? wrap1_per((strip << 7) - HW + i, nc)
+                            : (lane == 31 ? wrap1_per((strip << 7) + 128 + i, nc) : x0);
     float* out_t = out + (strip << 8) + 8 * lane;
 
     if (HAAR) {
@@ -296,29 +335,12 @@ k_inv_reg(const float* __restrict__ A, const float* __restrict__ Hb, const float
     }
 
     struct Row8 { float u1[8], u2[8]; };     // horizontally synthesised band row: u1 = syn_x(A,V), u2 = syn_x(H,D)
-    auto load_row = [&](int grow, float4* b, float (*eL)[HW > 0 ? HW : 1], float (*eR)[HW > 0 ? HW : 1]) {
-        const long long ro = (long long)wrap1_per(grow, nr) * nc;
-        b[0] = ldg4(A + ro + x0, pol_in);
-        b[1] = ldg4(Hb + ro + x0, pol_in);
-        b[2] = ldg4(V + ro + x0, pol_in);
-        b[3] = ldg4(D + ro + x0, pol_in);
-        const float* bp[4] = {A, Hb, V, D};
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-#pragma unroll
-            for (int i = 0; i < HW; i++) {
-                eL[k][i] = 0.f;
-                eR[k][i] = 0.f;
-                if (lane == 0) eL[k][i] = __ldg(bp[k] + ro + cL[i]);
-                if (lane == 31) eR[k][i] = __ldg(bp[k] + ro + cR[i]);
-            }
-    };
-    auto hpass = [&](const float4* b, float (*eL)[HW > 0 ? HW : 1], float (*eR)[HW > 0 ? HW : 1]) -> Row8 {
+    auto hpass = [&](const float4* b, float (*e)[HW > 0 ? HW : 1]) -> Row8 {
         float xa[4 + 2 * HW], xh[4 + 2 * HW], xv[4 + 2 * HW], xd[4 + 2 * HW];
-        build_ext<HW>(b[0], eL[0], eR[0], lane, xa);
-        build_ext<HW>(b[1], eL[1], eR[1], lane, xh);
-        build_ext<HW>(b[2], eL[2], eR[2], lane, xv);
-        build_ext<HW>(b[3], eL[3], eR[3], lane, xd);
+        build_ext<HW>(b[0], e[0], lane, xa);
+        build_ext<HW>(b[1], e[1], lane, xh);
+        build_ext<HW>(b[2], e[2], lane, xv);
+        build_ext<HW>(b[3], e[3], lane, xd);
         Row8 r;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
@@ -347,45 +369,43 @@ k_inv_reg(const float* __restrict__ A, const float* __restrict__ Hb, const float
     // vertical window: w[j] <-> band row q + S0 - (HALF-1) + j
     Row8 w[WIN];
     {
-        float4 b[4];
-        float eL[4][HW > 0 ? HW : 1], eR[4][HW > 0 ? HW : 1];
+        constexpr int NPRE = WIN > 1 ? WIN - 1 : 1;
+        float4 b[NPRE][4];
+        float e[NPRE][4][HW > 0 ? HW : 1];
+        load_rows_inv<WIN - 1, HW>(A, Hb, V, D, q0 + S0 - (HALF - 1), nr, nc, x0, ecol, pol_in, b, e);
 #pragma unroll
-        for (int j = 0; j < WIN - 1; j++) {
-            load_row(q0 + S0 - (HALF - 1) + j, b, eL, eR);
-            w[j] = hpass(b, eL, eR);
-        }
+        for (int j = 0; j < WIN - 1; j++) w[j] = hpass(b[j], e[j]);
     }
     for (int q = q0; q < q1; q += U) {
         float4 b[U][4];
-        float eL[U][4][HW > 0 ? HW : 1], eR[U][4][HW > 0 ? HW : 1];
-#pragma unroll
-        for (int u = 0; u < U; u++) load_row(q + u + S1, b[u], eL[u], eR[u]);
+        float e[U][4][HW > 0 ? HW : 1];
+        load_rows_inv<U, HW>(A, Hb, V, D, q + S1, nr, nc, x0, ecol, pol_in, b, e);
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            w[WIN - 1] = hpass(b[u], eL[u], eR[u]);
-            float e[8], o[8];
+            w[WIN - 1] = hpass(b[u], e[u]);
+            float ev[8], od[8];
 #pragma unroll
             for (int c = 0; c < 8; c++) {
-                float ev = 0.f, od = 0.f;
+                float s0 = 0.f, s1 = 0.f;
 #pragma unroll
                 for (int jj = 0; jj < HALF; jj++) {
                     const int je = HALF - 1 - jj, jo = HALF - 1 - jj + (S1 - S0);
-                    ev = fmaf(w[je].u1[c], f.IL[2 * jj + E0], ev);
-                    ev = fmaf(w[je].u2[c], f.IH[2 * jj + E0], ev);
-                    od = fmaf(w[jo].u1[c], f.IL[2 * jj + E1], od);
-                    od = fmaf(w[jo].u2[c], f.IH[2 * jj + E1], od);
+                    s0 = fmaf(w[je].u1[c], f.IL[2 * jj + E0], s0);
+                    s0 = fmaf(w[je].u2[c], f.IH[2 * jj + E0], s0);
+                    s1 = fmaf(w[jo].u1[c], f.IL[2 * jj + E1], s1);
+                    s1 = fmaf(w[jo].u2[c], f.IH[2 * jj + E1], s1);
                 }
-                e[c] = ev;
-                o[c] = od;
+                ev[c] = s0;
+                od[c] = s1;
             }
             const int gy = 2 * (q + u);
             if (q + u < q1) {
                 float* p = out_t + (long long)gy * Nc_out;
-                stg4(p, e[0], e[1], e[2], e[3], pol_out);
-                stg4(p + 4, e[4], e[5], e[6], e[7], pol_out);
+                stg4(p, ev[0], ev[1], ev[2], ev[3], pol_out);
+                stg4(p + 4, ev[4], ev[5], ev[6], ev[7], pol_out);
                 if (gy + 1 < Nr_out) {
-                    stg4(p + Nc_out, o[0], o[1], o[2], o[3], pol_out);
-                    stg4(p + Nc_out + 4, o[4], o[5], o[6], o[7], pol_out);
+                    stg4(p + Nc_out, od[0], od[1], od[2], od[3], pol_out);
+                    stg4(p + Nc_out + 4, od[4], od[5], od[6], od[7], pol_out);
                 }
             }
 #pragma unroll

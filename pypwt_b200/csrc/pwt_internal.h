@@ -106,3 +106,17 @@ int pwt_reg_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, 
 int pwt_reg_dwt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out,
                       int batch, int nr, int nc, int Nr_out, int Nc_out, long long in_bs,
                       long long out_bs, const PwtFilters& f, bool haar, int hint_flags, cudaStream_t st);
+
+// kernels_fused.cu : levels 1..3 in one launch (register cascade).  Return 0 when not covered.
+// Dynamic task queue of the persistent kernels: a device counter that only ever grows; the host
+// tracks how far each launch advances it (tasks + one failing pull per warp), so no reset is needed.
+struct PwtTaskQueue {
+    unsigned* counter;     // device memory, zero-initialised at plan creation
+    unsigned base;         // value of *counter when the next launch starts
+};
+int pwt_fused_dwt_fwd3(const float* in, float* A3, float* const* H, float* const* V, float* const* D,
+                       int batch, int Nr, int Nc, const PwtFilters& f, bool haar, PwtTaskQueue* q,
+                       cudaStream_t st);
+int pwt_fused_dwt_inv3(const float* A3, const float* const* H, const float* const* V, const float* const* D,
+                       float* out, int batch, int Nr, int Nc, const PwtFilters& f, bool haar, PwtTaskQueue* q,
+                       cudaStream_t st);

@@ -103,6 +103,7 @@ struct pwt_plan {
     float* d_band[PWT_MAX_BANDS];
     int band_nr[PWT_MAX_BANDS], band_nc[PWT_MAX_BANDS];
     double* d_acc;      // device accumulators for the norms
+    PwtTaskQueue queue; // dynamic task queue of the persistent kernels
     double* h_acc;      // pinned mirror
     void* d_flush;
     size_t flush_bytes;
@@ -218,6 +219,9 @@ static int alloc_plan(pwt_plan* p) {
     CK(cudaMalloc((void**)&p->d_k2d_fwd, k2d));
     CK(cudaMalloc((void**)&p->d_k2d_inv, k2d));
     CK(cudaMalloc((void**)&p->d_acc, 2 * sizeof(double)));
+    CK(cudaMalloc((void**)&p->queue.counter, sizeof(unsigned)));
+    CK(cudaMemsetAsync(p->queue.counter, 0, sizeof(unsigned), p->stream));
+    p->queue.base = 0;
     CK(cudaMallocHost((void**)&p->h_acc, 2 * sizeof(double)));
     return PWT_OK;
 }
@@ -231,6 +235,7 @@ extern "C" void pwt_destroy(pwt_plan* p) {
     if (p->d_k2d_fwd) cudaFree(p->d_k2d_fwd);
     if (p->d_k2d_inv) cudaFree(p->d_k2d_inv);
     if (p->d_acc) cudaFree(p->d_acc);
+    if (p->queue.counter) cudaFree(p->queue.counter);
     if (p->h_acc) cudaFreeHost(p->h_acc);
     if (p->d_flush) cudaFree(p->d_flush);
     if (p->prof_ev) {
@@ -363,6 +368,7 @@ extern "C" int pwt_clone(pwt_plan** out, const pwt_plan* src) {
     p->slab = nullptr;
     p->d_k2d_fwd = p->d_k2d_inv = nullptr;
     p->d_acc = nullptr;
+    p->queue.counter = nullptr;
     p->h_acc = nullptr;
     p->d_flush = nullptr;
     p->flush_bytes = 0;
@@ -536,7 +542,27 @@ extern "C" int pwt_forward(pwt_plan* p) {
         }
     } else {
         const long long plane = (long long)B * img_elems(p);
-        for (int l = 1; l <= L; l++) {
+        int l_first = 1;
+        // levels 1..3 in one launch when the fused register cascade covers the configuration
+        if (!p->do_swt && L >= 3 && (haar || p->do_separable) && p->kernel_mode == 0) {
+            float* Hs[3] = {p->d_band[1], p->d_band[4], p->d_band[7]};
+            float* Vs[3] = {p->d_band[2], p->d_band[5], p->d_band[8]};
+            float* Ds[3] = {p->d_band[3], p->d_band[6], p->d_band[9]};
+            float* dstA = approx_dst(p, 3, p->d_tmp);
+            prof_begin(p, 100 * 3 + 1 + 10);      // tag x1y: fused levels 1..3
+            if (p->queue.base > 0x70000000u) {   // far from wrapping: re-arm the queue
+                cudaMemsetAsync(p->queue.counter, 0, sizeof(unsigned), st);
+                p->queue.base = 0;
+            }
+            const int n = pwt_fused_dwt_fwd3(src, dstA, Hs, Vs, Ds, B, p->Nr, p->Nc, p->filt, haar, &p->queue, st);
+            if (n) {
+                prof_end(p);
+                p->launches += n;
+                src = dstA;
+                l_first = 4;
+            }
+        }
+        for (int l = l_first; l <= L; l++) {
             float* Hb = p->d_band[3 * (l - 1) + 1];
             float* V = p->d_band[3 * (l - 1) + 2];
             float* D = p->d_band[3 * (l - 1) + 3];
@@ -555,9 +581,9 @@ extern "C" int pwt_forward(pwt_plan* p) {
                 if (haar || p->do_separable) {
                     int n = 0;
                     const int hints = (l < L ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l > 1 ? PWT_HINT_IN_FROM_PREV : 0);
-                    if (p->kernel_mode == 0)
+                    if (p->kernel_mode == 0 || p->kernel_mode == 3)
                         n = pwt_reg_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, hints, st);
-                    if (!n && (p->kernel_mode == 0 || p->kernel_mode == 2))
+                    if (!n && p->kernel_mode != 1)
                         n = pwt_fast_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar,
                                                (l < L ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l > 1 ? PWT_HINT_IN_FROM_PREV : 0), st);
                     if (!n) n = pwt_launch_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, st);
@@ -622,9 +648,9 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                 if (haar || p->do_separable) {
                     int n = 0;
                     const int hints = (l > 1 ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l < L ? PWT_HINT_IN_FROM_PREV : 0);
-                    if (p->kernel_mode == 0)
+                    if (p->kernel_mode == 0 || p->kernel_mode == 3)
                         n = pwt_reg_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, hints, st);
-                    if (!n && (p->kernel_mode == 0 || p->kernel_mode == 2))
+                    if (!n && p->kernel_mode != 1)
                         n = pwt_fast_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar,
                                                (l > 1 ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l < L ? PWT_HINT_IN_FROM_PREV : 0), st);
                     if (!n) n = pwt_launch_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, st);

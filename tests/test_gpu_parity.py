@@ -423,6 +423,29 @@ def test_generic_kernels_agree_with_auto(wname):
     assert_close(A.image, G.image, 255.0, "auto vs generic inverse")
 
 
+@pytest.mark.parametrize("shape", [(512, 1024), (1024, 512), (2048, 2048), (3, 512, 512)])
+@pytest.mark.parametrize("wname", ["haar", "db2", "db3", "sym4"])
+def test_fused_cascade_is_bit_identical_to_per_level_kernels(wname, shape):
+    """The fused 3-level register cascade performs the same arithmetic in the same order as three
+    launches of the single-level register kernels: results must be bit-identical, and within
+    tolerance of the generic tiled kernels."""
+    img = synth_image(shape, seed=17, kind="smooth")
+    F = _W(img, wname, 4); P = _W(img, wname, 4); G = _W(img, wname, 4)
+    P.set_kernel_mode(3)
+    G.set_kernel_mode(1)
+    F.forward(); P.forward(); G.forward()
+    assert F.launch_count < P.launch_count
+    cf, cp, cg = F.coeffs, P.coeffs, G.coeffs
+    assert np.array_equal(cf[0], cp[0])
+    for i in range(1, 5):
+        for j in range(3):
+            assert np.array_equal(cf[i][j], cp[i][j]), "level %d band %d differs" % (i, j)
+            assert_close(cf[i][j], cg[i][j], 255.0, "fused vs generic")
+    F.inverse(); P.inverse(); G.inverse()
+    assert_close(F.image, G.image, 255.0, "fused inverse vs generic")
+    assert_close(F.image, img, 255.0, "roundtrip")
+
+
 @pytest.mark.parametrize("wname", ["haar", "db2"])
 def test_full_size_roundtrip_properties(wname):
     """BASELINE metric size (8192^2, 3 levels): size-independent properties -- perfect reconstruction,

@@ -1,3 +1,5 @@
-for mb in 0 32 64 200; do for nh in 0; do
-  echo "L2_PERSIST_MB=$mb"; PWT_VERBOSE=1 PWT_L2_PERSIST_MB=$mb PWT_NO_HINTS=$nh PWT_REG_TILE_ROWS=16 PWT_REG_FWD_VARIANT=2 python bench.py --steps 20 --no-pdwt 2>&1 | grep -o "pwt: pers.*\|\"value\": [0-9.]*, \"unit\": \"Mpixel/s\", \"n_gpus\"\|kernel_ms_by_level[^}]*}"
+python -m pytest tests -m gpu -q -x --timeout=900 -p no:cacheprovider -k "fused or agree or stack or test_dwt2 or idwt2 or vs_pdwt or odd" 2>&1 | tail -2
+for v in 0 2 3; do for t3 in 8 16; do
+  echo "FUSED VARIANT=$v T3=$t3"; PWT_FUSED_VARIANT=$v PWT_FUSED_T3=$t3 python bench.py --steps 20 --no-pdwt 2>&1 | grep -o "\"value\": [0-9.]*, \"unit\": \"Mpixel/s\", \"n_gpus\"\|kernel_ms_by_level[^}]*}"
 done; done
+echo "NO FUSED"; PWT_NO_FUSED=1 python bench.py --steps 20 --no-pdwt 2>&1 | grep -o "\"value\": [0-9.]*, \"unit\": \"Mpixel/s\", \"n_gpus\"\|kernel_ms_by_level[^}]*}"
