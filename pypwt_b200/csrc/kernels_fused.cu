@@ -19,6 +19,8 @@
 // (every level then has an even size: pure periodic wrap, no odd-size extension), >= 3 levels.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "pwt_internal.h"
 
 namespace {
@@ -378,7 +380,295 @@ int pwt_fused_dwt_fwd3(const float* in, float* A3, float* const* H, float* const
     }
 }
 
-int pwt_fused_dwt_inv3(const float*, const float* const*, const float* const*, const float* const*, float*,
-                       int, int, int, const PwtFilters&, bool, PwtTaskQueue*, cudaStream_t) {
-    return 0;
+// =========================================================================================
+// inverse cascade: levels 3 -> 2 -> 1 -> image in one launch
+// =========================================================================================
+namespace {
+
+struct Inv3Args {
+    const float* A3;
+    const float* H[3];     // index 0 = level 1 (finest)
+    const float* V[3];
+    const float* D[3];
+    float* out;
+    int Nr, Nc;            // image size
+    int n3;                // level-3 columns owned by one warp
+    int T3;                // level-3 rows (= 8 image rows each) per task
+    long long out_bs;
+    long long bs[3];
+    unsigned* counter;
+    unsigned base;
+    int ntasks, batch;
+};
+
+// one horizontally synthesised band row held CW band columns per lane: u1 = syn_x(A, V), u2 = syn_x(H, D)
+template <int CW>
+struct URow {
+    float u1[2 * CW], u2[2 * CW];
+};
+
+template <int F, bool HAAR, int MINB>
+__global__ void __launch_bounds__(32 * kWarps, MINB)
+k_inv3(const __grid_constant__ Inv3Args a, const __grid_constant__ PwtFilters f) {
+    constexpr int P = F / 2 - 1, HALF = F / 2;
+    constexpr int S0 = P >> 1, E0 = P & 1;
+    constexpr int S1 = (P + 1) >> 1, E1 = (P + 1) & 1;
+    constexpr int WIN = HALF + (S1 - S0);
+    constexpr int HW = S1;                               // 0 (haar) or 1 (F = 4, 6)
+    static_assert(HW <= 1, "fused inverse supports a horizontal reach of one band sample");
+    constexpr int OWN0 = (6 * S1 + 7) & ~7;              // image columns given up on each side of the 256 loaded
+    constexpr int DT0 = S1 ? 2 : 0, DT1 = S1 ? 1 : -1;   // iterations before n0 / after n1-1
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Nr = a.Nr, Nc = a.Nc;
+    const int W1 = Nc >> 1, W2 = Nc >> 2, W3 = Nc >> 3;
+    const int R1 = Nr >> 1, R2 = Nr >> 2, R3 = Nr >> 3;
+    const int strips = (W3 + a.n3 - 1) / a.n3;
+    const bool first_lane = lane == 0, last_lane = lane == 31;
+  for (;;) {
+    unsigned t_ = 0;
+    if (lane == 0) t_ = atomicAdd(a.counter, 1u) - a.base;
+    t_ = __shfl_sync(FULL, t_, 0);
+    if (t_ >= (unsigned)a.ntasks * (unsigned)a.batch) return;
+    const int img = t_ / a.ntasks, task = t_ - img * a.ntasks;
+    const int strip = task % strips, band = task / strips;
+    const int n0 = band * a.T3;
+    const int n1 = min(n0 + a.T3, R3);
+    const int c3 = strip * a.n3;
+    const int n3e = min(a.n3, W3 - c3);
+    const int K3 = c3 - OWN0 / 8;                        // level-3 column of lane 0 (may be -1: wraps)
+
+    const float* A3 = a.A3 + img * a.bs[2];
+    const float* H3 = a.H[2] + img * a.bs[2]; const float* V3 = a.V[2] + img * a.bs[2]; const float* D3 = a.D[2] + img * a.bs[2];
+    const float* H2 = a.H[1] + img * a.bs[1]; const float* V2 = a.V[1] + img * a.bs[1]; const float* D2 = a.D[1] + img * a.bs[1];
+    const float* H1 = a.H[0] + img * a.bs[0]; const float* V1 = a.V[0] + img * a.bs[0]; const float* D1 = a.D[0] + img * a.bs[0];
+    float* out = a.out + img * a.out_bs;
+
+    const int x3 = wrap1_per(K3 + lane, W3);
+    const int x2 = wrap1_per(2 * (K3 + lane), W2);
+    const int x1 = wrap1_per(4 * (K3 + lane), W1);
+    const int e3col = first_lane ? wrap1_per(K3 - 1, W3) : (last_lane ? wrap1_per(K3 + 32, W3) : x3);
+    const int px = 8 * (K3 + lane);                      // first image column of this lane
+    const bool own = px >= 8 * c3 && px < 8 * (c3 + n3e);
+
+    // ---- horizontal synthesis of a band row held CW columns per lane (same arithmetic as k_inv_reg) ----
+    // neighbours: lane-1's last column / lane+1's first column by shuffle; `edge` supplies them for the strip edge
+    auto hsyn = [&](auto cw, const float* ba, const float* bh, const float* bv, const float* bd, const float* edge,
+                    float* u1, float* u2) {
+        constexpr int CW = decltype(cw)::value;
+        if (HAAR) {
+            // haar.cu:41-58 order: (a + h) and (v + d) first; rows are split in vsyn
+#pragma unroll
+            for (int c = 0; c < CW; c++) {
+                u1[2 * c] = ba[c] + bh[c];       // ac
+                u1[2 * c + 1] = bv[c] + bd[c];   // bd
+                u2[2 * c] = ba[c] - bh[c];       // am
+                u2[2 * c + 1] = bv[c] - bd[c];   // bm
+            }
+            return;
+        }
+        float xa[CW + 2 * HW], xh[CW + 2 * HW], xv[CW + 2 * HW], xd[CW + 2 * HW];
+        const float* src[4] = {ba, bh, bv, bd};
+        float* dst[4] = {xa, xh, xv, xd};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+            for (int c = 0; c < CW; c++) dst[k][HW + c] = src[k][c];
+            if (HW > 0) {
+                const float l = __shfl_up_sync(FULL, src[k][CW - 1], 1);
+                const float r = __shfl_down_sync(FULL, src[k][0], 1);
+                dst[k][0] = (edge && first_lane) ? edge[k] : l;
+                dst[k][HW + CW] = (edge && last_lane) ? edge[k] : r;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CW; c++) {
+            float e1 = 0.f, o1 = 0.f, e2 = 0.f, o2 = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < HALF; jj++) {
+                const float le = f.IL[2 * jj + E0], he = f.IH[2 * jj + E0];
+                const float lo = f.IL[2 * jj + E1], ho = f.IH[2 * jj + E1];
+                e1 = fmaf(xa[HW + c + S0 - jj], le, e1);
+                e1 = fmaf(xv[HW + c + S0 - jj], he, e1);
+                o1 = fmaf(xa[HW + c + S1 - jj], lo, o1);
+                o1 = fmaf(xv[HW + c + S1 - jj], ho, o1);
+                e2 = fmaf(xh[HW + c + S0 - jj], le, e2);
+                e2 = fmaf(xd[HW + c + S0 - jj], he, e2);
+                o2 = fmaf(xh[HW + c + S1 - jj], lo, o2);
+                o2 = fmaf(xd[HW + c + S1 - jj], ho, o2);
+            }
+            u1[2 * c] = e1;
+            u1[2 * c + 1] = o1;
+            u2[2 * c] = e2;
+            u2[2 * c + 1] = o2;
+        }
+    };
+    // ---- vertical synthesis: window of WIN rows -> output rows 2q (ev) and 2q+1 (od), then shift ----
+    auto vsyn = [&](auto nv, auto* w, float* ev, float* od) {
+        constexpr int NV = decltype(nv)::value;
+        if (HAAR) {
+#pragma unroll
+            for (int c = 0; c < NV; c += 2) {
+                const float ac = w[0].u1[c], bd = w[0].u1[c + 1], am = w[0].u2[c], bm = w[0].u2[c + 1];
+                ev[c] = 0.5f * (ac + bd);
+                ev[c + 1] = 0.5f * (ac - bd);
+                od[c] = 0.5f * (am + bm);
+                od[c + 1] = 0.5f * (am - bm);
+            }
+            return;
+        }
+#pragma unroll
+        for (int c = 0; c < NV; c++) {
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < HALF; jj++) {
+                const int je = HALF - 1 - jj, jo = HALF - 1 - jj + (S1 - S0);
+                s0 = fmaf(w[je].u1[c], f.IL[2 * jj + E0], s0);
+                s0 = fmaf(w[je].u2[c], f.IH[2 * jj + E0], s0);
+                s1 = fmaf(w[jo].u1[c], f.IL[2 * jj + E1], s1);
+                s1 = fmaf(w[jo].u2[c], f.IH[2 * jj + E1], s1);
+            }
+            ev[c] = s0;
+            od[c] = s1;
+        }
+#pragma unroll
+        for (int j = 0; j < WIN - 1; j++) w[j] = w[j + 1];
+    };
+
+    URow<1> w3[WIN];
+    URow<2> w2[WIN];
+    URow<4> w1[WIN];
+
+    for (int t = n0 - DT0; t <= n1 + DT1; t++) {
+        const bool do2 = HAAR || t >= n0;            // level-2 section (and level-3 emission) needed
+        const bool do1 = HAAR || t >= n0 + 1;        // level-1 section needed
+        // ---- loads of this iteration, issued up front ----
+        float b3[4], e3[4];
+        {
+            const long long ro = (long long)wrap1_per(t, R3) * W3;
+            b3[0] = __ldg(A3 + ro + x3); b3[1] = __ldg(H3 + ro + x3); b3[2] = __ldg(V3 + ro + x3); b3[3] = __ldg(D3 + ro + x3);
+            if (HW > 0) {
+                e3[0] = __ldg(A3 + ro + e3col); e3[1] = __ldg(H3 + ro + e3col);
+                e3[2] = __ldg(V3 + ro + e3col); e3[3] = __ldg(D3 + ro + e3col);
+            }
+        }
+        float2 h2[2], v2[2], d2[2];
+        float4 h1[4], v1[4], d1[4];
+        if (do2) {
+            const long long ro = (long long)wrap1_per(2 * (t - S1), R2) * W2 + x2;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                h2[i] = __ldg(reinterpret_cast<const float2*>(H2 + ro + (long long)i * W2));
+                v2[i] = __ldg(reinterpret_cast<const float2*>(V2 + ro + (long long)i * W2));
+                d2[i] = __ldg(reinterpret_cast<const float2*>(D2 + ro + (long long)i * W2));
+            }
+        }
+        if (do1) {
+#pragma unroll
+            for (int pr = 0; pr < 2; pr++) {
+                const long long ro = (long long)wrap1_per(4 * t - 6 * S1 + 2 * pr, R1) * W1 + x1;
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    h1[2 * pr + i] = ldg4(H1 + ro + (long long)i * W1);
+                    v1[2 * pr + i] = ldg4(V1 + ro + (long long)i * W1);
+                    d1[2 * pr + i] = ldg4(D1 + ro + (long long)i * W1);
+                }
+            }
+        }
+        // ---- level 3: push row t ----
+        hsyn(std::integral_constant<int, 1>{}, &b3[0], &b3[1], &b3[2], &b3[3], HW > 0 ? e3 : nullptr,
+             w3[WIN - 1].u1, w3[WIN - 1].u2);
+        if (!do2) {
+#pragma unroll
+            for (int j = 0; j < WIN - 1; j++) w3[j] = w3[j + 1];
+            continue;
+        }
+        float a2[2][2];                                // [row 2q3 / 2q3+1][2 columns]
+        vsyn(std::integral_constant<int, 2>{}, w3, a2[0], a2[1]);
+        // ---- level 2: two A2 rows ----
+#pragma unroll
+        for (int i2 = 0; i2 < 2; i2++) {
+            const float bh[2] = {h2[i2].x, h2[i2].y}, bv[2] = {v2[i2].x, v2[i2].y}, bd[2] = {d2[i2].x, d2[i2].y};
+            hsyn(std::integral_constant<int, 2>{}, a2[i2], bh, bv, bd, nullptr, w2[WIN - 1].u1, w2[WIN - 1].u2);
+            float a1[2][4];
+            vsyn(std::integral_constant<int, 4>{}, w2, a1[0], a1[1]);
+            if (!do1) continue;
+            // ---- level 1: two A1 rows -> four image rows ----
+#pragma unroll
+            for (int i1 = 0; i1 < 2; i1++) {
+                const int r = 2 * i2 + i1;               // index of the A1 row inside this iteration
+                const float bh1[4] = {h1[r].x, h1[r].y, h1[r].z, h1[r].w};
+                const float bv1[4] = {v1[r].x, v1[r].y, v1[r].z, v1[r].w};
+                const float bd1[4] = {d1[r].x, d1[r].y, d1[r].z, d1[r].w};
+                hsyn(std::integral_constant<int, 4>{}, a1[i1], bh1, bv1, bd1, nullptr, w1[WIN - 1].u1, w1[WIN - 1].u2);
+                float ev[8], od[8];
+                vsyn(std::integral_constant<int, 8>{}, w1, ev, od);
+                const int y = 8 * t - 14 * S1 + 2 * r;   // image rows y, y+1
+                if (own && y >= 8 * n0 && y < 8 * n1) {
+                    float* p = out + (long long)y * Nc + px;
+                    *reinterpret_cast<float4*>(p) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+                    *reinterpret_cast<float4*>(p + 4) = make_float4(ev[4], ev[5], ev[6], ev[7]);
+                    *reinterpret_cast<float4*>(p + Nc) = make_float4(od[0], od[1], od[2], od[3]);
+                    *reinterpret_cast<float4*>(p + Nc + 4) = make_float4(od[4], od[5], od[6], od[7]);
+                }
+            }
+        }
+    }
+  }
+}
+
+template <int F, bool HAAR, int MINB>
+int launch_inv3(Inv3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cudaStream_t st) {
+    constexpr int S1 = (F / 2) >> 1;
+    constexpr int OWN0 = (6 * S1 + 7) & ~7;
+    a.n3 = (256 - 2 * OWN0) / 8;
+    a.T3 = env_int("PWT_FUSED_INV_T3", 32);
+    const int W3 = a.Nc / 8, R3 = a.Nr / 8;
+    a.ntasks = cdiv(W3, a.n3) * cdiv(R3, a.T3);
+    a.batch = batch;
+    static int resident = 0;
+    if (!resident) {
+        int dev = 0, sms = 148, per_sm = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inv3<F, HAAR, MINB>, 32 * kWarps, 0);
+        resident = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const long long total = (long long)a.ntasks * batch;
+    const int grid = (int)(total < (long long)resident * kWarps ? (total + kWarps - 1) / kWarps : resident);
+    a.counter = q->counter;
+    a.base = q->base;
+    q->base += (unsigned)total + (unsigned)grid * kWarps;
+    k_inv3<F, HAAR, MINB><<<grid, 32 * kWarps, 0, st>>>(a, f);
+    return 1;
+}
+
+}  // namespace
+
+// Levels 3..1 of the inverse transform in one launch.  H/V/D[0] = level 1 (finest).
+int pwt_fused_dwt_inv3(const float* A3, const float* const* H, const float* const* V, const float* const* D,
+                       float* out, int batch, int Nr, int Nc, const PwtFilters& f, bool haar, PwtTaskQueue* q,
+                       cudaStream_t st) {
+    const int F = haar ? 2 : f.hlen;
+    if (env_int("PWT_NO_FUSED", 0) || env_int("PWT_NO_FUSED_INV", 0)) return 0;
+    if (F > 6 || (F & 1) || Nr % 8 != 0 || Nc % 8 != 0 || Nc < 512 || Nr < 64 || batch > 65535) return 0;
+    if (((uintptr_t)out & 15) != 0) return 0;
+    Inv3Args a;
+    a.A3 = A3;
+    a.out = out;
+    for (int l = 0; l < 3; l++) {
+        a.H[l] = H[l];
+        a.V[l] = V[l];
+        a.D[l] = D[l];
+        a.bs[l] = (long long)(Nr >> (l + 1)) * (Nc >> (l + 1));
+        if (((uintptr_t)H[l] | (uintptr_t)V[l] | (uintptr_t)D[l]) & 15) return 0;
+    }
+    a.Nr = Nr;
+    a.Nc = Nc;
+    a.out_bs = (long long)Nr * Nc;
+    if (haar) return launch_inv3<2, true, 4>(a, batch, f, q, st);
+    switch (F) {
+        case 4: return launch_inv3<4, false, 3>(a, batch, f, q, st);
+        case 6: return launch_inv3<6, false, 2>(a, batch, f, q, st);
+        default: return 0;
+    }
 }

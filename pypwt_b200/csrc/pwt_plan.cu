@@ -629,6 +629,24 @@ extern "C" int pwt_inverse(pwt_plan* p) {
     } else {
         const long long plane = (long long)B * img_elems(p);
         for (int l = L; l >= 1; l--) {
+            // levels 3..1 in one launch when the fused register cascade covers the configuration
+            if (l == 3 && !p->do_swt && (haar || p->do_separable) && p->kernel_mode == 0) {
+                const float* Hs[3] = {p->d_band[1], p->d_band[4], p->d_band[7]};
+                const float* Vs[3] = {p->d_band[2], p->d_band[5], p->d_band[8]};
+                const float* Ds[3] = {p->d_band[3], p->d_band[6], p->d_band[9]};
+                if (p->queue.base > 0x70000000u) {
+                    cudaMemsetAsync(p->queue.counter, 0, sizeof(unsigned), st);
+                    p->queue.base = 0;
+                }
+                prof_begin(p, 100 * 3 + 2 + 10);      // tag 312: fused levels 3..1
+                const int n = pwt_fused_dwt_inv3(cur, Hs, Vs, Ds, p->d_image, B, p->Nr, p->Nc, p->filt, haar, &p->queue, st);
+                if (n) {
+                    prof_end(p);
+                    p->launches += n;
+                    cur = p->d_image;
+                    break;
+                }
+            }
             const float* Hb = p->d_band[3 * (l - 1) + 1];
             const float* V = p->d_band[3 * (l - 1) + 2];
             const float* D = p->d_band[3 * (l - 1) + 3];

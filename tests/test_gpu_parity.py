@@ -442,6 +442,12 @@ def test_fused_cascade_is_bit_identical_to_per_level_kernels(wname, shape):
             assert np.array_equal(cf[i][j], cp[i][j]), "level %d band %d differs" % (i, j)
             assert_close(cf[i][j], cg[i][j], 255.0, "fused vs generic")
     F.inverse(); P.inverse(); G.inverse()
+    if shape[-1] >= 1024:
+        assert np.array_equal(F.image, P.image), "fused inverse differs from the per-level register kernels"
+    else:
+        # the level-3 bands are narrower than 128 columns: the per-level path falls back to the
+        # shared-memory kernel there, which filters columns first (different fp32 rounding)
+        assert_close(F.image, P.image, 255.0, "fused inverse vs per-level")
     assert_close(F.image, G.image, 255.0, "fused inverse vs generic")
     assert_close(F.image, img, 255.0, "roundtrip")
 
