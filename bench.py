@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -252,7 +252,7 @@ def run_ours(args):
 
     # ---- per-kernel durations (same loop, every launch bracketed by events) --------------------
     W.profile_enable(1)
-    for _ in range(args.steps):
+    for _ in range(min(args.steps, 40)):
         W.forward(); W.inverse()
     recs = W.profile_read()
     W.profile_enable(0)
@@ -261,11 +261,23 @@ def run_ours(args):
         by_tag.setdefault(tag, []).append(t)
     avg = {tag: float(np.mean(v)) for tag, v in by_tag.items()}
     peak, peak_src = measured_peak()
-    k_ms = avg.get(101) or avg.get(311)
-    alg_bytes = 8.0 * pix                      # level-1 forward: read 4 B/px + write 4 B/px of coefficients
-    roof = {"bound": "hbm", "kernel": "level-1 forward (fused row+column analysis)",
+    fused = 311 in avg
+    k_ms = avg.get(311) or avg.get(101)
+    # dominant kernel: the fused 3-level forward (k_fwd3) reads the image once and writes all N coefficients:
+    # 8 B per pixel.  Without the fused path the level-1 kernel moves the same 8 B per pixel.
+    alg_bytes = 8.0 * pix
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as fh:
+            traffic = json.load(fh).get("k_fwd3" if fused else "k_fwd_reg", {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "kernel": "k_fwd3: forward levels 1-3, one launch" if fused else "level-1 forward",
             "achieved": alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None, "peak": peak, "unit": "GB/s",
-            "frac": (alg_bytes / (k_ms * 1e-3) / 1e9 / peak) if k_ms else None, "traffic": None,
+            "frac": (alg_bytes / (k_ms * 1e-3) / 1e9 / peak) if k_ms else None, "traffic": traffic,
+            "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch at the 8192^2 "
+                              "workload (profiles/r01_ncu_traffic.json)" if traffic else None,
+            "algorithmic_bytes": alg_bytes,
             "peak_source": peak_src, "kernel_ms": k_ms,
             "kernel_ms_by_level": {{1: "fwd", 2: "inv", 11: "fwd1-", 12: "inv1-"}.get(t % 100, "k") + str(t // 100): round(v, 5) for t, v in sorted(avg.items())},
             "share_of_step": (k_ms / sum(avg.values())) if k_ms else None}
@@ -333,8 +345,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="8192^2 images per GPU per step")
     ap.add_argument("--no-pdwt", action="store_true", help="skip the side-by-side timing of the reference's CUDA build")
