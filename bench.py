@@ -16,11 +16,11 @@ Keys of the JSON line (one line, rank 0):
   roofline     dominant kernel (level-1 forward), algorithmic bytes (8 B per level-1 pixel) / its
                CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth
   roofline_step  whole step at 16 B/px (the BASELINE.md headline fraction)
-  cpu_baseline the numpy oracle port of the same transform timed on the host (bounded sample)
+  cpu_baseline the plain-C/OpenMP oracle port of the same transform timed on the host cores (bounded sample)
   pdwt_cuda    the reference's own CUDA kernels (oracle/_ref, recompiled for sm_100a) on the same GPU,
                same workload, device-resident -- reported beside, not part of `value`
---impl reference: the CPU path of the reference workflow (pywt-equivalent numpy restatement; pywt itself
-is not installable here) on the host cores, same metric/config.
+--impl reference: the CPU path of the reference workflow (pywt-equivalent C/OpenMP restatement
+oracle/dwt_cpu.c; pywt itself is not installable here) on all host cores, same metric/config.
 """
 import argparse
 import json
@@ -103,26 +103,37 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_CPU_PLANS = {}
+
+
 def cpu_port_fwd_inv(img):
-    """The CPU restatement of the reference path (oracle port): 3-level db2 forward + inverse, fp32."""
-    from oracle import pdwt_oracle as O
-    W = O.OracleWavelets(img, WNAME, LEVELS, dtype=np.float32)
-    W.forward()
-    W.inverse()
-    return W.image
+    """The CPU restatement of the reference path (oracle/dwt_cpu.c, plain C + OpenMP on all host threads):
+    3-level db2 forward + inverse, fp32 -- stands in for pywt.wavedec2/waverec2(mode="periodization")."""
+    from oracle import dwt_cpu
+    P = _CPU_PLANS.get(img.shape)
+    if P is None:
+        P = _CPU_PLANS[img.shape] = dwt_cpu.CpuDwt2(img.shape, WNAME, LEVELS)
+    P.forward(img)
+    return P.inverse()
 
 
-def time_cpu_port(budget_s=float(os.environ.get("PWT_BENCH_CPU_BUDGET", "10")), side=2048):
+def cpu_cores():
+    from oracle import dwt_cpu
+    return dwt_cpu.threads()
+
+
+def time_cpu_port(budget_s=float(os.environ.get("PWT_BENCH_CPU_BUDGET", "10")), side=4096):
     img = synth((side, side), 99)
-    cpu_port_fwd_inv(img[:256, :256])      # warm numpy
+    cpu_port_fwd_inv(img)                  # warm up (page faults, thread pool)
     n, t0 = 0, time.perf_counter()
     while True:
         cpu_port_fwd_inv(img)
         n += 1
         dt = time.perf_counter() - t0
-        if dt >= budget_s or n >= 50:
+        if dt >= budget_s or n >= 200:
             break
-    return n * side * side / dt / 1e6, "%d x (%dx%d db2 3-level fwd+inv), numpy fp32, %.1f s" % (n, side, side, dt)
+    return n * side * side / dt / 1e6, "%d x (%dx%d db2 3-level fwd+inv), oracle/dwt_cpu.c fp32, %d OpenMP threads, %.1f s" % (
+        n, side, side, cpu_cores(), dt)
 
 
 def dist_env():
@@ -136,7 +147,18 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    side = 2048     # bounded sample of the workload (one step = one 2048^2 fwd+inv on the host)
+    # bounded sample of the workload: one step = one SxS image on the host, S the largest of
+    # 4096/2048/1024/512 for which warmup + K steps stay within ~2.5 minutes
+    probe = synth((1024, 1024), 98)
+    cpu_port_fwd_inv(probe)
+    t0 = time.perf_counter()
+    cpu_port_fwd_inv(probe)
+    t_px = (time.perf_counter() - t0) / probe.size
+    side = 512
+    for cand in (4096, 2048, 1024):
+        if (args.steps + max(args.warmup, 1)) * t_px * cand * cand * 1.3 <= 150.0:
+            side = cand
+            break
     img = synth((side, side), 99)
     for _ in range(max(args.warmup, 1)):
         cpu_port_fwd_inv(img)
@@ -145,7 +167,7 @@ def run_reference(args):
         cpu_port_fwd_inv(img)
     dt = time.perf_counter() - t0
     val = args.steps * side * side / dt / 1e6
-    cores = 1
+    cores = cpu_cores()
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mpixel/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -155,8 +177,8 @@ def run_reference(args):
                    "sample": "each step = one %dx%d image (bounded sample of the 8192^2 workload)" % (side, side),
                    "l2": "n/a (CPU)"},
         "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": cores, "kind": "port",
-                         "sample": "%d steps x %dx%d, numpy fp32 restatement of pywt mode=periodization "
-                                   "(pywt not installable here); host has %d cores" % (args.steps, side, side, os.cpu_count() or 0)},
+                         "sample": "%d steps x %dx%d, plain-C/OpenMP restatement (oracle/dwt_cpu.c) of pywt "
+                                   "mode=periodization (pywt not installable here); host has %d cores" % (args.steps, side, side, os.cpu_count() or 0)},
         "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -232,12 +254,12 @@ def run_ours(args):
     W = pycudwt.Wavelets(img, WNAME, LEVELS)
 
     # ---- device-resident timing ---------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()      # runs through warm-up, the timed region and the per-kernel pass (all GPU-loaded)
     for _ in range(max(args.warmup, 3)):
         W.forward(); W.inverse()
     W.sync()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = W.launch_count
     barrier(); W.sync()
     W.timer_start()
@@ -247,7 +269,6 @@ def run_ours(args):
     W.sync(); barrier()
     launches = W.launch_count - l0
     ms = max_over_ranks(ms)
-    clocks = sampler.stop() if rank == 0 else None
     value = world * pix * args.steps / (ms * 1e-3) / 1e6
 
     # ---- per-kernel durations (same loop, every launch bracketed by events) --------------------
@@ -256,6 +277,7 @@ def run_ours(args):
         W.forward(); W.inverse()
     recs = W.profile_read()
     W.profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
     by_tag = {}
     for tag, t in recs:
         by_tag.setdefault(tag, []).append(t)
@@ -333,7 +355,7 @@ def run_ours(args):
                        "parallelism": "independent images per GPU, no data-path collective"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "roofline_step": roof_step,
-            "cpu_baseline": {"value": cpu_v, "unit": "Mpixel/s", "cores": 1, "kind": "port", "sample": cpu_s},
+            "cpu_baseline": {"value": cpu_v, "unit": "Mpixel/s", "cores": cpu_cores(), "kind": "port", "sample": cpu_s},
             "pdwt_cuda": pd,
         }
         line.update(extra)

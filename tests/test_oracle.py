@@ -253,3 +253,23 @@ def test_against_pywt_if_available():
         for i in range(3):
             for j in range(3):
                 assert np.abs(c[i + 1][j] - ref[3 - i][j]).max() < 1e-3
+
+
+@pytest.mark.parametrize("shape", [(64, 96), (63, 97), (100, 77)])
+@pytest.mark.parametrize("wname", ["haar", "db2", "sym4", "bior2.2", "db8"])
+def test_c_port_matches_numpy_oracle(wname, shape):
+    """oracle/dwt_cpu.c (the CPU baseline of bench.py) computes the same transform as the numpy oracle."""
+    from oracle import dwt_cpu
+    x = synth_image(shape, seed=6)
+    P = dwt_cpu.CpuDwt2(shape, wname, 3)
+    b = P.forward(x)
+    W = O.OracleWavelets(x, wname, 3)
+    assert P.levels == W.levels
+    W.forward()
+    c = W.coeffs
+    tol = 1e-5 * max(255.0, np.abs(c[0]).max())
+    assert np.abs(b[0] - c[0]).max() <= tol
+    for i in range(P.levels):
+        for j in range(3):
+            assert np.abs(b[3 * i + 1 + j] - c[i + 1][j]).max() <= tol
+    assert np.abs(P.inverse() - x).max() <= 1e-5 * 255 * (20 if wname in ("bior3.1", "rbio3.1") else 1) * 4
