@@ -323,10 +323,7 @@ int env_int(const char* name, int dflt) {
 template <int F, bool HAAR, int MINB, bool PF>
 int launch_fwd3(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cudaStream_t st) {
     a.n3 = HAAR ? 16 : Geo<F>::N3;
-    a.T3 = env_int("PWT_FUSED_T3", 16);
     const int W3 = a.Nc / 8, R3 = a.Nr / 8;
-    a.ntasks = cdiv(W3, a.n3) * cdiv(R3, a.T3);
-    a.batch = batch;
     static int resident = 0;
     if (!resident) {
         int dev = 0, sms = 148, per_sm = 1;
@@ -335,6 +332,14 @@ int launch_fwd3(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cud
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fwd3<F, HAAR, MINB, PF>, 32 * kWarps, 0);
         resident = sms * (per_sm > 0 ? per_sm : 1);
     }
+    // task height: as tall as possible (less warm-up) while leaving >= 3 tasks per resident warp
+    a.T3 = env_int("PWT_FUSED_T3", 0);
+    if (a.T3 <= 0) {
+        a.T3 = 16;
+        while (a.T3 > 4 && (long long)cdiv(W3, a.n3) * cdiv(R3, a.T3) * batch < 3LL * resident * kWarps) a.T3 >>= 1;
+    }
+    a.ntasks = cdiv(W3, a.n3) * cdiv(R3, a.T3);
+    a.batch = batch;
     long long total = (long long)a.ntasks * batch;
     int grid = (int)(total < (long long)resident * kWarps ? (total + kWarps - 1) / kWarps : resident);
     a.counter = q->counter;
@@ -621,10 +626,7 @@ int launch_inv3(Inv3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cud
     constexpr int S1 = (F / 2) >> 1;
     constexpr int OWN0 = (6 * S1 + 7) & ~7;
     a.n3 = (256 - 2 * OWN0) / 8;
-    a.T3 = env_int("PWT_FUSED_INV_T3", 32);
     const int W3 = a.Nc / 8, R3 = a.Nr / 8;
-    a.ntasks = cdiv(W3, a.n3) * cdiv(R3, a.T3);
-    a.batch = batch;
     static int resident = 0;
     if (!resident) {
         int dev = 0, sms = 148, per_sm = 1;
@@ -633,6 +635,13 @@ int launch_inv3(Inv3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cud
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inv3<F, HAAR, MINB>, 32 * kWarps, 0);
         resident = sms * (per_sm > 0 ? per_sm : 1);
     }
+    a.T3 = env_int("PWT_FUSED_INV_T3", 0);
+    if (a.T3 <= 0) {
+        a.T3 = 32;
+        while (a.T3 > 4 && (long long)cdiv(W3, a.n3) * cdiv(R3, a.T3) * batch < 3LL * resident * kWarps) a.T3 >>= 1;
+    }
+    a.ntasks = cdiv(W3, a.n3) * cdiv(R3, a.T3);
+    a.batch = batch;
     const long long total = (long long)a.ntasks * batch;
     const int grid = (int)(total < (long long)resident * kWarps ? (total + kWarps - 1) / kWarps : resident);
     a.counter = q->counter;
