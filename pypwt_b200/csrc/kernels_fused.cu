@@ -332,11 +332,11 @@ int launch_fwd3(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cud
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fwd3<F, HAAR, MINB, PF>, 32 * kWarps, 0);
         resident = sms * (per_sm > 0 ? per_sm : 1);
     }
-    // task height: as tall as possible (less warm-up) while leaving >= 3 tasks per resident warp
+    // task height: as tall as possible (less warm-up) while every resident warp still gets a task
     a.T3 = env_int("PWT_FUSED_T3", 0);
     if (a.T3 <= 0) {
         a.T3 = 16;
-        while (a.T3 > 4 && (long long)cdiv(W3, a.n3) * cdiv(R3, a.T3) * batch < 3LL * resident * kWarps) a.T3 >>= 1;
+        while (a.T3 > 4 && (long long)cdiv(W3, a.n3) * cdiv(R3, a.T3) * batch < 1LL * resident * kWarps) a.T3 >>= 1;
     }
     a.ntasks = cdiv(W3, a.n3) * cdiv(R3, a.T3);
     a.batch = batch;
@@ -638,7 +638,7 @@ int launch_inv3(Inv3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cud
     a.T3 = env_int("PWT_FUSED_INV_T3", 0);
     if (a.T3 <= 0) {
         a.T3 = 32;
-        while (a.T3 > 4 && (long long)cdiv(W3, a.n3) * cdiv(R3, a.T3) * batch < 3LL * resident * kWarps) a.T3 >>= 1;
+        while (a.T3 > 4 && (long long)cdiv(W3, a.n3) * cdiv(R3, a.T3) * batch < 1LL * resident * kWarps) a.T3 >>= 1;
     }
     a.ntasks = cdiv(W3, a.n3) * cdiv(R3, a.T3);
     a.batch = batch;

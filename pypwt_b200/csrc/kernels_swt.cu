@@ -1,0 +1,266 @@
+// Stationary (a trous) wavelet transform, 2D separable, one fused launch per level, in registers.
+//
+//   forward  out[g] = sum_j f[F-1-j] * x[(g + (j-c)*s) mod N], c = F/2-1, s = 2^(level-1)   separable.cu:409-493
+//   inverse  x[g]   = sum_j (fl[F-1-j]/2) * a[(g + (j-F/2)*s) mod N] + (fh[F-1-j]/2) * d[...]  separable.cu:553-626
+//
+// Design (B200): no decimation means 4 output planes per input plane (20 B/px/level compulsory), so the
+// kernel must not add intermediate planes (the reference, and our generic fallback, write and re-read
+// two full-size row-pass planes: 36 B/px/level).  One thread owns 4 adjacent columns:
+//   * row pass straight from global memory: the F taps of a dilated filter are F aligned 128-bit loads
+//     at x + (j-c)*s (s % 4 == 0; periodic wrap is just the address) or the few aligned vectors covering
+//     the window (s = 1, 2); neighbouring threads re-read the same lines from L1, DRAM sees each once;
+//   * column pass as a sliding window in registers over the LATTICE rows y0 + k*s (a task walks one
+//     residue class of rows), exactly like the decimated register kernels.
+// No shared memory, no barriers, 128-bit coalesced stores of the four bands.
+// The inverse runs rows first, then columns (the reference runs columns first); fp32 rounding differs
+// in the last bits only.
+#include <stdlib.h>
+
+#include "pwt_internal.h"
+
+namespace {
+
+__device__ __forceinline__ int wrap1_per(int i, int N) {   // -N <= i < 2N
+    if (i < 0) i += N;
+    if (i >= N) i -= N;
+    return i;
+}
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void stg4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void fma4(float4& acc, const float4& v, float t) {
+    acc.x = fmaf(v.x, t, acc.x);
+    acc.y = fmaf(v.y, t, acc.y);
+    acc.z = fmaf(v.z, t, acc.z);
+    acc.w = fmaf(v.w, t, acc.w);
+}
+
+constexpr int kThreads = 128;
+
+// Row filtering of one plane row for this thread's 4 columns with two filters (fa, fb):
+//   ra[i] = sum_j fa[F-1-j] * row[(x + i + (j-C)*s) mod Nc], rb likewise.      SMODE: 1 -> s=1, 2 -> s=2, 0 -> s%4==0
+template <int F, int C, int SMODE>
+__device__ __forceinline__ void row_filter(const float* __restrict__ row, int x, int Nc, int s, const float* fa,
+                                           const float* fb, float scale, float4& ra, float4& rb) {
+    if (SMODE == 0) {
+#pragma unroll
+        for (int j = 0; j < F; j++) {
+            const float4 v = ldg4(row + wrap1_per(x + (j - C) * s, Nc));
+            fma4(ra, v, scale * fa[F - 1 - j]);
+            fma4(rb, v, scale * fb[F - 1 - j]);
+        }
+    } else {
+        constexpr int S = SMODE;
+        constexpr int BL = ((C * S + 3) / 4) * 4;                       // aligned reach to the left
+        constexpr int BR = (((F - 1 - C) * S + 3) / 4) * 4;             // and to the right
+        constexpr int NE = (BL + 4 + BR) / 4;
+        float ext[4 * NE];
+#pragma unroll
+        for (int k = 0; k < NE; k++) {
+            const float4 v = ldg4(row + wrap1_per(x - BL + 4 * k, Nc));
+            ext[4 * k] = v.x; ext[4 * k + 1] = v.y; ext[4 * k + 2] = v.z; ext[4 * k + 3] = v.w;
+        }
+#pragma unroll
+        for (int j = 0; j < F; j++) {
+            const float ta = scale * fa[F - 1 - j], tb = scale * fb[F - 1 - j];
+            const int o = BL + (j - C) * S;
+            ra.x = fmaf(ext[o], ta, ra.x);     rb.x = fmaf(ext[o], tb, rb.x);
+            ra.y = fmaf(ext[o + 1], ta, ra.y); rb.y = fmaf(ext[o + 1], tb, rb.y);
+            ra.z = fmaf(ext[o + 2], ta, ra.z); rb.z = fmaf(ext[o + 2], tb, rb.z);
+            ra.w = fmaf(ext[o + 3], ta, ra.w); rb.w = fmaf(ext[o + 3], tb, rb.w);
+        }
+    }
+}
+
+struct SwtGeom {
+    int Nr, Nc, s, TQ;           // plane size, dilation, lattice steps per task
+    int strips, chunks;          // column strips of 4*kThreads, chunks of TQ steps per residue class
+    long long plane;             // elements per image
+};
+
+// ---- forward: in -> A, H, V, D -----------------------------------------------------------------
+template <int F, int SMODE, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+k_swt_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ Hb, float* __restrict__ V,
+          float* __restrict__ D, const SwtGeom g, const __grid_constant__ PwtFilters f) {
+    constexpr int C = F / 2 - 1;
+    const int Nr = g.Nr, Nc = g.Nc, s = g.s;
+    const int strip = blockIdx.x % g.strips;
+    const int rc = blockIdx.x / g.strips;
+    const int r = rc % s, chunk = rc / s;                    // residue class of rows, chunk along the lattice
+    const int x = strip * (4 * kThreads) + 4 * threadIdx.x;
+    const int nq = (Nr - r + s - 1) / s;                     // lattice length of this class
+    const int q0 = chunk * g.TQ;
+    if (x >= Nc || q0 >= nq) return;
+    const int q1 = min(q0 + g.TQ, nq);
+    const long long ib = blockIdx.y * g.plane;
+    in += ib; A += ib; Hb += ib; V += ib; D += ib;
+
+    // wl[j], wh[j]: row-filtered rows y + (j-C)*s of the current output row y
+    float4 wl[F], wh[F];
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < F - 1; j++) {
+        const int yy = wrap1_per(r + (q0 + j - C) * s, Nr);
+        wl[j] = z; wh[j] = z;
+        row_filter<F, C, SMODE>(in + (long long)yy * Nc, x, Nc, s, f.L, f.H, 1.0f, wl[j], wh[j]);
+    }
+    for (int q = q0; q < q1; q++) {
+        const int yn = wrap1_per(r + (q + F - 1 - C) * s, Nr);
+        wl[F - 1] = z; wh[F - 1] = z;
+        row_filter<F, C, SMODE>(in + (long long)yn * Nc, x, Nc, s, f.L, f.H, 1.0f, wl[F - 1], wh[F - 1]);
+        float4 a = z, h = z, v = z, d = z;
+#pragma unroll
+        for (int j = 0; j < F; j++) {
+            const float tl = f.L[F - 1 - j], th = f.H[F - 1 - j];
+            fma4(a, wl[j], tl);
+            fma4(h, wl[j], th);      // (Lx, Hy)
+            fma4(v, wh[j], tl);      // (Hx, Ly)
+            fma4(d, wh[j], th);
+        }
+        const long long o = (long long)(r + q * s) * Nc + x;
+        stg4(A + o, a);
+        stg4(Hb + o, h);
+        stg4(V + o, v);
+        stg4(D + o, d);
+#pragma unroll
+        for (int j = 0; j < F - 1; j++) {
+            wl[j] = wl[j + 1];
+            wh[j] = wh[j + 1];
+        }
+    }
+}
+
+// ---- inverse: A, H, V, D -> out (rows first: u1 = syn_x(A, V), u2 = syn_x(H, D); then columns) ----
+template <int F, int SMODE, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+k_swt_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float* __restrict__ V,
+          const float* __restrict__ D, float* __restrict__ out, const SwtGeom g,
+          const __grid_constant__ PwtFilters f) {
+    constexpr int C = F / 2;                                 // separable.cu:565-568
+    const int Nr = g.Nr, Nc = g.Nc, s = g.s;
+    const int strip = blockIdx.x % g.strips;
+    const int rc = blockIdx.x / g.strips;
+    const int r = rc % s, chunk = rc / s;
+    const int x = strip * (4 * kThreads) + 4 * threadIdx.x;
+    const int nq = (Nr - r + s - 1) / s;
+    const int q0 = chunk * g.TQ;
+    if (x >= Nc || q0 >= nq) return;
+    const int q1 = min(q0 + g.TQ, nq);
+    const long long ib = blockIdx.y * g.plane;
+    A += ib; Hb += ib; V += ib; D += ib; out += ib;
+
+    float4 w1[F], w2[F];
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto hrow = [&](int yy, float4& u1, float4& u2) {
+        const long long ro = (long long)yy * Nc;
+        float4 t = z;                                        // every tap carries a factor 1/2 (separable.cu:621-622)
+        u1 = z; u2 = z;
+        row_filter<F, C, SMODE>(A + ro, x, Nc, s, f.IL, f.IL, 0.5f, u1, t);
+        t = z;
+        row_filter<F, C, SMODE>(V + ro, x, Nc, s, f.IH, f.IH, 0.5f, u1, t);
+        t = z;
+        row_filter<F, C, SMODE>(Hb + ro, x, Nc, s, f.IL, f.IL, 0.5f, u2, t);
+        t = z;
+        row_filter<F, C, SMODE>(D + ro, x, Nc, s, f.IH, f.IH, 0.5f, u2, t);
+    };
+#pragma unroll
+    for (int j = 0; j < F - 1; j++) hrow(wrap1_per(r + (q0 + j - C) * s, Nr), w1[j], w2[j]);
+    for (int q = q0; q < q1; q++) {
+        hrow(wrap1_per(r + (q + F - 1 - C) * s, Nr), w1[F - 1], w2[F - 1]);
+        float4 o = z;
+#pragma unroll
+        for (int j = 0; j < F; j++) {
+            fma4(o, w1[j], 0.5f * f.IL[F - 1 - j]);
+            fma4(o, w2[j], 0.5f * f.IH[F - 1 - j]);
+        }
+        stg4(out + (long long)(r + q * s) * Nc + x, o);
+#pragma unroll
+        for (int j = 0; j < F - 1; j++) {
+            w1[j] = w1[j + 1];
+            w2[j] = w2[j + 1];
+        }
+    }
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+SwtGeom make_geom(int Nr, int Nc, int level) {
+    SwtGeom g;
+    g.Nr = Nr;
+    g.Nc = Nc;
+    g.s = 1 << (level - 1);
+    g.strips = cdiv(Nc, 4 * kThreads);
+    const int nq = cdiv(Nr, g.s);
+    int tq = 64;
+    if (const char* e = getenv("PWT_SWT_TQ")) tq = atoi(e) > 0 ? atoi(e) : tq;
+    while (tq > 16 && (long long)g.strips * g.s * cdiv(nq, tq) < 2 * 148 * 4) tq >>= 1;   // keep the GPU full
+    g.TQ = tq;
+    g.chunks = cdiv(nq, tq);
+    g.plane = (long long)Nr * Nc;
+    return g;
+}
+
+template <int F, int MINB>
+int launch_fwd(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc, int level,
+               const PwtFilters& f, cudaStream_t st) {
+    const SwtGeom g = make_geom(Nr, Nc, level);
+    dim3 grid(g.strips * g.s * g.chunks, batch);
+    if (g.s == 1) k_swt_fwd<F, 1, MINB><<<grid, kThreads, 0, st>>>(in, A, Hb, V, D, g, f);
+    else if (g.s == 2) k_swt_fwd<F, 2, MINB><<<grid, kThreads, 0, st>>>(in, A, Hb, V, D, g, f);
+    else k_swt_fwd<F, 0, MINB><<<grid, kThreads, 0, st>>>(in, A, Hb, V, D, g, f);
+    return 1;
+}
+template <int F, int MINB>
+int launch_inv(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch, int Nr,
+               int Nc, int level, const PwtFilters& f, cudaStream_t st) {
+    const SwtGeom g = make_geom(Nr, Nc, level);
+    dim3 grid(g.strips * g.s * g.chunks, batch);
+    if (g.s == 1) k_swt_inv<F, 1, MINB><<<grid, kThreads, 0, st>>>(A, Hb, V, D, out, g, f);
+    else if (g.s == 2) k_swt_inv<F, 2, MINB><<<grid, kThreads, 0, st>>>(A, Hb, V, D, out, g, f);
+    else k_swt_inv<F, 0, MINB><<<grid, kThreads, 0, st>>>(A, Hb, V, D, out, g, f);
+    return 1;
+}
+
+bool covered(int F, int batch, int Nr, int Nc, int level, const void* p0, const void* p1) {
+    const int s = 1 << (level - 1);
+    if ((F & 1) || F < 2 || F > 12 || Nc % 4 != 0 || batch > 65535) return false;
+    if ((F - 1) * s >= Nc || (F - 1) * s >= Nr) return false;          // single-step wrap must suffice
+    if ((((uintptr_t)p0 | (uintptr_t)p1) & 15) != 0) return false;
+    if (getenv("PWT_NO_FAST_SWT")) return false;
+    return true;
+}
+
+}  // namespace
+
+// Return 0 when the configuration is not covered (the generic two-pass kernels take over).
+int pwt_fast_swt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
+                       int level, const PwtFilters& f, cudaStream_t st) {
+    const int F = f.hlen;
+    if (!covered(F, batch, Nr, Nc, level, in, A) || in == A) return 0;
+    if ((((uintptr_t)Hb | (uintptr_t)V | (uintptr_t)D) & 15) != 0) return 0;
+    switch (F) {
+        case 2: return launch_fwd<2, 4>(in, A, Hb, V, D, batch, Nr, Nc, level, f, st);
+        case 4: return launch_fwd<4, 4>(in, A, Hb, V, D, batch, Nr, Nc, level, f, st);
+        case 6: return launch_fwd<6, 3>(in, A, Hb, V, D, batch, Nr, Nc, level, f, st);
+        case 8: return launch_fwd<8, 3>(in, A, Hb, V, D, batch, Nr, Nc, level, f, st);
+        case 10: return launch_fwd<10, 2>(in, A, Hb, V, D, batch, Nr, Nc, level, f, st);
+        case 12: return launch_fwd<12, 2>(in, A, Hb, V, D, batch, Nr, Nc, level, f, st);
+        default: return 0;
+    }
+}
+
+int pwt_fast_swt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
+                       int Nr, int Nc, int level, const PwtFilters& f, cudaStream_t st) {
+    const int F = f.hlen;
+    if (!covered(F, batch, Nr, Nc, level, A, out) || out == A) return 0;
+    if ((((uintptr_t)Hb | (uintptr_t)V | (uintptr_t)D) & 15) != 0) return 0;
+    switch (F) {
+        case 2: return launch_inv<2, 4>(A, Hb, V, D, out, batch, Nr, Nc, level, f, st);
+        case 4: return launch_inv<4, 4>(A, Hb, V, D, out, batch, Nr, Nc, level, f, st);
+        case 6: return launch_inv<6, 3>(A, Hb, V, D, out, batch, Nr, Nc, level, f, st);
+        case 8: return launch_inv<8, 3>(A, Hb, V, D, out, batch, Nr, Nc, level, f, st);
+        case 10: return launch_inv<10, 2>(A, Hb, V, D, out, batch, Nr, Nc, level, f, st);
+        case 12: return launch_inv<12, 2>(A, Hb, V, D, out, batch, Nr, Nc, level, f, st);
+        default: return 0;
+    }
+}

@@ -120,3 +120,9 @@ int pwt_fused_dwt_fwd3(const float* in, float* A3, float* const* H, float* const
 int pwt_fused_dwt_inv3(const float* A3, const float* const* H, const float* const* V, const float* const* D,
                        float* out, int batch, int Nr, int Nc, const PwtFilters& f, bool haar, PwtTaskQueue* q,
                        cudaStream_t st);
+
+// kernels_swt.cu : fused (row + column) a-trous level in registers.  Return 0 when not covered.
+int pwt_fast_swt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
+                       int level, const PwtFilters& f, cudaStream_t st);
+int pwt_fast_swt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
+                       int Nr, int Nc, int level, const PwtFilters& f, cudaStream_t st);

@@ -569,8 +569,11 @@ extern "C" int pwt_forward(pwt_plan* p) {
             prof_begin(p, 100 * l + 1);
             if (p->do_swt) {
                 float* dstA = approx_dst(p, l, p->d_tmp + 2 * plane);
-                if (p->do_separable)
-                    p->launches += pwt_launch_swt_fwd2d(src, dstA, Hb, V, D, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
+                if (p->do_separable) {
+                    int n = p->kernel_mode == 1 ? 0 : pwt_fast_swt_fwd2d(src, dstA, Hb, V, D, B, p->Nr, p->Nc, l, p->filt, st);
+                    if (!n) n = pwt_launch_swt_fwd2d(src, dstA, Hb, V, D, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
+                    p->launches += n;
+                }
                 else
                     p->launches += pwt_launch_ns_swt_fwd2d(src, dstA, Hb, V, D, B, p->Nr, p->Nc, l, p->d_k2d_fwd, p->hlen, st);
                 src = dstA;
@@ -654,8 +657,11 @@ extern "C" int pwt_inverse(pwt_plan* p) {
             if (p->do_swt) {
                 float* alt = p->d_tmp + 2 * plane;
                 float* dst = (l == 1) ? p->d_image : (cur == p->d_band[0] ? alt : p->d_band[0]);
-                if (p->do_separable)
-                    p->launches += pwt_launch_swt_inv2d(cur, Hb, V, D, dst, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
+                if (p->do_separable) {
+                    int n = p->kernel_mode == 1 ? 0 : pwt_fast_swt_inv2d(cur, Hb, V, D, dst, B, p->Nr, p->Nc, l, p->filt, st);
+                    if (!n) n = pwt_launch_swt_inv2d(cur, Hb, V, D, dst, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
+                    p->launches += n;
+                }
                 else
                     p->launches += pwt_launch_ns_swt_inv2d(cur, Hb, V, D, dst, B, p->Nr, p->Nc, l, p->d_k2d_inv, p->hlen, st);
                 cur = dst;

@@ -452,6 +452,30 @@ def test_fused_cascade_is_bit_identical_to_per_level_kernels(wname, shape):
     assert_close(F.image, img, 255.0, "roundtrip")
 
 
+@pytest.mark.parametrize("shape", [(256, 512), (200, 300), (2, 96, 128)])
+@pytest.mark.parametrize("wname", ["haar", "db2", "db4", "sym5", "db6"])
+def test_fused_swt_kernels_agree_with_generic(wname, shape):
+    """The register SWT kernels (one fused launch per level) against the generic two-pass kernels and
+    the oracle, 4 levels (dilations 1, 2, 4, 8: all three tap-addressing modes)."""
+    img = synth_image(shape, seed=18, kind="smooth")
+    A = _W(img, wname, 4, do_swt=1); G = _W(img, wname, 4, do_swt=1)
+    G.set_kernel_mode(1)
+    A.forward(); G.forward()
+    assert A.levels == G.levels
+    if shape[-1] % 4 == 0:
+        assert A.launch_count < G.launch_count
+    for i in range(A.levels + 1):
+        for a, g in zip(A.coeffs[i] if i else [A.coeffs[0]], G.coeffs[i] if i else [G.coeffs[0]]):
+            assert_close(a, g, 255.0, "swt fused vs generic")
+    if len(shape) == 2:
+        Wo = O.OracleWavelets(img, wname, 4, do_swt=1)
+        Wo.forward()
+        compare_coeffs(A, Wo, 255.0, "swt fused vs oracle")
+    A.inverse(); G.inverse()
+    assert_close(A.image, G.image, 255.0, "iswt fused vs generic")
+    assert_close(A.image, img, 255.0, "swt roundtrip")
+
+
 @pytest.mark.parametrize("wname", ["haar", "db2"])
 def test_full_size_roundtrip_properties(wname):
     """BASELINE metric size (8192^2, 3 levels): size-independent properties -- perfect reconstruction,
