@@ -126,3 +126,10 @@ int pwt_fast_swt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D,
                        int level, const PwtFilters& f, cudaStream_t st);
 int pwt_fast_swt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
                        int Nr, int Nc, int level, const PwtFilters& f, cudaStream_t st);
+
+// kernels_tile.cu : compile-time F = 10..40 shared-memory tile kernels (FMA-bound regime), any size.
+int pwt_tile_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
+                       long long in_bs, long long out_bs, const PwtFilters& f, cudaStream_t st);
+int pwt_tile_dwt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
+                       int nr, int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs,
+                       const PwtFilters& f, cudaStream_t st);

@@ -109,6 +109,7 @@ struct pwt_plan {
     size_t flush_bytes;
     long long launches;
     int kernel_mode;
+    int tile_min_f;        // filter length from which the FMA-oriented tile kernels are preferred
     unsigned custom_len;   // taps given to set_filters_forward (0: built-in bank)
     int prof_on, prof_n;
     cudaEvent_t* prof_ev;  // 2 events per record
@@ -308,6 +309,7 @@ extern "C" int pwt_create_batch(pwt_plan** out, const float* img, int batch, int
     if (p->do_cs && p->do_swt)
         puts("Warning: makes little sense to use Cycle spinning with stationary Wavelet transform");
     compute_geometry(p);
+    p->tile_min_f = getenv("PWT_TILE_MIN_F") ? atoi(getenv("PWT_TILE_MIN_F")) : 22;
 
     // L2 residency of the ping-pong approximation planes: the kernels store them with an
     // L2::evict_last policy, which only has an effect when a persisting-L2 carve-out exists.
@@ -586,6 +588,8 @@ extern "C" int pwt_forward(pwt_plan* p) {
                     const int hints = (l < L ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l > 1 ? PWT_HINT_IN_FROM_PREV : 0);
                     if (p->kernel_mode == 0 || p->kernel_mode == 3)
                         n = pwt_reg_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, hints, st);
+                    if (!n && p->kernel_mode != 1 && !haar && p->hlen >= p->tile_min_f && nr >= 64 && nc >= 64)
+                        n = pwt_tile_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, st);
                     if (!n && p->kernel_mode != 1)
                         n = pwt_fast_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar,
                                                (l < L ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l > 1 ? PWT_HINT_IN_FROM_PREV : 0), st);
@@ -674,6 +678,8 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                     const int hints = (l > 1 ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l < L ? PWT_HINT_IN_FROM_PREV : 0);
                     if (p->kernel_mode == 0 || p->kernel_mode == 3)
                         n = pwt_reg_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, hints, st);
+                    if (!n && p->kernel_mode != 1 && !haar && p->hlen >= p->tile_min_f && nr >= 32 && nc >= 32)
+                        n = pwt_tile_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, st);
                     if (!n && p->kernel_mode != 1)
                         n = pwt_fast_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar,
                                                (l > 1 ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l < L ? PWT_HINT_IN_FROM_PREV : 0), st);
