@@ -1,18 +1,16 @@
-python -m pytest tests -m gpu -q --timeout=900 -p no:cacheprovider -k "test_dwt2 or test_idwt2 or odd_sizes or vs_pdwt or stack or agree" 2>&1 | grep -v "^Warn\|^Forc" | tail -8
+python bench.py --steps 500 --no-pdwt 2>&1 | grep -o "\"value\": [0-9.]*, \"unit\": \"Mpixel/s\", \"n_gpus\"\|kernel_ms_by_level[^}]*}"
 python - <<'PY'
-import sys, time, numpy as np
+import sys, numpy as np
 sys.path.insert(0,'.')
 import pycudwt
-img=(np.random.default_rng(1).standard_normal((8192,8192),dtype=np.float32)*50+128)
-for w in ['db6','sym8','db10','db12','db20']:
-    for minf in (12, 99):
-        import os; os.environ['PWT_TILE_MIN_F']=str(minf)
-        W=pycudwt.Wavelets(img,w,5)
-        def f(): W.forward(); W.inverse()
-        for _ in range(3): f()
-        W.sync(); W.timer_start()
-        for _ in range(10): f()
-        ms=W.timer_stop()/10
-        print("%-6s F=%2d tile_min_f=%2d: %.3f ms  %.0f Mpx/s"%(w,W.hlen,minf,ms,img.size/ms/1e3), flush=True)
-        del W
+for shape,w in [((4096,4096),'haar'),((4096,4096),'db2'),((8192,8192),'haar'),((2048,2048),'db2'),((16,2048,2048),'db2'),((8192,8192),'db3')]:
+    img=(np.random.default_rng(1).standard_normal(shape,dtype=np.float32)*50+128)
+    W=pycudwt.Wavelets(img,w,3)
+    def f(): W.forward(); W.inverse()
+    for _ in range(5): f()
+    W.sync(); W.timer_start()
+    for _ in range(50): f()
+    ms=W.timer_stop()/50
+    print("%s %s: %.4f ms  %.0f Mpx/s  frac %.3f"%(shape,w,ms,img.size/ms/1e3, 16*img.size/ms/1e6/6549.4), flush=True)
+    del W
 PY
