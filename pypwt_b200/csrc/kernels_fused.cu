@@ -418,7 +418,25 @@ struct Inv3Args {
     unsigned* counter;
     unsigned base;
     int ntasks, batch;
+    // deferred coefficient operator applied to the coefficients as they are loaded (0 extra bytes):
+    int thr_op;            // -1 none, PWT_OP_SOFT, PWT_OP_HARD
+    int thr_app;           // also threshold A3
+    float thr_beta[3];     // per level (index 0 = level 1)
+    float thr_beta_app;
 };
+
+template <int THR>
+__device__ __forceinline__ float thr1(float v, float beta) {
+    // common.cu:19 (soft) / common.cu:63 (hard, strict >)
+    if (THR == 1) return copysignf(fmaxf(fabsf(v) - beta, 0.0f), v);
+    return (fabsf(v) - beta > 0.0f) ? v : 0.0f * v;
+}
+template <int THR>
+__device__ __forceinline__ float2 thr2(float2 v, float b) { return make_float2(thr1<THR>(v.x, b), thr1<THR>(v.y, b)); }
+template <int THR>
+__device__ __forceinline__ float4 thr4(float4 v, float b) {
+    return make_float4(thr1<THR>(v.x, b), thr1<THR>(v.y, b), thr1<THR>(v.z, b), thr1<THR>(v.w, b));
+}
 
 // one horizontally synthesised band row held CW band columns per lane: u1 = syn_x(A, V), u2 = syn_x(H, D)
 template <int CW>
@@ -426,7 +444,7 @@ struct URow {
     float u1[2 * CW], u2[2 * CW];
 };
 
-template <int F, bool HAAR, int MINB>
+template <int F, bool HAAR, int MINB, int THR>   // THR: 0 none, 1 soft, 2 hard threshold applied on load
 __global__ void __launch_bounds__(32 * kWarps, MINB)
 k_inv3(const __grid_constant__ Inv3Args a, const __grid_constant__ PwtFilters f) {
     constexpr int P = F / 2 - 1, HALF = F / 2;
@@ -569,6 +587,17 @@ k_inv3(const __grid_constant__ Inv3Args a, const __grid_constant__ PwtFilters f)
                 e3[0] = __ldg(A3 + ro + e3col); e3[1] = __ldg(H3 + ro + e3col);
                 e3[2] = __ldg(V3 + ro + e3col); e3[3] = __ldg(D3 + ro + e3col);
             }
+            if (THR) {
+#pragma unroll
+                for (int k = 1; k < 4; k++) {
+                    b3[k] = thr1<THR>(b3[k], a.thr_beta[2]);
+                    if (HW > 0) e3[k] = thr1<THR>(e3[k], a.thr_beta[2]);
+                }
+                if (a.thr_app) {
+                    b3[0] = thr1<THR>(b3[0], a.thr_beta_app);
+                    if (HW > 0) e3[0] = thr1<THR>(e3[0], a.thr_beta_app);
+                }
+            }
         }
         float2 h2[2], v2[2], d2[2];
         float4 h1[4], v1[4], d1[4];
@@ -579,6 +608,11 @@ k_inv3(const __grid_constant__ Inv3Args a, const __grid_constant__ PwtFilters f)
                 h2[i] = __ldg(reinterpret_cast<const float2*>(H2 + ro + (long long)i * W2));
                 v2[i] = __ldg(reinterpret_cast<const float2*>(V2 + ro + (long long)i * W2));
                 d2[i] = __ldg(reinterpret_cast<const float2*>(D2 + ro + (long long)i * W2));
+                if (THR) {
+                    h2[i] = thr2<THR>(h2[i], a.thr_beta[1]);
+                    v2[i] = thr2<THR>(v2[i], a.thr_beta[1]);
+                    d2[i] = thr2<THR>(d2[i], a.thr_beta[1]);
+                }
             }
         }
         if (do1) {
@@ -590,6 +624,11 @@ k_inv3(const __grid_constant__ Inv3Args a, const __grid_constant__ PwtFilters f)
                     h1[2 * pr + i] = ldg4(H1 + ro + (long long)i * W1);
                     v1[2 * pr + i] = ldg4(V1 + ro + (long long)i * W1);
                     d1[2 * pr + i] = ldg4(D1 + ro + (long long)i * W1);
+                    if (THR) {
+                        h1[2 * pr + i] = thr4<THR>(h1[2 * pr + i], a.thr_beta[0]);
+                        v1[2 * pr + i] = thr4<THR>(v1[2 * pr + i], a.thr_beta[0]);
+                        d1[2 * pr + i] = thr4<THR>(d1[2 * pr + i], a.thr_beta[0]);
+                    }
                 }
             }
         }
@@ -635,8 +674,8 @@ k_inv3(const __grid_constant__ Inv3Args a, const __grid_constant__ PwtFilters f)
   }
 }
 
-template <int F, bool HAAR, int MINB>
-int launch_inv3(Inv3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cudaStream_t st) {
+template <int F, bool HAAR, int MINB, int THR>
+int launch_inv3t(Inv3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cudaStream_t st) {
     constexpr int S1 = (F / 2) >> 1;
     constexpr int OWN0 = (6 * S1 + 7) & ~7;
     a.n3 = (256 - 2 * OWN0) / 8;
@@ -646,7 +685,7 @@ int launch_inv3(Inv3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cud
         int dev = 0, sms = 148, per_sm = 1;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inv3<F, HAAR, MINB>, 32 * kWarps, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inv3<F, HAAR, MINB, THR>, 32 * kWarps, 0);
         resident = sms * (per_sm > 0 ? per_sm : 1);
     }
     a.T3 = env_int("PWT_FUSED_INV_T3", 0);
@@ -658,8 +697,15 @@ int launch_inv3(Inv3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cud
     a.counter = q->counter;
     a.base = q->base;
     q->base += (unsigned)total + (unsigned)grid * kWarps;
-    k_inv3<F, HAAR, MINB><<<grid, 32 * kWarps, 0, st>>>(a, f);
+    k_inv3<F, HAAR, MINB, THR><<<grid, 32 * kWarps, 0, st>>>(a, f);
     return 1;
+}
+
+template <int F, bool HAAR, int MINB>
+int launch_inv3(const Inv3Args& a, int batch, const PwtFilters& f, PwtTaskQueue* q, cudaStream_t st) {
+    if (a.thr_op == PWT_OP_SOFT) return launch_inv3t<F, HAAR, MINB, 1>(a, batch, f, q, st);
+    if (a.thr_op == PWT_OP_HARD) return launch_inv3t<F, HAAR, MINB, 2>(a, batch, f, q, st);
+    return launch_inv3t<F, HAAR, MINB, 0>(a, batch, f, q, st);
 }
 
 }  // namespace
@@ -667,7 +713,7 @@ int launch_inv3(Inv3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cud
 // Levels 3..1 of the inverse transform in one launch.  H/V/D[0] = level 1 (finest).
 int pwt_fused_dwt_inv3(const float* A3, const float* const* H, const float* const* V, const float* const* D,
                        float* out, int batch, int Nr, int Nc, const PwtFilters& f, bool haar, PwtTaskQueue* q,
-                       cudaStream_t st) {
+                       const PwtDeferredOp* op, cudaStream_t st) {
     const int F = haar ? 2 : f.hlen;
     if (env_int("PWT_NO_FUSED", 0) || env_int("PWT_NO_FUSED_INV", 0)) return 0;
     if (F > 6 || (F & 1) || Nr % 8 != 0 || Nc % 8 != 0 || Nc < 512 || Nr < 64 || batch > 65535) return 0;
@@ -685,6 +731,15 @@ int pwt_fused_dwt_inv3(const float* A3, const float* const* H, const float* cons
     a.Nr = Nr;
     a.Nc = Nc;
     a.out_bs = (long long)Nr * Nc;
+    a.thr_op = -1;
+    a.thr_app = 0;
+    a.thr_beta[0] = a.thr_beta[1] = a.thr_beta[2] = a.thr_beta_app = 0.f;
+    if (op && op->op >= 0) {
+        a.thr_op = op->op;
+        a.thr_app = op->app;
+        a.thr_beta_app = op->beta_app;
+        for (int l = 0; l < 3; l++) a.thr_beta[l] = op->beta[l];
+    }
     if (haar) return launch_inv3<2, true, 4>(a, batch, f, q, st);
     switch (F) {
         case 4: return launch_inv3<4, false, 3>(a, batch, f, q, st);

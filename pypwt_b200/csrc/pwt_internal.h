@@ -117,9 +117,18 @@ struct PwtTaskQueue {
 int pwt_fused_dwt_fwd3(const float* in, float* A3, float* const* H, float* const* V, float* const* D,
                        int batch, int Nr, int Nc, const PwtFilters& f, bool haar, PwtTaskQueue* q,
                        cudaStream_t st);
+// A threshold recorded by soft/hard_threshold() and not yet applied to memory: the fused inverse applies it
+// to the coefficients while loading them (the denoising loop forward -> threshold -> inverse then moves
+// no extra bytes).  beta[l] = threshold of level l+1 details, beta_app = threshold of A (if app).
+struct PwtDeferredOp {
+    int op;                // -1: nothing pending, else PWT_OP_SOFT / PWT_OP_HARD
+    int app;
+    float beta[PWT_MAX_LEVELS];
+    float beta_app;
+};
 int pwt_fused_dwt_inv3(const float* A3, const float* const* H, const float* const* V, const float* const* D,
                        float* out, int batch, int Nr, int Nc, const PwtFilters& f, bool haar, PwtTaskQueue* q,
-                       cudaStream_t st);
+                       const PwtDeferredOp* op, cudaStream_t st);
 
 // kernels_swt.cu : fused (row + column) a-trous level in registers.  Return 0 when not covered.
 int pwt_fast_swt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,

@@ -104,6 +104,8 @@ struct pwt_plan {
     int band_nr[PWT_MAX_BANDS], band_nc[PWT_MAX_BANDS];
     double* d_acc;      // device accumulators for the norms
     PwtTaskQueue queue; // dynamic task queue of the persistent kernels
+    PwtDeferredOp pend; // threshold recorded but not yet applied to memory (pend.op < 0: none)
+    int defer_ok;       // plan shape for which thresholds may be deferred into the fused inverse
     double* h_acc;      // pinned mirror
     void* d_flush;
     size_t flush_bytes;
@@ -117,6 +119,11 @@ struct pwt_plan {
     ncclComm_t comm;
     int comm_nranks;
 };
+
+// ---- deferred thresholds (see PwtDeferredOp) -------------------------------------------------
+// flush: apply the pending threshold to memory for levels >= first_level (1 = everything) and, if
+// with_app, to the approximation band; clears the pending state when everything was flushed.
+static int flush_pending(pwt_plan* p, int first_level, bool with_app);
 
 static inline int div2i(int n) { return (n + 1) >> 1; }            // utils.cu:24-27
 static inline int ilog2i(int i) {                                   // utils.cu:14-20 (guarded)
@@ -271,6 +278,7 @@ extern "C" int pwt_create_batch(pwt_plan** out, const float* img, int batch, int
     p->do_swt = do_swt ? 1 : 0;
     p->do_cs = do_cycle_spinning ? 1 : 0;
     p->state = PWT_INIT;
+    p->pend.op = -1;
     p->ndims = (ndim < 2 || Nr == 1) ? 1 : 2;                       // wt.cu:133-136
     p->do_separable = (p->ndims == 1) ? 1 : (do_separable ? 1 : 0); // wt.cu:138-142
     strncpy(p->wname, wname, sizeof(p->wname) - 1);
@@ -309,6 +317,8 @@ extern "C" int pwt_create_batch(pwt_plan** out, const float* img, int batch, int
     if (p->do_cs && p->do_swt)
         puts("Warning: makes little sense to use Cycle spinning with stationary Wavelet transform");
     compute_geometry(p);
+    p->defer_ok = p->ndims == 2 && !p->do_swt && p->do_separable && p->nlevels >= 3 && Nr % 8 == 0 && Nc % 8 == 0 &&
+                  Nc >= 512 && Nr >= 64 && (p->hlen <= 6) && !getenv("PWT_NO_DEFER");
     p->tile_min_f = getenv("PWT_TILE_MIN_F") ? atoi(getenv("PWT_TILE_MIN_F")) : 22;
 
     // L2 residency of the ping-pong approximation planes: the kernels store them with an
@@ -381,6 +391,8 @@ extern "C" int pwt_clone(pwt_plan** out, const pwt_plan* src) {
     p->prof_on = p->prof_n = 0;
     *out = nullptr;
     cudaSetDevice(src->device);
+    flush_pending(const_cast<pwt_plan*>(src), 1, true);
+    p->pend.op = -1;
     cudaStreamSynchronize(src->stream);
     int rc = PWT_OK;
     cudaError_t e = cudaStreamCreate(&p->stream);
@@ -520,6 +532,7 @@ extern "C" int pwt_forward(pwt_plan* p) {
     if (!p) return fail(PWT_ERR_ARG, "null plan");
     if (p->state == PWT_CREATION_ERROR) return fail(PWT_ERR_STATE, "plan is in creation-error state");
     cudaSetDevice(p->device);
+    p->pend.op = -1;                                                // the coefficients are about to be overwritten
     if (p->do_cs) {                                                 // wt.cu:242-246
         p->shift_r = rand() % p->Nr;
         p->shift_c = rand() % p->Nc;
@@ -635,7 +648,17 @@ extern "C" int pwt_inverse(pwt_plan* p) {
         }
     } else {
         const long long plane = (long long)B * img_elems(p);
+        PwtDeferredOp fop = p->pend;                                // what the fused launch applies while loading
+        if (p->pend.op >= 0 && L > 3) {
+            int rc = flush_pending(p, 4, true);                     // coarser levels + A go through memory (1/64 of the data)
+            if (rc != PWT_OK) return rc;
+            fop.app = 0;
+        }
         for (int l = L; l >= 1; l--) {
+            if (l == 3 && p->pend.op >= 0 && !(!p->do_swt && (haar || p->do_separable) && p->kernel_mode == 0)) {
+                int rc = flush_pending(p, 1, L == 3);
+                if (rc != PWT_OK) return rc;
+            }
             // levels 3..1 in one launch when the fused register cascade covers the configuration
             if (l == 3 && !p->do_swt && (haar || p->do_separable) && p->kernel_mode == 0) {
                 const float* Hs[3] = {p->d_band[1], p->d_band[4], p->d_band[7]};
@@ -646,12 +669,18 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                     p->queue.base = 0;
                 }
                 prof_begin(p, 100 * 3 + 2 + 10);      // tag 312: fused levels 3..1
-                const int n = pwt_fused_dwt_inv3(cur, Hs, Vs, Ds, p->d_image, B, p->Nr, p->Nc, p->filt, haar, &p->queue, st);
+                const int n = pwt_fused_dwt_inv3(cur, Hs, Vs, Ds, p->d_image, B, p->Nr, p->Nc, p->filt, haar, &p->queue,
+                                                 p->pend.op >= 0 ? &fop : nullptr, st);
                 if (n) {
                     prof_end(p);
                     p->launches += n;
                     cur = p->d_image;
+                    p->pend.op = -1;
                     break;
+                }
+                if (p->pend.op >= 0) {                              // not covered after all: apply through memory
+                    int rc = flush_pending(p, 1, L == 3);
+                    if (rc != PWT_OK) return rc;
                 }
             }
             const float* Hb = p->d_band[3 * (l - 1) + 1];
@@ -752,13 +781,39 @@ static int run_thresh(pwt_plan* p, int op, float beta, int app, int normalize, b
         return 1;
     }
     cudaSetDevice(p->device);
+    int rc = flush_pending(p, 1, true);                             // an older pending threshold comes first
+    if (rc != PWT_OK) return rc;
     PwtSegTable t;
     if (op == PWT_OP_SCALE)
         build_thresh_table(p, &t, beta, app, 0, false, true, 1.0f / (1.0f + beta));   // common.cu:355
     else
         build_thresh_table(p, &t, beta, app, normalize, app_scaled, false, 0.f);
+    if ((op == PWT_OP_SOFT || op == PWT_OP_HARD) && p->defer_ok && p->kernel_mode == 0) {
+        // record instead of launching: the fused inverse applies it on load; any observer of the
+        // coefficients (coeffs, norms, pointers, another operator) flushes it to memory first
+        p->pend.op = op;
+        p->pend.app = app ? 1 : 0;
+        int k = 0;
+        p->pend.beta_app = app ? t.seg[k++].beta : 0.f;
+        for (int i = 0; i < p->nlevels; i++, k += 3) p->pend.beta[i] = t.seg[k].beta;
+        return PWT_OK;
+    }
     p->launches += pwt_launch_eltwise(t, op, p->stream);
     CK_LAUNCH();
+    return PWT_OK;
+}
+
+static int flush_pending(pwt_plan* p, int first_level, bool with_app) {
+    if (p->pend.op < 0) return PWT_OK;
+    PwtSegTable t;
+    t.nseg = 0;
+    const long long B = p->batch;
+    if (with_app && p->pend.app) add_seg(&t, p->d_band[0], B * band_elems(p, 0), p->pend.beta_app);
+    for (int i = first_level - 1; i < p->nlevels; i++)
+        for (int j = 1; j <= 3; j++) add_seg(&t, p->d_band[3 * i + j], B * band_elems(p, 3 * i + j), p->pend.beta[i]);
+    p->launches += pwt_launch_eltwise(t, p->pend.op, p->stream);
+    CK_LAUNCH();
+    if (first_level <= 1) p->pend.op = -1;
     return PWT_OK;
 }
 
@@ -783,6 +838,10 @@ extern "C" int pwt_group_soft_threshold(pwt_plan* p, float beta, int app, int no
         return 1;
     }
     cudaSetDevice(p->device);
+    {
+        int rc0 = flush_pending(p, 1, true);
+        if (rc0 != PWT_OK) return rc0;
+    }
     const int L = p->nlevels;
     for (int i = 0; i < L; i++) {
         if (normalize > 0) beta = (float)(beta / kSqrt2);
@@ -801,6 +860,8 @@ extern "C" int pwt_group_soft_threshold(pwt_plan* p, float beta, int app, int no
 
 // ---- norms ------------------------------------------------------------------------------------
 static int local_norms_async(pwt_plan* p) {
+    int rc0 = flush_pending(p, 1, true);
+    if (rc0 != PWT_OK) return rc0;
     PwtSegTable t;
     t.nseg = 0;
     for (int b = 0; b < p->nbands; b++) add_seg(&t, p->d_band[b], (long long)p->batch * band_elems(p, b), 0.f);
@@ -858,6 +919,7 @@ extern "C" int pwt_add_wavelet(pwt_plan* d, const pwt_plan* s, float alpha) {
         return -4;
     }
     cudaSetDevice(d->device);
+    if (flush_pending(d, 1, true) != PWT_OK || flush_pending(const_cast<pwt_plan*>(s), 1, true) != PWT_OK) return PWT_ERR_CUDA;
     cudaStreamSynchronize(s->stream);   // the source's pending work must be visible
     PwtSegTable td, ts;
     td.nseg = ts.nseg = 0;
@@ -902,6 +964,7 @@ extern "C" int pwt_get_coeff(pwt_plan* p, float* dst, int num) {
         return 0;
     }
     cudaSetDevice(p->device);
+    if (flush_pending(p, 1, true) != PWT_OK) return 0;
     const size_t n = (size_t)p->batch * band_elems(p, num);
     if (cudaMemcpyAsync(dst, p->d_band[num], n * sizeof(float), cudaMemcpyDeviceToHost, p->stream) != cudaSuccess ||
         cudaStreamSynchronize(p->stream) != cudaSuccess) {
@@ -914,6 +977,10 @@ extern "C" int pwt_get_coeff(pwt_plan* p, float* dst, int num) {
 extern "C" int pwt_set_coeff(pwt_plan* p, const float* src, int num, int on_device) {
     if (!p || !src || num < 0 || num >= p->nbands) return fail(PWT_ERR_ARG, "bad argument");
     cudaSetDevice(p->device);
+    {
+        int rc0 = flush_pending(p, 1, true);
+        if (rc0 != PWT_OK) return rc0;
+    }
     const size_t n = (size_t)p->batch * band_elems(p, num);
     CK(cudaMemcpyAsync(p->d_band[num], src, n * sizeof(float),
                        on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, p->stream));
@@ -923,7 +990,10 @@ extern "C" int pwt_set_coeff(pwt_plan* p, const float* src, int num, int on_devi
 
 extern "C" intptr_t pwt_image_ptr(pwt_plan* p) { return p ? (intptr_t)p->d_image : 0; }
 extern "C" intptr_t pwt_coeff_ptr(pwt_plan* p, int num) {
-    return (p && num >= 0 && num < p->nbands) ? (intptr_t)p->d_band[num] : 0;
+    if (!p || num < 0 || num >= p->nbands) return 0;
+    cudaSetDevice(p->device);
+    flush_pending(p, 1, true);          // a raw pointer lets the caller see memory: make it current
+    return (intptr_t)p->d_band[num];
 }
 
 // ---- custom filters ---------------------------------------------------------------------------

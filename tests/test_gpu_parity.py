@@ -452,6 +452,52 @@ def test_fused_cascade_is_bit_identical_to_per_level_kernels(wname, shape):
     assert_close(F.image, img, 255.0, "roundtrip")
 
 
+@pytest.mark.parametrize("levels", [3, 5])
+@pytest.mark.parametrize("op,app,normalize", [("soft_threshold", 0, 0), ("soft_threshold", 1, 1),
+                                              ("hard_threshold", 0, 1), ("hard_threshold", 1, 0)])
+@pytest.mark.parametrize("wname", ["haar", "db2", "db3"])
+def test_deferred_threshold_is_unobservable(wname, op, app, normalize, levels):
+    """soft/hard_threshold on a plan served by the fused inverse is recorded and applied while the
+    inverse loads the coefficients.  Every way of observing the coefficients must behave as if the
+    threshold had been applied immediately (compared with the generic path, kernel mode 1)."""
+    img = synth_image((512, 1024), seed=19, kind="smooth")
+    # reference: same kernels level by level (mode 3: no fused cascade, thresholds applied immediately);
+    # its arithmetic is bit-identical to the fused path, so every comparison below is exact
+    D = _W(img, wname, levels); G = _W(img, wname, levels)
+    G.set_kernel_mode(3)
+    D.forward(); G.forward()
+    l0, g0 = D.launch_count, G.launch_count
+    getattr(D, op)(12.0, app, normalize); getattr(G, op)(12.0, app, normalize)
+    assert D.launch_count == l0, "the threshold should have been deferred (no launch)"
+    assert G.launch_count == g0 + 1
+    D.inverse(); G.inverse()                                   # consumed inside the fused inverse
+    assert np.array_equal(D.image, G.image), "deferred threshold + fused inverse != threshold + per-level inverse"
+    # observers flush the pending operator first
+    D.forward(img); G.forward(img)
+    getattr(D, op)(12.0, app, normalize); getattr(G, op)(12.0, app, normalize)
+    assert D.norm1() == G.norm1()
+    cd, cg = D.coeffs, G.coeffs
+    assert np.array_equal(cd[0], cg[0])
+    for i in range(1, levels + 1):
+        for j in range(3):
+            assert np.array_equal(cd[i][j], cg[i][j])
+    # two thresholds in a row: the first is flushed, the second deferred
+    D.forward(img); G.forward(img)
+    D.soft_threshold(5.0); D.hard_threshold(9.0, 1, 0)
+    G.soft_threshold(5.0); G.hard_threshold(9.0, 1, 0)
+    D.inverse(); G.inverse()
+    assert np.array_equal(D.image, G.image)
+    # and against the oracle semantics (generic kernels, immediate threshold), within tolerance
+    R = _W(img, wname, levels)
+    R.set_kernel_mode(1)
+    R.forward(); R.soft_threshold(12.0, app, normalize); R.inverse()
+    D.forward(img); D.soft_threshold(12.0, app, normalize); D.inverse()
+    assert_close(D.image, R.image, 255.0, "deferred soft threshold vs generic")
+    # forward() discards a pending threshold (the coefficients are recomputed)
+    D.forward(img); D.soft_threshold(1e6); D.forward(); D.inverse()
+    assert np.abs(D.image - img).max() < 1e-2
+
+
 @pytest.mark.parametrize("shape", [(256, 512), (200, 300), (2, 96, 128)])
 @pytest.mark.parametrize("wname", ["haar", "db2", "db4", "sym5", "db6"])
 def test_fused_swt_kernels_agree_with_generic(wname, shape):
