@@ -55,6 +55,8 @@ struct Fwd3Args {
     unsigned base;
     int ntasks;            // tasks per image (strips * bands); total = ntasks * batch
     int batch;
+    double* partials;      // [ntasks*batch][2]: per-task sum |c| and sum c^2 of everything the task stored (or null)
+    int count_a3;          // A3 is the final approximation (3-level transform): include it in the sums
 };
 
 // geometry shared by host and device
@@ -192,6 +194,11 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ PwtFilters f)
         return make_float2(lo, hi);
     };
 
+    float nrm1 = 0.f, nrm2 = 0.f;      // this lane's share of sum |c|, sum c^2 over the coefficients it stores
+    auto acc = [&](float c) {
+        nrm1 += fabsf(c);
+        nrm2 = fmaf(c, c, nrm2);
+    };
     constexpr int FW = HAAR ? 2 : F;
     float4 w1[FW];     // level-1 window of horizontally filtered rows: (lo0, lo1, hi0, hi1)
     float2 w2[FW];     // level-2 window: (lo, hi)
@@ -230,6 +237,7 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ PwtFilters f)
             stg2(H1 + o, h0, h1);
             stg2(V1 + o, v0, v1);
             stg2(D1 + o, d0, d1);
+            if (a.partials) { acc(h0); acc(h1); acc(v0); acc(v1); acc(d0); acc(d1); }
         }
 #pragma unroll
         for (int j = 0; j < FW - 2; j++) w1[j] = w1[j + 2];
@@ -291,6 +299,7 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ PwtFilters f)
                     H2[o] = h2;
                     V2[o] = v2;
                     D2p[o] = d2;
+                    if (a.partials) { acc(h2); acc(v2); acc(d2); }
                 }
                 w3[FW - 2 + (t >> 1)] = hpass3(a2);
             }
@@ -303,6 +312,10 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ PwtFilters f)
             H3[o] = h3;
             V3[o] = v3;
             D3[o] = d3;
+            if (a.partials) {
+                acc(h3); acc(v3); acc(d3);
+                if (a.count_a3) acc(a3);
+            }
         }
     };
 
@@ -311,6 +324,18 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ PwtFilters f)
     // iteration() keep it from being stored.  J = ceil((3E + 4C - 3) / 4): 0 (haar), 2 (F=4), 4 (F=6), 6 (F=8).
     constexpr int J = HAAR ? 0 : (3 * E + 4 * C - 3 + 3) / 4;
     for (int n = n0 - J; n < n1; n++) iteration(n, true);
+    if (a.partials) {      // fused norm reduction: warp shuffle, one pair of plain stores per task (no atomics, no memset)
+        double d1 = (double)nrm1, d2 = (double)nrm2;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            d1 += __shfl_xor_sync(FULL, d1, o);
+            d2 += __shfl_xor_sync(FULL, d2, o);
+        }
+        if (lane == 0) {
+            a.partials[2 * (size_t)t_] = d1;
+            a.partials[2 * (size_t)t_ + 1] = d2;
+        }
+    }
   }
 }
 
@@ -337,6 +362,12 @@ int pick_t3(int R3, int strips, int batch, int slots) {
     return 16;
 }
 
+struct NormSink {     // host-side: where the launcher reports how many per-task partial sums were written
+    int cap;
+    int* ntasks_out;
+};
+NormSink g_sink = {0, nullptr};
+
 template <int F, bool HAAR, int MINB, bool PF>
 int launch_fwd3(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cudaStream_t st) {
     a.n3 = HAAR ? 16 : Geo<F>::N3;
@@ -355,6 +386,8 @@ int launch_fwd3(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cud
     a.ntasks = cdiv(W3, a.n3) * cdiv(R3, a.T3);
     a.batch = batch;
     long long total = (long long)a.ntasks * batch;
+    if (total > g_sink.cap) a.partials = nullptr;      // never write past the plan's buffer
+    if (g_sink.ntasks_out) *g_sink.ntasks_out = a.partials ? (int)total : 0;
     int grid = (int)(total < (long long)resident * kWarps ? (total + kWarps - 1) / kWarps : resident);
     a.counter = q->counter;
     a.base = q->base;
@@ -366,9 +399,15 @@ int launch_fwd3(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cud
 }  // namespace
 
 // Levels 1..3 of the forward transform in one launch.  band pointers: H/V/D of levels 1, 2, 3; A3.
+int pwt_fused_fwd3_max_tasks(int batch, int Nr, int Nc) {
+    // upper bound of the task count of one launch (smallest strips of 11 columns, task height >= 4 rows)
+    const long long W3 = Nc / 8, R3 = Nr / 8;
+    return (int)(((W3 + 10) / 11) * ((R3 + 3) / 4) * batch);
+}
+
 int pwt_fused_dwt_fwd3(const float* in, float* A3, float* const* H, float* const* V, float* const* D,
                        int batch, int Nr, int Nc, const PwtFilters& f, bool haar, PwtTaskQueue* q,
-                       cudaStream_t st) {
+                       double* partials, int partials_cap, int count_a3, int* ntasks_out, cudaStream_t st) {
     const int F = haar ? 2 : f.hlen;
     if (env_int("PWT_NO_FUSED", 0)) return 0;
     if (F > 8 || (F & 1) || Nr % 8 != 0 || Nc % 8 != 0 || Nc < 512 || Nr < 64 || batch > 65535) return 0;
@@ -386,6 +425,10 @@ int pwt_fused_dwt_fwd3(const float* in, float* A3, float* const* H, float* const
     a.Nr = Nr;
     a.Nc = Nc;
     a.in_bs = (long long)Nr * Nc;
+    a.partials = partials;
+    a.count_a3 = count_a3;
+    g_sink.cap = partials ? partials_cap : 0;
+    g_sink.ntasks_out = ntasks_out;
     const int variant = env_int("PWT_FUSED_VARIANT", 0);
     if (haar) return launch_fwd3<2, true, 6, false>(a, batch, f, q, st);
     switch (F) {

@@ -155,6 +155,34 @@ k_circshift(const float* __restrict__ in, float* __restrict__ out, int Nr, int N
     }
 }
 
+// adds the per-task partial sums written by the fused forward kernel to acc[0..1]
+__global__ void __launch_bounds__(kThreads) k_reduce_partials(const double* __restrict__ part, int n, double* __restrict__ acc, int add) {
+    double l1 = 0.0, l2 = 0.0;
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+        l1 += part[2 * i];
+        l2 += part[2 * i + 1];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+        l2 += __shfl_xor_sync(0xffffffffu, l2, o);
+    }
+    __shared__ double s1[kThreads / 32], s2[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) {
+        s1[threadIdx.x >> 5] = l1;
+        s2[threadIdx.x >> 5] = l2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kThreads / 32; w++) {
+            l1 += s1[w];
+            l2 += s2[w];
+        }
+        // single thread, stream-ordered after the k_norms of this call when there is one (add != 0)
+        acc[0] = add ? acc[0] + l1 : l1;
+        acc[1] = add ? acc[1] + l2 : l2;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) k_fill(float* p, long long n, float v) {
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n;
          i += (long long)gridDim.x * kThreads)
@@ -222,6 +250,11 @@ int pwt_launch_circshift(const float* in, float* out, int batch, int Nr, int Nc,
                          cudaStream_t st) {
     dim3 grid((Nc + kThreads - 1) / kThreads, Nr < 65535 ? Nr : 65535, batch);
     k_circshift<<<grid, kThreads, 0, st>>>(in, out, Nr, Nc, sr, sc);
+    return 1;
+}
+
+int pwt_launch_reduce_partials(const double* partials, int n, double* d_acc, int add, cudaStream_t st) {
+    k_reduce_partials<<<1, kThreads, 0, st>>>(partials, n, d_acc, add);
     return 1;
 }
 

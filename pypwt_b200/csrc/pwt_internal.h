@@ -114,9 +114,13 @@ struct PwtTaskQueue {
     unsigned* counter;     // device memory, zero-initialised at plan creation
     unsigned base;         // value of *counter when the next launch starts
 };
+// partials (may be null): [tasks][2] doubles receiving each task's sum |c| and sum c^2 of the coefficients it
+// stored (levels 1-3 details, plus A3 when count_a3) -- the norm reduction fused into the transform pass.
+int pwt_fused_fwd3_max_tasks(int batch, int Nr, int Nc);
 int pwt_fused_dwt_fwd3(const float* in, float* A3, float* const* H, float* const* V, float* const* D,
                        int batch, int Nr, int Nc, const PwtFilters& f, bool haar, PwtTaskQueue* q,
-                       cudaStream_t st);
+                       double* partials, int partials_cap, int count_a3, int* ntasks_out, cudaStream_t st);
+int pwt_launch_reduce_partials(const double* partials, int n, double* d_acc, int add, cudaStream_t st);
 // A threshold recorded by soft/hard_threshold() and not yet applied to memory: the fused inverse applies it
 // to the coefficients while loading them (the denoising loop forward -> threshold -> inverse then moves
 // no extra bytes).  beta[l] = threshold of level l+1 details, beta_app = threshold of A (if app).

@@ -104,6 +104,10 @@ struct pwt_plan {
     int band_nr[PWT_MAX_BANDS], band_nc[PWT_MAX_BANDS];
     double* d_acc;      // device accumulators for the norms
     PwtTaskQueue queue; // dynamic task queue of the persistent kernels
+    double* d_partials; // per-task |c|, c^2 sums written by the fused forward (norm reduction fused into the pass)
+    int partials_n;     // > 0: d_partials holds the sums of bands 1..9 (+A if 3 levels) of the CURRENT coefficients
+    int partials_cap;
+    int want_norms;     // norms were requested after a forward: later forwards accumulate them in-kernel (~2 % of the pass)
     PwtDeferredOp pend; // threshold recorded but not yet applied to memory (pend.op < 0: none)
     int defer_ok;       // plan shape for which thresholds may be deferred into the fused inverse
     double* h_acc;      // pinned mirror
@@ -227,6 +231,13 @@ static int alloc_plan(pwt_plan* p) {
     CK(cudaMalloc((void**)&p->d_k2d_fwd, k2d));
     CK(cudaMalloc((void**)&p->d_k2d_inv, k2d));
     CK(cudaMalloc((void**)&p->d_acc, 2 * sizeof(double)));
+    p->partials_cap = (p->ndims == 2 && !p->do_swt && p->nlevels >= 3 && p->Nr % 8 == 0 && p->Nc % 8 == 0)
+                          ? pwt_fused_fwd3_max_tasks(p->batch, p->Nr, p->Nc) : 0;
+    p->d_partials = nullptr;
+    p->partials_n = 0;
+    p->want_norms = 0;
+    if (getenv("PWT_NO_FUSED_NORMS")) p->partials_cap = 0;
+    if (p->partials_cap > 0) CK(cudaMalloc((void**)&p->d_partials, (size_t)p->partials_cap * 2 * sizeof(double)));
     CK(cudaMalloc((void**)&p->queue.counter, sizeof(unsigned)));
     CK(cudaMemsetAsync(p->queue.counter, 0, sizeof(unsigned), p->stream));
     p->queue.base = 0;
@@ -244,6 +255,7 @@ extern "C" void pwt_destroy(pwt_plan* p) {
     if (p->d_k2d_inv) cudaFree(p->d_k2d_inv);
     if (p->d_acc) cudaFree(p->d_acc);
     if (p->queue.counter) cudaFree(p->queue.counter);
+    if (p->d_partials) cudaFree(p->d_partials);
     if (p->h_acc) cudaFreeHost(p->h_acc);
     if (p->d_flush) cudaFree(p->d_flush);
     if (p->prof_ev) {
@@ -381,6 +393,8 @@ extern "C" int pwt_clone(pwt_plan** out, const pwt_plan* src) {
     p->d_k2d_fwd = p->d_k2d_inv = nullptr;
     p->d_acc = nullptr;
     p->queue.counter = nullptr;
+    p->d_partials = nullptr;
+    p->partials_n = 0;
     p->h_acc = nullptr;
     p->d_flush = nullptr;
     p->flush_bytes = 0;
@@ -533,6 +547,7 @@ extern "C" int pwt_forward(pwt_plan* p) {
     if (p->state == PWT_CREATION_ERROR) return fail(PWT_ERR_STATE, "plan is in creation-error state");
     cudaSetDevice(p->device);
     p->pend.op = -1;                                                // the coefficients are about to be overwritten
+    p->partials_n = 0;
     if (p->do_cs) {                                                 // wt.cu:242-246
         p->shift_r = rand() % p->Nr;
         p->shift_c = rand() % p->Nc;
@@ -569,12 +584,15 @@ extern "C" int pwt_forward(pwt_plan* p) {
                 cudaMemsetAsync(p->queue.counter, 0, sizeof(unsigned), st);
                 p->queue.base = 0;
             }
-            const int n = pwt_fused_dwt_fwd3(src, dstA, Hs, Vs, Ds, B, p->Nr, p->Nc, p->filt, haar, &p->queue, st);
+            int ntasks = 0;
+            const int n = pwt_fused_dwt_fwd3(src, dstA, Hs, Vs, Ds, B, p->Nr, p->Nc, p->filt, haar, &p->queue,
+                                             p->want_norms ? p->d_partials : nullptr, p->partials_cap, L == 3, &ntasks, st);
             if (n) {
                 prof_end(p);
                 p->launches += n;
                 src = dstA;
                 l_first = 4;
+                p->partials_n = ntasks;
             }
         }
         for (int l = l_first; l <= L; l++) {
@@ -727,6 +745,7 @@ extern "C" int pwt_inverse(pwt_plan* p) {
         int rc = do_circshift(p, -p->shift_r, -p->shift_c, 1);
         if (rc != PWT_OK) return rc;
     }
+    p->partials_n = 0;
     p->state = PWT_INVERSE;
     return PWT_OK;
 }
@@ -798,6 +817,7 @@ static int run_thresh(pwt_plan* p, int op, float beta, int app, int normalize, b
         for (int i = 0; i < p->nlevels; i++, k += 3) p->pend.beta[i] = t.seg[k].beta;
         return PWT_OK;
     }
+    p->partials_n = 0;
     p->launches += pwt_launch_eltwise(t, op, p->stream);
     CK_LAUNCH();
     return PWT_OK;
@@ -811,6 +831,7 @@ static int flush_pending(pwt_plan* p, int first_level, bool with_app) {
     if (with_app && p->pend.app) add_seg(&t, p->d_band[0], B * band_elems(p, 0), p->pend.beta_app);
     for (int i = first_level - 1; i < p->nlevels; i++)
         for (int j = 1; j <= 3; j++) add_seg(&t, p->d_band[3 * i + j], B * band_elems(p, 3 * i + j), p->pend.beta[i]);
+    p->partials_n = 0;
     p->launches += pwt_launch_eltwise(t, p->pend.op, p->stream);
     CK_LAUNCH();
     if (first_level <= 1) p->pend.op = -1;
@@ -842,6 +863,7 @@ extern "C" int pwt_group_soft_threshold(pwt_plan* p, float beta, int app, int no
         int rc0 = flush_pending(p, 1, true);
         if (rc0 != PWT_OK) return rc0;
     }
+    p->partials_n = 0;
     const int L = p->nlevels;
     for (int i = 0; i < L; i++) {
         if (normalize > 0) beta = (float)(beta / kSqrt2);
@@ -864,8 +886,14 @@ static int local_norms_async(pwt_plan* p) {
     if (rc0 != PWT_OK) return rc0;
     PwtSegTable t;
     t.nseg = 0;
-    for (int b = 0; b < p->nbands; b++) add_seg(&t, p->d_band[b], (long long)p->batch * band_elems(p, b), 0.f);
-    p->launches += pwt_launch_norms(t, p->d_acc, p->stream);
+    // bands 1..9 (and A of a 3-level transform) were already reduced inside the fused forward kernel
+    const bool fusedn = p->partials_n > 0 && p->state == PWT_FORWARD;
+    if (p->state == PWT_FORWARD) p->want_norms = 1;
+    const int first = fusedn ? 10 : 0;
+    if (fusedn && p->nlevels > 3) add_seg(&t, p->d_band[0], (long long)p->batch * band_elems(p, 0), 0.f);
+    for (int b = first; b < p->nbands; b++) add_seg(&t, p->d_band[b], (long long)p->batch * band_elems(p, b), 0.f);
+    if (t.nseg > 0) p->launches += pwt_launch_norms(t, p->d_acc, p->stream);
+    if (fusedn) p->launches += pwt_launch_reduce_partials(p->d_partials, p->partials_n, p->d_acc, t.nseg > 0, p->stream);
     CK_LAUNCH();
     return PWT_OK;
 }
@@ -928,6 +956,7 @@ extern "C" int pwt_add_wavelet(pwt_plan* d, const pwt_plan* s, float alpha) {
         add_seg(&td, d->d_band[b], n, 0.f);
         add_seg(&ts, s->d_band[b], n, 0.f);
     }
+    d->partials_n = 0;
     d->launches += pwt_launch_axpy(td, ts, alpha, d->stream);
     CK_LAUNCH();
     return 0;
@@ -981,6 +1010,7 @@ extern "C" int pwt_set_coeff(pwt_plan* p, const float* src, int num, int on_devi
         int rc0 = flush_pending(p, 1, true);
         if (rc0 != PWT_OK) return rc0;
     }
+    p->partials_n = 0;
     const size_t n = (size_t)p->batch * band_elems(p, num);
     CK(cudaMemcpyAsync(p->d_band[num], src, n * sizeof(float),
                        on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, p->stream));
