@@ -36,6 +36,48 @@ __device__ __forceinline__ void stg2(float* p, float a, float b) { *reinterpret_
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int kWarps = 4;
 
+// ---- asynchronous bulk copies (TMA, SASS UBLKCP) global -> shared, completion on an mbarrier ----
+// Used by the PF ("prefetch") variant of the forward cascade: the input rows of the next two iterations are
+// in flight in a per-warp shared-memory ring while the warp computes, at no register cost.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned mb, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mb, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mb) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mb, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(mb), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ float4 lds4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds1(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(unsigned dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+constexpr int kStages = 2;          // iterations of input rows in flight per warp
+
 __device__ __forceinline__ float comp(const float4& v, int c) {
     return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w));
 }
@@ -57,7 +99,15 @@ struct Fwd3Args {
     int batch;
     double* partials;      // [ntasks*batch][2]: per-task sum |c| and sum c^2 of everything the task stored (or null)
     int count_a3;          // A3 is the final approximation (3-level transform): include it in the sums
+    long long dV[3], dD[3], dA3;   // byte distance from the H plane of a level to its V / D plane (and level-3 H -> A3)
 };
+
+// analysis taps packed for the 2-wide FMA (FFMA2): t[j] = (L[F-1-j], H[F-1-j]).  One FFMA2 multiplies a
+// broadcast sample by the (low-pass, high-pass) pair, so every multiply-add of the cascade is issued 2-wide.
+struct TapsLH {
+    float2 t[8];
+};
+__device__ __forceinline__ float2 fma2s(float x, float2 t, float2 acc) { return __ffma2_rn(make_float2(x, x), t, acc); }
 
 // geometry shared by host and device
 template <int F>
@@ -69,9 +119,9 @@ struct Geo {
     static constexpr int N3 = (63 - O1 - 3 * F / 2 + 4) / 4;
 };
 
-template <int F, bool HAAR, int MINB, bool PF>
+template <int F, bool HAAR, int MINB, int PF, bool NRM>      // PF: 0 direct loads, 1 bulk-copy (TMA) ring, 2 cp.async ring; NRM: accumulate norms
 __global__ void __launch_bounds__(32 * kWarps, MINB)
-k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ PwtFilters f) {
+k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ TapsLH f) {
     using G = Geo<F>;
     constexpr int C = G::C;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -79,6 +129,23 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ PwtFilters f)
     const int W1 = Nc >> 1, W2 = Nc >> 2, W3 = Nc >> 3;
     const int R3 = Nr >> 3;
     const int strips = (W3 + a.n3 - 1) / a.n3;
+    // PF: per-warp ring of kStages x 8 input rows of HB + 128 + HB samples, filled by bulk copies
+    constexpr int HB = (PF && C > 0) ? 4 : 0;                // halo block (16 B aligned) on either side
+    constexpr int ROWB = (128 + 2 * HB) * 4;                 // bytes per staged row
+    __shared__ __align__(128) float ring[PF ? kWarps * kStages * 8 * (128 + 2 * HB) : 1];
+    __shared__ __align__(8) unsigned long long mbars[PF ? kWarps * kStages : 1];
+    const unsigned ring0 = smem_u32(ring) + warp * (kStages * 8 * ROWB);
+    const unsigned mbar0 = smem_u32(mbars) + warp * (kStages * 8);
+    unsigned uses = 0;                                       // stage uses so far: stage = uses % kStages, parity from uses / kStages
+    if (PF == 1) {
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < kStages; s++) mbar_init(mbar0 + 8 * s, 8);     // lanes 0..7 arrive, one row each
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+    }
   for (;;) {
     // persistent warp: pull the next (image, band, strip) task from the queue
     unsigned t_ = 0;
@@ -111,10 +178,12 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ PwtFilters f)
     const int i3 = lane - G::D2;                         // level-3: column c3 + i3/2 lives on lane D2 + 2*i
     const int k3 = c3 + (i3 >> 1);
     const bool own3 = i3 >= 0 && !(i3 & 1) && (i3 >> 1) < n3e;
-    float* H1 = a.H[0] + img * a.bs[0]; float* V1 = a.V[0] + img * a.bs[0]; float* D1 = a.D[0] + img * a.bs[0];
-    float* H2 = a.H[1] + img * a.bs[1]; float* V2 = a.V[1] + img * a.bs[1]; float* D2p = a.D[1] + img * a.bs[1];
-    float* H3 = a.H[2] + img * a.bs[2]; float* V3 = a.V[2] + img * a.bs[2]; float* D3 = a.D[2] + img * a.bs[2];
-    float* A3 = a.A3 + img * a.bs[2];
+    // one pointer per level: the H plane at this lane's column, row 0; a row is reached with a single
+    // multiply-add (IMAD.WIDE), the V / D / A planes with a warp-uniform byte distance
+    char* const q1 = reinterpret_cast<char*>(a.H[0] + img * a.bs[0] + k1);
+    char* const q2 = reinterpret_cast<char*>(a.H[1] + img * a.bs[1] + k2);
+    char* const q3 = reinterpret_cast<char*>(a.H[2] + img * a.bs[2] + k3);
+    const int W1b = W1 * 4, W2b = W2 * 4, W3b = W3 * 4;
 
     // ---- level 1: horizontal pass of one input row (same arithmetic as k_fwd_reg) ----
     // eight consecutive rows starting at rb; the wrap test is hoisted out (uniform)
@@ -150,32 +219,28 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ PwtFilters f)
             ext[i] = first_lane ? e[i] : l;
             ext[C + 4 + i] = last_lane ? e[i] : r;
         }
-        float lo0 = 0.f, lo1 = 0.f, hi0 = 0.f, hi1 = 0.f;
+        float2 p0 = make_float2(0.f, 0.f), p1 = p0;          // (lo0, hi0), (lo1, hi1)
 #pragma unroll
         for (int j = 0; j < F; j++) {
-            const float tl = f.L[F - 1 - j], th = f.H[F - 1 - j];
-            lo0 = fmaf(ext[j], tl, lo0);
-            lo1 = fmaf(ext[j + 2], tl, lo1);
-            hi0 = fmaf(ext[j], th, hi0);
-            hi1 = fmaf(ext[j + 2], th, hi1);
+            p0 = fma2s(ext[j], f.t[j], p0);
+            p1 = fma2s(ext[j + 2], f.t[j], p1);
         }
-        return make_float4(lo0, lo1, hi0, hi1);
+        return make_float4(p0.x, p0.y, p1.x, p1.y);
     };
     // ---- levels 2 and 3: horizontal pass of an approximation row held one/two columns per lane ----
     // level 2: this lane's output column is 2*k2 = its own pair (a0, a1); offset d lives in lane + floor(d/2)
     auto hpass2 = [&](float a0, float a1) -> float2 {
         if (HAAR) return make_float2(a0, a1);
-        float lo = 0.f, hi = 0.f;
+        float2 p = make_float2(0.f, 0.f);                    // (lo, hi)
 #pragma unroll
         for (int j = 0; j < F; j++) {
             const int d = j - C;                         // column offset relative to a0
             const int dl = d >= 0 ? d / 2 : -((1 - d) / 2);   // floor(d / 2)
             const float src = (d & 1) ? a1 : a0;
             const float val = dl == 0 ? src : __shfl_sync(FULL, src, lane + dl);
-            lo = fmaf(val, f.L[F - 1 - j], lo);
-            hi = fmaf(val, f.H[F - 1 - j], hi);
+            p = fma2s(val, f.t[j], p);
         }
-        return make_float2(lo, hi);
+        return p;
     };
     // level 3: one column per lane; column offset d lives in lane + d
     auto hpass3 = [&](float a2) -> float2 {
@@ -183,15 +248,14 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ PwtFilters f)
             const float nb = __shfl_down_sync(FULL, a2, 1);
             return make_float2(a2, nb);
         }
-        float lo = 0.f, hi = 0.f;
+        float2 p = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < F; j++) {
             const int d = j - C;
             const float val = d == 0 ? a2 : __shfl_sync(FULL, a2, lane + d);
-            lo = fmaf(val, f.L[F - 1 - j], lo);
-            hi = fmaf(val, f.H[F - 1 - j], hi);
+            p = fma2s(val, f.t[j], p);
         }
-        return make_float2(lo, hi);
+        return p;
     };
 
     float nrm1 = 0.f, nrm2 = 0.f;      // this lane's share of sum |c|, sum c^2 over the coefficients it stores
@@ -200,7 +264,7 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ PwtFilters f)
         nrm2 = fmaf(c, c, nrm2);
     };
     constexpr int FW = HAAR ? 2 : F;
-    float4 w1[FW];     // level-1 window of horizontally filtered rows: (lo0, lo1, hi0, hi1)
+    float4 w1[FW];     // level-1 window of horizontally filtered rows: (lo0, hi0, lo1, hi1); Haar: raw samples
     float2 w2[FW];     // level-2 window: (lo, hi)
     float2 w3[FW];     // level-3 window
 #pragma unroll
@@ -222,22 +286,23 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ PwtFilters f)
             h0 = 0.5f * (dx + dy); h1 = 0.5f * (dz + dw);
             d0 = 0.5f * (dx - dy); d1 = 0.5f * (dz - dw);
         } else {
-            a0 = a1 = h0 = h1 = v0 = v1 = d0 = d1 = 0.f;
+            float2 ah0 = make_float2(0.f, 0.f), vd0 = ah0, ah1 = ah0, vd1 = ah0;      // (a, h) and (v, d) of both columns
 #pragma unroll
             for (int j = 0; j < F; j++) {
-                const float tl = f.L[F - 1 - j], th = f.H[F - 1 - j];
-                a0 = fmaf(w1[j].x, tl, a0); a1 = fmaf(w1[j].y, tl, a1);
-                h0 = fmaf(w1[j].x, th, h0); h1 = fmaf(w1[j].y, th, h1);
-                v0 = fmaf(w1[j].z, tl, v0); v1 = fmaf(w1[j].w, tl, v1);
-                d0 = fmaf(w1[j].z, th, d0); d1 = fmaf(w1[j].w, th, d1);
+                ah0 = fma2s(w1[j].x, f.t[j], ah0);
+                vd0 = fma2s(w1[j].y, f.t[j], vd0);
+                ah1 = fma2s(w1[j].z, f.t[j], ah1);
+                vd1 = fma2s(w1[j].w, f.t[j], vd1);
             }
+            a0 = ah0.x; h0 = ah0.y; v0 = vd0.x; d0 = vd0.y;
+            a1 = ah1.x; h1 = ah1.y; v1 = vd1.x; d1 = vd1.y;
         }
         if (row_owned && own1) {
-            const int o = krow * W1 + k1;
-            stg2(H1 + o, h0, h1);
-            stg2(V1 + o, v0, v1);
-            stg2(D1 + o, d0, d1);
-            if (a.partials) { acc(h0); acc(h1); acc(v0); acc(v1); acc(d0); acc(d1); }
+            char* r = q1 + (long long)krow * (long long)W1b;
+            stg2(reinterpret_cast<float*>(r), h0, h1);
+            stg2(reinterpret_cast<float*>(r + a.dV[0]), v0, v1);
+            stg2(reinterpret_cast<float*>(r + a.dD[0]), d0, d1);
+            if (NRM) { acc(h0); acc(h1); acc(v0); acc(v1); acc(d0); acc(d1); }
         }
 #pragma unroll
         for (int j = 0; j < FW - 2; j++) w1[j] = w1[j + 2];
@@ -248,15 +313,13 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ PwtFilters f)
             av = 0.5f * (sp + sq); vv = 0.5f * (sp - sq);
             hv = 0.5f * (dp + dq); dv = 0.5f * (dp - dq);
         } else {
-            av = hv = vv = dv = 0.f;
+            float2 ah = make_float2(0.f, 0.f), vd = ah;
 #pragma unroll
             for (int j = 0; j < F; j++) {
-                const float tl = f.L[F - 1 - j], th = f.H[F - 1 - j];
-                av = fmaf(w[j].x, tl, av);
-                hv = fmaf(w[j].x, th, hv);
-                vv = fmaf(w[j].y, tl, vv);
-                dv = fmaf(w[j].y, th, dv);
+                ah = fma2s(w[j].x, f.t[j], ah);
+                vd = fma2s(w[j].y, f.t[j], vd);
             }
+            av = ah.x; hv = ah.y; vv = vd.x; dv = vd.y;
         }
 #pragma unroll
         for (int j = 0; j < FW - 2; j++) w[j] = w[j + 2];
@@ -275,13 +338,58 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ PwtFilters f)
     // input rows of iteration n start at rbase(n); PREFETCH: the 8 rows of iteration n+1 are requested
     // before iteration n is computed (template parameter PF), so a warp always has loads in flight.
     auto rbase_of = [&](int n) { return 2 * (2 * (2 * n + E - 1) + E - 1) + E - 1; };
+    // PF: the strip's HB + 128 + HB columns of a row are one contiguous piece of memory, or two when the
+    // strip straddles the periodic wrap (first / last strip); all pieces are multiples of 16 bytes
+    const int s0 = wrap1_per(X0 - HB, Nc);
+    const int len0 = min(128 + 2 * HB, Nc - s0);
+    const unsigned eoff = lane == 0 ? (HB - C) * 4 : (lane == 31 ? (HB + 128) * 4 : 0);   // other lanes: one broadcast word
+    auto issue_rows = [&](int n, unsigned stage) {           // lanes 0..7 request one row each of iteration n
+        if (PF == 2) {                                       // cp.async: every lane copies exactly the bytes it will read
+            const int rb = rbase_of(n);
+            const bool inside = rb >= 0 && rb + 8 <= Nr;
+            const unsigned dst = ring0 + stage * (8 * ROWB);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float* src = in + (long long)(inside ? rb + i : wrap1_per(rb + i, Nr)) * Nc;
+                cp_async16(dst + i * ROWB + HB * 4 + 16 * lane, src + xcol);
+                if (C > 0 && (lane == 0 || lane == 31)) {
+#pragma unroll
+                    for (int c = 0; c < C; c++) cp_async4(dst + i * ROWB + eoff + 4 * c, src + ecol[c]);
+                }
+            }
+        } else if (lane < 8) {
+            const float* src = in + (long long)wrap1_per(rbase_of(n) + lane, Nr) * Nc;
+            const unsigned dst = ring0 + (stage * 8 + lane) * ROWB;
+            const unsigned mb = mbar0 + 8 * stage;
+            mbar_expect_tx(mb, ROWB);
+            bulk_g2s(dst, src + s0, len0 * 4, mb);
+            if (len0 < 128 + 2 * HB) bulk_g2s(dst + len0 * 4, src, ROWB - len0 * 4, mb);
+        }
+    };
     auto iteration = [&](int n, bool store_ok) {
         // level-2 rows produced here: m0 = 2n + E - 1, m1 = 2n + E ; level-1 rows: k = 2*m0 + E - 1 .. 2*m1 + E
         const int m0 = 2 * n + E - 1;
         const int kbase = 2 * m0 + E - 1;                 // four level-1 rows kbase .. kbase+3
         float4 v[8];
         float e[8][C > 0 ? C : 1];
-        load_rows8(rbase_of(n), v, e);
+        if (PF) {
+            const unsigned stage = uses % kStages, parity = (uses / kStages) & 1;
+            const unsigned base = ring0 + stage * (8 * ROWB);
+            if (PF == 1) mbar_wait(mbar0 + 8 * stage, parity);
+            else cp_async_wait<kStages - 1>();                // this lane's own copies of iteration n have landed
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                v[i] = lds4(base + i * ROWB + HB * 4 + 16 * lane);
+#pragma unroll
+                for (int c = 0; c < C; c++) e[i][c] = lds1(base + i * ROWB + eoff + 4 * c);
+            }
+            if (PF == 1) __syncwarp();                        // every lane has its copy: the stage may be refilled
+            if (n + kStages < n1) issue_rows(n + kStages, stage);
+            if (PF == 2) cp_async_commit();                   // (possibly empty) group: keeps the group count uniform
+            uses++;
+        } else {
+            load_rows8(rbase_of(n), v, e);
+        }
 #pragma unroll
         for (int t = 0; t < 4; t++) {
             w1[FW - 2] = hpass1(v[2 * t], e[2 * t]);
@@ -295,11 +403,11 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ PwtFilters f)
                 float a2, h2, v2, d2;
                 vstep23(w2, a2, h2, v2, d2);
                 if (store_ok && own2 && m >= 2 * n0 && m < 2 * n1) {
-                    const int o = m * W2 + k2;
-                    H2[o] = h2;
-                    V2[o] = v2;
-                    D2p[o] = d2;
-                    if (a.partials) { acc(h2); acc(v2); acc(d2); }
+                    char* r = q2 + (long long)m * (long long)W2b;
+                    *reinterpret_cast<float*>(r) = h2;
+                    *reinterpret_cast<float*>(r + a.dV[1]) = v2;
+                    *reinterpret_cast<float*>(r + a.dD[1]) = d2;
+                    if (NRM) { acc(h2); acc(v2); acc(d2); }
                 }
                 w3[FW - 2 + (t >> 1)] = hpass3(a2);
             }
@@ -307,12 +415,12 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ PwtFilters f)
         float a3, h3, v3, d3;
         vstep23(w3, a3, h3, v3, d3);
         if (store_ok && own3 && n >= n0 && n < n1) {
-            const int o = n * W3 + k3;
-            A3[o] = a3;
-            H3[o] = h3;
-            V3[o] = v3;
-            D3[o] = d3;
-            if (a.partials) {
+            char* r = q3 + (long long)n * (long long)W3b;
+            *reinterpret_cast<float*>(r + a.dA3) = a3;
+            *reinterpret_cast<float*>(r) = h3;
+            *reinterpret_cast<float*>(r + a.dV[2]) = v3;
+            *reinterpret_cast<float*>(r + a.dD[2]) = d3;
+            if (NRM) {
                 acc(h3); acc(v3); acc(d3);
                 if (a.count_a3) acc(a3);
             }
@@ -323,8 +431,15 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ PwtFilters f)
     // incomplete window belongs to rows this task does not own, and the ownership tests inside
     // iteration() keep it from being stored.  J = ceil((3E + 4C - 3) / 4): 0 (haar), 2 (F=4), 4 (F=6), 6 (F=8).
     constexpr int J = HAAR ? 0 : (3 * E + 4 * C - 3 + 3) / 4;
+    if (PF) {
+#pragma unroll
+        for (int s = 0; s < kStages; s++) {
+            if (n0 - J + s < n1) issue_rows(n0 - J + s, (uses + s) % kStages);
+            if (PF == 2) cp_async_commit();
+        }
+    }
     for (int n = n0 - J; n < n1; n++) iteration(n, true);
-    if (a.partials) {      // fused norm reduction: warp shuffle, one pair of plain stores per task (no atomics, no memset)
+    if (NRM) {             // fused norm reduction: warp shuffle, one pair of plain stores per task (no atomics, no memset)
         double d1 = (double)nrm1, d2 = (double)nrm2;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -368,8 +483,8 @@ struct NormSink {     // host-side: where the launcher reports how many per-task
 };
 NormSink g_sink = {0, nullptr};
 
-template <int F, bool HAAR, int MINB, bool PF>
-int launch_fwd3(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cudaStream_t st) {
+template <int F, bool HAAR, int MINB, int PF, bool NRM>
+int launch_fwd3n(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cudaStream_t st) {
     a.n3 = HAAR ? 16 : Geo<F>::N3;
     const int W3 = a.Nc / 8, R3 = a.Nr / 8;
     static int resident = 0;
@@ -377,7 +492,7 @@ int launch_fwd3(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cud
         int dev = 0, sms = 148, per_sm = 1;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fwd3<F, HAAR, MINB, PF>, 32 * kWarps, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fwd3<F, HAAR, MINB, PF, NRM>, 32 * kWarps, 0);
         resident = sms * (per_sm > 0 ? per_sm : 1);
     }
     // task height: as tall as possible (less warm-up) while every resident warp still gets a task
@@ -386,14 +501,26 @@ int launch_fwd3(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cud
     a.ntasks = cdiv(W3, a.n3) * cdiv(R3, a.T3);
     a.batch = batch;
     long long total = (long long)a.ntasks * batch;
-    if (total > g_sink.cap) a.partials = nullptr;      // never write past the plan's buffer
-    if (g_sink.ntasks_out) *g_sink.ntasks_out = a.partials ? (int)total : 0;
+    if (NRM && total > g_sink.cap) {                   // never write past the plan's buffer
+        a.partials = nullptr;
+        if constexpr (NRM) return launch_fwd3n<F, HAAR, MINB, PF, false>(a, batch, f, q, st);
+    }
+    if (g_sink.ntasks_out) *g_sink.ntasks_out = NRM ? (int)total : 0;
     int grid = (int)(total < (long long)resident * kWarps ? (total + kWarps - 1) / kWarps : resident);
     a.counter = q->counter;
     a.base = q->base;
     q->base += (unsigned)total + (unsigned)grid * kWarps;      // every warp makes exactly one failing pull
-    k_fwd3<F, HAAR, MINB, PF><<<grid, 32 * kWarps, 0, st>>>(a, f);
+    TapsLH taps;
+    for (int j = 0; j < 8; j++) taps.t[j] = (!HAAR && j < F) ? make_float2(f.L[F - 1 - j], f.H[F - 1 - j]) : make_float2(0.f, 0.f);
+    k_fwd3<F, HAAR, MINB, PF, NRM><<<grid, 32 * kWarps, 0, st>>>(a, taps);
     return 1;
+}
+
+template <int F, bool HAAR, int MINB, int PF>
+int launch_fwd3(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cudaStream_t st) {
+    // the norm accumulation is compiled in only when the plan asked for it (~2 % of the pass)
+    return a.partials ? launch_fwd3n<F, HAAR, MINB, PF, true>(a, batch, f, q, st)
+                      : launch_fwd3n<F, HAAR, MINB, PF, false>(a, batch, f, q, st);
 }
 
 }  // namespace
@@ -420,8 +547,11 @@ int pwt_fused_dwt_fwd3(const float* in, float* A3, float* const* H, float* const
         a.V[l] = V[l];
         a.D[l] = D[l];
         a.bs[l] = (long long)(Nr >> (l + 1)) * (Nc >> (l + 1));
+        a.dV[l] = (long long)((const char*)V[l] - (const char*)H[l]);
+        a.dD[l] = (long long)((const char*)D[l] - (const char*)H[l]);
         if (((uintptr_t)H[l] | (uintptr_t)V[l] | (uintptr_t)D[l]) & 7) return 0;
     }
+    a.dA3 = (long long)((const char*)A3 - (const char*)H[2]);
     a.Nr = Nr;
     a.Nc = Nc;
     a.in_bs = (long long)Nr * Nc;
@@ -430,14 +560,18 @@ int pwt_fused_dwt_fwd3(const float* in, float* A3, float* const* H, float* const
     g_sink.cap = partials ? partials_cap : 0;
     g_sink.ntasks_out = ntasks_out;
     const int variant = env_int("PWT_FUSED_VARIANT", 0);
-    if (haar) return launch_fwd3<2, true, 6, false>(a, batch, f, q, st);
+    if (haar) return launch_fwd3<2, true, 6, 0>(a, batch, f, q, st);
     switch (F) {
         case 4:
-            if (variant == 2) return launch_fwd3<4, false, 5, false>(a, batch, f, q, st);
-            if (variant == 3) return launch_fwd3<4, false, 6, false>(a, batch, f, q, st);
-            return launch_fwd3<4, false, 4, false>(a, batch, f, q, st);
-        case 6: return launch_fwd3<6, false, 3, false>(a, batch, f, q, st);
-        case 8: return launch_fwd3<8, false, 3, false>(a, batch, f, q, st);
+            if (variant == 2) return launch_fwd3<4, false, 5, 0>(a, batch, f, q, st);
+            if (variant == 3) return launch_fwd3<4, false, 6, 0>(a, batch, f, q, st);
+            if (variant == 4) return launch_fwd3<4, false, 4, 1>(a, batch, f, q, st);
+            if (variant == 5) return launch_fwd3<4, false, 4, 2>(a, batch, f, q, st);
+            if (variant == 6) return launch_fwd3<4, false, 3, 0>(a, batch, f, q, st);
+            if (variant == 7) return launch_fwd3<4, false, 2, 0>(a, batch, f, q, st);
+            return launch_fwd3<4, false, 4, 0>(a, batch, f, q, st);
+        case 6: return launch_fwd3<6, false, 3, 0>(a, batch, f, q, st);
+        case 8: return launch_fwd3<8, false, 3, 0>(a, batch, f, q, st);
         default: return 0;
     }
 }
