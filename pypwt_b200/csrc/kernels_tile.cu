@@ -2,7 +2,10 @@
 // register-blocked accumulators.  At these lengths the transform is FMA-bound (2F FMA per pixel and
 // direction: db20 = 213 FMA/px for a 3-level fwd+inv), so the design goal is FMA issue efficiency:
 // every 128-bit shared-memory read feeds 16-32 FMAs, taps are constant-bank operands (full unroll),
-// no sliding-window register shuffling.
+// no sliding-window register shuffling.  Every multiply-add is issued 2-wide (FFMA2, sm_100): one sample times
+// a packed pair of taps -- (low-pass, high-pass) in the analysis, (even-phase, odd-phase) in the synthesis.
+// FFMA2 has half the issue rate of FFMA (same FMA-pipe throughput, tools/bench/fma2bench.cu), so this
+// halves the issue slots the arithmetic needs and leaves them to the shared-memory reads.
 //   forward : stage the haloed input tile (wrap / odd sizes resolved while staging), row pass IN PLACE
 //             (one warp per tile row: each lane reads its window, then the row is overwritten with its
 //             lo | hi halves), column pass streaming over the F+2 rows of an output-row pair.
@@ -31,6 +34,28 @@ __device__ __forceinline__ void fma4(float4& acc, const float4& v, float t) {
     acc.w = fmaf(v.w, t, acc.w);
 }
 
+// asynchronous global -> shared copies (LDGSTS): the whole haloed tile is requested back to back, so the
+// staging phase costs about one memory latency instead of one per row
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ float2 fma2s(float x, float2 t, float2 acc) { return __ffma2_rn(make_float2(x, x), t, acc); }
+
+// analysis taps, reversed and interleaved: t[j] = (L[F-1-j], H[F-1-j])
+struct TapsFwd {
+    float2 t[PWT_MAX_TAPS];
+};
+// synthesis taps by window position w = band offset + S1: l[w] = (IL[2*je+E0] | 0, IL[2*jo+E1] | 0) with
+// je = S0 + S1 - w (even output phase), jo = 2*S1 - w (odd output phase); h[w] likewise from IH
+struct TapsInv {
+    float2 l[PWT_MAX_TAPS / 2 + 2], h[PWT_MAX_TAPS / 2 + 2];
+};
+
 constexpr int NT = 256;
 constexpr int TX = 64;        // forward: output columns per tile (one warp row = 32 lanes x 2 outputs)
 constexpr int TY = 32;        // forward: output rows per tile (16 row pairs x 16 column groups = 256 items)
@@ -50,7 +75,7 @@ template <int F>
 __global__ void __launch_bounds__(NT)
 k_tile_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ Hb, float* __restrict__ V,
            float* __restrict__ D, int Nr, int Nc, long long in_bs, long long out_bs,
-           const __grid_constant__ PwtFilters f) {
+           const __grid_constant__ TapsFwd f) {
     using G = FwdGeo<F>;
     constexpr int C = G::C, CL = G::CL, DX = G::DX, IH = G::IH, IW = G::IW, P = G::P;
     constexpr int IW4 = (IW + 3) / 4;
@@ -72,12 +97,12 @@ k_tile_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restric
     for (int r = warp; r < IH; r += NT / 32) {
         const float* row = in + (long long)wrap_dwt(2 * ky0 - C + r, Nr) * Nc;
         if (vec) {
-            for (int c4 = lane; c4 < IW4; c4 += 32)
-                *reinterpret_cast<float4*>(s + r * P + 4 * c4) = __ldg(reinterpret_cast<const float4*>(row + xs) + c4);
+            for (int c4 = lane; c4 < IW4; c4 += 32) cp_async16(s + r * P + 4 * c4, row + xs + 4 * c4);
         } else {
-            for (int cc = lane; cc < IW; cc += 32) s[r * P + cc] = __ldg(row + colidx[cc]);
+            for (int cc = lane; cc < IW; cc += 32) cp_async4(s + r * P + cc, row + colidx[cc]);
         }
     }
+    cp_async_wait_all();
     __syncthreads();
     // ---- row pass, in place: lane l owns outputs 2l, 2l+1 of the row; window = s[r][4l .. 4l+F+1] ----
     constexpr int NV = (DX + F + 2 + 3) / 4;
@@ -88,39 +113,49 @@ k_tile_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restric
             const float4 v = *reinterpret_cast<const float4*>(s + r * P + 4 * lane + 4 * k);
             win[4 * k] = v.x; win[4 * k + 1] = v.y; win[4 * k + 2] = v.z; win[4 * k + 3] = v.w;
         }
-        float lo0 = 0.f, lo1 = 0.f, hi0 = 0.f, hi1 = 0.f;
+        float2 p0 = make_float2(0.f, 0.f), p1 = p0;            // (lo, hi) of outputs 2l and 2l+1
 #pragma unroll
         for (int j = 0; j < F; j++) {
-            const float tl = f.L[F - 1 - j], th = f.H[F - 1 - j];
-            lo0 = fmaf(win[DX + j], tl, lo0);
-            lo1 = fmaf(win[DX + j + 2], tl, lo1);
-            hi0 = fmaf(win[DX + j], th, hi0);
-            hi1 = fmaf(win[DX + j + 2], th, hi1);
+            p0 = fma2s(win[DX + j], f.t[j], p0);
+            p1 = fma2s(win[DX + j + 2], f.t[j], p1);
         }
         __syncwarp();                                           // everybody has read the row
-        *reinterpret_cast<float2*>(s + r * P + 2 * lane) = make_float2(lo0, lo1);
-        *reinterpret_cast<float2*>(s + r * P + TX + 2 * lane) = make_float2(hi0, hi1);
+        *reinterpret_cast<float2*>(s + r * P + 2 * lane) = make_float2(p0.x, p1.x);
+        *reinterpret_cast<float2*>(s + r * P + TX + 2 * lane) = make_float2(p0.y, p1.y);
     }
     __syncthreads();
     // ---- column pass: item = (4 columns, 2 output rows); streams over the F+2 rows it needs ----
     {
         const int g = tid & 15, yp = tid >> 4;                  // column group, row pair
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 a0 = z, h0 = z, v0 = z, d0 = z, a1 = z, h1 = z, v1 = z, d1 = z;
+        // accumulators: (a, h) pairs from the low-pass rows, (v, d) pairs from the high-pass rows, 4 columns, 2 rows
+        float2 ah0[4], vd0[4], ah1[4], vd1[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) ah0[c] = vd0[c] = ah1[c] = vd1[c] = make_float2(0.f, 0.f);
         const float* pl = s + (4 * yp) * P + 4 * g;
 #pragma unroll
         for (int m = 0; m < F + 2; m++) {
             const float4 l = *reinterpret_cast<const float4*>(pl + m * P);
             const float4 h = *reinterpret_cast<const float4*>(pl + m * P + TX);
+            const float lc[4] = {l.x, l.y, l.z, l.w}, hc[4] = {h.x, h.y, h.z, h.w};
             if (m < F) {
-                const float tl = f.L[F - 1 - m], th = f.H[F - 1 - m];
-                fma4(a0, l, tl); fma4(h0, l, th); fma4(v0, h, tl); fma4(d0, h, th);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    ah0[c] = fma2s(lc[c], f.t[m], ah0[c]);
+                    vd0[c] = fma2s(hc[c], f.t[m], vd0[c]);
+                }
             }
             if (m >= 2) {
-                const float tl = f.L[F + 1 - m], th = f.H[F + 1 - m];
-                fma4(a1, l, tl); fma4(h1, l, th); fma4(v1, h, tl); fma4(d1, h, th);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    ah1[c] = fma2s(lc[c], f.t[m - 2], ah1[c]);
+                    vd1[c] = fma2s(hc[c], f.t[m - 2], vd1[c]);
+                }
             }
         }
+        const float4 a0 = make_float4(ah0[0].x, ah0[1].x, ah0[2].x, ah0[3].x), h0 = make_float4(ah0[0].y, ah0[1].y, ah0[2].y, ah0[3].y);
+        const float4 v0 = make_float4(vd0[0].x, vd0[1].x, vd0[2].x, vd0[3].x), d0 = make_float4(vd0[0].y, vd0[1].y, vd0[2].y, vd0[3].y);
+        const float4 a1 = make_float4(ah1[0].x, ah1[1].x, ah1[2].x, ah1[3].x), h1 = make_float4(ah1[0].y, ah1[1].y, ah1[2].y, ah1[3].y);
+        const float4 v1 = make_float4(vd1[0].x, vd1[1].x, vd1[2].x, vd1[3].x), d1 = make_float4(vd1[0].y, vd1[1].y, vd1[2].y, vd1[3].y);
         const int kx = kx0 + 4 * g;
 #pragma unroll
         for (int rr = 0; rr < 2; rr++) {
@@ -165,7 +200,7 @@ template <int F>
 __global__ void __launch_bounds__(NT)
 k_tile_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float* __restrict__ V,
            const float* __restrict__ D, float* __restrict__ out, int nr, int nc, int Nr_out, int Nc_out,
-           long long in_bs, long long out_bs, const __grid_constant__ PwtFilters f) {
+           long long in_bs, long long out_bs, const __grid_constant__ TapsInv f) {
     using G = InvGeo<F>;
     constexpr int HALF = G::HALF, S0 = G::S0, E0 = G::E0, S1 = G::S1, E1 = G::E1;
     constexpr int HL = G::HL, HLr = G::HLr, BH = G::BH, BW = G::BW, P = G::P;
@@ -191,19 +226,20 @@ k_tile_inv(const float* __restrict__ A, const float* __restrict__ Hb, const floa
         const float* row = bands[b] + (long long)wrap_per(y0 - HL + rr, nr) * nc;
         float* dst = sb + (b * BH + rr) * P;
         if (vec) {
-            for (int c4 = lane; c4 < BW / 4; c4 += 32)
-                *reinterpret_cast<float4*>(dst + 4 * c4) = __ldg(reinterpret_cast<const float4*>(row + xs) + c4);
+            for (int c4 = lane; c4 < BW / 4; c4 += 32) cp_async16(dst + 4 * c4, row + xs + 4 * c4);
         } else {
-            for (int cc = lane; cc < BW; cc += 32) dst[cc] = __ldg(row + colidx[cc]);
+            for (int cc = lane; cc < BW; cc += 32) cp_async4(dst + cc, row + colidx[cc]);
         }
     }
+    cp_async_wait_all();
     __syncthreads();
     // ---- column synthesis: item = (4 band columns incl. halo, band row q) -> t1/t2 rows 2q, 2q+1 ----
     constexpr int NG = BW / 4;
     for (int it = tid; it < NG * BY; it += NT) {
         const int g = it % NG, q = it / NG;
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 t1e = z, t1o = z, t2e = z, t2o = z;
+        float2 t1[4], t2[4];                                    // (even row, odd row) of t1 / t2, 4 columns
+#pragma unroll
+        for (int c = 0; c < 4; c++) t1[c] = t2[c] = make_float2(0.f, 0.f);
         // band rows q - S1 .. q + S1 (local rows q .. q + 2*HL), window index w <-> band row q - S1 + w
         const float* pa = sb + (0 * BH + q) * P + 4 * g;
         const float* ph = sb + (1 * BH + q) * P + 4 * g;
@@ -219,20 +255,21 @@ k_tile_inv(const float* __restrict__ A, const float* __restrict__ Hb, const floa
                 const float4 vh = *reinterpret_cast<const float4*>(ph + w * P);
                 const float4 vv = *reinterpret_cast<const float4*>(pv + w * P);
                 const float4 vd = *reinterpret_cast<const float4*>(pd + w * P);
-                if (ue) {
-                    const float tl = f.IL[2 * je + E0], th = f.IH[2 * je + E0];
-                    fma4(t1e, va, tl); fma4(t1e, vh, th); fma4(t2e, vv, tl); fma4(t2e, vd, th);
-                }
-                if (uo) {
-                    const float tl = f.IL[2 * jo + E1], th = f.IH[2 * jo + E1];
-                    fma4(t1o, va, tl); fma4(t1o, vh, th); fma4(t2o, vv, tl); fma4(t2o, vd, th);
+                const float ca[4] = {va.x, va.y, va.z, va.w}, ch[4] = {vh.x, vh.y, vh.z, vh.w};
+                const float cv[4] = {vv.x, vv.y, vv.z, vv.w}, cd[4] = {vd.x, vd.y, vd.z, vd.w};
+#pragma unroll
+                for (int c = 0; c < 4; c++) {                   // a tap that a phase does not use is 0 in the table
+                    t1[c] = fma2s(ca[c], f.l[w], t1[c]);
+                    t1[c] = fma2s(ch[c], f.h[w], t1[c]);
+                    t2[c] = fma2s(cv[c], f.l[w], t2[c]);
+                    t2[c] = fma2s(cd[c], f.h[w], t2[c]);
                 }
             }
         }
-        *reinterpret_cast<float4*>(st + (2 * q) * P + 4 * g) = t1e;
-        *reinterpret_cast<float4*>(st + (2 * q + 1) * P + 4 * g) = t1o;
-        *reinterpret_cast<float4*>(st + (2 * BY + 2 * q) * P + 4 * g) = t2e;
-        *reinterpret_cast<float4*>(st + (2 * BY + 2 * q + 1) * P + 4 * g) = t2o;
+        *reinterpret_cast<float4*>(st + (2 * q) * P + 4 * g) = make_float4(t1[0].x, t1[1].x, t1[2].x, t1[3].x);
+        *reinterpret_cast<float4*>(st + (2 * q + 1) * P + 4 * g) = make_float4(t1[0].y, t1[1].y, t1[2].y, t1[3].y);
+        *reinterpret_cast<float4*>(st + (2 * BY + 2 * q) * P + 4 * g) = make_float4(t2[0].x, t2[1].x, t2[2].x, t2[3].x);
+        *reinterpret_cast<float4*>(st + (2 * BY + 2 * q + 1) * P + 4 * g) = make_float4(t2[0].y, t2[1].y, t2[2].y, t2[3].y);
     }
     __syncthreads();
     // ---- row synthesis: item = (output row n, 4 band columns) -> 8 output columns ----
@@ -252,16 +289,19 @@ k_tile_inv(const float* __restrict__ A, const float* __restrict__ Hb, const floa
         float o[8];
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            float e = 0.f, od = 0.f;
+            // sample at band offset k = w - S1 feeds the even output with jj = S0 - k and the odd one with
+            // jj = S1 - k; walking w downwards keeps the reference's summation order (jj ascending)
+            float2 eo = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int jj = 0; jj < HALF; jj++) {
-                e = fmaf(v1[HLr + c + S0 - jj], f.IL[2 * jj + E0], e);
-                e = fmaf(v2[HLr + c + S0 - jj], f.IH[2 * jj + E0], e);
-                od = fmaf(v1[HLr + c + S1 - jj], f.IL[2 * jj + E1], od);
-                od = fmaf(v2[HLr + c + S1 - jj], f.IH[2 * jj + E1], od);
+            for (int w = 2 * HL; w >= 0; w--) {
+                const int je = S0 + S1 - w, jo = 2 * S1 - w;
+                if ((je >= 0 && je < HALF) || (jo >= 0 && jo < HALF)) {
+                    eo = fma2s(v1[HLr + c + w - S1], f.l[w], eo);
+                    eo = fma2s(v2[HLr + c + w - S1], f.h[w], eo);
+                }
             }
-            o[2 * c] = e;
-            o[2 * c + 1] = od;
+            o[2 * c] = eo.x;
+            o[2 * c + 1] = eo.y;
         }
         const int gx = 2 * (x0 + 4 * u);
         float* dst = out + (long long)gy * Nc_out + gx;
@@ -287,7 +327,9 @@ int launch_fwd(const float* in, float* A, float* Hb, float* V, float* D, int bat
         done = true;
     }
     dim3 grid(cdiv((Nc + 1) / 2, TX), cdiv((Nr + 1) / 2, TY), batch);
-    k_tile_fwd<F><<<grid, NT, FwdGeo<F>::smem, st>>>(in, A, Hb, V, D, Nr, Nc, in_bs, out_bs, f);
+    TapsFwd t;
+    for (int j = 0; j < PWT_MAX_TAPS; j++) t.t[j] = j < F ? make_float2(f.L[F - 1 - j], f.H[F - 1 - j]) : make_float2(0.f, 0.f);
+    k_tile_fwd<F><<<grid, NT, FwdGeo<F>::smem, st>>>(in, A, Hb, V, D, Nr, Nc, in_bs, out_bs, t);
     return 1;
 }
 template <int F>
@@ -300,7 +342,15 @@ int launch_inv(const float* A, const float* Hb, const float* V, const float* D, 
         done = true;
     }
     dim3 grid(cdiv(nc, BX), cdiv(nr, BY), batch);
-    k_tile_inv<F><<<grid, NT, InvGeo<F>::smem, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f);
+    using G = InvGeo<F>;
+    TapsInv t;
+    for (int w = 0; w < PWT_MAX_TAPS / 2 + 2; w++) {
+        const int je = G::S0 + G::S1 - w, jo = 2 * G::S1 - w;
+        const bool ue = je >= 0 && je < G::HALF, uo = jo >= 0 && jo < G::HALF;
+        t.l[w] = make_float2(ue ? f.IL[2 * je + G::E0] : 0.f, uo ? f.IL[2 * jo + G::E1] : 0.f);
+        t.h[w] = make_float2(ue ? f.IH[2 * je + G::E0] : 0.f, uo ? f.IH[2 * jo + G::E1] : 0.f);
+    }
+    k_tile_inv<F><<<grid, NT, InvGeo<F>::smem, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out, in_bs, out_bs, t);
     return 1;
 }
 
