@@ -130,55 +130,137 @@ k_swt_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict
     }
 }
 
-// ---- inverse: A, H, V, D -> out (rows first: u1 = syn_x(A, V), u2 = syn_x(H, D); then columns) ----
-template <int F, int SMODE, int MINB>
+// ---- inverse: A, H, V, D -> out ---------------------------------------------------------------
+// Columns first, like the reference (separable.cu:553-626): t1 = syn_y(A, H), t2 = syn_y(V, D), then
+// out = syn_x(t1, t2).  The column synthesis runs in TRANSPOSED form: a thread keeps the F pending output
+// rows of t1 and t2 as accumulators and adds every band row it loads to all of them, so each coefficient
+// is read from memory exactly once (4 x 128-bit loads per lattice row and thread; the direct form would
+// need 4 sliding windows = 4F vector registers).  That single visit is also where a deferred soft / hard
+// threshold is applied (THR), at no extra traffic.  Finished t1/t2 rows go through a double-buffered
+// shared-memory row (one barrier per output row) for the dilated row synthesis; column strips overlap by
+// the reach of the row filter (C*s on the left, (F/2-1)*s on the right), recomputed instead of exchanged.
+template <int THR>
+__device__ __forceinline__ float thr1(float v, float beta) {
+    // common.cu:19 (soft) / common.cu:63 (hard, strict >)
+    if (THR == 1) return copysignf(fmaxf(fabsf(v) - beta, 0.0f), v);
+    return (fabsf(v) - beta > 0.0f) ? v : 0.0f * v;
+}
+template <int THR>
+__device__ __forceinline__ float4 thr4(float4 v, float b) {
+    return make_float4(thr1<THR>(v.x, b), thr1<THR>(v.y, b), thr1<THR>(v.z, b), thr1<THR>(v.w, b));
+}
+
+struct SwtThr {
+    float beta;       // detail bands of this level
+    float beta_app;   // approximation (only when app != 0: coarsest level of a thresholded-approximation call)
+    int app;
+};
+
+template <int F, int SMODE>
+struct SwtInvGeo {
+    static constexpr int C = F / 2;                                          // separable.cu:565-568
+    static constexpr int S = SMODE;                                          // 1, 2, or 0 (runtime s, s % 4 == 0)
+};
+__host__ __device__ inline int swt_halo_l(int F, int s) { return ((F / 2) * s + 3) & ~3; }
+__host__ __device__ inline int swt_halo_r(int F, int s) { return ((F / 2 - 1) * s + 3) & ~3; }
+
+template <int F, int SMODE, int MINB, int THR>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_swt_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float* __restrict__ V,
-          const float* __restrict__ D, float* __restrict__ out, const SwtGeom g,
+          const float* __restrict__ D, float* __restrict__ out, const SwtGeom g, const SwtThr thr,
           const __grid_constant__ PwtFilters f) {
-    constexpr int C = F / 2;                                 // separable.cu:565-568
+    constexpr int C = F / 2;
     const int Nr = g.Nr, Nc = g.Nc, s = g.s;
+    const int HLa = swt_halo_l(F, s), HRa = swt_halo_r(F, s);
+    const int OWN = 4 * kThreads - HLa - HRa;                // columns a strip owns (stores)
     const int strip = blockIdx.x % g.strips;
     const int rc = blockIdx.x / g.strips;
-    const int r = rc % s, chunk = rc / s;
-    const int x = strip * (4 * kThreads) + 4 * threadIdx.x;
+    const int r = rc % s, chunk = rc / s;                    // residue class of rows, chunk along the lattice
     const int nq = (Nr - r + s - 1) / s;
     const int q0 = chunk * g.TQ;
-    if (x >= Nc || q0 >= nq) return;
+    if (q0 >= nq) return;                                    // CTA-uniform
     const int q1 = min(q0 + g.TQ, nq);
+    const int tid = threadIdx.x;
+    const int lc = 4 * tid;                                  // local column of this thread's vector
+    const int xg = strip * OWN - HLa + lc;                   // global column (may lie outside [0, Nc): wraps)
+    int xw = xg % Nc;
+    if (xw < 0) xw += Nc;                                    // Nc % 4 == 0: a vector never straddles the wrap
+    const bool own = lc >= HLa && lc < HLa + OWN && xg < Nc;
     const long long ib = blockIdx.y * g.plane;
-    A += ib; Hb += ib; V += ib; D += ib; out += ib;
+    A += ib + xw; Hb += ib + xw; V += ib + xw; D += ib + xw;
+    out += ib + xw;
 
-    float4 w1[F], w2[F];
+    __shared__ float4 sbuf[2][2][kThreads];                  // [buffer][t1 | t2][thread]
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto hrow = [&](int yy, float4& u1, float4& u2) {
-        const long long ro = (long long)yy * Nc;
-        float4 t = z;                                        // every tap carries a factor 1/2 (separable.cu:621-622)
-        u1 = z; u2 = z;
-        row_filter<F, C, SMODE>(A + ro, x, Nc, s, f.IL, f.IL, 0.5f, u1, t);
-        t = z;
-        row_filter<F, C, SMODE>(V + ro, x, Nc, s, f.IH, f.IH, 0.5f, u1, t);
-        t = z;
-        row_filter<F, C, SMODE>(Hb + ro, x, Nc, s, f.IL, f.IL, 0.5f, u2, t);
-        t = z;
-        row_filter<F, C, SMODE>(D + ro, x, Nc, s, f.IH, f.IH, 0.5f, u2, t);
-    };
+    float4 acc1[F], acc2[F];                                 // pending rows of t1 / t2; slot 0 completes next
 #pragma unroll
-    for (int j = 0; j < F - 1; j++) hrow(wrap1_per(r + (q0 + j - C) * s, Nr), w1[j], w2[j]);
-    for (int q = q0; q < q1; q++) {
-        hrow(wrap1_per(r + (q + F - 1 - C) * s, Nr), w1[F - 1], w2[F - 1]);
-        float4 o = z;
-#pragma unroll
-        for (int j = 0; j < F; j++) {
-            fma4(o, w1[j], 0.5f * f.IL[F - 1 - j]);
-            fma4(o, w2[j], 0.5f * f.IH[F - 1 - j]);
+    for (int i = 0; i < F; i++) acc1[i] = acc2[i] = z;
+    int buf = 0;
+    for (int m = q0 - C; m <= q1 - 1 + (F - 1 - C); m++) {   // input lattice index
+        const long long ro = (long long)wrap1_per(r + m * s, Nr) * Nc;
+        float4 a = ldg4(A + ro), h = ldg4(Hb + ro), v = ldg4(V + ro), d = ldg4(D + ro);
+        if (THR) {
+            h = thr4<THR>(h, thr.beta);
+            v = thr4<THR>(v, thr.beta);
+            d = thr4<THR>(d, thr.beta);
+            if (thr.app) a = thr4<THR>(a, thr.beta_app);
         }
-        stg4(out + (long long)(r + q * s) * Nc + x, o);
+        // input m feeds output q = m - j + C with tap IL[F-1-j] / 2; slot i = F-1-j  (separable.cu:621-622)
 #pragma unroll
-        for (int j = 0; j < F - 1; j++) {
-            w1[j] = w1[j + 1];
-            w2[j] = w2[j + 1];
+        for (int i = 0; i < F; i++) {
+            const float cl = 0.5f * f.IL[i], ch = 0.5f * f.IH[i];
+            fma4(acc1[i], a, cl);
+            fma4(acc1[i], h, ch);
+            fma4(acc2[i], v, cl);
+            fma4(acc2[i], d, ch);
         }
+        const int q = m - (F - 1) + C;                       // the output row that is complete now
+        if (q >= q0) {                                       // CTA-uniform
+            sbuf[buf][0][tid] = acc1[0];
+            sbuf[buf][1][tid] = acc2[0];
+            __syncthreads();
+            if (own) {
+                float4 o = z;
+                if (SMODE == 0) {
+                    const int step = s >> 2;                 // vectors per tap
+#pragma unroll
+                    for (int j = 0; j < F; j++) {
+                        const int k = tid + (j - C) * step;
+                        fma4(o, sbuf[buf][0][k], 0.5f * f.IL[F - 1 - j]);
+                        fma4(o, sbuf[buf][1][k], 0.5f * f.IH[F - 1 - j]);
+                    }
+                } else {
+                    constexpr int S = SMODE;
+                    constexpr int BL = ((C * S + 3) / 4) * 4, BR = (((F - 1 - C) * S + 3) / 4) * 4;
+                    constexpr int NE = (BL + 4 + BR) / 4;
+                    float e1[4 * NE], e2[4 * NE];
+#pragma unroll
+                    for (int k = 0; k < NE; k++) {
+                        const float4 p1 = sbuf[buf][0][tid - BL / 4 + k], p2 = sbuf[buf][1][tid - BL / 4 + k];
+                        e1[4 * k] = p1.x; e1[4 * k + 1] = p1.y; e1[4 * k + 2] = p1.z; e1[4 * k + 3] = p1.w;
+                        e2[4 * k] = p2.x; e2[4 * k + 1] = p2.y; e2[4 * k + 2] = p2.z; e2[4 * k + 3] = p2.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < F; j++) {
+                        const float tl = 0.5f * f.IL[F - 1 - j], th = 0.5f * f.IH[F - 1 - j];
+                        const int o0 = BL + (j - C) * S;
+                        o.x = fmaf(e1[o0], tl, o.x);     o.x = fmaf(e2[o0], th, o.x);
+                        o.y = fmaf(e1[o0 + 1], tl, o.y); o.y = fmaf(e2[o0 + 1], th, o.y);
+                        o.z = fmaf(e1[o0 + 2], tl, o.z); o.z = fmaf(e2[o0 + 2], th, o.z);
+                        o.w = fmaf(e1[o0 + 3], tl, o.w); o.w = fmaf(e2[o0 + 3], th, o.w);
+                    }
+                }
+                stg4(out + (long long)(r + q * s) * Nc, o);
+            }
+            buf ^= 1;
+        }
+#pragma unroll
+        for (int i = 0; i < F - 1; i++) {
+            acc1[i] = acc1[i + 1];
+            acc2[i] = acc2[i + 1];
+        }
+        acc1[F - 1] = z;
+        acc2[F - 1] = z;
     }
 }
 
@@ -210,15 +292,25 @@ int launch_fwd(const float* in, float* A, float* Hb, float* V, float* D, int bat
     else k_swt_fwd<F, 0, MINB><<<grid, kThreads, 0, st>>>(in, A, Hb, V, D, g, f);
     return 1;
 }
+template <int F, int MINB, int THR>
+int launch_inv_t(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch, int Nr,
+                 int Nc, int level, const PwtFilters& f, const SwtThr& thr, cudaStream_t st) {
+    SwtGeom g = make_geom(Nr, Nc, level);
+    const int own = 4 * kThreads - swt_halo_l(F, g.s) - swt_halo_r(F, g.s);
+    if (own < 2 * kThreads) return 0;                        // dilation too large for overlapping strips
+    g.strips = cdiv(Nc, own);
+    dim3 grid(g.strips * g.s * g.chunks, batch);
+    if (g.s == 1) k_swt_inv<F, 1, MINB, THR><<<grid, kThreads, 0, st>>>(A, Hb, V, D, out, g, thr, f);
+    else if (g.s == 2) k_swt_inv<F, 2, MINB, THR><<<grid, kThreads, 0, st>>>(A, Hb, V, D, out, g, thr, f);
+    else k_swt_inv<F, 0, MINB, THR><<<grid, kThreads, 0, st>>>(A, Hb, V, D, out, g, thr, f);
+    return 1;
+}
 template <int F, int MINB>
 int launch_inv(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch, int Nr,
-               int Nc, int level, const PwtFilters& f, cudaStream_t st) {
-    const SwtGeom g = make_geom(Nr, Nc, level);
-    dim3 grid(g.strips * g.s * g.chunks, batch);
-    if (g.s == 1) k_swt_inv<F, 1, MINB><<<grid, kThreads, 0, st>>>(A, Hb, V, D, out, g, f);
-    else if (g.s == 2) k_swt_inv<F, 2, MINB><<<grid, kThreads, 0, st>>>(A, Hb, V, D, out, g, f);
-    else k_swt_inv<F, 0, MINB><<<grid, kThreads, 0, st>>>(A, Hb, V, D, out, g, f);
-    return 1;
+               int Nc, int level, const PwtFilters& f, int thr_op, const SwtThr& thr, cudaStream_t st) {
+    if (thr_op == PWT_OP_SOFT) return launch_inv_t<F, MINB, 1>(A, Hb, V, D, out, batch, Nr, Nc, level, f, thr, st);
+    if (thr_op == PWT_OP_HARD) return launch_inv_t<F, MINB, 2>(A, Hb, V, D, out, batch, Nr, Nc, level, f, thr, st);
+    return launch_inv_t<F, MINB, 0>(A, Hb, V, D, out, batch, Nr, Nc, level, f, thr, st);
 }
 
 bool covered(int F, int batch, int Nr, int Nc, int level, const void* p0, const void* p1) {
@@ -249,18 +341,33 @@ int pwt_fast_swt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D,
     }
 }
 
-int pwt_fast_swt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
-                       int Nr, int Nc, int level, const PwtFilters& f, cudaStream_t st) {
-    const int F = f.hlen;
+// Can the fused inverse run this level (and therefore apply a deferred threshold while loading)?
+int pwt_fast_swt_inv2d_covers(int batch, int Nr, int Nc, int level, const PwtFilters& f, const void* A,
+                              const void* out) {
+    const int F = f.hlen, s = 1 << (level - 1);
     if (!covered(F, batch, Nr, Nc, level, A, out) || out == A) return 0;
+    return 4 * kThreads - swt_halo_l(F, s) - swt_halo_r(F, s) >= 2 * kThreads;
+}
+
+// thr_op < 0: no deferred operator; otherwise PWT_OP_SOFT / PWT_OP_HARD with beta (details of this level) and,
+// when app != 0, beta_app for the approximation input.
+int pwt_fast_swt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
+                       int Nr, int Nc, int level, const PwtFilters& f, int thr_op, float beta, int app,
+                       float beta_app, cudaStream_t st) {
+    const int F = f.hlen;
+    if (!pwt_fast_swt_inv2d_covers(batch, Nr, Nc, level, f, A, out)) return 0;
     if ((((uintptr_t)Hb | (uintptr_t)V | (uintptr_t)D) & 15) != 0) return 0;
+    SwtThr thr;
+    thr.beta = beta;
+    thr.beta_app = beta_app;
+    thr.app = app;
     switch (F) {
-        case 2: return launch_inv<2, 4>(A, Hb, V, D, out, batch, Nr, Nc, level, f, st);
-        case 4: return launch_inv<4, 4>(A, Hb, V, D, out, batch, Nr, Nc, level, f, st);
-        case 6: return launch_inv<6, 3>(A, Hb, V, D, out, batch, Nr, Nc, level, f, st);
-        case 8: return launch_inv<8, 3>(A, Hb, V, D, out, batch, Nr, Nc, level, f, st);
-        case 10: return launch_inv<10, 2>(A, Hb, V, D, out, batch, Nr, Nc, level, f, st);
-        case 12: return launch_inv<12, 2>(A, Hb, V, D, out, batch, Nr, Nc, level, f, st);
+        case 2: return launch_inv<2, 4>(A, Hb, V, D, out, batch, Nr, Nc, level, f, thr_op, thr, st);
+        case 4: return launch_inv<4, 4>(A, Hb, V, D, out, batch, Nr, Nc, level, f, thr_op, thr, st);
+        case 6: return launch_inv<6, 3>(A, Hb, V, D, out, batch, Nr, Nc, level, f, thr_op, thr, st);
+        case 8: return launch_inv<8, 3>(A, Hb, V, D, out, batch, Nr, Nc, level, f, thr_op, thr, st);
+        case 10: return launch_inv<10, 2>(A, Hb, V, D, out, batch, Nr, Nc, level, f, thr_op, thr, st);
+        case 12: return launch_inv<12, 2>(A, Hb, V, D, out, batch, Nr, Nc, level, f, thr_op, thr, st);
         default: return 0;
     }
 }

@@ -46,15 +46,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 __device__ __forceinline__ float2 fma2s(float x, float2 t, float2 acc) { return __ffma2_rn(make_float2(x, x), t, acc); }
 
-// analysis taps, reversed and interleaved: t[j] = (L[F-1-j], H[F-1-j])
-struct TapsFwd {
-    float2 t[PWT_MAX_TAPS];
-};
-// synthesis taps by window position w = band offset + S1: l[w] = (IL[2*je+E0] | 0, IL[2*jo+E1] | 0) with
-// je = S0 + S1 - w (even output phase), jo = 2*S1 - w (odd output phase); h[w] likewise from IH
-struct TapsInv {
-    float2 l[PWT_MAX_TAPS / 2 + 2], h[PWT_MAX_TAPS / 2 + 2];
-};
+using TapsFwd = PwtTapsFwd;
+using TapsInv = PwtTapsInv;
 
 constexpr int NT = 256;
 constexpr int TX = 64;        // forward: output columns per tile (one warp row = 32 lanes x 2 outputs)
@@ -327,8 +320,7 @@ int launch_fwd(const float* in, float* A, float* Hb, float* V, float* D, int bat
         done = true;
     }
     dim3 grid(cdiv((Nc + 1) / 2, TX), cdiv((Nr + 1) / 2, TY), batch);
-    TapsFwd t;
-    for (int j = 0; j < PWT_MAX_TAPS; j++) t.t[j] = j < F ? make_float2(f.L[F - 1 - j], f.H[F - 1 - j]) : make_float2(0.f, 0.f);
+    const TapsFwd t = pwt_pack_taps_fwd(f, F);
     k_tile_fwd<F><<<grid, NT, FwdGeo<F>::smem, st>>>(in, A, Hb, V, D, Nr, Nc, in_bs, out_bs, t);
     return 1;
 }
@@ -342,14 +334,7 @@ int launch_inv(const float* A, const float* Hb, const float* V, const float* D, 
         done = true;
     }
     dim3 grid(cdiv(nc, BX), cdiv(nr, BY), batch);
-    using G = InvGeo<F>;
-    TapsInv t;
-    for (int w = 0; w < PWT_MAX_TAPS / 2 + 2; w++) {
-        const int je = G::S0 + G::S1 - w, jo = 2 * G::S1 - w;
-        const bool ue = je >= 0 && je < G::HALF, uo = jo >= 0 && jo < G::HALF;
-        t.l[w] = make_float2(ue ? f.IL[2 * je + G::E0] : 0.f, uo ? f.IL[2 * jo + G::E1] : 0.f);
-        t.h[w] = make_float2(ue ? f.IH[2 * je + G::E0] : 0.f, uo ? f.IH[2 * jo + G::E1] : 0.f);
-    }
+    const TapsInv t = pwt_pack_taps_inv(f, F);
     k_tile_inv<F><<<grid, NT, InvGeo<F>::smem, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out, in_bs, out_bs, t);
     return 1;
 }

@@ -18,6 +18,38 @@ struct PwtFilters {
     int hlen;
 };
 
+// Taps packed for the 2-wide FMA of sm_100 (FFMA2: one sample times a pair of taps).  FFMA2 issues at half the
+// rate of FFMA with the same FMA-pipe throughput (tools/bench/fma2bench.cu): it halves the issue slots the
+// arithmetic needs.  The summation order of every output is the reference's; taps a phase does not use are 0.
+struct PwtTapsFwd {           // analysis, reversed and interleaved: t[j] = (L[F-1-j], H[F-1-j])
+    float2 t[PWT_MAX_TAPS];
+};
+struct PwtTapsInv {           // synthesis by window position w (band offset + S1), (even phase, odd phase):
+    float2 l[PWT_MAX_TAPS / 2 + 2];   //   l[w] = (IL[2*je+E0], IL[2*jo+E1]),  je = S0+S1-w, jo = 2*S1-w
+    float2 h[PWT_MAX_TAPS / 2 + 2];   //   h[w] likewise from IH
+};
+static inline PwtTapsFwd pwt_pack_taps_fwd(const PwtFilters& f, int F) {
+    PwtTapsFwd t;
+    for (int j = 0; j < PWT_MAX_TAPS; j++) {
+        t.t[j].x = j < F ? f.L[F - 1 - j] : 0.f;
+        t.t[j].y = j < F ? f.H[F - 1 - j] : 0.f;
+    }
+    return t;
+}
+static inline PwtTapsInv pwt_pack_taps_inv(const PwtFilters& f, int F) {
+    const int P = F / 2 - 1, HALF = F / 2, S0 = P >> 1, E0 = P & 1, S1 = (P + 1) >> 1, E1 = (P + 1) & 1;
+    PwtTapsInv t;
+    for (int w = 0; w < PWT_MAX_TAPS / 2 + 2; w++) {
+        const int je = S0 + S1 - w, jo = 2 * S1 - w;
+        const bool ue = je >= 0 && je < HALF, uo = jo >= 0 && jo < HALF;
+        t.l[w].x = ue ? f.IL[2 * je + E0] : 0.f;
+        t.l[w].y = uo ? f.IL[2 * jo + E1] : 0.f;
+        t.h[w].x = ue ? f.IH[2 * je + E0] : 0.f;
+        t.h[w].y = uo ? f.IH[2 * jo + E1] : 0.f;
+    }
+    return t;
+}
+
 // Geometry of one 2D plane set processed by a launch (all strides in elements).
 struct PwtPlane {
     int nr, nc;               // rows, cols of ONE image of the stack
@@ -137,8 +169,11 @@ int pwt_fused_dwt_inv3(const float* A3, const float* const* H, const float* cons
 // kernels_swt.cu : fused (row + column) a-trous level in registers.  Return 0 when not covered.
 int pwt_fast_swt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
                        int level, const PwtFilters& f, cudaStream_t st);
+int pwt_fast_swt_inv2d_covers(int batch, int Nr, int Nc, int level, const PwtFilters& f, const void* A,
+                              const void* out);
 int pwt_fast_swt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
-                       int Nr, int Nc, int level, const PwtFilters& f, cudaStream_t st);
+                       int Nr, int Nc, int level, const PwtFilters& f, int thr_op, float beta, int app,
+                       float beta_app, cudaStream_t st);
 
 // kernels_tile.cu : compile-time F = 10..40 shared-memory tile kernels (FMA-bound regime), any size.
 int pwt_tile_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,

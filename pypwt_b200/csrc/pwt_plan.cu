@@ -110,6 +110,7 @@ struct pwt_plan {
     int want_norms;     // norms were requested after a forward: later forwards accumulate them in-kernel (~2 % of the pass)
     PwtDeferredOp pend; // threshold recorded but not yet applied to memory (pend.op < 0: none)
     int defer_ok;       // plan shape for which thresholds may be deferred into the fused inverse
+    int defer_swt_ok;   // SWT plan whose every level is served by the fused SWT inverse (threshold applied on load)
     double* h_acc;      // pinned mirror
     void* d_flush;
     size_t flush_bytes;
@@ -205,6 +206,14 @@ static void compute_geometry(pwt_plan* p) {
     p->band_nc[0] = p->lvNc[L];
 }
 
+// every level of a separable 2D SWT plan is served by the fused SWT inverse (re-evaluated when filters change)
+static int swt_all_levels_fused(const pwt_plan* p) {
+    if (!(p->ndims == 2 && p->do_swt && p->do_separable)) return 0;
+    for (int l = 1; l <= p->nlevels; l++)
+        if (!pwt_fast_swt_inv2d_covers(p->batch, p->Nr, p->Nc, l, p->filt, p->d_band[0], p->d_image)) return 0;
+    return 1;
+}
+
 static int alloc_plan(pwt_plan* p) {
     const size_t B = (size_t)p->batch;
     const size_t img = align64(B * img_elems(p));
@@ -242,6 +251,8 @@ static int alloc_plan(pwt_plan* p) {
     CK(cudaMemsetAsync(p->queue.counter, 0, sizeof(unsigned), p->stream));
     p->queue.base = 0;
     CK(cudaMallocHost((void**)&p->h_acc, 2 * sizeof(double)));
+    // SWT plans whose every level the fused inverse serves may defer thresholds into it (pointers are known now)
+    p->defer_swt_ok = swt_all_levels_fused(p) && !getenv("PWT_NO_DEFER");
     return PWT_OK;
 }
 
@@ -667,13 +678,18 @@ extern "C" int pwt_inverse(pwt_plan* p) {
     } else {
         const long long plane = (long long)B * img_elems(p);
         PwtDeferredOp fop = p->pend;                                // what the fused launch applies while loading
-        if (p->pend.op >= 0 && L > 3) {
+        const bool swt_defer = p->pend.op >= 0 && p->defer_swt_ok && p->kernel_mode == 0 && swt_all_levels_fused(p);
+        if (p->pend.op >= 0 && p->do_swt && !swt_defer) {
+            int rc = flush_pending(p, 1, true);
+            if (rc != PWT_OK) return rc;
+        }
+        if (p->pend.op >= 0 && !p->do_swt && L > 3) {
             int rc = flush_pending(p, 4, true);                     // coarser levels + A go through memory (1/64 of the data)
             if (rc != PWT_OK) return rc;
             fop.app = 0;
         }
         for (int l = L; l >= 1; l--) {
-            if (l == 3 && p->pend.op >= 0 && !(!p->do_swt && (haar || p->do_separable) && p->kernel_mode == 0)) {
+            if (l == 3 && p->pend.op >= 0 && !p->do_swt && !((haar || p->do_separable) && p->kernel_mode == 0)) {
                 int rc = flush_pending(p, 1, L == 3);
                 if (rc != PWT_OK) return rc;
             }
@@ -709,7 +725,15 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                 float* alt = p->d_tmp + 2 * plane;
                 float* dst = (l == 1) ? p->d_image : (cur == p->d_band[0] ? alt : p->d_band[0]);
                 if (p->do_separable) {
-                    int n = p->kernel_mode == 1 ? 0 : pwt_fast_swt_inv2d(cur, Hb, V, D, dst, B, p->Nr, p->Nc, l, p->filt, st);
+                    int n = 0;
+                    if (p->kernel_mode != 1) {
+                        if (swt_defer)      // the deferred threshold of this level is applied while its bands are loaded
+                            n = pwt_fast_swt_inv2d(cur, Hb, V, D, dst, B, p->Nr, p->Nc, l, p->filt, fop.op, fop.beta[l - 1],
+                                                   l == L && fop.app, fop.beta_app, st);
+                        else
+                            n = pwt_fast_swt_inv2d(cur, Hb, V, D, dst, B, p->Nr, p->Nc, l, p->filt, -1, 0.f, 0, 0.f, st);
+                    }
+                    if (!n && swt_defer) return fail(PWT_ERR_CUDA, "fused SWT inverse declined a level it had accepted");
                     if (!n) n = pwt_launch_swt_inv2d(cur, Hb, V, D, dst, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
                     p->launches += n;
                 }
@@ -741,6 +765,7 @@ extern "C" int pwt_inverse(pwt_plan* p) {
         }
     }
     CK_LAUNCH();
+    if (p->do_swt) p->pend.op = -1;                                 // consumed by the fused SWT inverse (or flushed above)
     if (p->do_cs) {                                                 // wt.cu:303
         int rc = do_circshift(p, -p->shift_r, -p->shift_c, 1);
         if (rc != PWT_OK) return rc;
@@ -807,7 +832,7 @@ static int run_thresh(pwt_plan* p, int op, float beta, int app, int normalize, b
         build_thresh_table(p, &t, beta, app, 0, false, true, 1.0f / (1.0f + beta));   // common.cu:355
     else
         build_thresh_table(p, &t, beta, app, normalize, app_scaled, false, 0.f);
-    if ((op == PWT_OP_SOFT || op == PWT_OP_HARD) && p->defer_ok && p->kernel_mode == 0) {
+    if ((op == PWT_OP_SOFT || op == PWT_OP_HARD) && (p->defer_ok || p->defer_swt_ok) && p->kernel_mode == 0) {
         // record instead of launching: the fused inverse applies it on load; any observer of the
         // coefficients (coeffs, norms, pointers, another operator) flushes it to memory first
         p->pend.op = op;

@@ -598,3 +598,45 @@ def test_fused_norms_batched():
     n, g = D.norms(), G.norms()
     assert D.launch_count - l0 == 1
     assert abs(n[0] - g[0]) <= 2e-6 * g[0] and abs(n[1] - g[1]) <= 2e-6 * g[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("op,app,normalize", [("soft_threshold", 0, 0), ("soft_threshold", 1, 1),
+                                              ("hard_threshold", 0, 1), ("hard_threshold", 1, 0)])
+@pytest.mark.parametrize("wname,shape", [("haar", (256, 512)), ("db2", (200, 300 * 4)), ("db4", (256, 2048)),
+                                         ("db6", (2, 96, 640))])
+def test_swt_deferred_threshold_is_unobservable(wname, shape, op, app, normalize):
+    """SWT plans served by the fused inverse record soft/hard thresholds and apply them while the
+    inverse loads each band (once per coefficient).  Same contract as the decimated transform: the
+    result equals thresholding in memory first (kernel mode 3: same kernels, immediate threshold),
+    and every observer of the coefficients sees the thresholded values."""
+    img = synth_image(shape, seed=29, kind="smooth")
+    D = _W(img, wname, 4, do_swt=1); G = _W(img, wname, 4, do_swt=1)
+    G.set_kernel_mode(3)
+    D.forward(); G.forward()
+    l0, g0 = D.launch_count, G.launch_count
+    getattr(D, op)(9.0, app, normalize); getattr(G, op)(9.0, app, normalize)
+    assert D.launch_count == l0, "the threshold should have been deferred (no launch)"
+    assert G.launch_count == g0 + 1
+    D.inverse(); G.inverse()
+    assert np.array_equal(D.image, G.image)
+    # observers flush
+    D.forward(img); G.forward(img)
+    getattr(D, op)(9.0, app, normalize); getattr(G, op)(9.0, app, normalize)
+    cd, cg = D.coeffs, G.coeffs
+    assert np.array_equal(cd[0], cg[0])
+    for i in range(1, D.levels + 1):
+        for j in range(3):
+            assert np.array_equal(cd[i][j], cg[i][j])
+    D.inverse(); G.inverse()                                   # flushed: nothing left to apply
+    assert np.array_equal(D.image, G.image)
+    # against the generic kernels (oracle arithmetic order), within tolerance
+    R = _W(img, wname, 4, do_swt=1)
+    R.set_kernel_mode(1)
+    R.forward(); getattr(R, op)(9.0, app, normalize); R.inverse()
+    D.forward(img); getattr(D, op)(9.0, app, normalize); D.inverse()
+    if op == "soft_threshold":                                  # hard threshold: last-bit differences flip samples
+        assert_close(D.image, R.image, 255.0, "deferred SWT soft threshold vs generic")
+    # forward() discards a pending threshold
+    D.forward(img); D.soft_threshold(1e6); D.forward(); D.inverse()
+    assert np.abs(D.image - img).max() < 2e-2
