@@ -4,16 +4,16 @@
 //   inverse  x[g]   = sum_j (fl[F-1-j]/2) * a[(g + (j-F/2)*s) mod N] + (fh[F-1-j]/2) * d[...]  separable.cu:553-626
 //
 // Design (B200): no decimation means 4 output planes per input plane (20 B/px/level compulsory), so the
-// kernel must not add intermediate planes (the reference, and our generic fallback, write and re-read
-// two full-size row-pass planes: 36 B/px/level).  One thread owns 4 adjacent columns:
-//   * row pass straight from global memory: the F taps of a dilated filter are F aligned 128-bit loads
-//     at x + (j-c)*s (s % 4 == 0; periodic wrap is just the address) or the few aligned vectors covering
-//     the window (s = 1, 2); neighbouring threads re-read the same lines from L1, DRAM sees each once;
-//   * column pass as a sliding window in registers over the LATTICE rows y0 + k*s (a task walks one
-//     residue class of rows), exactly like the decimated register kernels.
-// No shared memory, no barriers, 128-bit coalesced stores of the four bands.
-// The inverse runs rows first, then columns (the reference runs columns first); fp32 rounding differs
-// in the last bits only.
+// kernels must not add intermediate planes (the reference, and our generic fallback, write and re-read
+// two full-size row-pass planes: 36 B/px/level).  One thread owns 4 adjacent columns of a column strip and
+// a CTA walks one residue class of rows (the lattice y = r + q*s), so the dilated column filter is an
+// ordinary sliding window in registers.  The dilated ROW filter needs the neighbours' samples: each row is
+// published once through a double-buffered shared-memory row (one barrier per row), every tap is an aligned
+// 128-bit shared load at +-(j*s/4) vectors (s % 4 == 0) or comes from the few aligned vectors covering the
+// window (s = 1, 2).  Each sample is read from HBM exactly once, with the next row's load already in flight.
+//   forward : row filter (shared row) -> column sliding window (registers) -> 4 x 128-bit stores
+//   inverse : column synthesis in transposed form (F pending output rows as accumulators) -> row synthesis
+//             from the shared row; a deferred soft/hard threshold is applied to the bands as they are loaded.
 #include <stdlib.h>
 
 #include "pwt_internal.h"
@@ -36,41 +36,6 @@ __device__ __forceinline__ void fma4(float4& acc, const float4& v, float t) {
 
 constexpr int kThreads = 128;
 
-// Row filtering of one plane row for this thread's 4 columns with two filters (fa, fb):
-//   ra[i] = sum_j fa[F-1-j] * row[(x + i + (j-C)*s) mod Nc], rb likewise.      SMODE: 1 -> s=1, 2 -> s=2, 0 -> s%4==0
-template <int F, int C, int SMODE>
-__device__ __forceinline__ void row_filter(const float* __restrict__ row, int x, int Nc, int s, const float* fa,
-                                           const float* fb, float scale, float4& ra, float4& rb) {
-    if (SMODE == 0) {
-#pragma unroll
-        for (int j = 0; j < F; j++) {
-            const float4 v = ldg4(row + wrap1_per(x + (j - C) * s, Nc));
-            fma4(ra, v, scale * fa[F - 1 - j]);
-            fma4(rb, v, scale * fb[F - 1 - j]);
-        }
-    } else {
-        constexpr int S = SMODE;
-        constexpr int BL = ((C * S + 3) / 4) * 4;                       // aligned reach to the left
-        constexpr int BR = (((F - 1 - C) * S + 3) / 4) * 4;             // and to the right
-        constexpr int NE = (BL + 4 + BR) / 4;
-        float ext[4 * NE];
-#pragma unroll
-        for (int k = 0; k < NE; k++) {
-            const float4 v = ldg4(row + wrap1_per(x - BL + 4 * k, Nc));
-            ext[4 * k] = v.x; ext[4 * k + 1] = v.y; ext[4 * k + 2] = v.z; ext[4 * k + 3] = v.w;
-        }
-#pragma unroll
-        for (int j = 0; j < F; j++) {
-            const float ta = scale * fa[F - 1 - j], tb = scale * fb[F - 1 - j];
-            const int o = BL + (j - C) * S;
-            ra.x = fmaf(ext[o], ta, ra.x);     rb.x = fmaf(ext[o], tb, rb.x);
-            ra.y = fmaf(ext[o + 1], ta, ra.y); rb.y = fmaf(ext[o + 1], tb, rb.y);
-            ra.z = fmaf(ext[o + 2], ta, ra.z); rb.z = fmaf(ext[o + 2], tb, rb.z);
-            ra.w = fmaf(ext[o + 3], ta, ra.w); rb.w = fmaf(ext[o + 3], tb, rb.w);
-        }
-    }
-}
-
 struct SwtGeom {
     int Nr, Nc, s, TQ;           // plane size, dilation, lattice steps per task
     int strips, chunks;          // column strips of 4*kThreads, chunks of TQ steps per residue class
@@ -78,55 +43,107 @@ struct SwtGeom {
 };
 
 // ---- forward: in -> A, H, V, D -----------------------------------------------------------------
+// One CTA walks a residue class of rows (lattice y = r + q*s) down a column strip.  Every input row is read
+// from memory once (one 128-bit load per thread, the next row already in flight), published through a
+// double-buffered shared-memory row (one barrier per row) and row-filtered from there with the dilated taps;
+// the column pass is a sliding window of the F filtered rows in registers.  Column strips overlap by the reach
+// of the row filter (threads in the overlap only load).
+__host__ __device__ inline int swt_fwd_halo_l(int F, int s) { return ((F / 2 - 1) * s + 3) & ~3; }
+__host__ __device__ inline int swt_fwd_halo_r(int F, int s) { return ((F / 2) * s + 3) & ~3; }
+
 template <int F, int SMODE, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_swt_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ Hb, float* __restrict__ V,
           float* __restrict__ D, const SwtGeom g, const __grid_constant__ PwtFilters f) {
     constexpr int C = F / 2 - 1;
     const int Nr = g.Nr, Nc = g.Nc, s = g.s;
+    const int HLa = swt_fwd_halo_l(F, s), HRa = swt_fwd_halo_r(F, s);
+    const int OWN = 4 * kThreads - HLa - HRa;
     const int strip = blockIdx.x % g.strips;
     const int rc = blockIdx.x / g.strips;
     const int r = rc % s, chunk = rc / s;                    // residue class of rows, chunk along the lattice
-    const int x = strip * (4 * kThreads) + 4 * threadIdx.x;
     const int nq = (Nr - r + s - 1) / s;                     // lattice length of this class
     const int q0 = chunk * g.TQ;
-    if (x >= Nc || q0 >= nq) return;
+    if (q0 >= nq) return;                                    // CTA-uniform
     const int q1 = min(q0 + g.TQ, nq);
+    const int tid = threadIdx.x;
+    const int lc = 4 * tid;
+    const int xg = strip * OWN - HLa + lc;
+    int xw = xg % Nc;
+    if (xw < 0) xw += Nc;
+    const bool own = lc >= HLa && lc < HLa + OWN && xg < Nc;
     const long long ib = blockIdx.y * g.plane;
-    in += ib; A += ib; Hb += ib; V += ib; D += ib;
+    in += ib + xw;
+    const long long ob = ib + xw;
 
-    // wl[j], wh[j]: row-filtered rows y + (j-C)*s of the current output row y
-    float4 wl[F], wh[F];
+    __shared__ float4 srow[2][kThreads];
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 wl[F], wh[F];                                     // row-filtered rows y + (j-C)*s of the current output row
 #pragma unroll
-    for (int j = 0; j < F - 1; j++) {
-        const int yy = wrap1_per(r + (q0 + j - C) * s, Nr);
-        wl[j] = z; wh[j] = z;
-        row_filter<F, C, SMODE>(in + (long long)yy * Nc, x, Nc, s, f.L, f.H, 1.0f, wl[j], wh[j]);
-    }
-    for (int q = q0; q < q1; q++) {
-        const int yn = wrap1_per(r + (q + F - 1 - C) * s, Nr);
-        wl[F - 1] = z; wh[F - 1] = z;
-        row_filter<F, C, SMODE>(in + (long long)yn * Nc, x, Nc, s, f.L, f.H, 1.0f, wl[F - 1], wh[F - 1]);
-        float4 a = z, h = z, v = z, d = z;
+    for (int j = 0; j < F; j++) wl[j] = wh[j] = z;
+    int buf = 0;
+    const int m_last = q1 - 1 + (F - 1 - C);
+    float4 nx = ldg4(in + (long long)wrap1_per(r + (q0 - C) * s, Nr) * Nc);
+    for (int m = q0 - C; m <= m_last; m++) {                 // input lattice index
+        srow[buf][tid] = nx;
+        if (m < m_last) nx = ldg4(in + (long long)wrap1_per(r + (m + 1) * s, Nr) * Nc);
+        __syncthreads();
+        if (own) {
+            float4 lo = z, hi = z;
+            if (SMODE == 0) {
+                const int step = s >> 2;
 #pragma unroll
-        for (int j = 0; j < F; j++) {
-            const float tl = f.L[F - 1 - j], th = f.H[F - 1 - j];
-            fma4(a, wl[j], tl);
-            fma4(h, wl[j], th);      // (Lx, Hy)
-            fma4(v, wh[j], tl);      // (Hx, Ly)
-            fma4(d, wh[j], th);
+                for (int j = 0; j < F; j++) {
+                    const float4 v = srow[buf][tid + (j - C) * step];
+                    fma4(lo, v, f.L[F - 1 - j]);
+                    fma4(hi, v, f.H[F - 1 - j]);
+                }
+            } else {
+                constexpr int S = SMODE;
+                constexpr int BL = ((C * S + 3) / 4) * 4, BR = (((F - 1 - C) * S + 3) / 4) * 4;
+                constexpr int NE = (BL + 4 + BR) / 4;
+                float ext[4 * NE];
+#pragma unroll
+                for (int k = 0; k < NE; k++) {
+                    const float4 v = srow[buf][tid - BL / 4 + k];
+                    ext[4 * k] = v.x; ext[4 * k + 1] = v.y; ext[4 * k + 2] = v.z; ext[4 * k + 3] = v.w;
+                }
+#pragma unroll
+                for (int j = 0; j < F; j++) {
+                    const float ta = f.L[F - 1 - j], tb = f.H[F - 1 - j];
+                    const int o = BL + (j - C) * S;
+                    lo.x = fmaf(ext[o], ta, lo.x);     hi.x = fmaf(ext[o], tb, hi.x);
+                    lo.y = fmaf(ext[o + 1], ta, lo.y); hi.y = fmaf(ext[o + 1], tb, hi.y);
+                    lo.z = fmaf(ext[o + 2], ta, lo.z); hi.z = fmaf(ext[o + 2], tb, hi.z);
+                    lo.w = fmaf(ext[o + 3], ta, lo.w); hi.w = fmaf(ext[o + 3], tb, hi.w);
+                }
+            }
+            wl[F - 1] = lo;
+            wh[F - 1] = hi;
+            const int q = m - (F - 1) + C;                   // output row whose window is complete
+            if (q >= q0) {
+                float4 a = z, h = z, v = z, d = z;
+#pragma unroll
+                for (int j = 0; j < F; j++) {
+                    const float tl = f.L[F - 1 - j], th = f.H[F - 1 - j];
+                    fma4(a, wl[j], tl);
+                    fma4(h, wl[j], th);      // (Lx, Hy)
+                    fma4(v, wh[j], tl);      // (Hx, Ly)
+                    fma4(d, wh[j], th);
+                }
+                const long long o = ob + (long long)(r + q * s) * Nc;
+                stg4(A + o, a);
+                stg4(Hb + o, h);
+                stg4(V + o, v);
+                stg4(D + o, d);
+            }
+#pragma unroll
+            for (int j = 0; j < F - 1; j++) {
+                wl[j] = wl[j + 1];
+                wh[j] = wh[j + 1];
+            }
         }
-        const long long o = (long long)(r + q * s) * Nc + x;
-        stg4(A + o, a);
-        stg4(Hb + o, h);
-        stg4(V + o, v);
-        stg4(D + o, d);
-#pragma unroll
-        for (int j = 0; j < F - 1; j++) {
-            wl[j] = wl[j + 1];
-            wh[j] = wh[j + 1];
-        }
+        buf ^= 1;
     }
 }
 
@@ -196,9 +213,15 @@ k_swt_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float
 #pragma unroll
     for (int i = 0; i < F; i++) acc1[i] = acc2[i] = z;
     int buf = 0;
-    for (int m = q0 - C; m <= q1 - 1 + (F - 1 - C); m++) {   // input lattice index
-        const long long ro = (long long)wrap1_per(r + m * s, Nr) * Nc;
-        float4 a = ldg4(A + ro), h = ldg4(Hb + ro), v = ldg4(V + ro), d = ldg4(D + ro);
+    const int m_last = q1 - 1 + (F - 1 - C);
+    long long ro = (long long)wrap1_per(r + (q0 - C) * s, Nr) * Nc;
+    float4 na = ldg4(A + ro), nh = ldg4(Hb + ro), nv = ldg4(V + ro), nd = ldg4(D + ro);
+    for (int m = q0 - C; m <= m_last; m++) {                 // input lattice index
+        float4 a = na, h = nh, v = nv, d = nd;
+        if (m < m_last) {                                    // the next band rows are in flight during this one
+            ro = (long long)wrap1_per(r + (m + 1) * s, Nr) * Nc;
+            na = ldg4(A + ro); nh = ldg4(Hb + ro); nv = ldg4(V + ro); nd = ldg4(D + ro);
+        }
         if (THR) {
             h = thr4<THR>(h, thr.beta);
             v = thr4<THR>(v, thr.beta);
@@ -285,7 +308,10 @@ SwtGeom make_geom(int Nr, int Nc, int level) {
 template <int F, int MINB>
 int launch_fwd(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc, int level,
                const PwtFilters& f, cudaStream_t st) {
-    const SwtGeom g = make_geom(Nr, Nc, level);
+    SwtGeom g = make_geom(Nr, Nc, level);
+    const int own = 4 * kThreads - swt_fwd_halo_l(F, g.s) - swt_fwd_halo_r(F, g.s);
+    if (own < 2 * kThreads) return 0;                        // dilation too large for overlapping strips
+    g.strips = cdiv(Nc, own);
     dim3 grid(g.strips * g.s * g.chunks, batch);
     if (g.s == 1) k_swt_fwd<F, 1, MINB><<<grid, kThreads, 0, st>>>(in, A, Hb, V, D, g, f);
     else if (g.s == 2) k_swt_fwd<F, 2, MINB><<<grid, kThreads, 0, st>>>(in, A, Hb, V, D, g, f);
