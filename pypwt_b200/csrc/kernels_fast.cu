@@ -80,6 +80,7 @@ __device__ __forceinline__ void stg1(float* p, float a, unsigned long long pol) 
     asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(a), "l"(pol) : "memory");
 }
 
+__device__ __forceinline__ float2 fma2s(float x, float2 t, float2 acc) { return __ffma2_rn(make_float2(x, x), t, acc); }
 __device__ __forceinline__ void fma4(float4& acc, const float4& v, float t) {
     acc.x = fmaf(v.x, t, acc.x);
     acc.y = fmaf(v.y, t, acc.y);
@@ -102,7 +103,7 @@ template <int F, bool HAAR, int NT, int R, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 k_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ Hb, float* __restrict__ V,
       float* __restrict__ D, int Nr, int Nc, int TX, int TYT, long long in_bs, long long out_bs, int flags,
-      const __grid_constant__ PwtFilters f) {
+      const __grid_constant__ PwtFilters f, const __grid_constant__ PwtTapsFwd tp) {
     constexpr int C = F / 2 - 1;                  // window start offset (separable.cu:104)
     constexpr int CL = (C + 3) & ~3;              // left halo rounded to the vector width
     constexpr int DELTA = CL - C;
@@ -239,6 +240,16 @@ k_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ H
                     h0 = 0.5f * (vh[DELTA] + vh[DELTA + 1]);     h1 = 0.5f * (vh[DELTA + 2] + vh[DELTA + 3]);
                     d0 = 0.5f * (vh[DELTA] - vh[DELTA + 1]);     d1 = 0.5f * (vh[DELTA + 2] - vh[DELTA + 3]);
                 } else {
+                    if (F >= 10) {      // long rows of FMAs: issue them 2-wide (sample x (low-pass, high-pass) tap pair)
+                        float2 av0 = make_float2(0.f, 0.f), av1 = av0, hd0 = av0, hd1 = av0;
+#pragma unroll
+                        for (int j = 0; j < F; j++) {
+                            av0 = fma2s(vl[DELTA + j], tp.t[j], av0);     av1 = fma2s(vl[DELTA + 2 + j], tp.t[j], av1);
+                            hd0 = fma2s(vh[DELTA + j], tp.t[j], hd0);     hd1 = fma2s(vh[DELTA + 2 + j], tp.t[j], hd1);
+                        }
+                        a0 = av0.x; v0 = av0.y; a1 = av1.x; v1 = av1.y;
+                        h0 = hd0.x; d0 = hd0.y; h1 = hd1.x; d1 = hd1.y;
+                    } else {
                     a0 = a1 = v0 = v1 = h0 = h1 = d0 = d1 = 0.f;
 #pragma unroll
                     for (int j = 0; j < F; j++) {
@@ -247,6 +258,7 @@ k_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ H
                         v0 = fmaf(vl[DELTA + j], th, v0);     v1 = fmaf(vl[DELTA + 2 + j], th, v1);
                         h0 = fmaf(vh[DELTA + j], tl, h0);     h1 = fmaf(vh[DELTA + 2 + j], tl, h1);
                         d0 = fmaf(vh[DELTA + j], th, d0);     d1 = fmaf(vh[DELTA + 2 + j], th, d1);
+                    }
                     }
                 }
                 if (pair_ok) {
@@ -281,7 +293,8 @@ template <int F, bool HAAR, int NT, int R, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 k_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float* __restrict__ V,
       const float* __restrict__ D, float* __restrict__ out, int nr, int nc, int Nr_out, int Nc_out, int TXH,
-      int TYH, long long in_bs, long long out_bs, int flags, const __grid_constant__ PwtFilters f) {
+      int TYH, long long in_bs, long long out_bs, int flags, const __grid_constant__ PwtFilters f,
+      const __grid_constant__ PwtTapsInv tp) {
     constexpr int NC = NT / 2;                           // column groups (threads per role)
     constexpr int P = F / 2 - 1, HALF = F / 2;
     constexpr int S0 = P >> 1, E0 = P & 1;               // output parity 0: row shift / first tap
@@ -436,6 +449,18 @@ k_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float* __
                     o[2 * c] = 0.5f * (v1[HLr + c] + v2[HLr + c]);
                     o[2 * c + 1] = 0.5f * (v1[HLr + c] - v2[HLr + c]);
                 } else {
+                    if (F >= 10) {
+                        // 2-wide: the sample at band offset w - S1 times the (even-phase, odd-phase) tap pair;
+                        // walking w downwards keeps the reference's summation order (jj ascending)
+                        float2 eo = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int w = 2 * HL; w >= 0; w--) {
+                            eo = fma2s(v1[HLr + c + w - S1], tp.l[w], eo);
+                            eo = fma2s(v2[HLr + c + w - S1], tp.h[w], eo);
+                        }
+                        o[2 * c] = eo.x;
+                        o[2 * c + 1] = eo.y;
+                    } else {
                     float e = 0.f, od = 0.f;
 #pragma unroll
                     for (int jj = 0; jj < HALF; jj++) {
@@ -446,6 +471,7 @@ k_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float* __
                     }
                     o[2 * c] = e;
                     o[2 * c + 1] = od;
+                    }
                 }
             }
             const int gy = 2 * qc + i;
@@ -519,7 +545,8 @@ int launch_fwd(const float* in, float* A, float* Hb, float* V, float* D, int bat
     if (resident < 1) resident = 1;
     const int TYT = pick_tile_rows(Nr2, cdiv(Nc2, TX), batch, R, resident);
     dim3 grid(cdiv(Nc2, TX), cdiv(Nr2, TYT), batch);
-    k_fwd<F, HAAR, NT, R, MINB><<<grid, NT, smem, st>>>(in, A, Hb, V, D, Nr, Nc, TX, TYT, in_bs, out_bs, flags, f);
+    k_fwd<F, HAAR, NT, R, MINB><<<grid, NT, smem, st>>>(in, A, Hb, V, D, Nr, Nc, TX, TYT, in_bs, out_bs, flags, f,
+                                                  pwt_pack_taps_fwd(f, F));
     return 1;
 }
 
@@ -545,7 +572,7 @@ int launch_inv(const float* A, const float* Hb, const float* V, const float* D, 
     const int TYH = pick_tile_rows(nr, cdiv(nc, TXH), batch, R, resident);
     dim3 grid(cdiv(nc, TXH), cdiv(nr, TYH), batch);
     k_inv<F, HAAR, NT, R, MINB><<<grid, NT, smem, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out, TXH, TYH, in_bs,
-                                                  out_bs, flags, f);
+                                                  out_bs, flags, f, pwt_pack_taps_inv(f, F));
     return 1;
 }
 
