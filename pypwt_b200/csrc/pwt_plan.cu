@@ -110,6 +110,8 @@ struct pwt_plan {
     int want_norms;     // norms were requested after a forward: later forwards accumulate them in-kernel (~2 % of the pass)
     PwtDeferredOp pend; // threshold recorded but not yet applied to memory (pend.op < 0: none)
     int defer_ok;       // plan shape for which thresholds may be deferred into the fused inverse
+    int ns_rank1;       // non-separable plan whose four 2D filters are outer products of the 1D bank (always, unless custom
+                        // 2D filters were loaded): evaluated with the separable kernels, detail slots 1/2 swapped (quirk Q1)
     int defer_swt_ok;   // SWT plan whose every level is served by the fused SWT inverse (threshold applied on load)
     double* h_acc;      // pinned mirror
     void* d_flush;
@@ -374,6 +376,7 @@ extern "C" int pwt_create_batch(pwt_plan** out, const float* img, int batch, int
         if (e != cudaSuccess) rc = fail(PWT_ERR_CUDA, "image upload failed: %s", cudaGetErrorString(e));
     }
     if (rc == PWT_OK && !p->do_separable) rc = build_k2d(p);
+    p->ns_rank1 = !p->do_separable && !getenv("PWT_NS_DIRECT");
     if (rc == PWT_OK) {
         e = cudaStreamSynchronize(p->stream);
         if (e != cudaSuccess) rc = fail(PWT_ERR_CUDA, "plan initialisation failed: %s", cudaGetErrorString(e));
@@ -567,6 +570,11 @@ extern "C" int pwt_forward(pwt_plan* p) {
     }
     const int L = p->nlevels, B = p->batch;
     const bool haar = is_haar(p);
+    // rank-1 non-separable filters: same numbers as the separable transform (up to fp32 rounding of the tap
+    // products), F^2 -> 2F multiply-adds per sample; the reference's slot order differs (Q1: bands 1 and 2 swapped)
+    const bool ns_sep = !p->do_separable && !haar && p->ns_rank1 && p->kernel_mode != 1;
+    const bool sep = haar || p->do_separable || ns_sep;
+    const int sH = ns_sep ? 2 : 1, sV = ns_sep ? 1 : 2;            // band slots that receive the separable H and V
     cudaStream_t st = p->stream;
     const float* src = p->d_image;
     if (p->ndims == 1) {
@@ -585,9 +593,9 @@ extern "C" int pwt_forward(pwt_plan* p) {
         const long long plane = (long long)B * img_elems(p);
         int l_first = 1;
         // levels 1..3 in one launch when the fused register cascade covers the configuration
-        if (!p->do_swt && L >= 3 && (haar || p->do_separable) && p->kernel_mode == 0) {
-            float* Hs[3] = {p->d_band[1], p->d_band[4], p->d_band[7]};
-            float* Vs[3] = {p->d_band[2], p->d_band[5], p->d_band[8]};
+        if (!p->do_swt && L >= 3 && sep && p->kernel_mode == 0) {
+            float* Hs[3] = {p->d_band[sH], p->d_band[3 + sH], p->d_band[6 + sH]};
+            float* Vs[3] = {p->d_band[sV], p->d_band[3 + sV], p->d_band[6 + sV]};
             float* Ds[3] = {p->d_band[3], p->d_band[6], p->d_band[9]};
             float* dstA = approx_dst(p, 3, p->d_tmp);
             prof_begin(p, 100 * 3 + 1 + 10);      // tag x1y: fused levels 1..3
@@ -607,13 +615,13 @@ extern "C" int pwt_forward(pwt_plan* p) {
             }
         }
         for (int l = l_first; l <= L; l++) {
-            float* Hb = p->d_band[3 * (l - 1) + 1];
-            float* V = p->d_band[3 * (l - 1) + 2];
+            float* Hb = p->d_band[3 * (l - 1) + sH];
+            float* V = p->d_band[3 * (l - 1) + sV];
             float* D = p->d_band[3 * (l - 1) + 3];
             prof_begin(p, 100 * l + 1);
             if (p->do_swt) {
                 float* dstA = approx_dst(p, l, p->d_tmp + 2 * plane);
-                if (p->do_separable) {
+                if (p->do_separable || ns_sep) {
                     int n = p->kernel_mode == 1 ? 0 : pwt_fast_swt_fwd2d(src, dstA, Hb, V, D, B, p->Nr, p->Nc, l, p->filt, st);
                     if (!n) n = pwt_launch_swt_fwd2d(src, dstA, Hb, V, D, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
                     p->launches += n;
@@ -625,7 +633,7 @@ extern "C" int pwt_forward(pwt_plan* p) {
                 float* dstA = approx_dst(p, l, p->d_tmp);
                 const long long in_bs = lvl_elems(p, l - 1), out_bs = lvl_elems(p, l);
                 const int nr = p->lvNr[l - 1], nc = p->lvNc[l - 1];
-                if (haar || p->do_separable) {
+                if (sep) {
                     int n = 0;
                     const int hints = (l < L ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l > 1 ? PWT_HINT_IN_FROM_PREV : 0);
                     if (p->kernel_mode == 0 || p->kernel_mode == 3)
@@ -661,6 +669,9 @@ extern "C" int pwt_inverse(pwt_plan* p) {
     cudaSetDevice(p->device);
     const int L = p->nlevels, B = p->batch;
     const bool haar = is_haar(p);
+    const bool ns_sep = !p->do_separable && !haar && p->ns_rank1 && p->kernel_mode != 1;     // see pwt_forward
+    const bool sep = haar || p->do_separable || ns_sep;
+    const int sH = ns_sep ? 2 : 1, sV = ns_sep ? 1 : 2;
     cudaStream_t st = p->stream;
     const float* cur = p->d_band[0];
     if (p->ndims == 1) {
@@ -689,14 +700,14 @@ extern "C" int pwt_inverse(pwt_plan* p) {
             fop.app = 0;
         }
         for (int l = L; l >= 1; l--) {
-            if (l == 3 && p->pend.op >= 0 && !p->do_swt && !((haar || p->do_separable) && p->kernel_mode == 0)) {
+            if (l == 3 && p->pend.op >= 0 && !p->do_swt && !(sep && p->kernel_mode == 0)) {
                 int rc = flush_pending(p, 1, L == 3);
                 if (rc != PWT_OK) return rc;
             }
             // levels 3..1 in one launch when the fused register cascade covers the configuration
-            if (l == 3 && !p->do_swt && (haar || p->do_separable) && p->kernel_mode == 0) {
-                const float* Hs[3] = {p->d_band[1], p->d_band[4], p->d_band[7]};
-                const float* Vs[3] = {p->d_band[2], p->d_band[5], p->d_band[8]};
+            if (l == 3 && !p->do_swt && sep && p->kernel_mode == 0) {
+                const float* Hs[3] = {p->d_band[sH], p->d_band[3 + sH], p->d_band[6 + sH]};
+                const float* Vs[3] = {p->d_band[sV], p->d_band[3 + sV], p->d_band[6 + sV]};
                 const float* Ds[3] = {p->d_band[3], p->d_band[6], p->d_band[9]};
                 if (p->queue.base > 0x70000000u) {
                     cudaMemsetAsync(p->queue.counter, 0, sizeof(unsigned), st);
@@ -717,14 +728,14 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                     if (rc != PWT_OK) return rc;
                 }
             }
-            const float* Hb = p->d_band[3 * (l - 1) + 1];
-            const float* V = p->d_band[3 * (l - 1) + 2];
+            const float* Hb = p->d_band[3 * (l - 1) + sH];
+            const float* V = p->d_band[3 * (l - 1) + sV];
             const float* D = p->d_band[3 * (l - 1) + 3];
             prof_begin(p, 100 * l + 2);
             if (p->do_swt) {
                 float* alt = p->d_tmp + 2 * plane;
                 float* dst = (l == 1) ? p->d_image : (cur == p->d_band[0] ? alt : p->d_band[0]);
-                if (p->do_separable) {
+                if (p->do_separable || ns_sep) {
                     int n = 0;
                     if (p->kernel_mode != 1) {
                         if (swt_defer)      // the deferred threshold of this level is applied while its bands are loaded
@@ -744,7 +755,7 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                 float* dst = (l == 1) ? p->d_image : (cur == p->d_band[0] ? p->d_tmp : p->d_band[0]);
                 const long long in_bs = lvl_elems(p, l), out_bs = lvl_elems(p, l - 1);
                 const int nr = p->lvNr[l], nc = p->lvNc[l], Nro = p->lvNr[l - 1], Nco = p->lvNc[l - 1];
-                if (haar || p->do_separable) {
+                if (sep) {
                     int n = 0;
                     const int hints = (l > 1 ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l < L ? PWT_HINT_IN_FROM_PREV : 0);
                     if (p->kernel_mode == 0 || p->kernel_mode == 3)
@@ -1094,6 +1105,7 @@ extern "C" int pwt_set_filters_forward(pwt_plan* p, const char* name, unsigned l
         }
         const float* f[4] = {f1, f2, f3, f4};
         res = upload_k2d(p, p->d_k2d_fwd, f, len, padded);
+        p->ns_rank1 = 0;                                             // arbitrary 2D filters: direct F x F kernels from now on
     }
     p->hlen = (int)padded;
     p->filt.hlen = (int)padded;

@@ -640,3 +640,27 @@ def test_swt_deferred_threshold_is_unobservable(wname, shape, op, app, normalize
     # forward() discards a pending threshold
     D.forward(img); D.soft_threshold(1e6); D.forward(); D.inverse()
     assert np.abs(D.image - img).max() < 2e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("do_swt", [0, 1])
+@pytest.mark.parametrize("wname", ["db2", "db4", "sym5", "bior2.2"])
+def test_nonseparable_rank1_path_agrees_with_direct_kernels(wname, do_swt):
+    """The four 2D filters of the non-separable mode are outer products of the 1D bank (nonseparable.cu:
+    w_compute_filters), so the default path evaluates them with the separable kernels (slots 1/2 swapped,
+    quirk Q1).  It must agree with the direct F x F kernels (kernel mode 1) and keep the band layout."""
+    img = synth_image((256, 384), seed=31, kind="smooth")
+    lv = 3 if not do_swt else 2
+    A = _W(img, wname, lv, do_separable=0, do_swt=do_swt); G = _W(img, wname, lv, do_separable=0, do_swt=do_swt)
+    G.set_kernel_mode(1)
+    A.forward(); G.forward()
+    assert A.launch_count < G.launch_count or do_swt
+    ca, cg = A.coeffs, G.coeffs
+    assert_close(ca[0], cg[0], 255.0, "nonsep A")
+    for i in range(1, lv + 1):
+        for j in range(3):
+            assert ca[i][j].shape == cg[i][j].shape
+            assert_close(ca[i][j], cg[i][j], 255.0, "nonsep level %d band %d" % (i, j))
+    A.inverse(); G.inverse()
+    assert_close(A.image, G.image, 255.0, "nonsep inverse")
+    assert_close(A.image, img, 255.0, "nonsep roundtrip")
