@@ -560,7 +560,11 @@ int pwt_fused_dwt_fwd3(const float* in, float* A3, float* const* H, float* const
     g_sink.cap = partials ? partials_cap : 0;
     g_sink.ntasks_out = ntasks_out;
     const int variant = env_int("PWT_FUSED_VARIANT", 0);
-    if (haar) return launch_fwd3<2, true, 6, 0>(a, batch, f, q, st);
+    if (haar) {
+        if (variant == 1) return launch_fwd3<2, true, 6, 0>(a, batch, f, q, st);
+        if (variant == 2) return launch_fwd3<2, true, 5, 0>(a, batch, f, q, st);
+        return launch_fwd3<2, true, 4, 0>(a, batch, f, q, st);
+    }
     switch (F) {
         case 4:
             if (variant == 2) return launch_fwd3<4, false, 5, 0>(a, batch, f, q, st);
