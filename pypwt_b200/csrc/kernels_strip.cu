@@ -1,0 +1,541 @@
+// Streaming strip kernels for the mid-length and long filters (F = 6 .. 40, compile-time), any image size.
+//
+// ncu on the shared-memory tile kernels (profiles/r01_ncu_long_filters.csv) showed, for sym8 (F = 16) at 8192^2:
+// L1/shared data pipe at 71 % (52 B of shared-memory traffic per pixel: every sample is re-read ~5x by the row
+// pass and ~4.5x by the column pass), 45 % of all executed instructions in the staging loop (a modulo per tile
+// row), a 22 % halo recompute in the row pass, FMA pipe only 48 % busy.  This design removes all three:
+//   * a CTA owns a strip of 256 image columns and walks DOWN a segment of rows in chunks of R rows
+//     (cp.async staging of chunk c+1 overlaps the arithmetic of chunk c; wrap resolved per 16-byte group);
+//   * first pass along the rows from shared memory, one warp per row, 8 pixels per lane: the F+6 sample window
+//     is read once per 8 pixels (swizzled layout, conflict-free 128-bit reads);
+//   * second pass down the columns in TRANSPOSED form: each thread owns one column of one intermediate plane,
+//     reads each intermediate sample exactly once and scatters it into the F/2 output rows it contributes to,
+//     held as rotating register accumulators (static indices: the chunk height is the rotation period);
+//     finished rows go straight to global memory, coalesced.  No vertical halo is ever recomputed inside a
+//     segment (only F-2 rows where a segment starts).
+//   Shared-memory traffic drops to ~25 B/px and the instruction stream is ~80 % FFMA2.
+// Every multiply-add is issued 2-wide (FFMA2): one sample times a packed pair of taps -- (low-pass, high-pass)
+// in the analysis, (even phase, odd phase) in the synthesis.
+// forward : rows then columns (the reference's order, separable.cu:196-197), taps in the reference's order.
+// inverse : rows then columns (the reference runs columns first, separable.cu:351-361; same sums, the result
+//           differs only by fp32 rounding, like kernels_reg.cu).
+#include <stdlib.h>
+
+#include "pwt_internal.h"
+
+namespace {
+
+constexpr int NT = 256;       // threads per CTA
+constexpr int NWARP = NT / 32;
+constexpr int SW = 256;       // image columns per strip (forward: input columns, inverse: output columns)
+constexpr int HC = SW / 2;    // half-resolution columns per strip
+
+__device__ __forceinline__ int mod_pos(int i, int n) {
+    i %= n;
+    return i < 0 ? i + n : i;
+}
+// reference extension of the analysis (separable.cu:98-131): periodic over the size rounded up to even, the
+// extra sample of an odd size repeats the last one
+__device__ __forceinline__ int wrap_dwt(int i, int N) {
+    const int Ne = N + (N & 1);
+    if (i < 0) i += Ne;
+    else if (i >= Ne) i -= Ne;
+    if ((unsigned)i >= (unsigned)Ne) i = mod_pos(i, Ne);      // tiny images only
+    return i >= N ? N - 1 : i;
+}
+__device__ __forceinline__ int wrap_per(int i, int N) {
+    if (i < 0) i += N;
+    else if (i >= N) i -= N;
+    if ((unsigned)i >= (unsigned)N) i = mod_pos(i, N);
+    return i;
+}
+
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ float2 fma2s(float x, float2 t, float2 acc) { return __ffma2_rn(make_float2(x, x), t, acc); }
+__device__ __forceinline__ float2 mul2s(float x, float2 t) { return make_float2(x * t.x, x * t.y); }
+
+// 128-bit groups of a staged row are stored at q ^ ((q >> 3) & 1): lanes that read windows 8 floats apart
+// (float4 index 2*lane + k) then hit 8 different 16-byte banks per quarter warp
+__device__ __forceinline__ int swz2(int q) { return q ^ ((q >> 3) & 1); }
+// rows written as 4 consecutive float4 per lane (float4 index 4*lane + k) use q ^ ((q >> 3) & 3)
+__device__ __forceinline__ int swz4(int q) { return q ^ ((q >> 3) & 3); }
+
+using TapsFwd = PwtTapsFwd;
+using TapsInv = PwtTapsInv;
+
+// chunk height = K rotation periods, K chosen so that the rows of a chunk fill the 8 warps of the row pass
+__host__ __device__ constexpr int pick_k(int period, int max_rows) {
+    int best = 1, best_eff = 0;
+    for (int k = 1; k * period <= max_rows || k == 1; k++) {
+        const int r = k * period, eff = 1000 * r / (NWARP * ((r + NWARP - 1) / NWARP));
+        if (eff > best_eff + 40) { best_eff = eff; best = k; }
+        if (k * period > max_rows) break;
+    }
+    return best;
+}
+
+// ---- forward ------------------------------------------------------------------------------------
+template <int F>
+struct FwdGeo {
+    static constexpr int C = F / 2 - 1;                    // output k reads inputs 2k - C .. 2k - C + F - 1
+    static constexpr int CL = (C + 3) & ~3;                // the staged row starts CL (aligned) columns left of 2*kx0
+    static constexpr int DX = CL - C;
+    static constexpr int NV = (DX + F + 6 + 3) / 4;        // float4 per lane window (8 pixels -> 4 outputs)
+    static constexpr int IW4 = 2 * 31 + NV;                // float4 groups of a staged row
+    static constexpr int P = 4 * ((IW4 + 1) & ~1);         // raw row pitch (floats)
+    static constexpr int K = pick_k(F, 24);
+    static constexpr int R = K * F;                        // rows per chunk (F = rotation period of the column pass)
+    static constexpr int NBUF = R <= 24 ? 2 : 1;           // staging buffers
+    static constexpr int NS = (R * IW4 + NT - 1) / NT;     // 16-byte staging slots per thread and chunk
+    static constexpr size_t smem = sizeof(float) * ((size_t)NBUF * R * P + (size_t)R * SW) + sizeof(int) * (size_t)(4 * IW4);
+};
+
+template <int F>
+__global__ void __launch_bounds__(NT, 2)
+k_strip_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ Hb, float* __restrict__ V,
+            float* __restrict__ D, int Nr, int Nc, long long in_bs, long long out_bs, int QS,
+            const __grid_constant__ TapsFwd f) {
+    using G = FwdGeo<F>;
+    constexpr int C = G::C, CL = G::CL, DX = G::DX, NV = G::NV, IW4 = G::IW4, P = G::P, R = G::R, NBUF = G::NBUF, NS = G::NS;
+    constexpr int HF = F / 2;
+    extern __shared__ __align__(16) float sm[];
+    float* raw = sm;                                  // [NBUF][R][P]
+    float* rp = sm + NBUF * R * P;                    // [R][SW]: low-pass half | high-pass half of every row
+    int* colidx = reinterpret_cast<int*>(rp + R * SW);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Nr2 = (Nr + 1) >> 1, Nc2 = (Nc + 1) >> 1;
+    const int kx0 = blockIdx.x * HC;
+    const int q0 = blockIdx.y * QS, q1 = min(q0 + QS, Nr2);
+    if (q0 >= q1) return;
+    in += blockIdx.z * in_bs;
+    const long long ob = blockIdx.z * out_bs;
+    const int i0 = 2 * q0 - C;                        // image row of stream row 0
+    const int nrows = 2 * (q1 - q0) + F - 2;          // stream rows this segment consumes
+    const int nchunks = (nrows + R - 1) / R;
+    const int xs = 2 * kx0 - CL;                      // image column of staged column 0 (multiple of 4)
+    const bool vec = (Nc & 3) == 0 && Nc >= 4 * IW4 && (((uintptr_t)in) & 15) == 0 && (in_bs & 3) == 0;
+
+    // staging slots of this thread: fixed (row in chunk, 16-byte group) -> shared offset, image offset (one image
+    // holds < 2^31 samples, so offsets inside an image are 32-bit)
+    int s_off[NS], s_img[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        const int idx = tid + s * NT, r = idx / IW4, q = idx - r * IW4;
+        s_off[s] = r * P + 4 * swz2(q);
+        int gc = xs + 4 * q;
+        if (gc < 0) gc += Nc;
+        else if (gc >= Nc) gc -= Nc;
+        s_img[s] = r * Nc + gc;
+    }
+    if (!vec) {
+        for (int j = tid; j < 4 * IW4; j += NT) colidx[j] = wrap_dwt(xs + j, Nc);
+        __syncthreads();
+    }
+    auto stage = [&](int c) {
+        float* dst = raw + (NBUF == 2 ? (c & 1) * R * P : 0);
+        const int ibase = i0 + c * R;
+        if (vec) {
+            if (ibase >= 0 && ibase + R <= Nr) {       // interior chunk: no wrap
+                const int b = ibase * Nc;
+#pragma unroll
+                for (int s = 0; s < NS; s++)
+                    if (s < NS - 1 || tid + s * NT < R * IW4) cp_async16(dst + s_off[s], in + (unsigned)(b + s_img[s]));
+            } else {
+#pragma unroll
+                for (int s = 0; s < NS; s++) {
+                    const int idx = tid + s * NT, r = idx / IW4;
+                    if (s < NS - 1 || idx < R * IW4)
+                        cp_async16(dst + s_off[s], in + (unsigned)(wrap_dwt(ibase + r, Nr) * Nc + (s_img[s] - r * Nc)));
+                }
+            }
+        } else {
+            for (int e = tid; e < R * 4 * IW4; e += NT) {
+                const int r = e / (4 * IW4), j = e - r * (4 * IW4);
+                const float* row = in + (long long)wrap_dwt(ibase + r, Nr) * Nc;
+                cp_async4(dst + r * P + 4 * swz2(j >> 2) + (j & 3), row + colidx[j]);
+            }
+        }
+        cp_async_commit();
+    };
+
+    // window offsets of this lane in a staged row (float4 index 2*lane + k, swizzled)
+    int w_off[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) w_off[k] = 4 * swz2(2 * lane + k);
+
+    // column pass ownership: thread -> (plane, half-resolution column)
+    const int pl = tid >> 7, col = tid & (HC - 1);
+    const int kx = kx0 + col;
+    const unsigned nvalid = kx < Nc2 ? (unsigned)(q1 - q0) : 0u;      // outputs u in [0, nvalid) are stored
+    float* o0 = (pl ? V : A) + ob + kx;                // low-pass down the column
+    float* o1 = (pl ? D : Hb) + ob + kx;               // high-pass down the column
+    int ubase = -HF;                                   // chunk c completes outputs u = ubase + 1 .. ubase + R/2
+    int obase = (q0 - HF) * Nc2;
+    const float2 zero2 = make_float2(0.f, 0.f);
+    float2 acc[HF];
+#pragma unroll
+    for (int a = 0; a < HF; a++) acc[a] = zero2;
+
+    stage(0);
+    for (int c = 0; c < nchunks; c++) {
+        if (NBUF == 2) {
+            if (c + 1 < nchunks) { stage(c + 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();                               // chunk c staged; everybody is done with rp
+        const float* rb = raw + (NBUF == 2 ? (c & 1) * R * P : 0);
+        // ---- row pass: warp per row, lane -> outputs 4*lane .. 4*lane+3 (both filters) ----
+        for (int r = warp; r < R; r += NWARP) {
+            float win[4 * NV];
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                const float4 v = *reinterpret_cast<const float4*>(rb + r * P + w_off[k]);
+                win[4 * k] = v.x; win[4 * k + 1] = v.y; win[4 * k + 2] = v.z; win[4 * k + 3] = v.w;
+            }
+            float2 p[4];
+#pragma unroll
+            for (int o = 0; o < 4; o++) p[o] = zero2;
+#pragma unroll
+            for (int j = 0; j < F; j++)
+#pragma unroll
+                for (int o = 0; o < 4; o++) p[o] = fma2s(win[DX + 2 * o + j], f.t[j], p[o]);
+            *reinterpret_cast<float4*>(rp + r * SW + 4 * lane) = make_float4(p[0].x, p[1].x, p[2].x, p[3].x);
+            *reinterpret_cast<float4*>(rp + r * SW + HC + 4 * lane) = make_float4(p[0].y, p[1].y, p[2].y, p[3].y);
+        }
+        __syncthreads();                               // rp complete, raw buffer free
+        if (NBUF == 1 && c + 1 < nchunks) stage(c + 1);
+        // ---- column pass, transposed form: stream row n = c*R + j feeds outputs u = n/2 - d with tap (n&1) + 2d ----
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const float x = rp[j * SW + tid];
+#pragma unroll
+            for (int d = 0; d < HF; d++) {
+                const int a = (((j >> 1) - d) % HF + HF) % HF, m = (j & 1) + 2 * d;
+                acc[a] = fma2s(x, f.t[m], m == 0 ? zero2 : acc[a]);
+            }
+            if (j & 1) {
+                // completes output u = ubase + (j+1)/2, accumulator ((j+1)/2) mod F/2
+                const int a = ((j + 1) >> 1) % HF, k = (j + 1) >> 1;
+                if ((unsigned)(ubase + k) < nvalid) {
+                    o0[(unsigned)(obase + k * Nc2)] = acc[a].x;
+                    o1[(unsigned)(obase + k * Nc2)] = acc[a].y;
+                }
+            }
+        }
+        ubase += R / 2;
+        obase += (R / 2) * Nc2;
+    }
+}
+
+// ---- inverse ------------------------------------------------------------------------------------
+// Synthesis taps of the column pass, packed DENSE: the even output row 2v and the odd output row 2(v-SH)+1 read
+// the same band rows v - S1 + w, w = 0 .. F/2-1, so every FFMA2 carries two useful products
+// (l[w] = (IL even-phase tap, IL odd-phase tap), h[w] likewise from IH).
+struct TapsInvDense {
+    float2 l[PWT_MAX_TAPS / 2];
+    float2 h[PWT_MAX_TAPS / 2];
+};
+
+template <int F>
+struct InvGeo {
+    static constexpr int Pp = F / 2 - 1, HALF = F / 2;
+    static constexpr int S0 = Pp >> 1, E0 = Pp & 1, S1 = (Pp + 1) >> 1, E1 = (Pp + 1) & 1;
+    static constexpr int NW = 2 * S1 + 1;                  // window of the row pass: band offsets -S1 .. +S1
+    static constexpr int SH = Pp & 1;                      // odd rows lag the even rows by SH row pairs in the column pass
+    static constexpr int HLr = (S1 + 3) & ~3;              // aligned column halo of the staged band rows
+    static constexpr int DX = HLr - S1;
+    static constexpr int NV = (DX + 8 + 2 * S1 + 3) / 4;   // float4 per lane window (8 band columns -> 16 outputs)
+    static constexpr int BW4 = 2 * 15 + NV;                // float4 groups of a staged band row
+    static constexpr int P = 4 * ((BW4 + 1) & ~1);
+    static constexpr int K = pick_k(HALF, 24);
+    static constexpr int R = K * HALF;                     // band rows per chunk (HALF = rotation period)
+    static constexpr int NBUF = R <= 12 ? 2 : 1;
+    static constexpr int NS = (4 * R * BW4 + NT - 1) / NT;
+    static constexpr size_t smem = sizeof(float) * ((size_t)NBUF * 4 * R * P + (size_t)R * 2 * SW) + sizeof(int) * (size_t)(4 * BW4);
+    // which output phases use window position w (same rule as pwt_pack_taps_inv)
+    __host__ __device__ static constexpr bool use_e(int w) { return S0 + S1 - w >= 0 && S0 + S1 - w < HALF; }
+    __host__ __device__ static constexpr bool use_o(int w) { return 2 * S1 - w >= 0 && 2 * S1 - w < HALF; }
+};
+
+template <int F>
+__global__ void __launch_bounds__(NT, 2)
+k_strip_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float* __restrict__ V,
+            const float* __restrict__ D, float* __restrict__ out, int nr, int nc, int Nr_out, int Nc_out,
+            long long in_bs, long long out_bs, int QS, const __grid_constant__ TapsInv f,
+            const __grid_constant__ TapsInvDense fd) {
+    using G = InvGeo<F>;
+    constexpr int S1 = G::S1, NW = G::NW, SH = G::SH, HALF = G::HALF, HLr = G::HLr, DX = G::DX, NV = G::NV, BW4 = G::BW4,
+                  P = G::P, R = G::R, NBUF = G::NBUF, NS = G::NS;
+    extern __shared__ __align__(16) float sm[];
+    float* raw = sm;                                  // [NBUF][4 bands][R][P]
+    float* us = sm + NBUF * 4 * R * P;                // [R][2 planes][SW] row-synthesised planes (swizzled float4 groups)
+    int* colidx = reinterpret_cast<int*>(us + R * 2 * SW);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * HC;                   // first band column of the strip
+    const int q0 = blockIdx.y * QS, q1 = min(q0 + QS, nr);
+    if (q0 >= q1) return;
+    const long long ib = blockIdx.z * in_bs;
+    out += blockIdx.z * out_bs;
+    A += ib; Hb += ib; V += ib; D += ib;
+    const int r0 = q0 - S1;                           // band row of stream row 0
+    const int nrows = (q1 - q0) + SH + HALF - 1;      // stream rows this segment consumes
+    const int nchunks = (nrows + R - 1) / R;
+    const int xs = x0 - HLr;
+    const bool vec = (nc & 3) == 0 && nc >= 4 * BW4 && (in_bs & 3) == 0 &&
+                     ((((uintptr_t)A) | ((uintptr_t)Hb) | ((uintptr_t)V) | ((uintptr_t)D)) & 15) == 0;
+
+    int s_off[NS], s_img[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        const int idx = tid + s * NT, br = idx / BW4, q = idx - br * BW4;     // br = band * R + row
+        s_off[s] = br * P + 4 * swz2(q);
+        int gc = xs + 4 * q;
+        if (gc < 0) gc += nc;
+        else if (gc >= nc) gc -= nc;
+        s_img[s] = (br % R) * nc + gc;
+    }
+    if (!vec) {
+        for (int j = tid; j < 4 * BW4; j += NT) colidx[j] = wrap_per(xs + j, nc);
+        __syncthreads();
+    }
+    auto stage = [&](int c) {
+        float* dst = raw + (NBUF == 2 ? (c & 1) * 4 * R * P : 0);
+        const int rbase = r0 + c * R;
+        if (vec) {
+            const bool interior = rbase >= 0 && rbase + R <= nr;
+            const int bofs = rbase * nc;
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                const int idx = tid + s * NT, br = idx / BW4;
+                if (s < NS - 1 || idx < 4 * R * BW4) {
+                    const int b = br / R, r = br - b * R;
+                    const float* band = b == 0 ? A : b == 1 ? Hb : b == 2 ? V : D;
+                    const int o = interior ? bofs + s_img[s] : wrap_per(rbase + r, nr) * nc + (s_img[s] - r * nc);
+                    cp_async16(dst + s_off[s], band + (unsigned)o);
+                }
+            }
+        } else {
+            for (int e = tid; e < 4 * R * 4 * BW4; e += NT) {
+                const int br = e / (4 * BW4), j = e - br * (4 * BW4);
+                const int b = br / R, r = br - b * R;
+                const float* row = (b == 0 ? A : b == 1 ? Hb : b == 2 ? V : D) + (long long)wrap_per(rbase + r, nr) * nc;
+                cp_async4(dst + br * P + 4 * swz2(j >> 2) + (j & 3), row + colidx[j]);
+            }
+        }
+        cp_async_commit();
+    };
+
+    // row pass ownership: lanes 0-15 -> plane 0 (A with V), lanes 16-31 -> plane 1 (H with D); 8 band columns each
+    const int rpl = lane >> 4, g = lane & 15;
+    int w_off[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) w_off[k] = 4 * swz2(2 * g + k);
+    int u_off[4];                                     // where this lane writes its 16 outputs in a us row
+#pragma unroll
+    for (int k = 0; k < 4; k++) u_off[k] = rpl * SW + 4 * swz4(4 * g + k);
+
+    // column pass ownership: thread -> output column.  Stream row n feeds the row pairs u = n - w (relative to q0);
+    // pair u = (output row 2(q0+u), output row 2(q0+u-SH)+1).
+    const int X = 2 * x0 + tid;
+    const int cu_off = 4 * swz4(tid >> 2) + (tid & 3);
+    const unsigned nv_e = X < Nc_out ? (unsigned)(q1 - q0) : 0u;
+    const unsigned nv_o = X < Nc_out ? (unsigned)max(min(q1, Nr_out >> 1) - q0, 0) : 0u;
+    float* op = out + X;
+    int ubase = -(HALF - 1);                          // chunk c completes pairs u = ubase .. ubase + R - 1
+    int obase = 2 * (q0 - (HALF - 1)) * Nc_out;
+    const float2 zero2 = make_float2(0.f, 0.f);
+    float2 acc[HALF];
+#pragma unroll
+    for (int a = 0; a < HALF; a++) acc[a] = zero2;
+
+    stage(0);
+    for (int c = 0; c < nchunks; c++) {
+        if (NBUF == 2) {
+            if (c + 1 < nchunks) { stage(c + 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const float* rb = raw + (NBUF == 2 ? (c & 1) * 4 * R * P : 0);
+        // ---- row synthesis: band row -> two planes of 2*HC samples (low-pass-column plane from A,V; high from H,D) ----
+        for (int r = warp; r < R; r += NWARP) {
+            const float* px = rb + (rpl * R + r) * P;            // A or H : row low-pass source
+            const float* py = rb + ((2 + rpl) * R + r) * P;      // V or D : row high-pass source
+            float wx[4 * NV], wy[4 * NV];
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                const float4 a = *reinterpret_cast<const float4*>(px + w_off[k]);
+                const float4 b = *reinterpret_cast<const float4*>(py + w_off[k]);
+                wx[4 * k] = a.x; wx[4 * k + 1] = a.y; wx[4 * k + 2] = a.z; wx[4 * k + 3] = a.w;
+                wy[4 * k] = b.x; wy[4 * k + 1] = b.y; wy[4 * k + 2] = b.z; wy[4 * k + 3] = b.w;
+            }
+            float o[16];
+#pragma unroll
+            for (int cidx = 0; cidx < 8; cidx++) {
+                float2 eo = zero2;
+#pragma unroll
+                for (int wi = 0; wi < NW; wi++) {
+                    const int w = NW - 1 - wi;             // the reference's order (jj ascending) walks the window downwards
+                    if (G::use_e(w) && G::use_o(w)) {
+                        eo = fma2s(wx[DX + cidx + w], f.l[w], eo);
+                        eo = fma2s(wy[DX + cidx + w], f.h[w], eo);
+                    } else if (G::use_e(w)) {
+                        eo.x = fmaf(wx[DX + cidx + w], f.l[w].x, eo.x);
+                        eo.x = fmaf(wy[DX + cidx + w], f.h[w].x, eo.x);
+                    } else if (G::use_o(w)) {
+                        eo.y = fmaf(wx[DX + cidx + w], f.l[w].y, eo.y);
+                        eo.y = fmaf(wy[DX + cidx + w], f.h[w].y, eo.y);
+                    }
+                }
+                o[2 * cidx] = eo.x;
+                o[2 * cidx + 1] = eo.y;
+            }
+            float* ur = us + r * 2 * SW;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                *reinterpret_cast<float4*>(ur + u_off[k]) = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+        }
+        __syncthreads();
+        if (NBUF == 1 && c + 1 < nchunks) stage(c + 1);
+        // ---- column synthesis, transposed form ----
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const float ul = us[j * 2 * SW + cu_off];
+            const float uh = us[j * 2 * SW + SW + cu_off];
+#pragma unroll
+            for (int w = 0; w < HALF; w++) {
+                const int a = ((j - w) % HALF + HALF) % HALF;
+                acc[a] = fma2s(ul, fd.l[w], w == 0 ? zero2 : acc[a]);
+                acc[a] = fma2s(uh, fd.h[w], acc[a]);
+            }
+            {
+                // completes pair u = ubase + j, accumulator (j+1) mod HALF
+                const int a = (j + 1) % HALF;
+                const int u = ubase + j;
+                if ((unsigned)u < nv_e) op[(unsigned)(obase + 2 * j * Nc_out)] = acc[a].x;
+                if ((unsigned)(u - SH) < nv_o) op[(unsigned)(obase + (2 * (j - SH) + 1) * Nc_out)] = acc[a].y;
+            }
+        }
+        ubase += R;
+        obase += 2 * R * Nc_out;
+    }
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Segment height: the grid is (strips, segments, images); pick the segment count whose last wave is fullest,
+// discounting the rows a segment start costs (halo rows + rounding of the stream to whole chunks).
+int pick_segments(int nstrips, int batch, int rows_out, int rows_per_out, int halo, int R, int slots) {
+    const long long base = (long long)nstrips * batch;
+    int best = 1;
+    double best_eff = -1.0;
+    const int max_seg = rows_out < 512 ? (rows_out + 7) / 8 : 64;
+    for (int ns = 1; ns <= max_seg; ns++) {
+        const int qs = cdiv(rows_out, ns);
+        const int nseg = cdiv(rows_out, qs);
+        const double ctas = (double)base * nseg;
+        const double waves = ctas / slots;
+        const double wave_eff = waves / (double)((long long)((ctas + slots - 1) / slots));
+        const int stream = qs * rows_per_out + halo;
+        const double chunk_eff = (double)(qs * rows_per_out) / (double)(cdiv(stream, R) * R);
+        const double eff = wave_eff * chunk_eff;
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = nseg; }
+    }
+    return best;
+}
+
+int g_sm_count = 0;
+int sm_count() {
+    if (!g_sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+template <int F>
+int launch_fwd(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
+               long long in_bs, long long out_bs, const PwtFilters& f, cudaStream_t st) {
+    using G = FwdGeo<F>;
+    static int per_sm = 0;
+    if (!per_sm) {
+        cudaFuncSetAttribute(k_strip_fwd<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_fwd<F>, NT, G::smem);
+        if (per_sm <= 0) per_sm = 1;
+    }
+    const int Nr2 = (Nr + 1) / 2, Nc2 = (Nc + 1) / 2;
+    const int nstrips = cdiv(Nc2, HC);
+    static int force = getenv("PWT_STRIP_SEGS") ? atoi(getenv("PWT_STRIP_SEGS")) : 0;
+    const int nseg = force > 0 ? force : pick_segments(nstrips, batch, Nr2, 2, F - 2, G::R, per_sm * sm_count());
+    const int QS = cdiv(Nr2, nseg);
+    dim3 grid(nstrips, cdiv(Nr2, QS), batch);
+    const TapsFwd t = pwt_pack_taps_fwd(f, F);
+    k_strip_fwd<F><<<grid, NT, G::smem, st>>>(in, A, Hb, V, D, Nr, Nc, in_bs, out_bs, QS, t);
+    return 1;
+}
+template <int F>
+int launch_inv(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch, int nr,
+               int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs, const PwtFilters& f,
+               cudaStream_t st) {
+    using G = InvGeo<F>;
+    static int per_sm = 0;
+    if (!per_sm) {
+        cudaFuncSetAttribute(k_strip_inv<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_inv<F>, NT, G::smem);
+        if (per_sm <= 0) per_sm = 1;
+    }
+    const int nstrips = cdiv(nc, HC);
+    static int force = getenv("PWT_STRIP_SEGS") ? atoi(getenv("PWT_STRIP_SEGS")) : 0;
+    const int nseg = force > 0 ? force : pick_segments(nstrips, batch, nr, 1, G::SH + G::HALF - 1, G::R, per_sm * sm_count());
+    const int QS = cdiv(nr, nseg);
+    dim3 grid(nstrips, cdiv(nr, QS), batch);
+    const TapsInv t = pwt_pack_taps_inv(f, F);
+    TapsInvDense td;
+    for (int w = 0; w < PWT_MAX_TAPS / 2; w++) {
+        td.l[w] = make_float2(t.l[w].x, t.l[w + G::SH].y);
+        td.h[w] = make_float2(t.h[w].x, t.h[w + G::SH].y);
+    }
+    k_strip_inv<F><<<grid, NT, G::smem, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out, in_bs, out_bs, QS, t, td);
+    return 1;
+}
+
+}  // namespace
+
+#define PWT_STRIP_CASES(X) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20) X(22) X(24) X(26) X(28) X(30) X(32) X(34) X(36) X(38) X(40)
+
+int pwt_strip_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
+                        long long in_bs, long long out_bs, const PwtFilters& f, cudaStream_t st) {
+    if (batch > 65535 || Nr < 2 || Nc < 2) return 0;
+    switch (f.hlen) {
+#define X(FF) case FF: return launch_fwd<FF>(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, f, st);
+        PWT_STRIP_CASES(X)
+#undef X
+        default: return 0;
+    }
+}
+
+int pwt_strip_dwt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
+                        int nr, int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs,
+                        const PwtFilters& f, cudaStream_t st) {
+    if (batch > 65535 || nr < 1 || nc < 1) return 0;
+    switch (f.hlen) {
+#define X(FF) case FF: return launch_inv<FF>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, st);
+        PWT_STRIP_CASES(X)
+#undef X
+        default: return 0;
+    }
+}

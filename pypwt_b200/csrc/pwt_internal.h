@@ -181,3 +181,11 @@ int pwt_tile_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D,
 int pwt_tile_dwt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
                        int nr, int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs,
                        const PwtFilters& f, cudaStream_t st);
+
+// kernels_strip.cu : compile-time F = 6..40 streaming strip kernels (row pass from shared memory, transposed-form
+// column pass in registers), any size.  Return 0 when not covered.
+int pwt_strip_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
+                        long long in_bs, long long out_bs, const PwtFilters& f, cudaStream_t st);
+int pwt_strip_dwt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
+                        int nr, int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs,
+                        const PwtFilters& f, cudaStream_t st);

@@ -119,6 +119,7 @@ struct pwt_plan {
     long long launches;
     int kernel_mode;
     int tile_min_f;        // filter length from which the FMA-oriented tile kernels are preferred
+    int strip_min_f;       // filter length from which the streaming strip kernels are preferred
     unsigned custom_len;   // taps given to set_filters_forward (0: built-in bank)
     int prof_on, prof_n;
     cudaEvent_t* prof_ev;  // 2 events per record
@@ -345,6 +346,7 @@ extern "C" int pwt_create_batch(pwt_plan** out, const float* img, int batch, int
     p->defer_ok = p->ndims == 2 && !p->do_swt && p->do_separable && p->nlevels >= 3 && Nr % 8 == 0 && Nc % 8 == 0 &&
                   Nc >= 512 && Nr >= 64 && (p->hlen <= 6) && !getenv("PWT_NO_DEFER");
     p->tile_min_f = getenv("PWT_TILE_MIN_F") ? atoi(getenv("PWT_TILE_MIN_F")) : 22;
+    p->strip_min_f = getenv("PWT_STRIP_MIN_F") ? atoi(getenv("PWT_STRIP_MIN_F")) : 12;
 
     // L2 residency of the ping-pong approximation planes: the kernels store them with an
     // L2::evict_last policy, which only has an effect when a persisting-L2 carve-out exists.
@@ -638,6 +640,8 @@ extern "C" int pwt_forward(pwt_plan* p) {
                     const int hints = (l < L ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l > 1 ? PWT_HINT_IN_FROM_PREV : 0);
                     if (p->kernel_mode == 0 || p->kernel_mode == 3)
                         n = pwt_reg_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, hints, st);
+                    if (!n && !haar && ((p->kernel_mode == 0 && p->hlen >= p->strip_min_f && nr >= 64 && nc >= 256) || p->kernel_mode == 4))
+                        n = pwt_strip_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, st);
                     if (!n && p->kernel_mode != 1 && !haar && p->hlen >= p->tile_min_f && nr >= 64 && nc >= 64)
                         n = pwt_tile_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, st);
                     if (!n && p->kernel_mode != 1)
@@ -760,6 +764,8 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                     const int hints = (l > 1 ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l < L ? PWT_HINT_IN_FROM_PREV : 0);
                     if (p->kernel_mode == 0 || p->kernel_mode == 3)
                         n = pwt_reg_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, hints, st);
+                    if (!n && !haar && ((p->kernel_mode == 0 && p->hlen >= p->strip_min_f && nr >= 32 && nc >= 128) || p->kernel_mode == 4))
+                        n = pwt_strip_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, st);
                     if (!n && p->kernel_mode != 1 && !haar && p->hlen >= p->tile_min_f && nr >= 32 && nc >= 32)
                         n = pwt_tile_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, st);
                     if (!n && p->kernel_mode != 1)

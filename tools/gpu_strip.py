@@ -1,0 +1,67 @@
+"""Strip kernels (kernel mode 4) against the generic kernels (mode 1) on many shapes / filters, then timings.
+usage: python tools/gpu_strip.py [check] [time] [wname ...]"""
+import sys, numpy as np
+sys.path.insert(0, ".")
+import pycudwt
+
+def check():
+    rng = np.random.default_rng(3)
+    bad = 0
+    shapes = [(512, 768), (511, 509), (64, 1000), (1001, 777), (40, 36), (300, 2048), (2048, 300), (3, 260, 516), (17, 23), (2048, 2048)]
+    wns = ["db3", "db4", "sym5", "db6", "db7", "sym8", "coif3", "db10", "db12", "coif5", "db16", "db20", "bior6.8", "rbio2.8", "bior3.9"]
+    for shp in shapes:
+        img = (rng.standard_normal(shp) * 50 + 128).astype(np.float32)
+        for wn in wns:
+            for L in (1, 3):
+                try:
+                    S = pycudwt.Wavelets(img, wn, L); G = pycudwt.Wavelets(img, wn, L)
+                except ValueError:
+                    continue
+                S.set_kernel_mode(4); G.set_kernel_mode(1)
+                S.forward(); G.forward()
+                cs, cg = S.coeffs, G.coeffs
+                scale = 1e-5 * max(np.abs(img).max(), 1.0)
+                errs = [np.abs(cs[0] - cg[0]).max() / max(scale, 1e-5 * np.abs(cg[0]).max())]
+                for i in range(1, len(cs)):
+                    for j in range(3):
+                        errs.append(np.abs(cs[i][j] - cg[i][j]).max() / max(scale, 1e-5 * np.abs(cg[i][j]).max()))
+                S.inverse(); G.inverse()
+                ei = np.abs(S.image - G.image).max() / scale
+                # strip inverse on the generic coefficients' own forward: also check reconstruction
+                er = np.abs(S.image - img).max() / scale
+                tol_r = 40 if wn in ("bior3.9",) else 8
+                ok = max(errs) < 1.0 and ei < 1.0 and er < tol_r
+                if not ok:
+                    bad += 1
+                    print("FAIL", shp, wn, L, S.levels, "fwd %.3g inv %.3g rec %.3g" % (max(errs), ei, er), flush=True)
+    print("check done, failures:", bad)
+    return bad
+
+def timeit(wn, shape=(8192, 8192), L=1, mode=0, n=20):
+    img = np.random.default_rng(0).standard_normal(shape).astype(np.float32)
+    W = pycudwt.Wavelets(img, wn, L)
+    W.set_kernel_mode(mode)
+    out = []
+    for what in ("f", "fi"):
+        for _ in range(3):
+            W.forward(); W.inverse()
+        W.timer_start()
+        for _ in range(n):
+            W.forward()
+            if what == "fi": W.inverse()
+        out.append(W.timer_stop() / n)
+    return out[0], out[1] - out[0]
+
+if __name__ == "__main__":
+    args = sys.argv[1:]
+    if "check" in args:
+        if check(): sys.exit(1)
+    if "time" in args:
+        wns = [a for a in args if a not in ("check", "time")] or ["db3", "db4", "db6", "sym8", "db10", "db12", "coif5", "db20"]
+        for wn in wns:
+            a = timeit(wn, mode=0); b = timeit(wn, mode=4)
+            print("%-6s 8192^2 L1  auto fwd %.4f inv %.4f | strip fwd %.4f inv %.4f ms" % (wn, a[0], a[1], b[0], b[1]), flush=True)
+        for wn in ("sym8",):
+            for mode in (0, 4):
+                f, i = timeit(wn, shape=(64, 2048, 2048), L=3, mode=mode, n=5)
+                print("%-6s 64x2048^2 L3 mode %d fwd %.4f inv %.4f ms" % (wn, mode, f, i), flush=True)
