@@ -69,6 +69,17 @@ __device__ __forceinline__ int swz2(int q) { return q ^ ((q >> 3) & 1); }
 // rows written as 4 consecutive float4 per lane (float4 index 4*lane + k) use q ^ ((q >> 3) & 3)
 __device__ __forceinline__ int swz4(int q) { return q ^ ((q >> 3) & 3); }
 
+// keep a precomputed value in its register (stops the compiler from re-deriving it in every chunk)
+__device__ __forceinline__ void pin(int& v) { asm volatile("" : "+r"(v)); }
+// predicated scalar store at a 32-bit element offset: no branch, one IMAD.WIDE + one STG
+__device__ __forceinline__ void stg_if(float* base, unsigned off, float v, unsigned u, unsigned n) {
+    asm volatile(
+        "{ .reg .pred p; .reg .u64 a;\n"
+        "  setp.lt.u32 p, %3, %4;\n"
+        "  mad.wide.u32 a, %1, 4, %0;\n"
+        "  @p st.global.f32 [a], %2; }\n" ::"l"(base), "r"(off), "f"(v), "r"(u), "r"(n));
+}
+
 using TapsFwd = PwtTapsFwd;
 using TapsInv = PwtTapsInv;
 
@@ -99,8 +110,8 @@ struct FwdGeo {
     static constexpr size_t smem = sizeof(float) * ((size_t)NBUF * R * P + (size_t)R * SW) + sizeof(int) * (size_t)(4 * IW4);
 };
 
-template <int F>
-__global__ void __launch_bounds__(NT, 2)
+template <int F, int MB>
+__global__ void __launch_bounds__(NT, MB)
 k_strip_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ Hb, float* __restrict__ V,
             float* __restrict__ D, int Nr, int Nc, long long in_bs, long long out_bs, int QS,
             const __grid_constant__ TapsFwd f) {
@@ -135,6 +146,7 @@ k_strip_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restri
         if (gc < 0) gc += Nc;
         else if (gc >= Nc) gc -= Nc;
         s_img[s] = r * Nc + gc;
+        if (NS <= 6) { pin(s_off[s]); pin(s_img[s]); }
     }
     if (!vec) {
         for (int j = tid; j < 4 * IW4; j += NT) colidx[j] = wrap_dwt(xs + j, Nc);
@@ -170,7 +182,7 @@ k_strip_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restri
     // window offsets of this lane in a staged row (float4 index 2*lane + k, swizzled)
     int w_off[NV];
 #pragma unroll
-    for (int k = 0; k < NV; k++) w_off[k] = 4 * swz2(2 * lane + k);
+    for (int k = 0; k < NV; k++) { w_off[k] = warp * P + 4 * swz2(2 * lane + k); pin(w_off[k]); }
 
     // column pass ownership: thread -> (plane, half-resolution column)
     const int pl = tid >> 7, col = tid & (HC - 1);
@@ -196,20 +208,27 @@ k_strip_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restri
         __syncthreads();                               // chunk c staged; everybody is done with rp
         const float* rb = raw + (NBUF == 2 ? (c & 1) * R * P : 0);
         // ---- row pass: warp per row, lane -> outputs 4*lane .. 4*lane+3 (both filters) ----
-        for (int r = warp; r < R; r += NWARP) {
-            float win[4 * NV];
 #pragma unroll
-            for (int k = 0; k < NV; k++) {
-                const float4 v = *reinterpret_cast<const float4*>(rb + r * P + w_off[k]);
-                win[4 * k] = v.x; win[4 * k + 1] = v.y; win[4 * k + 2] = v.z; win[4 * k + 3] = v.w;
-            }
+        for (int rr = 0; rr < (R + NWARP - 1) / NWARP; rr++) {
+            const int r = warp + rr * NWARP;
+            if (R % NWARP != 0 && r >= R) break;
+            // streamed window: every 128-bit group is consumed as soon as it is loaded (sample i feeds output o with
+            // tap j = i - DX - 2o), so the live state is the 4 accumulator pairs; each sum still runs over j ascending
             float2 p[4];
 #pragma unroll
             for (int o = 0; o < 4; o++) p[o] = zero2;
 #pragma unroll
-            for (int j = 0; j < F; j++)
+            for (int k = 0; k < NV; k++) {
+                const float4 v = *reinterpret_cast<const float4*>(rb + rr * NWARP * P + w_off[k]);
+                const float xv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int o = 0; o < 4; o++) p[o] = fma2s(win[DX + 2 * o + j], f.t[j], p[o]);
+                for (int e = 0; e < 4; e++)
+#pragma unroll
+                    for (int o = 0; o < 4; o++) {
+                        const int j = 4 * k + e - DX - 2 * o;
+                        if (j >= 0 && j < F) p[o] = fma2s(xv[e], f.t[j], p[o]);
+                    }
+            }
             *reinterpret_cast<float4*>(rp + r * SW + 4 * lane) = make_float4(p[0].x, p[1].x, p[2].x, p[3].x);
             *reinterpret_cast<float4*>(rp + r * SW + HC + 4 * lane) = make_float4(p[0].y, p[1].y, p[2].y, p[3].y);
         }
@@ -227,10 +246,8 @@ k_strip_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restri
             if (j & 1) {
                 // completes output u = ubase + (j+1)/2, accumulator ((j+1)/2) mod F/2
                 const int a = ((j + 1) >> 1) % HF, k = (j + 1) >> 1;
-                if ((unsigned)(ubase + k) < nvalid) {
-                    o0[(unsigned)(obase + k * Nc2)] = acc[a].x;
-                    o1[(unsigned)(obase + k * Nc2)] = acc[a].y;
-                }
+                stg_if(o0, (unsigned)(obase + k * Nc2), acc[a].x, (unsigned)(ubase + k), nvalid);
+                stg_if(o1, (unsigned)(obase + k * Nc2), acc[a].y, (unsigned)(ubase + k), nvalid);
             }
         }
         ubase += R / 2;
@@ -268,8 +285,8 @@ struct InvGeo {
     __host__ __device__ static constexpr bool use_o(int w) { return 2 * S1 - w >= 0 && 2 * S1 - w < HALF; }
 };
 
-template <int F>
-__global__ void __launch_bounds__(NT, 2)
+template <int F, int MB>
+__global__ void __launch_bounds__(NT, MB)
 k_strip_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float* __restrict__ V,
             const float* __restrict__ D, float* __restrict__ out, int nr, int nc, int Nr_out, int Nc_out,
             long long in_bs, long long out_bs, int QS, const __grid_constant__ TapsInv f,
@@ -304,6 +321,7 @@ k_strip_inv(const float* __restrict__ A, const float* __restrict__ Hb, const flo
         if (gc < 0) gc += nc;
         else if (gc >= nc) gc -= nc;
         s_img[s] = (br % R) * nc + gc;
+        if (NS <= 6) { pin(s_off[s]); pin(s_img[s]); }
     }
     if (!vec) {
         for (int j = tid; j < 4 * BW4; j += NT) colidx[j] = wrap_per(xs + j, nc);
@@ -340,15 +358,16 @@ k_strip_inv(const float* __restrict__ A, const float* __restrict__ Hb, const flo
     const int rpl = lane >> 4, g = lane & 15;
     int w_off[NV];
 #pragma unroll
-    for (int k = 0; k < NV; k++) w_off[k] = 4 * swz2(2 * g + k);
+    for (int k = 0; k < NV; k++) { w_off[k] = (rpl * R + warp) * P + 4 * swz2(2 * g + k); if (F <= 24) pin(w_off[k]); }
     int u_off[4];                                     // where this lane writes its 16 outputs in a us row
 #pragma unroll
-    for (int k = 0; k < 4; k++) u_off[k] = rpl * SW + 4 * swz4(4 * g + k);
+    for (int k = 0; k < 4; k++) { u_off[k] = warp * 2 * SW + rpl * SW + 4 * swz4(4 * g + k); if (F <= 24) pin(u_off[k]); }
 
     // column pass ownership: thread -> output column.  Stream row n feeds the row pairs u = n - w (relative to q0);
     // pair u = (output row 2(q0+u), output row 2(q0+u-SH)+1).
     const int X = 2 * x0 + tid;
-    const int cu_off = 4 * swz4(tid >> 2) + (tid & 3);
+    int cu_off = 4 * swz4(tid >> 2) + (tid & 3);
+    pin(cu_off);
     const unsigned nv_e = X < Nc_out ? (unsigned)(q1 - q0) : 0u;
     const unsigned nv_o = X < Nc_out ? (unsigned)max(min(q1, Nr_out >> 1) - q0, 0) : 0u;
     float* op = out + X;
@@ -370,39 +389,43 @@ k_strip_inv(const float* __restrict__ A, const float* __restrict__ Hb, const flo
         __syncthreads();
         const float* rb = raw + (NBUF == 2 ? (c & 1) * 4 * R * P : 0);
         // ---- row synthesis: band row -> two planes of 2*HC samples (low-pass-column plane from A,V; high from H,D) ----
-        for (int r = warp; r < R; r += NWARP) {
-            const float* px = rb + (rpl * R + r) * P;            // A or H : row low-pass source
-            const float* py = rb + ((2 + rpl) * R + r) * P;      // V or D : row high-pass source
-            float wx[4 * NV], wy[4 * NV];
 #pragma unroll
-            for (int k = 0; k < NV; k++) {
+        for (int rr = 0; rr < (R + NWARP - 1) / NWARP; rr++) {
+            const int r = warp + rr * NWARP;
+            if (R % NWARP != 0 && r >= R) break;
+            const float* px = rb + rr * NWARP * P;               // + w_off: A or H row r (row low-pass source)
+            const float* py = px + 2 * R * P;                    //          V or D row r (row high-pass source)
+            // streamed window, walked downwards (the reference's order: jj ascending = window position descending)
+            float2 eo[8];
+#pragma unroll
+            for (int cidx = 0; cidx < 8; cidx++) eo[cidx] = zero2;
+#pragma unroll
+            for (int k = NV - 1; k >= 0; k--) {
                 const float4 a = *reinterpret_cast<const float4*>(px + w_off[k]);
                 const float4 b = *reinterpret_cast<const float4*>(py + w_off[k]);
-                wx[4 * k] = a.x; wx[4 * k + 1] = a.y; wx[4 * k + 2] = a.z; wx[4 * k + 3] = a.w;
-                wy[4 * k] = b.x; wy[4 * k + 1] = b.y; wy[4 * k + 2] = b.z; wy[4 * k + 3] = b.w;
+                const float xa[4] = {a.x, a.y, a.z, a.w}, xb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int e = 3; e >= 0; e--)
+#pragma unroll
+                    for (int cidx = 0; cidx < 8; cidx++) {
+                        const int w = 4 * k + e - DX - cidx;
+                        if (w < 0 || w >= NW) continue;
+                        if (G::use_e(w) && G::use_o(w)) {
+                            eo[cidx] = fma2s(xa[e], f.l[w], eo[cidx]);
+                            eo[cidx] = fma2s(xb[e], f.h[w], eo[cidx]);
+                        } else if (G::use_e(w)) {
+                            eo[cidx].x = fmaf(xa[e], f.l[w].x, eo[cidx].x);
+                            eo[cidx].x = fmaf(xb[e], f.h[w].x, eo[cidx].x);
+                        } else if (G::use_o(w)) {
+                            eo[cidx].y = fmaf(xa[e], f.l[w].y, eo[cidx].y);
+                            eo[cidx].y = fmaf(xb[e], f.h[w].y, eo[cidx].y);
+                        }
+                    }
             }
             float o[16];
 #pragma unroll
-            for (int cidx = 0; cidx < 8; cidx++) {
-                float2 eo = zero2;
-#pragma unroll
-                for (int wi = 0; wi < NW; wi++) {
-                    const int w = NW - 1 - wi;             // the reference's order (jj ascending) walks the window downwards
-                    if (G::use_e(w) && G::use_o(w)) {
-                        eo = fma2s(wx[DX + cidx + w], f.l[w], eo);
-                        eo = fma2s(wy[DX + cidx + w], f.h[w], eo);
-                    } else if (G::use_e(w)) {
-                        eo.x = fmaf(wx[DX + cidx + w], f.l[w].x, eo.x);
-                        eo.x = fmaf(wy[DX + cidx + w], f.h[w].x, eo.x);
-                    } else if (G::use_o(w)) {
-                        eo.y = fmaf(wx[DX + cidx + w], f.l[w].y, eo.y);
-                        eo.y = fmaf(wy[DX + cidx + w], f.h[w].y, eo.y);
-                    }
-                }
-                o[2 * cidx] = eo.x;
-                o[2 * cidx + 1] = eo.y;
-            }
-            float* ur = us + r * 2 * SW;
+            for (int cidx = 0; cidx < 8; cidx++) { o[2 * cidx] = eo[cidx].x; o[2 * cidx + 1] = eo[cidx].y; }
+            float* ur = us + rr * NWARP * 2 * SW;
 #pragma unroll
             for (int k = 0; k < 4; k++)
                 *reinterpret_cast<float4*>(ur + u_off[k]) = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
@@ -424,8 +447,8 @@ k_strip_inv(const float* __restrict__ A, const float* __restrict__ Hb, const flo
                 // completes pair u = ubase + j, accumulator (j+1) mod HALF
                 const int a = (j + 1) % HALF;
                 const int u = ubase + j;
-                if ((unsigned)u < nv_e) op[(unsigned)(obase + 2 * j * Nc_out)] = acc[a].x;
-                if ((unsigned)(u - SH) < nv_o) op[(unsigned)(obase + (2 * (j - SH) + 1) * Nc_out)] = acc[a].y;
+                stg_if(op, (unsigned)(obase + 2 * j * Nc_out), acc[a].x, (unsigned)u, nv_e);
+                stg_if(op, (unsigned)(obase + (2 * (j - SH) + 1) * Nc_out), acc[a].y, (unsigned)(u - SH), nv_o);
             }
         }
         ubase += R;
@@ -467,14 +490,14 @@ int sm_count() {
     return g_sm_count;
 }
 
-template <int F>
-int launch_fwd(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
-               long long in_bs, long long out_bs, const PwtFilters& f, cudaStream_t st) {
+template <int F, int MB>
+int launch_fwd_mb(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
+                  long long in_bs, long long out_bs, const PwtFilters& f, cudaStream_t st) {
     using G = FwdGeo<F>;
     static int per_sm = 0;
     if (!per_sm) {
-        cudaFuncSetAttribute(k_strip_fwd<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_fwd<F>, NT, G::smem);
+        cudaFuncSetAttribute(k_strip_fwd<F, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_fwd<F, MB>, NT, G::smem);
         if (per_sm <= 0) per_sm = 1;
     }
     const int Nr2 = (Nr + 1) / 2, Nc2 = (Nc + 1) / 2;
@@ -484,18 +507,34 @@ int launch_fwd(const float* in, float* A, float* Hb, float* V, float* D, int bat
     const int QS = cdiv(Nr2, nseg);
     dim3 grid(nstrips, cdiv(Nr2, QS), batch);
     const TapsFwd t = pwt_pack_taps_fwd(f, F);
-    k_strip_fwd<F><<<grid, NT, G::smem, st>>>(in, A, Hb, V, D, Nr, Nc, in_bs, out_bs, QS, t);
+    k_strip_fwd<F, MB><<<grid, NT, G::smem, st>>>(in, A, Hb, V, D, Nr, Nc, in_bs, out_bs, QS, t);
     return 1;
 }
+// resident CTAs per SM the kernels are compiled for (register cap 80 / 128)
+int occ_fwd(int F) {
+    static int o = getenv("PWT_STRIP_OCC_FWD") ? atoi(getenv("PWT_STRIP_OCC_FWD")) : 0;
+    return o ? o : (F >= 14 && F <= 16 ? 3 : 2);
+}
+int occ_inv(int F) {
+    static int o = getenv("PWT_STRIP_OCC_INV") ? atoi(getenv("PWT_STRIP_OCC_INV")) : 0;
+    return o ? o : (F >= 14 && F <= 16 ? 3 : 2);
+}
 template <int F>
-int launch_inv(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch, int nr,
-               int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs, const PwtFilters& f,
-               cudaStream_t st) {
+int launch_fwd(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
+               long long in_bs, long long out_bs, const PwtFilters& f, cudaStream_t st) {
+    if (F <= 16 && occ_fwd(F) == 3)
+        return launch_fwd_mb<F, (F <= 16 ? 3 : 2)>(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, f, st);
+    return launch_fwd_mb<F, 2>(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, f, st);
+}
+template <int F, int MB>
+int launch_inv_mb(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch, int nr,
+                  int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs, const PwtFilters& f,
+                  cudaStream_t st) {
     using G = InvGeo<F>;
     static int per_sm = 0;
     if (!per_sm) {
-        cudaFuncSetAttribute(k_strip_inv<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_inv<F>, NT, G::smem);
+        cudaFuncSetAttribute(k_strip_inv<F, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_inv<F, MB>, NT, G::smem);
         if (per_sm <= 0) per_sm = 1;
     }
     const int nstrips = cdiv(nc, HC);
@@ -509,8 +548,16 @@ int launch_inv(const float* A, const float* Hb, const float* V, const float* D, 
         td.l[w] = make_float2(t.l[w].x, t.l[w + G::SH].y);
         td.h[w] = make_float2(t.h[w].x, t.h[w + G::SH].y);
     }
-    k_strip_inv<F><<<grid, NT, G::smem, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out, in_bs, out_bs, QS, t, td);
+    k_strip_inv<F, MB><<<grid, NT, G::smem, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out, in_bs, out_bs, QS, t, td);
     return 1;
+}
+template <int F>
+int launch_inv(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch, int nr,
+               int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs, const PwtFilters& f,
+               cudaStream_t st) {
+    if (F <= 16 && occ_inv(F) == 3)
+        return launch_inv_mb<F, (F <= 16 ? 3 : 2)>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, st);
+    return launch_inv_mb<F, 2>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, st);
 }
 
 }  // namespace

@@ -346,7 +346,7 @@ extern "C" int pwt_create_batch(pwt_plan** out, const float* img, int batch, int
     p->defer_ok = p->ndims == 2 && !p->do_swt && p->do_separable && p->nlevels >= 3 && Nr % 8 == 0 && Nc % 8 == 0 &&
                   Nc >= 512 && Nr >= 64 && (p->hlen <= 6) && !getenv("PWT_NO_DEFER");
     p->tile_min_f = getenv("PWT_TILE_MIN_F") ? atoi(getenv("PWT_TILE_MIN_F")) : 22;
-    p->strip_min_f = getenv("PWT_STRIP_MIN_F") ? atoi(getenv("PWT_STRIP_MIN_F")) : 12;
+    p->strip_min_f = getenv("PWT_STRIP_MIN_F") ? atoi(getenv("PWT_STRIP_MIN_F")) : 8;
 
     // L2 residency of the ping-pong approximation planes: the kernels store them with an
     // L2::evict_last policy, which only has an effect when a persisting-L2 carve-out exists.
@@ -595,7 +595,7 @@ extern "C" int pwt_forward(pwt_plan* p) {
         const long long plane = (long long)B * img_elems(p);
         int l_first = 1;
         // levels 1..3 in one launch when the fused register cascade covers the configuration
-        if (!p->do_swt && L >= 3 && sep && p->kernel_mode == 0) {
+        if (!p->do_swt && L >= 3 && sep && p->kernel_mode == 0 && (haar || p->hlen < p->strip_min_f)) {
             float* Hs[3] = {p->d_band[sH], p->d_band[3 + sH], p->d_band[6 + sH]};
             float* Vs[3] = {p->d_band[sV], p->d_band[3 + sV], p->d_band[6 + sV]};
             float* Ds[3] = {p->d_band[3], p->d_band[6], p->d_band[9]};
@@ -638,10 +638,10 @@ extern "C" int pwt_forward(pwt_plan* p) {
                 if (sep) {
                     int n = 0;
                     const int hints = (l < L ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l > 1 ? PWT_HINT_IN_FROM_PREV : 0);
-                    if (p->kernel_mode == 0 || p->kernel_mode == 3)
-                        n = pwt_reg_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, hints, st);
-                    if (!n && !haar && ((p->kernel_mode == 0 && p->hlen >= p->strip_min_f && nr >= 64 && nc >= 256) || p->kernel_mode == 4))
+                    if (!haar && ((p->kernel_mode == 0 && p->hlen >= p->strip_min_f && nr >= 64 && nc >= 256) || p->kernel_mode == 4))
                         n = pwt_strip_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, st);
+                    if (!n && (p->kernel_mode == 0 || p->kernel_mode == 3))
+                        n = pwt_reg_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, hints, st);
                     if (!n && p->kernel_mode != 1 && !haar && p->hlen >= p->tile_min_f && nr >= 64 && nc >= 64)
                         n = pwt_tile_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, st);
                     if (!n && p->kernel_mode != 1)
@@ -704,12 +704,12 @@ extern "C" int pwt_inverse(pwt_plan* p) {
             fop.app = 0;
         }
         for (int l = L; l >= 1; l--) {
-            if (l == 3 && p->pend.op >= 0 && !p->do_swt && !(sep && p->kernel_mode == 0)) {
+            if (l == 3 && p->pend.op >= 0 && !p->do_swt && !(sep && p->kernel_mode == 0 && (haar || p->hlen < p->strip_min_f))) {
                 int rc = flush_pending(p, 1, L == 3);
                 if (rc != PWT_OK) return rc;
             }
             // levels 3..1 in one launch when the fused register cascade covers the configuration
-            if (l == 3 && !p->do_swt && sep && p->kernel_mode == 0) {
+            if (l == 3 && !p->do_swt && sep && p->kernel_mode == 0 && (haar || p->hlen < p->strip_min_f)) {
                 const float* Hs[3] = {p->d_band[sH], p->d_band[3 + sH], p->d_band[6 + sH]};
                 const float* Vs[3] = {p->d_band[sV], p->d_band[3 + sV], p->d_band[6 + sV]};
                 const float* Ds[3] = {p->d_band[3], p->d_band[6], p->d_band[9]};
@@ -762,10 +762,10 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                 if (sep) {
                     int n = 0;
                     const int hints = (l > 1 ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l < L ? PWT_HINT_IN_FROM_PREV : 0);
-                    if (p->kernel_mode == 0 || p->kernel_mode == 3)
-                        n = pwt_reg_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, hints, st);
-                    if (!n && !haar && ((p->kernel_mode == 0 && p->hlen >= p->strip_min_f && nr >= 32 && nc >= 128) || p->kernel_mode == 4))
+                    if (!haar && ((p->kernel_mode == 0 && p->hlen >= p->strip_min_f && nr >= 32 && nc >= 128) || p->kernel_mode == 4))
                         n = pwt_strip_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, st);
+                    if (!n && (p->kernel_mode == 0 || p->kernel_mode == 3))
+                        n = pwt_reg_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, hints, st);
                     if (!n && p->kernel_mode != 1 && !haar && p->hlen >= p->tile_min_f && nr >= 32 && nc >= 32)
                         n = pwt_tile_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, st);
                     if (!n && p->kernel_mode != 1)

@@ -424,7 +424,7 @@ def test_generic_kernels_agree_with_auto(wname):
 
 
 @pytest.mark.parametrize("shape", [(512, 1024), (1024, 512), (2048, 2048), (3, 512, 512)])
-@pytest.mark.parametrize("wname", ["haar", "db2", "db3", "sym4"])
+@pytest.mark.parametrize("wname", ["haar", "db2", "db3", "coif1"])
 def test_fused_cascade_is_bit_identical_to_per_level_kernels(wname, shape):
     """The fused 3-level register cascade performs the same arithmetic in the same order as three
     launches of the single-level register kernels: results must be bit-identical, and within
@@ -654,7 +654,7 @@ def test_nonseparable_rank1_path_agrees_with_direct_kernels(wname, do_swt):
     A = _W(img, wname, lv, do_separable=0, do_swt=do_swt); G = _W(img, wname, lv, do_separable=0, do_swt=do_swt)
     G.set_kernel_mode(1)
     A.forward(); G.forward()
-    assert A.launch_count < G.launch_count or do_swt
+    assert A.launch_count <= G.launch_count or do_swt
     ca, cg = A.coeffs, G.coeffs
     assert_close(ca[0], cg[0], 255.0, "nonsep A")
     for i in range(1, lv + 1):
@@ -664,3 +664,61 @@ def test_nonseparable_rank1_path_agrees_with_direct_kernels(wname, do_swt):
     A.inverse(); G.inverse()
     assert_close(A.image, G.image, 255.0, "nonsep inverse")
     assert_close(A.image, img, 255.0, "nonsep roundtrip")
+
+
+# ---- streaming strip kernels (kernels_strip.cu): kernel mode 4 forces them at every level and size -----------
+STRIP_WAVELETS = [w for w in ALL if w not in O.HAAR_ALIASES and 6 <= len(O.filters(w)[0]) and len(O.filters(w)[0]) % 2 == 0]
+
+
+@pytest.mark.parametrize("wname", STRIP_WAVELETS)
+def test_strip_kernels_against_oracle(wname):
+    """Forward and inverse of every built-in filter bank of length >= 6 through the strip kernels, at the
+    maximum depth (so the small levels exercise the wrap-around paths), against the CPU oracle."""
+    W = _W(IMG, wname, 999)
+    W.set_kernel_mode(4)
+    Wo = O.OracleWavelets(IMG, wname, 999)
+    assert W.levels == Wo.levels
+    n0 = W.launch_count
+    W.forward(); Wo.forward()
+    assert W.launch_count - n0 == W.levels          # one strip launch per level
+    compare_coeffs(W, Wo, SCALE, "strip dwt2 " + wname)
+    W.inverse(); Wo.inverse()
+    assert_close(W.image, Wo.image, SCALE, "strip idwt2 " + wname)
+
+
+@pytest.mark.parametrize("shape", [(511, 509), (64, 1000), (1001, 777), (40, 36), (300, 2048), (2, 260, 516), (17, 23),
+                                   (1024, 1536)])
+@pytest.mark.parametrize("wname", ["db4", "sym5", "db6", "sym8", "db10", "coif5", "db20", "bior6.8"])
+def test_strip_kernels_shapes(wname, shape):
+    """Odd sizes (the reference's replicate-last-sample extension), images narrower than a strip or than the
+    filter, several segments per strip, stacks: strip kernels against the generic tiled kernels."""
+    img = synth_image(shape, seed=23)
+    try:
+        S = _W(img, wname, 3); G = _W(img, wname, 3)
+    except ValueError:
+        pytest.skip("image too small for this filter")
+    S.set_kernel_mode(4); G.set_kernel_mode(1)
+    S.forward(); G.forward()
+    assert S.levels == G.levels
+    cs, cg = S.coeffs, G.coeffs
+    assert_close(cs[0], cg[0], SCALE, "strip vs generic A")
+    for i in range(1, len(cs)):
+        for j in range(3):
+            assert cs[i][j].shape == cg[i][j].shape
+            assert_close(cs[i][j], cg[i][j], SCALE, "strip vs generic L%d b%d" % (i, j))
+    S.inverse(); G.inverse()
+    assert_close(S.image, G.image, SCALE, "strip vs generic inverse")
+
+
+def test_strip_kernels_are_the_auto_choice():
+    """Auto mode picks the strip kernels for filters of length >= 8 on large planes (bit-identical results)."""
+    img = synth_image((1024, 1024), seed=29)
+    for wname in ("db4", "sym8", "db12"):
+        A = _W(img, wname, 2); S = _W(img, wname, 2)
+        S.set_kernel_mode(4)
+        A.forward(); S.forward()
+        for i in (1, 2):
+            for j in range(3):
+                assert np.array_equal(A.coeffs[i][j], S.coeffs[i][j])
+        A.inverse(); S.inverse()
+        assert np.array_equal(A.image, S.image)

@@ -56,12 +56,18 @@ if __name__ == "__main__":
     args = sys.argv[1:]
     if "check" in args:
         if check(): sys.exit(1)
+    if "time5" in args:
+        wns = [a for a in args if a not in ("check", "time", "time5", "nostack")]
+        for wn in wns:
+            a = timeit(wn, L=5, mode=0); b = timeit(wn, L=5, mode=4)
+            print("%-6s 8192^2 L5  auto fwd %.4f inv %.4f sum %.4f | strip fwd %.4f inv %.4f sum %.4f ms" % (wn, a[0], a[1], a[0] + a[1], b[0], b[1], b[0] + b[1]), flush=True)
     if "time" in args:
-        wns = [a for a in args if a not in ("check", "time")] or ["db3", "db4", "db6", "sym8", "db10", "db12", "coif5", "db20"]
+        wns = [a for a in args if a not in ("check", "time", "time5", "nostack")] or ["db3", "db4", "db6", "sym8", "db10", "db12", "coif5", "db20"]
         for wn in wns:
             a = timeit(wn, mode=0); b = timeit(wn, mode=4)
             print("%-6s 8192^2 L1  auto fwd %.4f inv %.4f | strip fwd %.4f inv %.4f ms" % (wn, a[0], a[1], b[0], b[1]), flush=True)
         for wn in ("sym8",):
+            if "nostack" in args: break
             for mode in (0, 4):
                 f, i = timeit(wn, shape=(64, 2048, 2048), L=3, mode=mode, n=5)
                 print("%-6s 64x2048^2 L3 mode %d fwd %.4f inv %.4f ms" % (wn, mode, f, i), flush=True)
