@@ -456,6 +456,248 @@ k_strip_inv(const float* __restrict__ A, const float* __restrict__ Hb, const flo
     }
 }
 
+// ---- batched 1D (ndim = 1: every row of the input is an independent signal) ------------------------------
+// The row passes of the 2D kernels on their own: a CTA walks down a strip of 256 columns in chunks of 16 rows
+// (cp.async double buffer), one warp per row, results go straight to global memory (the synthesis regroups its
+// 16 outputs per lane through a warp-private shared row so that the stores are contiguous 512-byte runs).
+// Reference: separable.cu:91-131 (w_kern_forward_pass1 on its own), 210-255 (inverse).
+constexpr int R1 = 16;
+
+template <int F>
+struct Fwd1Geo {
+    static constexpr int C = FwdGeo<F>::C, CL = FwdGeo<F>::CL, DX = FwdGeo<F>::DX, NV = FwdGeo<F>::NV, IW4 = FwdGeo<F>::IW4,
+                         P = FwdGeo<F>::P;
+    static constexpr int NS = (R1 * IW4 + NT - 1) / NT;
+    static constexpr size_t smem = sizeof(float) * ((size_t)2 * R1 * P) + sizeof(int) * (size_t)(4 * IW4);
+};
+
+template <int F>
+__global__ void __launch_bounds__(NT, 3)
+k_strip_fwd1d(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ D, int rows, int Nc, int QS,
+              const __grid_constant__ TapsFwd f) {
+    using G = Fwd1Geo<F>;
+    constexpr int CL = G::CL, DX = G::DX, NV = G::NV, IW4 = G::IW4, P = G::P, NS = G::NS, R = R1;
+    extern __shared__ __align__(16) float sm[];
+    float* raw = sm;                                  // [2][R][P]
+    int* colidx = reinterpret_cast<int*>(sm + 2 * R * P);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Nc2 = (Nc + 1) >> 1;
+    const int kx0 = blockIdx.x * HC;
+    const int q0 = blockIdx.y * QS, q1 = min(q0 + QS, rows);
+    if (q0 >= q1) return;
+    const int nchunks = (q1 - q0 + R - 1) / R;
+    const int xs = 2 * kx0 - CL;
+    const bool vec = (Nc & 3) == 0 && Nc >= 4 * IW4 && (((uintptr_t)in) & 15) == 0;
+    int s_off[NS], s_col[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        const int idx = tid + s * NT, r = idx / IW4, q = idx - r * IW4;
+        s_off[s] = r * P + 4 * swz2(q);
+        int gc = xs + 4 * q;
+        if (gc < 0) gc += Nc;
+        else if (gc >= Nc) gc -= Nc;
+        s_col[s] = gc;
+        if (NS <= 6) { pin(s_off[s]); pin(s_col[s]); }
+    }
+    if (!vec) {
+        for (int j = tid; j < 4 * IW4; j += NT) colidx[j] = wrap_dwt(xs + j, Nc);
+        __syncthreads();
+    }
+    auto stage = [&](int c) {
+        float* dst = raw + (c & 1) * R * P;
+        const int ibase = q0 + c * R;
+        const int rmax = rows - 1 - ibase;            // rows past the end re-read the last one (never stored)
+        const float* src = in + (long long)ibase * Nc;
+        if (vec) {
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                const int idx = tid + s * NT, r = idx / IW4;
+                if (s < NS - 1 || idx < R * IW4) cp_async16(dst + s_off[s], src + (unsigned)(min(r, rmax) * Nc + s_col[s]));
+            }
+        } else {
+            for (int e = tid; e < R * 4 * IW4; e += NT) {
+                const int r = e / (4 * IW4), j = e - r * (4 * IW4);
+                cp_async4(dst + r * P + 4 * swz2(j >> 2) + (j & 3), src + (unsigned)(min(r, rmax) * Nc + colidx[j]));
+            }
+        }
+        cp_async_commit();
+    };
+    int w_off[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) { w_off[k] = warp * P + 4 * swz2(2 * lane + k); pin(w_off[k]); }
+    const int kx = kx0 + 4 * lane;
+    const bool vst = (Nc2 & 3) == 0 && kx + 3 < Nc2 && ((((uintptr_t)A) | ((uintptr_t)D)) & 15) == 0;
+    const float2 zero2 = make_float2(0.f, 0.f);
+
+    stage(0);
+    for (int c = 0; c < nchunks; c++) {
+        cp_async_wait<0>();
+        __syncthreads();                               // chunk c staged; the other buffer is free
+        if (c + 1 < nchunks) stage(c + 1);
+        const float* rb = raw + (c & 1) * R * P;
+#pragma unroll
+        for (int rr = 0; rr < R / NWARP; rr++) {
+            const int row = q0 + c * R + warp + rr * NWARP;
+            float2 p[4];
+#pragma unroll
+            for (int o = 0; o < 4; o++) p[o] = zero2;
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                const float4 v = *reinterpret_cast<const float4*>(rb + rr * NWARP * P + w_off[k]);
+                const float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+#pragma unroll
+                    for (int o = 0; o < 4; o++) {
+                        const int j = 4 * k + e - DX - 2 * o;
+                        if (j >= 0 && j < F) p[o] = fma2s(xv[e], f.t[j], p[o]);
+                    }
+            }
+            if (row < q1) {
+                const long long ofs = (long long)row * Nc2 + kx;
+                if (vst) {
+                    *reinterpret_cast<float4*>(A + ofs) = make_float4(p[0].x, p[1].x, p[2].x, p[3].x);
+                    *reinterpret_cast<float4*>(D + ofs) = make_float4(p[0].y, p[1].y, p[2].y, p[3].y);
+                } else {
+#pragma unroll
+                    for (int o = 0; o < 4; o++)
+                        if (kx + o < Nc2) { A[ofs + o] = p[o].x; D[ofs + o] = p[o].y; }
+                }
+            }
+        }
+    }
+}
+
+template <int F>
+struct Inv1Geo {
+    using G2 = InvGeo<F>;
+    static constexpr int NS = (2 * R1 * G2::BW4 + NT - 1) / NT;
+    static constexpr size_t smem = sizeof(float) * ((size_t)2 * 2 * R1 * G2::P + (size_t)NWARP * 2 * SW) + sizeof(int) * (size_t)(4 * G2::BW4);
+};
+
+template <int F>
+__global__ void __launch_bounds__(NT, 3)
+k_strip_inv1d(const float* __restrict__ A, const float* __restrict__ D, float* __restrict__ out, int rows, int nc,
+              int Nc_out, int QS, const __grid_constant__ TapsInv f) {
+    using G = InvGeo<F>;
+    constexpr int NW = G::NW, HLr = G::HLr, DX = G::DX, NV = G::NV, BW4 = G::BW4, P = G::P, R = R1, NS = Inv1Geo<F>::NS;
+    extern __shared__ __align__(16) float sm[];
+    float* raw = sm;                                  // [2][2 bands][R][P]
+    float* us = sm + 2 * 2 * R * P;                   // [NWARP][2 rows][SW] warp-private output rows
+    int* colidx = reinterpret_cast<int*>(us + NWARP * 2 * SW);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * HC;
+    const int q0 = blockIdx.y * QS, q1 = min(q0 + QS, rows);
+    if (q0 >= q1) return;
+    const int nchunks = (q1 - q0 + R - 1) / R;
+    const int xs = x0 - HLr;
+    const bool vec = (nc & 3) == 0 && nc >= 4 * BW4 && ((((uintptr_t)A) | ((uintptr_t)D)) & 15) == 0;
+    int s_off[NS], s_col[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        const int idx = tid + s * NT, br = idx / BW4, q = idx - br * BW4;     // br = band * R + row
+        s_off[s] = br * P + 4 * swz2(q);
+        int gc = xs + 4 * q;
+        if (gc < 0) gc += nc;
+        else if (gc >= nc) gc -= nc;
+        s_col[s] = gc;
+        if (NS <= 6) { pin(s_off[s]); pin(s_col[s]); }
+    }
+    if (!vec) {
+        for (int j = tid; j < 4 * BW4; j += NT) colidx[j] = wrap_per(xs + j, nc);
+        __syncthreads();
+    }
+    auto stage = [&](int c) {
+        float* dst = raw + (c & 1) * 2 * R * P;
+        const int ibase = q0 + c * R;
+        const int rmax = rows - 1 - ibase;
+        const long long rb = (long long)ibase * nc;
+        if (vec) {
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                const int idx = tid + s * NT, br = idx / BW4;
+                if (s < NS - 1 || idx < 2 * R * BW4) {
+                    const int b = br / R, r = br - b * R;
+                    cp_async16(dst + s_off[s], (b ? D : A) + rb + (unsigned)(min(r, rmax) * nc + s_col[s]));
+                }
+            }
+        } else {
+            for (int e = tid; e < 2 * R * 4 * BW4; e += NT) {
+                const int br = e / (4 * BW4), j = e - br * (4 * BW4);
+                const int b = br / R, r = br - b * R;
+                cp_async4(dst + br * P + 4 * swz2(j >> 2) + (j & 3), (b ? D : A) + rb + (unsigned)(min(r, rmax) * nc + colidx[j]));
+            }
+        }
+        cp_async_commit();
+    };
+    // lanes 0-15 -> row 2*warp, lanes 16-31 -> row 2*warp+1 of the chunk; 8 band columns (16 outputs) per lane
+    const int rpl = lane >> 4, g = lane & 15;
+    int w_off[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) { w_off[k] = (2 * warp + rpl) * P + 4 * swz2(2 * g + k); if (F <= 24) pin(w_off[k]); }
+    float* usw = us + warp * 2 * SW;
+    const bool vst = (Nc_out & 3) == 0 && (((uintptr_t)out) & 15) == 0;
+    const float2 zero2 = make_float2(0.f, 0.f);
+
+    stage(0);
+    for (int c = 0; c < nchunks; c++) {
+        cp_async_wait<0>();
+        __syncthreads();
+        if (c + 1 < nchunks) stage(c + 1);
+        const float* px = raw + (c & 1) * 2 * R * P;   // + w_off: approximation row
+        const float* py = px + R * P;                  //          detail row
+        float2 eo[8];
+#pragma unroll
+        for (int cidx = 0; cidx < 8; cidx++) eo[cidx] = zero2;
+#pragma unroll
+        for (int k = NV - 1; k >= 0; k--) {
+            const float4 a = *reinterpret_cast<const float4*>(px + w_off[k]);
+            const float4 b = *reinterpret_cast<const float4*>(py + w_off[k]);
+            const float xa[4] = {a.x, a.y, a.z, a.w}, xb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int e = 3; e >= 0; e--)
+#pragma unroll
+                for (int cidx = 0; cidx < 8; cidx++) {
+                    const int w = 4 * k + e - DX - cidx;
+                    if (w < 0 || w >= NW) continue;
+                    if (G::use_e(w) && G::use_o(w)) {
+                        eo[cidx] = fma2s(xa[e], f.l[w], eo[cidx]);
+                        eo[cidx] = fma2s(xb[e], f.h[w], eo[cidx]);
+                    } else if (G::use_e(w)) {
+                        eo[cidx].x = fmaf(xa[e], f.l[w].x, eo[cidx].x);
+                        eo[cidx].x = fmaf(xb[e], f.h[w].x, eo[cidx].x);
+                    } else if (G::use_o(w)) {
+                        eo[cidx].y = fmaf(xa[e], f.l[w].y, eo[cidx].y);
+                        eo[cidx].y = fmaf(xb[e], f.h[w].y, eo[cidx].y);
+                    }
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            *reinterpret_cast<float4*>(usw + rpl * SW + 4 * swz4(4 * g + k)) =
+                make_float4(eo[2 * k].x, eo[2 * k].y, eo[2 * k + 1].x, eo[2 * k + 1].y);
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 4; h++) {
+            const int idx = h * 32 + lane, rw = idx >> 6, q = idx & 63;
+            const float4 v = *reinterpret_cast<const float4*>(usw + rw * SW + 4 * swz4(q));
+            const int row = q0 + c * R + 2 * warp + rw, col = 2 * x0 + 4 * q;
+            if (row < q1) {
+                float* dst = out + (long long)row * Nc_out + col;
+                if (vst && col + 3 < Nc_out) {
+                    *reinterpret_cast<float4*>(dst) = v;
+                } else {
+                    const float ev[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                        if (col + e < Nc_out) dst[e] = ev[e];
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // Segment height: the grid is (strips, segments, images); pick the segment count whose last wave is fullest,
@@ -582,6 +824,113 @@ int pwt_strip_dwt_inv2d(const float* A, const float* Hb, const float* V, const f
     switch (f.hlen) {
 #define X(FF) case FF: return launch_inv<FF>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, st);
         PWT_STRIP_CASES(X)
+#undef X
+        default: return 0;
+    }
+}
+
+// Haar, batched 1D, widths that are a multiple of 8: no halo and dense rows make the whole stack one flat stream
+// (8 samples in -> 4 + 4 out per item).  Same butterfly as the generic kernel / reference (haar.cu:10-42).
+namespace {
+__global__ void __launch_bounds__(256)
+k_haar_fwd1d_flat(const float4* __restrict__ in, float4* __restrict__ A, float4* __restrict__ D, long long items) {
+    const float c = 0.70710678118654746f;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < items; i += gridDim.x * 256LL) {
+        const float4 u = __ldg(in + 2 * i), v = __ldg(in + 2 * i + 1);
+        A[i] = make_float4(c * (u.x + u.y), c * (u.z + u.w), c * (v.x + v.y), c * (v.z + v.w));
+        D[i] = make_float4(c * (u.x - u.y), c * (u.z - u.w), c * (v.x - v.y), c * (v.z - v.w));
+    }
+}
+__global__ void __launch_bounds__(256)
+k_haar_inv1d_flat(const float4* __restrict__ A, const float4* __restrict__ D, float4* __restrict__ out, long long items) {
+    const float c = 0.70710678118654746f;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < items; i += gridDim.x * 256LL) {
+        const float4 a = __ldg(A + i), d = __ldg(D + i);
+        out[2 * i] = make_float4(c * (a.x + d.x), c * (a.x - d.x), c * (a.y + d.y), c * (a.y - d.y));
+        out[2 * i + 1] = make_float4(c * (a.z + d.z), c * (a.z - d.z), c * (a.w + d.w), c * (a.w - d.w));
+    }
+}
+}  // namespace
+
+int pwt_haar_fwd1d_flat(const float* in, float* A, float* D, int rows, int Nc, cudaStream_t st) {
+    if ((Nc & 7) || ((((uintptr_t)in) | ((uintptr_t)A) | ((uintptr_t)D)) & 15)) return 0;
+    const long long items = (long long)rows * (Nc / 8);
+    const long long want = (items + 255) / 256, cap = (long long)sm_count() * 16;
+    k_haar_fwd1d_flat<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(reinterpret_cast<const float4*>(in),
+                                                                          reinterpret_cast<float4*>(A),
+                                                                          reinterpret_cast<float4*>(D), items);
+    return 1;
+}
+int pwt_haar_inv1d_flat(const float* A, const float* D, float* out, int rows, int nc, int Nc_out, cudaStream_t st) {
+    if ((nc & 3) || Nc_out != 2 * nc || ((((uintptr_t)out) | ((uintptr_t)A) | ((uintptr_t)D)) & 15)) return 0;
+    const long long items = (long long)rows * (nc / 4);
+    const long long want = (items + 255) / 256, cap = (long long)sm_count() * 16;
+    k_haar_inv1d_flat<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(reinterpret_cast<const float4*>(A),
+                                                                          reinterpret_cast<const float4*>(D),
+                                                                          reinterpret_cast<float4*>(out), items);
+    return 1;
+}
+
+#define PWT_STRIP1D_CASES(X) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20) X(22) X(24) X(26) X(28) X(30) X(32) X(34) X(36) X(38) X(40)
+
+namespace {
+int pick_segments_1d(int nstrips, int rows, int slots) {
+    // enough CTAs for ~4 waves, segments a multiple of the chunk height
+    const int want = (4 * slots + nstrips - 1) / nstrips;
+    int qs = (rows + want - 1) / want;
+    qs = ((qs + R1 - 1) / R1) * R1;
+    if (qs < R1) qs = R1;
+    while ((rows + qs - 1) / qs > 65535) qs += R1;
+    return qs;
+}
+template <int F>
+int launch_fwd1d(const float* in, float* A, float* D, int rows, int Nc, const PwtFilters& f, cudaStream_t st) {
+    using G = Fwd1Geo<F>;
+    static int per_sm = 0;
+    if (!per_sm) {
+        cudaFuncSetAttribute(k_strip_fwd1d<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_fwd1d<F>, NT, G::smem);
+        if (per_sm <= 0) per_sm = 1;
+    }
+    const int nstrips = cdiv((Nc + 1) / 2, HC);
+    const int QS = pick_segments_1d(nstrips, rows, per_sm * sm_count());
+    dim3 grid(nstrips, cdiv(rows, QS), 1);
+    k_strip_fwd1d<F><<<grid, NT, G::smem, st>>>(in, A, D, rows, Nc, QS, pwt_pack_taps_fwd(f, F));
+    return 1;
+}
+template <int F>
+int launch_inv1d(const float* A, const float* D, float* out, int rows, int nc, int Nc_out, const PwtFilters& f,
+                 cudaStream_t st) {
+    using G = Inv1Geo<F>;
+    static int per_sm = 0;
+    if (!per_sm) {
+        cudaFuncSetAttribute(k_strip_inv1d<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_inv1d<F>, NT, G::smem);
+        if (per_sm <= 0) per_sm = 1;
+    }
+    const int nstrips = cdiv(nc, HC);
+    const int QS = pick_segments_1d(nstrips, rows, per_sm * sm_count());
+    dim3 grid(nstrips, cdiv(rows, QS), 1);
+    k_strip_inv1d<F><<<grid, NT, G::smem, st>>>(A, D, out, rows, nc, Nc_out, QS, pwt_pack_taps_inv(f, F));
+    return 1;
+}
+}  // namespace
+
+int pwt_strip_dwt_fwd1d(const float* in, float* A, float* D, int rows, int Nc, const PwtFilters& f, cudaStream_t st) {
+    if (rows < 1 || Nc < 2) return 0;
+    switch (f.hlen) {
+#define X(FF) case FF: return launch_fwd1d<FF>(in, A, D, rows, Nc, f, st);
+        PWT_STRIP1D_CASES(X)
+#undef X
+        default: return 0;
+    }
+}
+int pwt_strip_dwt_inv1d(const float* A, const float* D, float* out, int rows, int nc, int Nc_out, const PwtFilters& f,
+                        cudaStream_t st) {
+    if (rows < 1 || nc < 1) return 0;
+    switch (f.hlen) {
+#define X(FF) case FF: return launch_inv1d<FF>(A, D, out, rows, nc, Nc_out, f, st);
+        PWT_STRIP1D_CASES(X)
 #undef X
         default: return 0;
     }

@@ -189,3 +189,15 @@ int pwt_strip_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D
 int pwt_strip_dwt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
                         int nr, int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs,
                         const PwtFilters& f, cudaStream_t st);
+// batched 1D (every row an independent signal): F = 4..40
+int pwt_strip_dwt_fwd1d(const float* in, float* A, float* D, int rows, int Nc, const PwtFilters& f, cudaStream_t st);
+int pwt_strip_dwt_inv1d(const float* A, const float* D, float* out, int rows, int nc, int Nc_out, const PwtFilters& f,
+                        cudaStream_t st);
+// Haar, batched 1D, width multiple of 8: flat streaming butterfly.  Return 0 when not covered.
+int pwt_haar_fwd1d_flat(const float* in, float* A, float* D, int rows, int Nc, cudaStream_t st);
+int pwt_haar_inv1d_flat(const float* A, const float* D, float* out, int rows, int nc, int Nc_out, cudaStream_t st);
+// kernels_swt1d.cu : batched 1D a-trous level from a staged shared-memory row.  Return 0 when not covered.
+int pwt_fast_swt_fwd1d(const float* in, float* A, float* D, int rows, int Nc, int level, const PwtFilters& f,
+                       cudaStream_t st);
+int pwt_fast_swt_inv1d(const float* A, const float* D, float* out, int rows, int Nc, int level, const PwtFilters& f,
+                       cudaStream_t st);

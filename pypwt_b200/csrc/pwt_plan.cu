@@ -584,10 +584,19 @@ extern "C" int pwt_forward(pwt_plan* p) {
         for (int l = 1; l <= L; l++) {
             float* dstA = approx_dst(p, l, p->d_tmp);
             prof_begin(p, 100 * l + 1);
-            if (p->do_swt)
-                p->launches += pwt_launch_swt_fwd1d(src, dstA, p->d_band[l], rows, p->Nc, l, p->filt, st);
-            else
-                p->launches += pwt_launch_dwt_fwd1d(src, dstA, p->d_band[l], rows, p->lvNc[l - 1], p->filt, haar, st);
+            if (p->do_swt) {
+                int n = p->kernel_mode == 1 ? 0 : pwt_fast_swt_fwd1d(src, dstA, p->d_band[l], rows, p->Nc, l, p->filt, st);
+                if (!n) n = pwt_launch_swt_fwd1d(src, dstA, p->d_band[l], rows, p->Nc, l, p->filt, st);
+                p->launches += n;
+            }
+            else {
+                int n = 0;
+                if (!haar && ((p->kernel_mode == 0 && p->lvNc[l - 1] >= 256) || p->kernel_mode == 4))
+                    n = pwt_strip_dwt_fwd1d(src, dstA, p->d_band[l], rows, p->lvNc[l - 1], p->filt, st);
+                if (haar && p->kernel_mode != 1) n = pwt_haar_fwd1d_flat(src, dstA, p->d_band[l], rows, p->lvNc[l - 1], st);
+                if (!n) n = pwt_launch_dwt_fwd1d(src, dstA, p->d_band[l], rows, p->lvNc[l - 1], p->filt, haar, st);
+                p->launches += n;
+            }
             prof_end(p);
             src = dstA;
         }
@@ -683,10 +692,19 @@ extern "C" int pwt_inverse(pwt_plan* p) {
         for (int l = L; l >= 1; l--) {
             float* dst = (l == 1) ? p->d_image : (cur == p->d_band[0] ? p->d_tmp : p->d_band[0]);
             prof_begin(p, 100 * l + 2);
-            if (p->do_swt)
-                p->launches += pwt_launch_swt_inv1d(cur, p->d_band[l], dst, rows, p->Nc, l, p->filt, st);
-            else
-                p->launches += pwt_launch_dwt_inv1d(cur, p->d_band[l], dst, rows, p->lvNc[l], p->lvNc[l - 1], p->filt, haar, st);
+            if (p->do_swt) {
+                int n = p->kernel_mode == 1 ? 0 : pwt_fast_swt_inv1d(cur, p->d_band[l], dst, rows, p->Nc, l, p->filt, st);
+                if (!n) n = pwt_launch_swt_inv1d(cur, p->d_band[l], dst, rows, p->Nc, l, p->filt, st);
+                p->launches += n;
+            }
+            else {
+                int n = 0;
+                if (!haar && ((p->kernel_mode == 0 && p->lvNc[l] >= 128) || p->kernel_mode == 4))
+                    n = pwt_strip_dwt_inv1d(cur, p->d_band[l], dst, rows, p->lvNc[l], p->lvNc[l - 1], p->filt, st);
+                if (haar && p->kernel_mode != 1) n = pwt_haar_inv1d_flat(cur, p->d_band[l], dst, rows, p->lvNc[l], p->lvNc[l - 1], st);
+                if (!n) n = pwt_launch_dwt_inv1d(cur, p->d_band[l], dst, rows, p->lvNc[l], p->lvNc[l - 1], p->filt, haar, st);
+                p->launches += n;
+            }
             prof_end(p);
             cur = dst;
         }

@@ -722,3 +722,40 @@ def test_strip_kernels_are_the_auto_choice():
                 assert np.array_equal(A.coeffs[i][j], S.coeffs[i][j])
         A.inverse(); S.inverse()
         assert np.array_equal(A.image, S.image)
+
+
+STRIP1D_WAVELETS = [w for w in ALL if w not in O.HAAR_ALIASES and len(O.filters(w)[0]) >= 4 and len(O.filters(w)[0]) % 2 == 0]
+
+
+@pytest.mark.parametrize("batched", [0, 1])
+@pytest.mark.parametrize("wname", STRIP1D_WAVELETS)
+def test_strip_kernels_1d_against_oracle(wname, batched):
+    """Batched 1D DWT / IDWT through the strip row kernels (kernel mode 4: every level, every width)."""
+    data = synth_image((37, 1000), seed=41) if batched else synth_image((1, 4099), seed=43)[0]
+    W = _W(data, wname, 999, ndim=1)
+    W.set_kernel_mode(4)
+    Wo = O.OracleWavelets(data, wname, 999, ndim=1)
+    assert W.levels == Wo.levels
+    W.forward(); Wo.forward()
+    compare_coeffs(W, Wo, SCALE, "strip dwt1d " + wname)
+    W.inverse(); Wo.inverse()
+    assert_close(W.image, Wo.image, SCALE, "strip idwt1d " + wname)
+
+
+@pytest.mark.parametrize("shape", [(64, 1024), (5, 8192), (3, 136), (4096,)])
+@pytest.mark.parametrize("wname", ["haar", "db2", "sym8", "db20"])
+def test_fast_1d_kernels_agree_with_generic(wname, shape):
+    """Auto mode (flat Haar butterfly, strip row kernels, staged-row SWT) against the generic kernels, DWT and SWT."""
+    img = synth_image(shape if len(shape) == 2 else (1, shape[0]), seed=47)
+    img = img if len(shape) == 2 else img[0]
+    for do_swt in (0, 1):
+        try:
+            A = _W(img, wname, 4, ndim=1, do_swt=do_swt); G = _W(img, wname, 4, ndim=1, do_swt=do_swt)
+        except ValueError:
+            continue
+        G.set_kernel_mode(1)
+        A.forward(); G.forward()
+        for a, g in zip(A.coeffs, G.coeffs):
+            assert_close(a, g, SCALE, "1d auto vs generic swt=%d" % do_swt)
+        A.inverse(); G.inverse()
+        assert_close(A.image, G.image, SCALE, "1d auto vs generic inverse swt=%d" % do_swt)
