@@ -804,7 +804,7 @@ int launch_inv(const float* A, const float* Hb, const float* V, const float* D, 
 
 }  // namespace
 
-#define PWT_STRIP_CASES(X) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20) X(22) X(24) X(26) X(28) X(30) X(32) X(34) X(36) X(38) X(40)
+#define PWT_STRIP_CASES(X) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20) X(22) X(24) X(26) X(28) X(30) X(32) X(34) X(36) X(38) X(40)
 
 int pwt_strip_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
                         long long in_bs, long long out_bs, const PwtFilters& f, cudaStream_t st) {

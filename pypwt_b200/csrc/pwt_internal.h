@@ -201,3 +201,10 @@ int pwt_fast_swt_fwd1d(const float* in, float* A, float* D, int rows, int Nc, in
                        cudaStream_t st);
 int pwt_fast_swt_inv1d(const float* A, const float* D, float* out, int rows, int Nc, int level, const PwtFilters& f,
                        cudaStream_t st);
+// kernels_swt_strip.cu : 2D a-trous forward level, streaming strip design (F <= 16).  Return 0 when not covered.
+int pwt_strip_swt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
+                        int level, const PwtFilters& f, cudaStream_t st);
+int pwt_strip_swt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
+                        int Nr, int Nc, int level, const PwtFilters& f, int thr_op, float beta, int app,
+                        float beta_app, cudaStream_t st);
+int pwt_strip_swt_inv2d_covers(int batch, int Nr, int Nc, int level, const PwtFilters& f, const void* A, const void* out);

@@ -213,7 +213,9 @@ static void compute_geometry(pwt_plan* p) {
 static int swt_all_levels_fused(const pwt_plan* p) {
     if (!(p->ndims == 2 && p->do_swt && p->do_separable)) return 0;
     for (int l = 1; l <= p->nlevels; l++)
-        if (!pwt_fast_swt_inv2d_covers(p->batch, p->Nr, p->Nc, l, p->filt, p->d_band[0], p->d_image)) return 0;
+        if (!pwt_strip_swt_inv2d_covers(p->batch, p->Nr, p->Nc, l, p->filt, p->d_band[0], p->d_image) &&
+            !pwt_fast_swt_inv2d_covers(p->batch, p->Nr, p->Nc, l, p->filt, p->d_band[0], p->d_image))
+            return 0;
     return 1;
 }
 
@@ -633,7 +635,8 @@ extern "C" int pwt_forward(pwt_plan* p) {
             if (p->do_swt) {
                 float* dstA = approx_dst(p, l, p->d_tmp + 2 * plane);
                 if (p->do_separable || ns_sep) {
-                    int n = p->kernel_mode == 1 ? 0 : pwt_fast_swt_fwd2d(src, dstA, Hb, V, D, B, p->Nr, p->Nc, l, p->filt, st);
+                    int n = p->kernel_mode == 0 ? pwt_strip_swt_fwd2d(src, dstA, Hb, V, D, B, p->Nr, p->Nc, l, p->filt, st) : 0;
+                    if (!n && p->kernel_mode != 1) n = pwt_fast_swt_fwd2d(src, dstA, Hb, V, D, B, p->Nr, p->Nc, l, p->filt, st);
                     if (!n) n = pwt_launch_swt_fwd2d(src, dstA, Hb, V, D, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
                     p->launches += n;
                 }
@@ -759,7 +762,14 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                 float* dst = (l == 1) ? p->d_image : (cur == p->d_band[0] ? alt : p->d_band[0]);
                 if (p->do_separable || ns_sep) {
                     int n = 0;
-                    if (p->kernel_mode != 1) {
+                    if (p->kernel_mode == 0) {
+                        if (swt_defer)
+                            n = pwt_strip_swt_inv2d(cur, Hb, V, D, dst, B, p->Nr, p->Nc, l, p->filt, fop.op, fop.beta[l - 1],
+                                                    l == L && fop.app, fop.beta_app, st);
+                        else
+                            n = pwt_strip_swt_inv2d(cur, Hb, V, D, dst, B, p->Nr, p->Nc, l, p->filt, -1, 0.f, 0, 0.f, st);
+                    }
+                    if (!n && p->kernel_mode != 1) {
                         if (swt_defer)      // the deferred threshold of this level is applied while its bands are loaded
                             n = pwt_fast_swt_inv2d(cur, Hb, V, D, dst, B, p->Nr, p->Nc, l, p->filt, fop.op, fop.beta[l - 1],
                                                    l == L && fop.app, fop.beta_app, st);

@@ -83,6 +83,33 @@ def check1d():
     print("check1d done, failures:", bad)
     return bad
 
+def checkswt():
+    rng = np.random.default_rng(7)
+    bad = 0
+    for shp in [(512, 768), (300, 520), (64, 1000), (1024, 1024), (2, 260, 516), (129, 260), (2048, 2048)]:
+        img = (rng.standard_normal(shp) * 50 + 128).astype(np.float32)
+        for wn in ["haar", "db2", "db3", "db4", "sym5", "db6", "sym7", "sym8"]:
+            for L in (1, 2, 4):
+                try:
+                    S = pycudwt.Wavelets(img, wn, L, do_swt=1); G = pycudwt.Wavelets(img, wn, L, do_swt=1)
+                except ValueError:
+                    continue
+                G.set_kernel_mode(1)
+                S.forward(); G.forward()
+                cs, cg = S.coeffs, G.coeffs
+                scale = 1e-5 * max(np.abs(img).max(), 1.0)
+                errs = [np.abs(cs[0] - cg[0]).max() / max(scale, 1e-5 * np.abs(cg[0]).max())]
+                for i in range(1, len(cs)):
+                    for j in range(3):
+                        errs.append(np.abs(cs[i][j] - cg[i][j]).max() / max(scale, 1e-5 * np.abs(cg[i][j]).max()))
+                S.inverse(); G.inverse()
+                ei = np.abs(S.image - G.image).max() / scale
+                if not (max(errs) < 1.0 and ei < 1.0):
+                    bad += 1
+                    print("FAILSWT2D", shp, wn, L, S.levels, "fwd %.3g inv %.3g" % (max(errs), ei), flush=True)
+    print("checkswt done, failures:", bad)
+    return bad
+
 def timeit(wn, shape=(8192, 8192), L=1, mode=0, n=20):
     img = np.random.default_rng(0).standard_normal(shape).astype(np.float32)
     W = pycudwt.Wavelets(img, wn, L)
@@ -102,15 +129,17 @@ if __name__ == "__main__":
     args = sys.argv[1:]
     if "check" in args:
         if check(): sys.exit(1)
+    if "checkswt" in args:
+        if checkswt(): sys.exit(1)
     if "check1d" in args:
         if check1d(): sys.exit(1)
     if "time5" in args:
-        wns = [a for a in args if a not in ("check", "check1d", "time", "time5", "nostack")]
+        wns = [a for a in args if a not in ("check", "check1d", "checkswt", "time", "time5", "nostack")]
         for wn in wns:
             a = timeit(wn, L=5, mode=0); b = timeit(wn, L=5, mode=4)
             print("%-6s 8192^2 L5  auto fwd %.4f inv %.4f sum %.4f | strip fwd %.4f inv %.4f sum %.4f ms" % (wn, a[0], a[1], a[0] + a[1], b[0], b[1], b[0] + b[1]), flush=True)
     if "time" in args:
-        wns = [a for a in args if a not in ("check", "check1d", "time", "time5", "nostack")] or ["db3", "db4", "db6", "sym8", "db10", "db12", "coif5", "db20"]
+        wns = [a for a in args if a not in ("check", "check1d", "checkswt", "time", "time5", "nostack")] or ["db3", "db4", "db6", "sym8", "db10", "db12", "coif5", "db20"]
         for wn in wns:
             a = timeit(wn, mode=0); b = timeit(wn, mode=4)
             print("%-6s 8192^2 L1  auto fwd %.4f inv %.4f | strip fwd %.4f inv %.4f ms" % (wn, a[0], a[1], b[0], b[1]), flush=True)
