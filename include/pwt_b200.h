@@ -140,7 +140,8 @@ int pwt_profile_enable(pwt_plan* p, int on);
 int pwt_profile_read(pwt_plan* p, float* ms, int* tags, int cap);
 /* choose kernel family: 0 = auto (default), 1 = force the generic tiled kernels,
  * 2 = shared-memory fast kernels + generic (skip the register-resident kernels),
- * 3 = everything except the fused 3-level cascade */
+ * 3 = everything except the fused 3-level cascade,
+ * 4 = streaming strip kernels at every level and size (2D and batched 1D DWT, filter length >= 4) */
 int pwt_set_kernel_mode(pwt_plan* p, int mode);
 
 /* ---- multi-GPU: one process per GPU, NCCL only for the scalar all-reduce --------------- */

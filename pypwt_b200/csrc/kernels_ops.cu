@@ -155,6 +155,37 @@ k_circshift(const float* __restrict__ in, float* __restrict__ out, int Nr, int N
     }
 }
 
+// Same shift for widths that are a multiple of 4 (16-byte aligned planes): a thread stores one aligned 128-bit
+// group and builds it from the two aligned groups that cover its (misaligned by sc & 3, uniform) source window.
+template <int K>
+__device__ __forceinline__ float4 shift_pick(const float4& a, const float4& b) {
+    if (K == 0) return a;
+    if (K == 1) return make_float4(a.y, a.z, a.w, b.x);
+    if (K == 2) return make_float4(a.z, a.w, b.x, b.y);
+    return make_float4(a.w, b.x, b.y, b.z);
+}
+template <int K>
+__global__ void __launch_bounds__(kThreads)
+k_circshift4(const float4* __restrict__ in, float4* __restrict__ out, int Nr, int G, int sr, int g0, long long total) {
+    // G = Nc/4 groups per row; source group of output group g is (g + g0) mod G (and the next one when K != 0)
+    for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        const long long row = i / G;
+        const int g = (int)(i - row * G);
+        const int y = (int)(row % Nr);
+        const long long pb = (row - y) * G;                  // first group of this image
+        int r = y - sr;
+        if (r < 0) r += Nr;
+        int ga = g + g0;
+        if (ga >= G) ga -= G;
+        int gb = ga + 1;
+        if (gb >= G) gb -= G;
+        const float4* src = in + pb + (long long)r * G;
+        const float4 a = __ldg(src + ga);
+        const float4 b = K ? __ldg(src + gb) : a;
+        out[i] = shift_pick<K>(a, b);
+    }
+}
+
 // adds the per-task partial sums written by the fused forward kernel to acc[0..1]
 __global__ void __launch_bounds__(kThreads) k_reduce_partials(const double* __restrict__ part, int n, double* __restrict__ acc, int add) {
     double l1 = 0.0, l2 = 0.0;
@@ -248,6 +279,21 @@ int pwt_launch_axpy(const PwtSegTable& dst, const PwtSegTable& src, float alpha,
 
 int pwt_launch_circshift(const float* in, float* out, int batch, int Nr, int Nc, int sr, int sc,
                          cudaStream_t st) {
+    if ((Nc & 3) == 0 && ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0) {
+        // out[x] = in[x - sc]: the source of output group g starts at column 4g - sc = 4(g + g0) + k, k = (-sc) & 3
+        const int G = Nc / 4;
+        int c0 = (Nc - sc) % Nc;                             // source column of output column 0
+        const int k = c0 & 3, g0 = c0 >> 2;
+        const long long total = (long long)batch * Nr * G;
+        const unsigned blocks = (unsigned)grid_for(total * 4);
+        const float4* i4 = reinterpret_cast<const float4*>(in);
+        float4* o4 = reinterpret_cast<float4*>(out);
+        if (k == 0) k_circshift4<0><<<blocks, kThreads, 0, st>>>(i4, o4, Nr, G, sr, g0, total);
+        else if (k == 1) k_circshift4<1><<<blocks, kThreads, 0, st>>>(i4, o4, Nr, G, sr, g0, total);
+        else if (k == 2) k_circshift4<2><<<blocks, kThreads, 0, st>>>(i4, o4, Nr, G, sr, g0, total);
+        else k_circshift4<3><<<blocks, kThreads, 0, st>>>(i4, o4, Nr, G, sr, g0, total);
+        return 1;
+    }
     dim3 grid((Nc + kThreads - 1) / kThreads, Nr < 65535 ? Nr : 65535, batch);
     k_circshift<<<grid, kThreads, 0, st>>>(in, out, Nr, Nc, sr, sc);
     return 1;

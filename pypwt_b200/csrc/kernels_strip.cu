@@ -808,7 +808,7 @@ int launch_inv(const float* A, const float* Hb, const float* V, const float* D, 
 
 int pwt_strip_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
                         long long in_bs, long long out_bs, const PwtFilters& f, cudaStream_t st) {
-    if (batch > 65535 || Nr < 2 || Nc < 2) return 0;
+    if (batch > 65535 || Nr < 2 || Nc < 2 || (long long)(Nr + 64) * Nc >= (1LL << 31)) return 0;   // 32-bit offsets inside an image
     switch (f.hlen) {
 #define X(FF) case FF: return launch_fwd<FF>(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, f, st);
         PWT_STRIP_CASES(X)
@@ -820,7 +820,7 @@ int pwt_strip_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D
 int pwt_strip_dwt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
                         int nr, int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs,
                         const PwtFilters& f, cudaStream_t st) {
-    if (batch > 65535 || nr < 1 || nc < 1) return 0;
+    if (batch > 65535 || nr < 1 || nc < 1 || (long long)(Nr_out + 64) * Nc_out >= (1LL << 31)) return 0;
     switch (f.hlen) {
 #define X(FF) case FF: return launch_inv<FF>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, st);
         PWT_STRIP_CASES(X)
@@ -917,7 +917,7 @@ int launch_inv1d(const float* A, const float* D, float* out, int rows, int nc, i
 }  // namespace
 
 int pwt_strip_dwt_fwd1d(const float* in, float* A, float* D, int rows, int Nc, const PwtFilters& f, cudaStream_t st) {
-    if (rows < 1 || Nc < 2) return 0;
+    if (rows < 1 || Nc < 2 || Nc >= (1 << 26)) return 0;
     switch (f.hlen) {
 #define X(FF) case FF: return launch_fwd1d<FF>(in, A, D, rows, Nc, f, st);
         PWT_STRIP1D_CASES(X)
@@ -927,7 +927,7 @@ int pwt_strip_dwt_fwd1d(const float* in, float* A, float* D, int rows, int Nc, c
 }
 int pwt_strip_dwt_inv1d(const float* A, const float* D, float* out, int rows, int nc, int Nc_out, const PwtFilters& f,
                         cudaStream_t st) {
-    if (rows < 1 || nc < 1) return 0;
+    if (rows < 1 || nc < 1 || nc >= (1 << 26)) return 0;
     switch (f.hlen) {
 #define X(FF) case FF: return launch_inv1d<FF>(A, D, out, rows, nc, Nc_out, f, st);
         PWT_STRIP1D_CASES(X)

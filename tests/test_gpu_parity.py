@@ -759,3 +759,16 @@ def test_fast_1d_kernels_agree_with_generic(wname, shape):
             assert_close(a, g, SCALE, "1d auto vs generic swt=%d" % do_swt)
         A.inverse(); G.inverse()
         assert_close(A.image, G.image, SCALE, "1d auto vs generic inverse swt=%d" % do_swt)
+
+
+@pytest.mark.parametrize("shape", [(64, 256), (33, 100), (3, 40, 64), (50, 101)])
+def test_circshift_all_alignments(shape):
+    """circshift (common.cu:202-211) for every column shift modulo 4 (the 128-bit path builds each aligned
+    output group from two aligned source groups), negative shifts, stacks, and a width that is not a multiple
+    of 4 (scalar path): exactly numpy's roll."""
+    img = synth_image(shape, seed=53)
+    W = _W(img, "db2", 1)
+    for sr, sc in [(0, 0), (1, 1), (5, 2), (-3, 3), (7, -1), (-9, -6), (shape[-2] - 1, shape[-1] - 1), (2, 4)]:
+        W.set_image(img)
+        W.circshift(sr, sc)
+        assert np.array_equal(W.image, np.roll(img, (sr, sc), axis=(-2, -1))), (sr, sc)

@@ -115,6 +115,10 @@ def main():
         add("C5 sep fwd+inv", (8192, 8192), w, 5, 16)
     for w in (["haar", "db2", "db4"] if quick else ["haar", "db2", "db3", "db4", "db6", "db8"]):
         add("C5 nonsep fwd+inv", (4096, 4096), w, 5, 16, do_separable=0)
+    # batched 1D (ndim=1: every row an independent signal), DWT and SWT
+    for w in (["db2"] if quick else ["haar", "db2", "sym8"]):
+        add("1D batched fwd+inv", (8192, 8192), w, 3, 16, ndim=1)
+        add("1D batched swt fwd+inv", (8192, 8192), w, 3, 2 * (3 + 2) * 4, ndim=1, do_swt=1)
     with open(out, "w") as f:
         f.write("| config | shape | wavelet | L | ms | Mpixel/s | GB/s (algorithmic) | frac of 6549 GB/s | launches | PDWT CUDA ms | speed-up vs PDWT |\n")
         f.write("|---|---|---|---:|---:|---:|---:|---:|---:|---:|---:|\n")
