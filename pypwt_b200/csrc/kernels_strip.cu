@@ -110,11 +110,15 @@ struct FwdGeo {
     static constexpr size_t smem = sizeof(float) * ((size_t)NBUF * R * P + (size_t)R * SW) + sizeof(int) * (size_t)(4 * IW4);
 };
 
-template <int F, int MB>
+// NRM: the norm reduction fused into the pass -- every thread sums |c| and c^2 of the coefficients it stores
+// (fp32 within a chunk, fp64 across chunks), the CTA writes one pair of doubles to partials[linear CTA index]
+// (plain stores, no atomics, no memset; wt.cu:368-416 computes the same sums with cuBLAS over the stored planes).
+// count_a: include the approximation plane (last level only).
+template <int F, int MB, bool NRM>
 __global__ void __launch_bounds__(NT, MB)
 k_strip_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ Hb, float* __restrict__ V,
             float* __restrict__ D, int Nr, int Nc, long long in_bs, long long out_bs, int QS,
-            const __grid_constant__ TapsFwd f) {
+            const __grid_constant__ TapsFwd f, double* __restrict__ partials, int count_a) {
     using G = FwdGeo<F>;
     constexpr int C = G::C, CL = G::CL, DX = G::DX, NV = G::NV, IW4 = G::IW4, P = G::P, R = G::R, NBUF = G::NBUF, NS = G::NS;
     constexpr int HF = F / 2;
@@ -126,7 +130,11 @@ k_strip_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restri
     const int Nr2 = (Nr + 1) >> 1, Nc2 = (Nc + 1) >> 1;
     const int kx0 = blockIdx.x * HC;
     const int q0 = blockIdx.y * QS, q1 = min(q0 + QS, Nr2);
-    if (q0 >= q1) return;
+    const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (q0 >= q1) {
+        if (NRM && tid == 0) partials[2 * cta] = partials[2 * cta + 1] = 0.0;
+        return;
+    }
     in += blockIdx.z * in_bs;
     const long long ob = blockIdx.z * out_bs;
     const int i0 = 2 * q0 - C;                        // image row of stream row 0
@@ -196,6 +204,9 @@ k_strip_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restri
     float2 acc[HF];
 #pragma unroll
     for (int a = 0; a < HF; a++) acc[a] = zero2;
+    float s1 = 0.f, s2 = 0.f;                          // norm partial sums of the current chunk
+    double d1 = 0.0, d2 = 0.0;
+    const bool cnt_x = pl || count_a;                  // plane 0 stores A in .x: counted on the last level only
 
     stage(0);
     for (int c = 0; c < nchunks; c++) {
@@ -248,10 +259,36 @@ k_strip_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restri
                 const int a = ((j + 1) >> 1) % HF, k = (j + 1) >> 1;
                 stg_if(o0, (unsigned)(obase + k * Nc2), acc[a].x, (unsigned)(ubase + k), nvalid);
                 stg_if(o1, (unsigned)(obase + k * Nc2), acc[a].y, (unsigned)(ubase + k), nvalid);
+                if (NRM) {
+                    const bool ok = (unsigned)(ubase + k) < nvalid;
+                    const float vx = ok && cnt_x ? acc[a].x : 0.f, vy = ok ? acc[a].y : 0.f;
+                    s1 += fabsf(vx) + fabsf(vy);
+                    s2 = fmaf(vx, vx, s2);
+                    s2 = fmaf(vy, vy, s2);
+                }
             }
         }
+        if (NRM) { d1 += (double)s1; d2 += (double)s2; s1 = s2 = 0.f; }
         ubase += R / 2;
         obase += (R / 2) * Nc2;
+    }
+    if (NRM) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+            d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        }
+        __syncthreads();                               // everybody is done with rp: reuse it for the 8 warp sums
+        double* red = reinterpret_cast<double*>(rp);
+        if (lane == 0) { red[2 * warp] = d1; red[2 * warp + 1] = d2; }
+        __syncthreads();
+        if (tid == 0) {
+            double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+            for (int w = 0; w < NWARP; w++) { t1 += red[2 * w]; t2 += red[2 * w + 1]; }
+            partials[2 * cta] = t1;
+            partials[2 * cta + 1] = t2;
+        }
     }
 }
 
@@ -732,14 +769,20 @@ int sm_count() {
     return g_sm_count;
 }
 
-template <int F, int MB>
+struct NormSink {             // optional fused norm reduction of a forward launch
+    double* partials;         // receives one (sum |c|, sum c^2) pair per CTA, or null
+    int cap;                  // pairs available
+    int count_a;              // include the approximation plane
+    int written;              // out: pairs written (0: the launch ran without the reduction)
+};
+template <int F, int MB, bool NRM>
 int launch_fwd_mb(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
-                  long long in_bs, long long out_bs, const PwtFilters& f, cudaStream_t st) {
+                  long long in_bs, long long out_bs, const PwtFilters& f, NormSink* ns, cudaStream_t st) {
     using G = FwdGeo<F>;
     static int per_sm = 0;
     if (!per_sm) {
-        cudaFuncSetAttribute(k_strip_fwd<F, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_fwd<F, MB>, NT, G::smem);
+        cudaFuncSetAttribute(k_strip_fwd<F, MB, NRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_fwd<F, MB, NRM>, NT, G::smem);
         if (per_sm <= 0) per_sm = 1;
     }
     const int Nr2 = (Nr + 1) / 2, Nc2 = (Nc + 1) / 2;
@@ -749,7 +792,14 @@ int launch_fwd_mb(const float* in, float* A, float* Hb, float* V, float* D, int 
     const int QS = cdiv(Nr2, nseg);
     dim3 grid(nstrips, cdiv(Nr2, QS), batch);
     const TapsFwd t = pwt_pack_taps_fwd(f, F);
-    k_strip_fwd<F, MB><<<grid, NT, G::smem, st>>>(in, A, Hb, V, D, Nr, Nc, in_bs, out_bs, QS, t);
+    if (NRM) {
+        const long long ctas = (long long)grid.x * grid.y * grid.z;
+        if (!ns || !ns->partials || ctas > ns->cap) return -1;      // caller retries without the reduction
+        k_strip_fwd<F, MB, NRM><<<grid, NT, G::smem, st>>>(in, A, Hb, V, D, Nr, Nc, in_bs, out_bs, QS, t, ns->partials, ns->count_a);
+        ns->written = (int)ctas;
+    } else {
+        k_strip_fwd<F, MB, NRM><<<grid, NT, G::smem, st>>>(in, A, Hb, V, D, Nr, Nc, in_bs, out_bs, QS, t, nullptr, 0);
+    }
     return 1;
 }
 // resident CTAs per SM the kernels are compiled for (register cap 80 / 128)
@@ -763,10 +813,14 @@ int occ_inv(int F) {
 }
 template <int F>
 int launch_fwd(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
-               long long in_bs, long long out_bs, const PwtFilters& f, cudaStream_t st) {
+               long long in_bs, long long out_bs, const PwtFilters& f, NormSink* ns, cudaStream_t st) {
+    if (ns && ns->partials) {                      // 2 CTAs/SM variant only: the sums cost 6 registers
+        ns->written = 0;
+        if (launch_fwd_mb<F, 2, true>(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, f, ns, st) == 1) return 1;
+    }
     if (F <= 16 && occ_fwd(F) == 3)
-        return launch_fwd_mb<F, (F <= 16 ? 3 : 2)>(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, f, st);
-    return launch_fwd_mb<F, 2>(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, f, st);
+        return launch_fwd_mb<F, (F <= 16 ? 3 : 2), false>(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, f, nullptr, st);
+    return launch_fwd_mb<F, 2, false>(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, f, nullptr, st);
 }
 template <int F, int MB>
 int launch_inv_mb(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch, int nr,
@@ -806,15 +860,31 @@ int launch_inv(const float* A, const float* Hb, const float* V, const float* D, 
 
 #define PWT_STRIP_CASES(X) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20) X(22) X(24) X(26) X(28) X(30) X(32) X(34) X(36) X(38) X(40)
 
-int pwt_strip_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
-                        long long in_bs, long long out_bs, const PwtFilters& f, cudaStream_t st) {
+// partials (may be null): receives one (sum |c|, sum c^2) pair per CTA of the launch for the detail planes (and
+// the approximation when count_a); *written = number of pairs (0 when the launch ran without the reduction).
+int pwt_strip_dwt_fwd2d_norms(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
+                              long long in_bs, long long out_bs, const PwtFilters& f, double* partials, int cap,
+                              int count_a, int* written, cudaStream_t st) {
+    if (written) *written = 0;
     if (batch > 65535 || Nr < 2 || Nc < 2 || (long long)(Nr + 64) * Nc >= (1LL << 31)) return 0;   // 32-bit offsets inside an image
+    NormSink ns;
+    ns.partials = partials;
+    ns.cap = cap;
+    ns.count_a = count_a;
+    ns.written = 0;
+    int rc = 0;
     switch (f.hlen) {
-#define X(FF) case FF: return launch_fwd<FF>(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, f, st);
+#define X(FF) case FF: rc = launch_fwd<FF>(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, f, partials ? &ns : nullptr, st); break;
         PWT_STRIP_CASES(X)
 #undef X
         default: return 0;
     }
+    if (written) *written = ns.written;
+    return rc;
+}
+int pwt_strip_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
+                        long long in_bs, long long out_bs, const PwtFilters& f, cudaStream_t st) {
+    return pwt_strip_dwt_fwd2d_norms(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, f, nullptr, 0, 0, nullptr, st);
 }
 
 int pwt_strip_dwt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,

@@ -208,3 +208,6 @@ int pwt_strip_swt_inv2d(const float* A, const float* Hb, const float* V, const f
                         int Nr, int Nc, int level, const PwtFilters& f, int thr_op, float beta, int app,
                         float beta_app, cudaStream_t st);
 int pwt_strip_swt_inv2d_covers(int batch, int Nr, int Nc, int level, const PwtFilters& f, const void* A, const void* out);
+int pwt_strip_dwt_fwd2d_norms(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
+                              long long in_bs, long long out_bs, const PwtFilters& f, double* partials, int cap,
+                              int count_a, int* written, cudaStream_t st);

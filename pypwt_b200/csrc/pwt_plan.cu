@@ -107,6 +107,8 @@ struct pwt_plan {
     double* d_partials; // per-task |c|, c^2 sums written by the fused forward (norm reduction fused into the pass)
     int partials_n;     // > 0: d_partials holds the sums of bands 1..9 (+A if 3 levels) of the CURRENT coefficients
     int partials_cap;
+    unsigned norm_lvl_mask;  // bit l-1: the detail bands of level l are covered by d_partials
+    int norm_a;              // the approximation band is covered by d_partials
     int want_norms;     // norms were requested after a forward: later forwards accumulate them in-kernel (~2 % of the pass)
     PwtDeferredOp pend; // threshold recorded but not yet applied to memory (pend.op < 0: none)
     int defer_ok;       // plan shape for which thresholds may be deferred into the fused inverse
@@ -144,6 +146,7 @@ static inline int ilog2i(int i) {                                   // utils.cu:
 }
 static inline size_t align64(size_t nfloats) { return (nfloats + 63) & ~(size_t)63; }
 static inline bool is_haar(const pwt_plan* p) { return p->hlen == 2 && !p->do_swt; }  // wt.cu:248,255
+static inline void clear_partials(pwt_plan* p) { p->partials_n = 0; p->norm_lvl_mask = 0; p->norm_a = 0; }
 static inline long long img_elems(const pwt_plan* p) { return (long long)p->Nr * p->Nc; }
 static inline long long band_elems(const pwt_plan* p, int b) {
     return (long long)p->band_nr[b] * p->band_nc[b];
@@ -247,8 +250,9 @@ static int alloc_plan(pwt_plan* p) {
     CK(cudaMalloc((void**)&p->d_acc, 2 * sizeof(double)));
     p->partials_cap = (p->ndims == 2 && !p->do_swt && p->nlevels >= 3 && p->Nr % 8 == 0 && p->Nc % 8 == 0)
                           ? pwt_fused_fwd3_max_tasks(p->batch, p->Nr, p->Nc) : 0;
+    if (p->ndims == 2 && !p->do_swt) p->partials_cap += 32768;      // one pair per CTA of the strip forward launches
     p->d_partials = nullptr;
-    p->partials_n = 0;
+    clear_partials(p);
     p->want_norms = 0;
     if (getenv("PWT_NO_FUSED_NORMS")) p->partials_cap = 0;
     if (p->partials_cap > 0) CK(cudaMalloc((void**)&p->d_partials, (size_t)p->partials_cap * 2 * sizeof(double)));
@@ -412,7 +416,7 @@ extern "C" int pwt_clone(pwt_plan** out, const pwt_plan* src) {
     p->d_acc = nullptr;
     p->queue.counter = nullptr;
     p->d_partials = nullptr;
-    p->partials_n = 0;
+    clear_partials(p);
     p->h_acc = nullptr;
     p->d_flush = nullptr;
     p->flush_bytes = 0;
@@ -565,7 +569,7 @@ extern "C" int pwt_forward(pwt_plan* p) {
     if (p->state == PWT_CREATION_ERROR) return fail(PWT_ERR_STATE, "plan is in creation-error state");
     cudaSetDevice(p->device);
     p->pend.op = -1;                                                // the coefficients are about to be overwritten
-    p->partials_n = 0;
+    clear_partials(p);
     if (p->do_cs) {                                                 // wt.cu:242-246
         p->shift_r = rand() % p->Nr;
         p->shift_c = rand() % p->Nc;
@@ -625,6 +629,7 @@ extern "C" int pwt_forward(pwt_plan* p) {
                 src = dstA;
                 l_first = 4;
                 p->partials_n = ntasks;
+                if (ntasks > 0) { p->norm_lvl_mask = 7u; p->norm_a = (L == 3); }
             }
         }
         for (int l = l_first; l <= L; l++) {
@@ -650,8 +655,19 @@ extern "C" int pwt_forward(pwt_plan* p) {
                 if (sep) {
                     int n = 0;
                     const int hints = (l < L ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l > 1 ? PWT_HINT_IN_FROM_PREV : 0);
-                    if (!haar && ((p->kernel_mode == 0 && p->hlen >= p->strip_min_f && nr >= 64 && nc >= 256) || p->kernel_mode == 4))
-                        n = pwt_strip_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, st);
+                    if (!haar && ((p->kernel_mode == 0 && p->hlen >= p->strip_min_f && nr >= 64 && nc >= 256) || p->kernel_mode == 4)) {
+                        // norms requested after an earlier forward: the strip kernel reduces |c|, c^2 of what it stores
+                        const bool nrm = p->want_norms && p->d_partials && p->do_separable && p->kernel_mode == 0 && l <= 32;
+                        int wr = 0;
+                        n = pwt_strip_dwt_fwd2d_norms(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt,
+                                                      nrm ? p->d_partials + 2 * (size_t)p->partials_n : nullptr,
+                                                      p->partials_cap - p->partials_n, l == L, &wr, st);
+                        if (n && wr > 0) {
+                            p->partials_n += wr;
+                            p->norm_lvl_mask |= 1u << (l - 1);
+                            if (l == L) p->norm_a = 1;
+                        }
+                    }
                     if (!n && (p->kernel_mode == 0 || p->kernel_mode == 3))
                         n = pwt_reg_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, hints, st);
                     if (!n && p->kernel_mode != 1 && !haar && p->hlen >= p->tile_min_f && nr >= 64 && nc >= 64)
@@ -815,7 +831,7 @@ extern "C" int pwt_inverse(pwt_plan* p) {
         int rc = do_circshift(p, -p->shift_r, -p->shift_c, 1);
         if (rc != PWT_OK) return rc;
     }
-    p->partials_n = 0;
+    clear_partials(p);
     p->state = PWT_INVERSE;
     return PWT_OK;
 }
@@ -887,7 +903,7 @@ static int run_thresh(pwt_plan* p, int op, float beta, int app, int normalize, b
         for (int i = 0; i < p->nlevels; i++, k += 3) p->pend.beta[i] = t.seg[k].beta;
         return PWT_OK;
     }
-    p->partials_n = 0;
+    clear_partials(p);
     p->launches += pwt_launch_eltwise(t, op, p->stream);
     CK_LAUNCH();
     return PWT_OK;
@@ -901,7 +917,7 @@ static int flush_pending(pwt_plan* p, int first_level, bool with_app) {
     if (with_app && p->pend.app) add_seg(&t, p->d_band[0], B * band_elems(p, 0), p->pend.beta_app);
     for (int i = first_level - 1; i < p->nlevels; i++)
         for (int j = 1; j <= 3; j++) add_seg(&t, p->d_band[3 * i + j], B * band_elems(p, 3 * i + j), p->pend.beta[i]);
-    p->partials_n = 0;
+    clear_partials(p);
     p->launches += pwt_launch_eltwise(t, p->pend.op, p->stream);
     CK_LAUNCH();
     if (first_level <= 1) p->pend.op = -1;
@@ -933,7 +949,7 @@ extern "C" int pwt_group_soft_threshold(pwt_plan* p, float beta, int app, int no
         int rc0 = flush_pending(p, 1, true);
         if (rc0 != PWT_OK) return rc0;
     }
-    p->partials_n = 0;
+    clear_partials(p);
     const int L = p->nlevels;
     for (int i = 0; i < L; i++) {
         if (normalize > 0) beta = (float)(beta / kSqrt2);
@@ -959,9 +975,11 @@ static int local_norms_async(pwt_plan* p) {
     // bands 1..9 (and A of a 3-level transform) were already reduced inside the fused forward kernel
     const bool fusedn = p->partials_n > 0 && p->state == PWT_FORWARD;
     if (p->state == PWT_FORWARD) p->want_norms = 1;
-    const int first = fusedn ? 10 : 0;
-    if (fusedn && p->nlevels > 3) add_seg(&t, p->d_band[0], (long long)p->batch * band_elems(p, 0), 0.f);
-    for (int b = first; b < p->nbands; b++) add_seg(&t, p->d_band[b], (long long)p->batch * band_elems(p, b), 0.f);
+    for (int b = 0; b < p->nbands; b++) {
+        // 2D DWT band b > 0 belongs to level (b-1)/3 + 1; bands the forward kernels reduced themselves are skipped
+        const bool covered = fusedn && (b == 0 ? p->norm_a != 0 : (((b - 1) / 3) < 32 && ((p->norm_lvl_mask >> ((b - 1) / 3)) & 1u)));
+        if (!covered) add_seg(&t, p->d_band[b], (long long)p->batch * band_elems(p, b), 0.f);
+    }
     if (t.nseg > 0) p->launches += pwt_launch_norms(t, p->d_acc, p->stream);
     if (fusedn) p->launches += pwt_launch_reduce_partials(p->d_partials, p->partials_n, p->d_acc, t.nseg > 0, p->stream);
     CK_LAUNCH();
@@ -1026,7 +1044,7 @@ extern "C" int pwt_add_wavelet(pwt_plan* d, const pwt_plan* s, float alpha) {
         add_seg(&td, d->d_band[b], n, 0.f);
         add_seg(&ts, s->d_band[b], n, 0.f);
     }
-    d->partials_n = 0;
+    clear_partials(d);
     d->launches += pwt_launch_axpy(td, ts, alpha, d->stream);
     CK_LAUNCH();
     return 0;
@@ -1080,7 +1098,7 @@ extern "C" int pwt_set_coeff(pwt_plan* p, const float* src, int num, int on_devi
         int rc0 = flush_pending(p, 1, true);
         if (rc0 != PWT_OK) return rc0;
     }
-    p->partials_n = 0;
+    clear_partials(p);
     const size_t n = (size_t)p->batch * band_elems(p, num);
     CK(cudaMemcpyAsync(p->d_band[num], src, n * sizeof(float),
                        on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, p->stream));

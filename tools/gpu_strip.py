@@ -1,14 +1,23 @@
 """Strip kernels (kernel mode 4) against the generic kernels (mode 1) on many shapes / filters, then timings.
 usage: python tools/gpu_strip.py [check] [time] [wname ...]"""
-import sys, numpy as np
+import os, sys, numpy as np
 sys.path.insert(0, ".")
 import pycudwt
+SMALL = bool(os.environ.get("SMALL"))     # compute-sanitizer runs: small shapes, fewer filters
+
+
+def _small(shapes, wns):
+    if not SMALL:
+        return shapes, wns
+    return [s for s in shapes if int(np.prod(s)) <= 400000], wns[::3] + wns[-1:]
+
 
 def check():
     rng = np.random.default_rng(3)
     bad = 0
     shapes = [(512, 768), (511, 509), (64, 1000), (1001, 777), (40, 36), (300, 2048), (2048, 300), (3, 260, 516), (17, 23), (2048, 2048)]
     wns = ["db3", "db4", "sym5", "db6", "db7", "sym8", "coif3", "db10", "db12", "coif5", "db16", "db20", "bior6.8", "rbio2.8", "bior3.9"]
+    shapes, wns = _small(shapes, wns)
     for shp in shapes:
         img = (rng.standard_normal(shp) * 50 + 128).astype(np.float32)
         for wn in wns:
@@ -42,6 +51,7 @@ def check1d():
     bad = 0
     shapes = [(512, 768), (511, 509), (64, 1000), (1001, 777), (40, 36), (300, 2048), (7, 8192), (1000003,), (4099,), (33, 130)]
     wns = ["db2", "db3", "db4", "sym5", "db6", "sym8", "db10", "coif5", "db20", "bior6.8", "bior3.9", "rbio2.8"]
+    shapes, wns = _small(shapes, wns)
     for shp in shapes:
         img = (rng.standard_normal(shp) * 50 + 128).astype(np.float32)
         for wn in wns:
@@ -62,7 +72,7 @@ def check1d():
                     bad += 1
                     print("FAIL1D", shp, wn, L, S.levels, "fwd %.3g inv %.3g" % (max(errs), ei), shp_ok, flush=True)
     # stationary transform, 1D: auto (staged-row kernels) against generic
-    for shp in [(512, 768), (64, 1000), (300, 2048), (7, 8192), (4100,), (33, 132), (5, 20)]:
+    for shp in [sh for sh in [(512, 768), (64, 1000), (300, 2048), (7, 8192), (4100,), (33, 132), (5, 20)] if not SMALL or int(np.prod(sh)) <= 100000]:
         img = (rng.standard_normal(shp) * 50 + 128).astype(np.float32)
         for wn in ["haar", "db2", "db4", "sym8", "db10", "coif5", "db20", "bior3.9"]:
             for L in (1, 2, 3, 5):
@@ -86,7 +96,7 @@ def check1d():
 def checkswt():
     rng = np.random.default_rng(7)
     bad = 0
-    for shp in [(512, 768), (300, 520), (64, 1000), (1024, 1024), (2, 260, 516), (129, 260), (2048, 2048)]:
+    for shp in [sh for sh in [(512, 768), (300, 520), (64, 1000), (1024, 1024), (2, 260, 516), (129, 260), (2048, 2048)] if not SMALL or int(np.prod(sh)) <= 300000]:
         img = (rng.standard_normal(shp) * 50 + 128).astype(np.float32)
         for wn in ["haar", "db2", "db3", "db4", "sym5", "db6", "sym7", "sym8"]:
             for L in (1, 2, 4):
