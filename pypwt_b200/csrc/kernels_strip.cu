@@ -322,12 +322,25 @@ struct InvGeo {
     __host__ __device__ static constexpr bool use_o(int w) { return 2 * S1 - w >= 0 && 2 * S1 - w < HALF; }
 };
 
-template <int F, int MB>
+// A soft / hard threshold recorded by the plan and not yet applied to memory (THR = 1 / 2): every thread applies
+// it to the 16-byte groups it staged itself, right after its cp.async copies land (common.cu:19 / :63).
+struct StripThr {
+    float beta;       // detail bands of this level
+    float beta_app;   // approximation band (coarsest level of a call with do_threshold_appcoeffs)
+    int app;
+};
+template <int THR>
+__device__ __forceinline__ float thr1(float v, float beta) {
+    if (THR == 1) return copysignf(fmaxf(fabsf(v) - beta, 0.0f), v);
+    return (fabsf(v) - beta > 0.0f) ? v : 0.0f * v;
+}
+
+template <int F, int MB, int THR>
 __global__ void __launch_bounds__(NT, MB)
 k_strip_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float* __restrict__ V,
             const float* __restrict__ D, float* __restrict__ out, int nr, int nc, int Nr_out, int Nc_out,
             long long in_bs, long long out_bs, int QS, const __grid_constant__ TapsInv f,
-            const __grid_constant__ TapsInvDense fd) {
+            const __grid_constant__ TapsInvDense fd, const StripThr thr) {
     using G = InvGeo<F>;
     constexpr int S1 = G::S1, NW = G::NW, SH = G::SH, HALF = G::HALF, HLr = G::HLr, DX = G::DX, NV = G::NV, BW4 = G::BW4,
                   P = G::P, R = G::R, NBUF = G::NBUF, NS = G::NS;
@@ -391,6 +404,31 @@ k_strip_inv(const float* __restrict__ A, const float* __restrict__ Hb, const flo
         cp_async_commit();
     };
 
+    auto apply_thr = [&](int c) {                       // this thread's own staged groups of chunk c
+        float* dst = raw + (NBUF == 2 ? (c & 1) * 4 * R * P : 0);
+        if (vec) {
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                const int idx = tid + s * NT, br = idx / BW4;
+                if (s < NS - 1 || idx < 4 * R * BW4) {
+                    const int b = br / R;
+                    if (b == 0 && !thr.app) continue;
+                    const float beta = b == 0 ? thr.beta_app : thr.beta;
+                    float4 v = *reinterpret_cast<float4*>(dst + s_off[s]);
+                    v.x = thr1<THR ? THR : 1>(v.x, beta); v.y = thr1<THR ? THR : 1>(v.y, beta);
+                    v.z = thr1<THR ? THR : 1>(v.z, beta); v.w = thr1<THR ? THR : 1>(v.w, beta);
+                    *reinterpret_cast<float4*>(dst + s_off[s]) = v;
+                }
+            }
+        } else {
+            for (int e = tid; e < 4 * R * 4 * BW4; e += NT) {
+                const int br = e / (4 * BW4), j = e - br * (4 * BW4), b = br / R;
+                if (b == 0 && !thr.app) continue;
+                float* q = dst + br * P + 4 * swz2(j >> 2) + (j & 3);
+                *q = thr1<THR ? THR : 1>(*q, b == 0 ? thr.beta_app : thr.beta);
+            }
+        }
+    };
     // row pass ownership: lanes 0-15 -> plane 0 (A with V), lanes 16-31 -> plane 1 (H with D); 8 band columns each
     const int rpl = lane >> 4, g = lane & 15;
     int w_off[NV];
@@ -423,6 +461,7 @@ k_strip_inv(const float* __restrict__ A, const float* __restrict__ Hb, const flo
         } else {
             cp_async_wait<0>();
         }
+        if (THR) apply_thr(c);
         __syncthreads();
         const float* rb = raw + (NBUF == 2 ? (c & 1) * 4 * R * P : 0);
         // ---- row synthesis: band row -> two planes of 2*HC samples (low-pass-column plane from A,V; high from H,D) ----
@@ -822,15 +861,15 @@ int launch_fwd(const float* in, float* A, float* Hb, float* V, float* D, int bat
         return launch_fwd_mb<F, (F <= 16 ? 3 : 2), false>(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, f, nullptr, st);
     return launch_fwd_mb<F, 2, false>(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, f, nullptr, st);
 }
-template <int F, int MB>
+template <int F, int MB, int THR>
 int launch_inv_mb(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch, int nr,
                   int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs, const PwtFilters& f,
-                  cudaStream_t st) {
+                  const StripThr& thr, cudaStream_t st) {
     using G = InvGeo<F>;
     static int per_sm = 0;
     if (!per_sm) {
-        cudaFuncSetAttribute(k_strip_inv<F, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_inv<F, MB>, NT, G::smem);
+        cudaFuncSetAttribute(k_strip_inv<F, MB, THR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_inv<F, MB, THR>, NT, G::smem);
         if (per_sm <= 0) per_sm = 1;
     }
     const int nstrips = cdiv(nc, HC);
@@ -844,16 +883,18 @@ int launch_inv_mb(const float* A, const float* Hb, const float* V, const float* 
         td.l[w] = make_float2(t.l[w].x, t.l[w + G::SH].y);
         td.h[w] = make_float2(t.h[w].x, t.h[w + G::SH].y);
     }
-    k_strip_inv<F, MB><<<grid, NT, G::smem, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out, in_bs, out_bs, QS, t, td);
+    k_strip_inv<F, MB, THR><<<grid, NT, G::smem, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out, in_bs, out_bs, QS, t, td, thr);
     return 1;
 }
 template <int F>
 int launch_inv(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch, int nr,
-               int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs, const PwtFilters& f,
-               cudaStream_t st) {
+               int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs, const PwtFilters& f, int thr_op,
+               const StripThr& thr, cudaStream_t st) {
+    if (thr_op == PWT_OP_SOFT) return launch_inv_mb<F, 2, 1>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, thr, st);
+    if (thr_op == PWT_OP_HARD) return launch_inv_mb<F, 2, 2>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, thr, st);
     if (F <= 16 && occ_inv(F) == 3)
-        return launch_inv_mb<F, (F <= 16 ? 3 : 2)>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, st);
-    return launch_inv_mb<F, 2>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, st);
+        return launch_inv_mb<F, (F <= 16 ? 3 : 2), 0>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, thr, st);
+    return launch_inv_mb<F, 2, 0>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, thr, st);
 }
 
 }  // namespace
@@ -887,16 +928,27 @@ int pwt_strip_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D
     return pwt_strip_dwt_fwd2d_norms(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, f, nullptr, 0, 0, nullptr, st);
 }
 
-int pwt_strip_dwt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
-                        int nr, int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs,
-                        const PwtFilters& f, cudaStream_t st) {
+// thr_op < 0: nothing pending; PWT_OP_SOFT / PWT_OP_HARD: the recorded threshold is applied to the staged
+// coefficients (beta: detail bands of this level; beta_app for the approximation band when app != 0).
+int pwt_strip_dwt_inv2d_thr(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
+                            int nr, int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs,
+                            const PwtFilters& f, int thr_op, float beta, int app, float beta_app, cudaStream_t st) {
     if (batch > 65535 || nr < 1 || nc < 1 || (long long)(Nr_out + 64) * Nc_out >= (1LL << 31)) return 0;
+    StripThr thr;
+    thr.beta = beta;
+    thr.beta_app = beta_app;
+    thr.app = app;
     switch (f.hlen) {
-#define X(FF) case FF: return launch_inv<FF>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, st);
+#define X(FF) case FF: return launch_inv<FF>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, thr_op, thr, st);
         PWT_STRIP_CASES(X)
 #undef X
         default: return 0;
     }
+}
+int pwt_strip_dwt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
+                        int nr, int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs,
+                        const PwtFilters& f, cudaStream_t st) {
+    return pwt_strip_dwt_inv2d_thr(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, -1, 0.f, 0, 0.f, st);
 }
 
 // Haar, batched 1D, widths that are a multiple of 8: no halo and dense rows make the whole stack one flat stream

@@ -211,3 +211,6 @@ int pwt_strip_swt_inv2d_covers(int batch, int Nr, int Nc, int level, const PwtFi
 int pwt_strip_dwt_fwd2d_norms(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
                               long long in_bs, long long out_bs, const PwtFilters& f, double* partials, int cap,
                               int count_a, int* written, cudaStream_t st);
+int pwt_strip_dwt_inv2d_thr(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
+                            int nr, int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs,
+                            const PwtFilters& f, int thr_op, float beta, int app, float beta_app, cudaStream_t st);

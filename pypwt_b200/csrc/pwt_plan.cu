@@ -114,6 +114,7 @@ struct pwt_plan {
     int defer_ok;       // plan shape for which thresholds may be deferred into the fused inverse
     int ns_rank1;       // non-separable plan whose four 2D filters are outer products of the 1D bank (always, unless custom
                         // 2D filters were loaded): evaluated with the separable kernels, detail slots 1/2 swapped (quirk Q1)
+    int defer_strip_ok; // 2D DWT plan whose finest level the strip inverse serves: thresholds applied as it stages the bands
     int defer_swt_ok;   // SWT plan whose every level is served by the fused SWT inverse (threshold applied on load)
     double* h_acc;      // pinned mirror
     void* d_flush;
@@ -134,6 +135,11 @@ struct pwt_plan {
 // flush: apply the pending threshold to memory for levels >= first_level (1 = everything) and, if
 // with_app, to the approximation band; clears the pending state when everything was flushed.
 static int flush_pending(pwt_plan* p, int first_level, bool with_app);
+// thresholds of this plan can be applied by the strip inverse while it stages the coefficients
+static inline bool strip_defer_capable(const pwt_plan* p) {
+    return p->defer_strip_ok && p->kernel_mode == 0 && p->do_separable && p->hlen >= p->strip_min_f && p->hlen <= 40 &&
+           (p->hlen & 1) == 0 && p->hlen != 2;
+}
 
 static inline int div2i(int n) { return (n + 1) >> 1; }            // utils.cu:24-27
 static inline int ilog2i(int i) {                                   // utils.cu:14-20 (guarded)
@@ -353,6 +359,8 @@ extern "C" int pwt_create_batch(pwt_plan** out, const float* img, int batch, int
                   Nc >= 512 && Nr >= 64 && (p->hlen <= 6) && !getenv("PWT_NO_DEFER");
     p->tile_min_f = getenv("PWT_TILE_MIN_F") ? atoi(getenv("PWT_TILE_MIN_F")) : 22;
     p->strip_min_f = getenv("PWT_STRIP_MIN_F") ? atoi(getenv("PWT_STRIP_MIN_F")) : 8;
+    p->defer_strip_ok = p->ndims == 2 && !p->do_swt && p->do_separable && p->nlevels >= 1 && p->lvNr[1] >= 32 &&
+                        p->lvNc[1] >= 128 && !getenv("PWT_NO_DEFER");     // + filter length, checked when used
 
     // L2 residency of the ping-pong approximation planes: the kernels store them with an
     // L2::evict_last policy, which only has an effect when a persisting-L2 carve-out exists.
@@ -735,13 +743,31 @@ extern "C" int pwt_inverse(pwt_plan* p) {
             int rc = flush_pending(p, 1, true);
             if (rc != PWT_OK) return rc;
         }
-        if (p->pend.op >= 0 && !p->do_swt && L > 3) {
+        // strip inverse (F >= 8): every level it serves applies its own part of a pending threshold while staging
+        // the bands; the coarser levels it does not serve (planes < 32 x 128) and their A go through memory first
+        bool strip_defer = false;
+        int strip_lmax = 0;
+        const bool cascade_ok = sep && p->kernel_mode == 0 && (haar || p->hlen < p->strip_min_f);
+        if (p->pend.op >= 0 && !p->do_swt) {
+            if (strip_defer_capable(p) && !haar) {
+                for (int l = 1; l <= L && p->lvNr[l] >= 32 && p->lvNc[l] >= 128; l++) strip_lmax = l;
+                strip_defer = strip_lmax >= 1;
+                if (strip_defer && strip_lmax < L) {
+                    int rc = flush_pending(p, strip_lmax + 1, true);
+                    if (rc != PWT_OK) return rc;
+                }
+            } else if (!(cascade_ok && p->defer_ok && L >= 3)) {     // nobody will consume it on load
+                int rc = flush_pending(p, 1, true);
+                if (rc != PWT_OK) return rc;
+            }
+        }
+        if (p->pend.op >= 0 && !p->do_swt && L > 3 && !strip_defer) {
             int rc = flush_pending(p, 4, true);                     // coarser levels + A go through memory (1/64 of the data)
             if (rc != PWT_OK) return rc;
             fop.app = 0;
         }
         for (int l = L; l >= 1; l--) {
-            if (l == 3 && p->pend.op >= 0 && !p->do_swt && !(sep && p->kernel_mode == 0 && (haar || p->hlen < p->strip_min_f))) {
+            if (l == 3 && p->pend.op >= 0 && !p->do_swt && !strip_defer && !cascade_ok) {
                 int rc = flush_pending(p, 1, L == 3);
                 if (rc != PWT_OK) return rc;
             }
@@ -806,8 +832,18 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                 if (sep) {
                     int n = 0;
                     const int hints = (l > 1 ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l < L ? PWT_HINT_IN_FROM_PREV : 0);
-                    if (!haar && ((p->kernel_mode == 0 && p->hlen >= p->strip_min_f && nr >= 32 && nc >= 128) || p->kernel_mode == 4))
-                        n = pwt_strip_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, st);
+                    if (!haar && ((p->kernel_mode == 0 && p->hlen >= p->strip_min_f && nr >= 32 && nc >= 128) || p->kernel_mode == 4)) {
+                        if (strip_defer && l <= strip_lmax)
+                            n = pwt_strip_dwt_inv2d_thr(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, p->pend.op,
+                                                        p->pend.beta[l - 1], l == L && p->pend.app, p->pend.beta_app, st);
+                        else
+                            n = pwt_strip_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, st);
+                    }
+                    if (!n && strip_defer && l <= strip_lmax) {      // declined after all: apply the rest through memory
+                        int rc = flush_pending(p, 1, l == L);
+                        if (rc != PWT_OK) return rc;
+                        strip_defer = false;
+                    }
                     if (!n && (p->kernel_mode == 0 || p->kernel_mode == 3))
                         n = pwt_reg_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, hints, st);
                     if (!n && p->kernel_mode != 1 && !haar && p->hlen >= p->tile_min_f && nr >= 32 && nc >= 32)
@@ -824,6 +860,7 @@ extern "C" int pwt_inverse(pwt_plan* p) {
             }
             prof_end(p);
         }
+        if (strip_defer) p->pend.op = -1;                           // consumed by the strip inverse launches
     }
     CK_LAUNCH();
     if (p->do_swt) p->pend.op = -1;                                 // consumed by the fused SWT inverse (or flushed above)
@@ -893,7 +930,7 @@ static int run_thresh(pwt_plan* p, int op, float beta, int app, int normalize, b
         build_thresh_table(p, &t, beta, app, 0, false, true, 1.0f / (1.0f + beta));   // common.cu:355
     else
         build_thresh_table(p, &t, beta, app, normalize, app_scaled, false, 0.f);
-    if ((op == PWT_OP_SOFT || op == PWT_OP_HARD) && (p->defer_ok || p->defer_swt_ok) && p->kernel_mode == 0) {
+    if ((op == PWT_OP_SOFT || op == PWT_OP_HARD) && (p->defer_ok || p->defer_swt_ok || strip_defer_capable(p)) && p->kernel_mode == 0) {
         // record instead of launching: the fused inverse applies it on load; any observer of the
         // coefficients (coeffs, norms, pointers, another operator) flushes it to memory first
         p->pend.op = op;

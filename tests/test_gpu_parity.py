@@ -772,3 +772,52 @@ def test_circshift_all_alignments(shape):
         W.set_image(img)
         W.circshift(sr, sc)
         assert np.array_equal(W.image, np.roll(img, (sr, sc), axis=(-2, -1))), (sr, sc)
+
+
+@pytest.mark.parametrize("levels", [3, 5])
+@pytest.mark.parametrize("op,app,normalize", [("soft_threshold", 0, 0), ("soft_threshold", 1, 1),
+                                              ("hard_threshold", 0, 1), ("hard_threshold", 1, 0)])
+@pytest.mark.parametrize("wname", ["db4", "sym8"])
+def test_strip_deferred_threshold_is_unobservable(wname, op, app, normalize, levels):
+    """Filters of length >= 8: soft/hard_threshold is recorded and applied by the strip inverse kernels while they
+    stage the coefficients (levels whose planes are too small for them are thresholded through memory first).
+    Must be indistinguishable from the immediate threshold."""
+    img = synth_image((512, 1024), seed=61, kind="smooth")
+    D = _W(img, wname, levels); S = _W(img, wname, levels); G = _W(img, wname, levels)
+    S.set_kernel_mode(4)          # strip kernels everywhere, thresholds applied immediately
+    G.set_kernel_mode(1)          # generic kernels, thresholds applied immediately
+    D.forward(); S.forward(); G.forward()
+    l0 = D.launch_count
+    for W in (D, S, G):
+        getattr(W, op)(12.0, app, normalize)
+    assert D.launch_count == l0, "the threshold should have been deferred (no launch)"
+    D.inverse(); S.inverse(); G.inverse()
+    if levels == 3:               # every level is served by the strip kernels in both plans: same arithmetic
+        assert np.array_equal(D.image, S.image)
+    assert_close(D.image, G.image, 255.0, "deferred threshold in the strip inverse vs generic")
+    # observers flush the pending operator first
+    D.forward(img); G.forward(img)
+    getattr(D, op)(12.0, app, normalize); getattr(G, op)(12.0, app, normalize)
+    assert abs(D.norm1() - G.norm1()) <= 2e-6 * G.norm1()
+    cd, cg = D.coeffs, G.coeffs
+    assert_close(cd[0], cg[0], 255.0, "A after flushed threshold")
+    for i in range(1, levels + 1):
+        for j in range(3):
+            assert_close(cd[i][j], cg[i][j], 255.0, "band after flushed threshold")
+    # two thresholds in a row, then inverse; forward() discards a pending one
+    D.forward(img); G.forward(img)
+    D.soft_threshold(5.0); D.hard_threshold(9.0, 1, 0)
+    G.soft_threshold(5.0); G.hard_threshold(9.0, 1, 0)
+    D.inverse(); G.inverse()
+    assert_close(D.image, G.image, 255.0, "two thresholds")
+    D.forward(img); D.soft_threshold(1e6); D.forward(); D.inverse()
+    assert np.abs(D.image - img).max() < 1e-2
+    # stacks and a kernel-mode change between the threshold and the inverse
+    st = np.stack([img[:256, :512], img[256:, 512:]])
+    D = _W(st, wname, 2); G = _W(st, wname, 2)
+    G.set_kernel_mode(1)
+    D.forward(); G.forward()
+    getattr(D, op)(7.0, app, normalize); getattr(G, op)(7.0, app, normalize)
+    D.set_kernel_mode(1)
+    D.inverse(); G.inverse()
+    assert_close(D.image, G.image, 255.0, "deferred, then generic inverse")
