@@ -819,7 +819,8 @@ int launch_fwd_mb(const float* in, float* A, float* Hb, float* V, float* D, int 
                   long long in_bs, long long out_bs, const PwtFilters& f, NormSink* ns, cudaStream_t st) {
     using G = FwdGeo<F>;
     static int per_sm = 0;
-    if (!per_sm) {
+    static unsigned long long seen = 0;
+    if (pwt_first_use_on_device(&seen)) {
         cudaFuncSetAttribute(k_strip_fwd<F, MB, NRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_fwd<F, MB, NRM>, NT, G::smem);
         if (per_sm <= 0) per_sm = 1;
@@ -867,7 +868,8 @@ int launch_inv_mb(const float* A, const float* Hb, const float* V, const float* 
                   const StripThr& thr, cudaStream_t st) {
     using G = InvGeo<F>;
     static int per_sm = 0;
-    if (!per_sm) {
+    static unsigned long long seen = 0;
+    if (pwt_first_use_on_device(&seen)) {
         cudaFuncSetAttribute(k_strip_inv<F, MB, THR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_inv<F, MB, THR>, NT, G::smem);
         if (per_sm <= 0) per_sm = 1;
@@ -1009,7 +1011,8 @@ template <int F>
 int launch_fwd1d(const float* in, float* A, float* D, int rows, int Nc, const PwtFilters& f, cudaStream_t st) {
     using G = Fwd1Geo<F>;
     static int per_sm = 0;
-    if (!per_sm) {
+    static unsigned long long seen = 0;
+    if (pwt_first_use_on_device(&seen)) {
         cudaFuncSetAttribute(k_strip_fwd1d<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_fwd1d<F>, NT, G::smem);
         if (per_sm <= 0) per_sm = 1;
@@ -1025,7 +1028,8 @@ int launch_inv1d(const float* A, const float* D, float* out, int rows, int nc, i
                  cudaStream_t st) {
     using G = Inv1Geo<F>;
     static int per_sm = 0;
-    if (!per_sm) {
+    static unsigned long long seen = 0;
+    if (pwt_first_use_on_device(&seen)) {
         cudaFuncSetAttribute(k_strip_inv1d<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_inv1d<F>, NT, G::smem);
         if (per_sm <= 0) per_sm = 1;

@@ -224,13 +224,14 @@ int launch_fwd(const float* in, float* A, float* D, int rows, int Nc, int s, con
     const int NG = (TW + halo_l(F / 2 - 1, s) + halo_l(F / 2, s)) >> 2;
     if (NG > MAXSLOT * NT) return 0;
     const size_t smem = sizeof(float) * 2 * RPS * 4 * (size_t)NG;
-    static size_t set = 0;
-    if (smem > set) {
-        if (cudaFuncSetAttribute(k_swt1d_fwd<F, SMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    static unsigned long long seen = 0;
+    if (pwt_first_use_on_device(&seen)) {              // largest staged row this instantiation accepts (NG <= MAXSLOT * NT)
+        const size_t smem_max = sizeof(float) * 2 * RPS * 4 * (size_t)(MAXSLOT * NT);
+        if (cudaFuncSetAttribute(k_swt1d_fwd<F, SMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess) {
             cudaGetLastError();
+            seen = 0;
             return 0;
         }
-        set = smem;
     }
     const int ntiles = (Nc + TW - 1) / TW, QS = pick_qs(ntiles, rows);
     dim3 grid(ntiles, (rows + QS - 1) / QS);
@@ -242,13 +243,14 @@ int launch_inv(const float* A, const float* D, float* out, int rows, int Nc, int
     const int NG = (TW + halo_l(F / 2, s) + halo_l(F / 2 - 1, s)) >> 2;
     if (NG > MAXSLOT * NT) return 0;
     const size_t smem = sizeof(float) * 2 * RPS * 2 * 4 * (size_t)NG;
-    static size_t set = 0;
-    if (smem > set) {
-        if (cudaFuncSetAttribute(k_swt1d_inv<F, SMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    static unsigned long long seen = 0;
+    if (pwt_first_use_on_device(&seen)) {              // largest staged row this instantiation accepts (NG <= MAXSLOT * NT)
+        const size_t smem_max = sizeof(float) * 2 * RPS * 2 * 4 * (size_t)(MAXSLOT * NT);
+        if (cudaFuncSetAttribute(k_swt1d_inv<F, SMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess) {
             cudaGetLastError();
+            seen = 0;
             return 0;
         }
-        set = smem;
     }
     TapsDup t;
     for (int j = 0; j < PWT_MAX_TAPS; j++) {

@@ -204,14 +204,16 @@ int launch(const float* in, float* A, float* Hb, float* V, float* D, int batch, 
     const int NG = (SWC + HL + HR) >> 2;
     if (NG > 128) return 0;                            // filter reach beyond the two staging groups per thread
     const size_t smem = sizeof(float) * ((size_t)2 * R * 4 * NG + (size_t)R * 2 * SWC);
-    static size_t set = 0;
     static int per_sm = 0;
-    if (smem > set) {
-        if (cudaFuncSetAttribute(k_swt_strip_fwd<F, SMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    // the staged row pitch depends on the dilation: opt in to the largest size this instantiation can ask for
+    static unsigned long long seen = 0;
+    if (pwt_first_use_on_device(&seen)) {
+        const size_t smem_max = sizeof(float) * ((size_t)2 * R * 4 * 128 + (size_t)R * 2 * SWC);
+        if (cudaFuncSetAttribute(k_swt_strip_fwd<F, SMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess) {
             cudaGetLastError();
+            seen = 0;
             return 0;
         }
-        set = smem;
     }
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_swt_strip_fwd<F, SMODE>, NT, smem);
     if (per_sm <= 0) per_sm = 1;
@@ -417,16 +419,15 @@ int launch_inv_n(const float* A, const float* Hb, const float* V, const float* D
     const int OWN = 256 - HL - HR;
     if (OWN < 128) return 0;                           // dilation too large for overlapping 256-column tiles
     const size_t smem = sizeof(float) * ((size_t)NBUF * R * 4 * 256 + (size_t)R * 2 * 256);
-    static bool set = false;
+    static unsigned long long seen = 0;
     static int per_sm = 0;
-    if (!set) {
+    if (pwt_first_use_on_device(&seen)) {
         if (cudaFuncSetAttribute(k_swt_strip_inv<F, SMODE, THR, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             cudaGetLastError();
             return 0;
         }
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_swt_strip_inv<F, SMODE, THR, NBUF>, NT, smem);
         if (per_sm <= 0) per_sm = 1;
-        set = true;
     }
     const int strips = cdiv(Nc, OWN);
     const int nq = cdiv(Nr, s);

@@ -50,6 +50,17 @@ static inline PwtTapsInv pwt_pack_taps_inv(const PwtFilters& f, int F) {
     return t;
 }
 
+// One-time per-DEVICE kernel set-up (cudaFuncSetAttribute is a per-device property): true the first time it is
+// called with this mask on the current device.  Launchers keep one static mask per kernel instantiation.
+static inline bool pwt_first_use_on_device(unsigned long long* mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (*mask & bit) return false;
+    *mask |= bit;
+    return true;
+}
+
 // Geometry of one 2D plane set processed by a launch (all strides in elements).
 struct PwtPlane {
     int nr, nc;               // rows, cols of ONE image of the stack
