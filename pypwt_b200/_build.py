@@ -27,7 +27,7 @@ def _newer(target, sources):
 
 
 def build_library():
-    _run(["make", "-j4", "-C", os.path.join(HERE, "csrc")])
+    _run(["make", "-j8", "-C", os.path.join(HERE, "csrc")])
     return os.path.join(HERE, "libpwt_b200.so")
 
 
