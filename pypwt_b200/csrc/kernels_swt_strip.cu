@@ -250,6 +250,10 @@ namespace {
 struct TapsDup {                  // synthesis taps, halved and duplicated: l[j] = (IL[F-1-j]/2, same), h likewise
     float2 l[PWT_MAX_TAPS];
     float2 h[PWT_MAX_TAPS];
+    // shifted pairs for two outputs one dilation step apart that read the same sample: lp[j] = (tap j, tap j-1)
+    // (tap -1 = tap F = 0), so that one FFMA2 serves both outputs in the contiguous-window row pass (s = 1, 2)
+    float2 lp[PWT_MAX_TAPS + 1];
+    float2 hp[PWT_MAX_TAPS + 1];
 };
 struct Thr {
     float beta, beta_app;
@@ -386,25 +390,30 @@ k_swt_strip_inv(const float* __restrict__ A, const float* __restrict__ Hb, const
                 const float* t2 = t1 + TWD;
                 constexpr int S = SMODE ? SMODE : 1;
                 constexpr int HLs = (C * S + 3) & ~3, DX = HLs - C * S, NV = (DX + 4 + (F - 1) * S + 3) / 4;
-                float ro[4] = {0.f, 0.f, 0.f, 0.f};
+                // outputs e and e + S read the same sample with taps j and j - 1: pairs (0, S) and (1 or 2, ...)
+                constexpr int EA0 = 0, EA1 = S == 1 ? 2 : 1;
+                float2 pa = zero2, pb = zero2;                               // (out[EA0], out[EA0+S]), (out[EA1], out[EA1+S])
 #pragma unroll
                 for (int k = 0; k < NV; k++) {
                     const float4 v1 = *reinterpret_cast<const float4*>(t1 + 4 * k);
                     const float4 v2 = *reinterpret_cast<const float4*>(t2 + 4 * k);
                     const float x1[4] = {v1.x, v1.y, v1.z, v1.w}, x2[4] = {v2.x, v2.y, v2.z, v2.w};
 #pragma unroll
-                    for (int ee = 0; ee < 4; ee++)
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const int d = 4 * k + ee - DX - e;
-                            if (d >= 0 && d % S == 0 && d / S < F) {
-                                ro[e] = fmaf(x1[ee], f.l[d / S].x, ro[e]);
-                                ro[e] = fmaf(x2[ee], f.h[d / S].x, ro[e]);
-                            }
+                    for (int ee = 0; ee < 4; ee++) {
+                        const int da = 4 * k + ee - DX - EA0, db = 4 * k + ee - DX - EA1;
+                        if (da >= 0 && da % S == 0 && da / S <= F) {
+                            pa = fma2s(x1[ee], f.lp[da / S], pa);
+                            pa = fma2s(x2[ee], f.hp[da / S], pa);
                         }
+                        if (db >= 0 && db % S == 0 && db / S <= F) {
+                            pb = fma2s(x1[ee], f.lp[db / S], pb);
+                            pb = fma2s(x2[ee], f.hp[db / S], pb);
+                        }
+                    }
                 }
                 if (pvalid && u >= 0 && u < q1 - q0)
-                    *reinterpret_cast<float4*>(out + (unsigned)((r + (q0 + u) * s) * Nc + X)) = make_float4(ro[0], ro[1], ro[2], ro[3]);
+                    *reinterpret_cast<float4*>(out + (unsigned)((r + (q0 + u) * s) * Nc + X)) =
+                        S == 1 ? make_float4(pa.x, pa.y, pb.x, pb.y) : make_float4(pa.x, pb.x, pa.y, pb.y);
             }
         }
         ubase += R;
@@ -439,6 +448,10 @@ int launch_inv_n(const float* A, const float* Hb, const float* V, const float* D
         const float l = j < F ? 0.5f * f.IL[F - 1 - j] : 0.f, h = j < F ? 0.5f * f.IH[F - 1 - j] : 0.f;
         t.l[j] = make_float2(l, l);
         t.h[j] = make_float2(h, h);
+    }
+    for (int j = 0; j <= PWT_MAX_TAPS; j++) {
+        t.lp[j] = make_float2(j < F ? t.l[j].x : 0.f, j >= 1 && j <= F ? t.l[j - 1].x : 0.f);
+        t.hp[j] = make_float2(j < F ? t.h[j].x : 0.f, j >= 1 && j <= F ? t.h[j - 1].x : 0.f);
     }
     dim3 grid(strips, s * cdiv(nq, TQ), batch);
     k_swt_strip_inv<F, SMODE, THR, NBUF><<<grid, NT, smem, st>>>(A, Hb, V, D, out, Nr, Nc, s, TQ, cdiv(nq, TQ),
