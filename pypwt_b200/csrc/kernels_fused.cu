@@ -124,6 +124,8 @@ __global__ void __launch_bounds__(32 * kWarps, MINB)
 k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ TapsLH f) {
     using G = Geo<F>;
     constexpr int C = G::C;
+    pwt_pdl_trigger();                    // programmatic dependent launch (pwt_internal.h): the next level's kernel may be
+    pwt_pdl_wait();                       // scheduled while this one drains; nothing global is touched before the wait
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Nr = a.Nr, Nc = a.Nc;
     const int W1 = Nc >> 1, W2 = Nc >> 2, W3 = Nc >> 3;
@@ -514,7 +516,7 @@ int launch_fwd3n(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cu
     q->base += (unsigned)total + (unsigned)grid * kWarps;      // every warp makes exactly one failing pull
     TapsLH taps;
     for (int j = 0; j < 8; j++) taps.t[j] = (!HAAR && j < F) ? make_float2(f.L[F - 1 - j], f.H[F - 1 - j]) : make_float2(0.f, 0.f);
-    k_fwd3<F, HAAR, MINB, PF, NRM><<<grid, 32 * kWarps, 0, st>>>(a, taps);
+    pwt_launch_pdl(k_fwd3<F, HAAR, MINB, PF, NRM>, dim3(grid), 32 * kWarps, 0, st, a, taps);
     return 1;
 }
 
@@ -636,6 +638,8 @@ k_inv3(const __grid_constant__ Inv3Args a, const __grid_constant__ PwtFilters f)
     constexpr int WIN = HALF + (S1 - S0);
     constexpr int HW = S1;                               // 0 (haar) or 1 (F = 4, 6)
     static_assert(HW <= 1, "fused inverse supports a horizontal reach of one band sample");
+    pwt_pdl_trigger();
+    pwt_pdl_wait();
     constexpr int OWN0 = (6 * S1 + 7) & ~7;              // image columns given up on each side of the 256 loaded
     constexpr int DT0 = S1 ? 2 : 0, DT1 = S1 ? 1 : -1;   // iterations before n0 / after n1-1
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -880,7 +884,7 @@ int launch_inv3t(Inv3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cu
     a.counter = q->counter;
     a.base = q->base;
     q->base += (unsigned)total + (unsigned)grid * kWarps;
-    k_inv3<F, HAAR, MINB, THR><<<grid, 32 * kWarps, 0, st>>>(a, f);
+    pwt_launch_pdl(k_inv3<F, HAAR, MINB, THR>, dim3(grid), 32 * kWarps, 0, st, a, f);
     return 1;
 }
 

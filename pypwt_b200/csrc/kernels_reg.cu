@@ -151,6 +151,8 @@ k_fwd_reg(const float* __restrict__ in, float* __restrict__ A, float* __restrict
           const __grid_constant__ PwtFilters f) {
     constexpr int C = F / 2 - 1;          // window start offset = halo on each side
     constexpr int HW = C;
+    pwt_pdl_trigger();                    // programmatic dependent launch: see pwt_internal.h
+    pwt_pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int strips = Nc >> 7;
     const int task = blockIdx.x * kWarps + warp;
@@ -274,6 +276,8 @@ k_inv_reg(const float* __restrict__ A, const float* __restrict__ Hb, const float
     constexpr int S1 = (P + 1) >> 1, E1 = (P + 1) & 1;   // output parity 1
     constexpr int WIN = HALF + (S1 - S0);                // band rows alive per output row pair
     constexpr int HW = S1;                               // horizontal halo (band samples) on each side
+    pwt_pdl_trigger();
+    pwt_pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int strips = nc >> 7;
     const int task = blockIdx.x * kWarps + warp;
@@ -429,7 +433,7 @@ int launch_fwd(const float* in, float* A, float* Hb, float* V, float* D, int bat
     TYW = ((TYW + U - 1) / U) * U;
     const int tasks = (Nc / 128) * cdiv(Nr2, TYW);
     dim3 grid(cdiv(tasks, kWarps), batch);
-    k_fwd_reg<F, HAAR, U, MINB><<<grid, 32 * kWarps, 0, st>>>(in, A, Hb, V, D, Nr, Nc, TYW, in_bs, out_bs, flags, f);
+    pwt_launch_pdl(k_fwd_reg<F, HAAR, U, MINB>, dim3(grid), 32 * kWarps, 0, st, in, A, Hb, V, D, Nr, Nc, TYW, in_bs, out_bs, flags, f);
     return 1;
 }
 
@@ -442,8 +446,8 @@ int launch_inv(const float* A, const float* Hb, const float* V, const float* D, 
     TYW = ((TYW + U - 1) / U) * U;
     const int tasks = (nc / 128) * cdiv(nr, TYW);
     dim3 grid(cdiv(tasks, kWarps), batch);
-    k_inv_reg<F, HAAR, U, MINB><<<grid, 32 * kWarps, 0, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out, TYW, in_bs,
-                                                             out_bs, flags, f);
+    pwt_launch_pdl(k_inv_reg<F, HAAR, U, MINB>, grid, 32 * kWarps, 0, st, A, Hb, V, D, out, nr, nc, Nr_out, Nc_out, TYW, in_bs,
+                   out_bs, flags, f);
     return 1;
 }
 

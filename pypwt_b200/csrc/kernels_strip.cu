@@ -208,8 +208,10 @@ k_strip_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restri
     double d1 = 0.0, d2 = 0.0;
     const bool cnt_x = pl || count_a;                  // plane 0 stores A in .x: counted on the last level only
 
+    pwt_pdl_wait();                                        // everything above is independent of the previous launch
     stage(0);
     for (int c = 0; c < nchunks; c++) {
+        if (c == nchunks - 1) pwt_pdl_trigger();           // last chunk: the next launch may start being scheduled
         if (NBUF == 2) {
             if (c + 1 < nchunks) { stage(c + 1); cp_async_wait<1>(); }
             else cp_async_wait<0>();
@@ -453,8 +455,10 @@ k_strip_inv(const float* __restrict__ A, const float* __restrict__ Hb, const flo
 #pragma unroll
     for (int a = 0; a < HALF; a++) acc[a] = zero2;
 
+    pwt_pdl_wait();                                        // everything above is independent of the previous launch
     stage(0);
     for (int c = 0; c < nchunks; c++) {
+        if (c == nchunks - 1) pwt_pdl_trigger();           // last chunk: the next launch may start being scheduled
         if (NBUF == 2) {
             if (c + 1 < nchunks) { stage(c + 1); cp_async_wait<1>(); }
             else cp_async_wait<0>();
@@ -605,8 +609,10 @@ k_strip_fwd1d(const float* __restrict__ in, float* __restrict__ A, float* __rest
     const bool vst = (Nc2 & 3) == 0 && kx + 3 < Nc2 && ((((uintptr_t)A) | ((uintptr_t)D)) & 15) == 0;
     const float2 zero2 = make_float2(0.f, 0.f);
 
+    pwt_pdl_wait();
     stage(0);
     for (int c = 0; c < nchunks; c++) {
+        if (c == nchunks - 1) pwt_pdl_trigger();
         cp_async_wait<0>();
         __syncthreads();                               // chunk c staged; the other buffer is free
         if (c + 1 < nchunks) stage(c + 1);
@@ -715,8 +721,10 @@ k_strip_inv1d(const float* __restrict__ A, const float* __restrict__ D, float* _
     const bool vst = (Nc_out & 3) == 0 && (((uintptr_t)out) & 15) == 0;
     const float2 zero2 = make_float2(0.f, 0.f);
 
+    pwt_pdl_wait();
     stage(0);
     for (int c = 0; c < nchunks; c++) {
+        if (c == nchunks - 1) pwt_pdl_trigger();
         cp_async_wait<0>();
         __syncthreads();
         if (c + 1 < nchunks) stage(c + 1);
@@ -775,6 +783,7 @@ k_strip_inv1d(const float* __restrict__ A, const float* __restrict__ D, float* _
 }
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
 
 // Segment height: the grid is (strips, segments, images); pick the segment count whose last wave is fullest,
 // discounting the rows a segment start costs (halo rows + rounding of the stream to whole chunks).
@@ -835,10 +844,10 @@ int launch_fwd_mb(const float* in, float* A, float* Hb, float* V, float* D, int 
     if (NRM) {
         const long long ctas = (long long)grid.x * grid.y * grid.z;
         if (!ns || !ns->partials || ctas > ns->cap) return -1;      // caller retries without the reduction
-        k_strip_fwd<F, MB, NRM><<<grid, NT, G::smem, st>>>(in, A, Hb, V, D, Nr, Nc, in_bs, out_bs, QS, t, ns->partials, ns->count_a);
+        pwt_launch_pdl(k_strip_fwd<F, MB, NRM>, grid, NT, G::smem, st, in, A, Hb, V, D, Nr, Nc, in_bs, out_bs, QS, t, ns->partials, ns->count_a);
         ns->written = (int)ctas;
     } else {
-        k_strip_fwd<F, MB, NRM><<<grid, NT, G::smem, st>>>(in, A, Hb, V, D, Nr, Nc, in_bs, out_bs, QS, t, nullptr, 0);
+        pwt_launch_pdl(k_strip_fwd<F, MB, NRM>, grid, NT, G::smem, st, in, A, Hb, V, D, Nr, Nc, in_bs, out_bs, QS, t, (double*)nullptr, 0);
     }
     return 1;
 }
@@ -885,7 +894,7 @@ int launch_inv_mb(const float* A, const float* Hb, const float* V, const float* 
         td.l[w] = make_float2(t.l[w].x, t.l[w + G::SH].y);
         td.h[w] = make_float2(t.h[w].x, t.h[w + G::SH].y);
     }
-    k_strip_inv<F, MB, THR><<<grid, NT, G::smem, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out, in_bs, out_bs, QS, t, td, thr);
+    pwt_launch_pdl(k_strip_inv<F, MB, THR>, grid, NT, G::smem, st, A, Hb, V, D, out, nr, nc, Nr_out, Nc_out, in_bs, out_bs, QS, t, td, thr);
     return 1;
 }
 template <int F>
@@ -959,6 +968,8 @@ namespace {
 __global__ void __launch_bounds__(256)
 k_haar_fwd1d_flat(const float4* __restrict__ in, float4* __restrict__ A, float4* __restrict__ D, long long items) {
     const float c = 0.70710678118654746f;
+    pwt_pdl_trigger();
+    pwt_pdl_wait();
     for (long long i = blockIdx.x * 256LL + threadIdx.x; i < items; i += gridDim.x * 256LL) {
         const float4 u = __ldg(in + 2 * i), v = __ldg(in + 2 * i + 1);
         A[i] = make_float4(c * (u.x + u.y), c * (u.z + u.w), c * (v.x + v.y), c * (v.z + v.w));
@@ -968,6 +979,8 @@ k_haar_fwd1d_flat(const float4* __restrict__ in, float4* __restrict__ A, float4*
 __global__ void __launch_bounds__(256)
 k_haar_inv1d_flat(const float4* __restrict__ A, const float4* __restrict__ D, float4* __restrict__ out, long long items) {
     const float c = 0.70710678118654746f;
+    pwt_pdl_trigger();
+    pwt_pdl_wait();
     for (long long i = blockIdx.x * 256LL + threadIdx.x; i < items; i += gridDim.x * 256LL) {
         const float4 a = __ldg(A + i), d = __ldg(D + i);
         out[2 * i] = make_float4(c * (a.x + d.x), c * (a.x - d.x), c * (a.y + d.y), c * (a.y - d.y));
@@ -980,18 +993,16 @@ int pwt_haar_fwd1d_flat(const float* in, float* A, float* D, int rows, int Nc, c
     if ((Nc & 7) || ((((uintptr_t)in) | ((uintptr_t)A) | ((uintptr_t)D)) & 15)) return 0;
     const long long items = (long long)rows * (Nc / 8);
     const long long want = (items + 255) / 256, cap = (long long)sm_count() * 16;
-    k_haar_fwd1d_flat<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(reinterpret_cast<const float4*>(in),
-                                                                          reinterpret_cast<float4*>(A),
-                                                                          reinterpret_cast<float4*>(D), items);
+    pwt_launch_pdl(k_haar_fwd1d_flat, dim3((unsigned)(want < cap ? want : cap)), 256, 0, st, reinterpret_cast<const float4*>(in),
+                   reinterpret_cast<float4*>(A), reinterpret_cast<float4*>(D), items);
     return 1;
 }
 int pwt_haar_inv1d_flat(const float* A, const float* D, float* out, int rows, int nc, int Nc_out, cudaStream_t st) {
     if ((nc & 3) || Nc_out != 2 * nc || ((((uintptr_t)out) | ((uintptr_t)A) | ((uintptr_t)D)) & 15)) return 0;
     const long long items = (long long)rows * (nc / 4);
     const long long want = (items + 255) / 256, cap = (long long)sm_count() * 16;
-    k_haar_inv1d_flat<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(reinterpret_cast<const float4*>(A),
-                                                                          reinterpret_cast<const float4*>(D),
-                                                                          reinterpret_cast<float4*>(out), items);
+    pwt_launch_pdl(k_haar_inv1d_flat, dim3((unsigned)(want < cap ? want : cap)), 256, 0, st, reinterpret_cast<const float4*>(A),
+                   reinterpret_cast<const float4*>(D), reinterpret_cast<float4*>(out), items);
     return 1;
 }
 
@@ -1020,7 +1031,7 @@ int launch_fwd1d(const float* in, float* A, float* D, int rows, int Nc, const Pw
     const int nstrips = cdiv((Nc + 1) / 2, HC);
     const int QS = pick_segments_1d(nstrips, rows, per_sm * sm_count());
     dim3 grid(nstrips, cdiv(rows, QS), 1);
-    k_strip_fwd1d<F><<<grid, NT, G::smem, st>>>(in, A, D, rows, Nc, QS, pwt_pack_taps_fwd(f, F));
+    pwt_launch_pdl(k_strip_fwd1d<F>, grid, NT, G::smem, st, in, A, D, rows, Nc, QS, pwt_pack_taps_fwd(f, F));
     return 1;
 }
 template <int F>
@@ -1037,7 +1048,7 @@ int launch_inv1d(const float* A, const float* D, float* out, int rows, int nc, i
     const int nstrips = cdiv(nc, HC);
     const int QS = pick_segments_1d(nstrips, rows, per_sm * sm_count());
     dim3 grid(nstrips, cdiv(rows, QS), 1);
-    k_strip_inv1d<F><<<grid, NT, G::smem, st>>>(A, D, out, rows, nc, Nc_out, QS, pwt_pack_taps_inv(f, F));
+    pwt_launch_pdl(k_strip_inv1d<F>, grid, NT, G::smem, st, A, D, out, rows, nc, Nc_out, QS, pwt_pack_taps_inv(f, F));
     return 1;
 }
 }  // namespace

@@ -68,6 +68,8 @@ k_swt1d_fwd(const float* __restrict__ in, float* __restrict__ A, float* __restri
     };
     const int col = x0 + 4 * tid;
     const float2 zero2 = make_float2(0.f, 0.f);
+    pwt_pdl_trigger();                                  // programmatic dependent launch: see pwt_internal.h
+    pwt_pdl_wait();
     stage(q0, 0);
     int buf = 0;
     for (int row = q0; row < q1; row += RPS, buf ^= 1) {
@@ -148,6 +150,8 @@ k_swt1d_inv(const float* __restrict__ A, const float* __restrict__ D, float* __r
     };
     const int col = x0 + 4 * tid;
     const float2 zero2 = make_float2(0.f, 0.f);
+    pwt_pdl_trigger();                                  // programmatic dependent launch: see pwt_internal.h
+    pwt_pdl_wait();
     stage(q0, 0);
     int buf = 0;
     for (int row = q0; row < q1; row += RPS, buf ^= 1) {
@@ -235,7 +239,7 @@ int launch_fwd(const float* in, float* A, float* D, int rows, int Nc, int s, con
     }
     const int ntiles = (Nc + TW - 1) / TW, QS = pick_qs(ntiles, rows);
     dim3 grid(ntiles, (rows + QS - 1) / QS);
-    k_swt1d_fwd<F, SMODE><<<grid, NT, smem, st>>>(in, A, D, rows, Nc, s, QS, pwt_pack_taps_fwd(f, F));
+    pwt_launch_pdl(k_swt1d_fwd<F, SMODE>, grid, NT, smem, st, in, A, D, rows, Nc, s, QS, pwt_pack_taps_fwd(f, F));
     return 1;
 }
 template <int F, int SMODE>
@@ -260,7 +264,7 @@ int launch_inv(const float* A, const float* D, float* out, int rows, int Nc, int
     }
     const int ntiles = (Nc + TW - 1) / TW, QS = pick_qs(ntiles, rows);
     dim3 grid(ntiles, (rows + QS - 1) / QS);
-    k_swt1d_inv<F, SMODE><<<grid, NT, smem, st>>>(A, D, out, rows, Nc, s, QS, t);
+    pwt_launch_pdl(k_swt1d_inv<F, SMODE>, grid, NT, smem, st, A, D, out, rows, Nc, s, QS, t);
     return 1;
 }
 template <int F>

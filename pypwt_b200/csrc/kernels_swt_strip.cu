@@ -105,8 +105,10 @@ k_swt_strip_fwd(const float* __restrict__ in, float* __restrict__ A, float* __re
     for (int a = 0; a < F; a++) acc[a][0] = acc[a][1] = zero2;
     int ubase = -(F - 1);                              // chunk c completes outputs u = ubase + j, j = 0 .. R-1
 
+    pwt_pdl_wait();                                    // programmatic dependent launch: see pwt_internal.h
     stage(0);
     for (int c = 0; c < nchunks; c++) {
+        if (c == nchunks - 1) pwt_pdl_trigger();
         if (c + 1 < nchunks) { stage(c + 1); cp_async_wait<1>(); }
         else cp_async_wait<0>();
         __syncthreads();                               // chunk c staged; everybody is done with rp
@@ -223,8 +225,8 @@ int launch(const float* in, float* A, float* Hb, float* V, float* D, int batch, 
     const int TQ = cdiv(nq, nseg);
     if ((long long)s * cdiv(nq, TQ) > 65535) return 0;
     dim3 grid(strips, s * cdiv(nq, TQ), batch);
-    k_swt_strip_fwd<F, SMODE><<<grid, NT, smem, st>>>(in, A, Hb, V, D, Nr, Nc, s, TQ, cdiv(nq, TQ), (long long)Nr * Nc,
-                                                      pwt_pack_taps_fwd(f, F));
+    pwt_launch_pdl(k_swt_strip_fwd<F, SMODE>, grid, NT, smem, st, in, A, Hb, V, D, Nr, Nc, s, TQ, cdiv(nq, TQ), (long long)Nr * Nc,
+                   pwt_pack_taps_fwd(f, F));
     return 1;
 }
 template <int F>
@@ -323,8 +325,10 @@ k_swt_strip_inv(const float* __restrict__ A, const float* __restrict__ Hb, const
     const bool pvalid2 = 4 * (pg + sig) < OWN && X + 4 * sig < Nc;
     int ubase = -(F - 1);
 
+    pwt_pdl_wait();
     stage(0);
     for (int c = 0; c < nchunks; c++) {
+        if (c == nchunks - 1) pwt_pdl_trigger();
         if (NBUF == 2 && c + 1 < nchunks) { stage(c + 1); cp_async_wait<1>(); }
         else cp_async_wait<0>();
         __syncthreads();                               // chunk c staged; everybody is done with tb
@@ -454,8 +458,8 @@ int launch_inv_n(const float* A, const float* Hb, const float* V, const float* D
         t.hp[j] = make_float2(j < F ? t.h[j].x : 0.f, j >= 1 && j <= F ? t.h[j - 1].x : 0.f);
     }
     dim3 grid(strips, s * cdiv(nq, TQ), batch);
-    k_swt_strip_inv<F, SMODE, THR, NBUF><<<grid, NT, smem, st>>>(A, Hb, V, D, out, Nr, Nc, s, TQ, cdiv(nq, TQ),
-                                                          (long long)Nr * Nc, thr, t);
+    pwt_launch_pdl(k_swt_strip_inv<F, SMODE, THR, NBUF>, grid, NT, smem, st, A, Hb, V, D, out, Nr, Nc, s, TQ, cdiv(nq, TQ),
+                   (long long)Nr * Nc, thr, t);
     return 1;
 }
 template <int F, int SMODE, int THR>
