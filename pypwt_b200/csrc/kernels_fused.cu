@@ -124,8 +124,7 @@ __global__ void __launch_bounds__(32 * kWarps, MINB)
 k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ TapsLH f) {
     using G = Geo<F>;
     constexpr int C = G::C;
-    pwt_pdl_trigger();                    // programmatic dependent launch (pwt_internal.h): the next level's kernel may be
-    pwt_pdl_wait();                       // scheduled while this one drains; nothing global is touched before the wait
+    pwt_pdl_wait();                       // programmatic dependent launch (pwt_internal.h): nothing global is touched before
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Nr = a.Nr, Nc = a.Nc;
     const int W1 = Nc >> 1, W2 = Nc >> 2, W3 = Nc >> 3;
@@ -153,6 +152,8 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ TapsLH f) {
     unsigned t_ = 0;
     if (lane == 0) t_ = atomicAdd(a.counter, 1u) - a.base;
     t_ = __shfl_sync(FULL, t_, 0);
+    // last wave of tasks (or none left): the next launch may start being scheduled into the slots that free up
+    if (t_ + gridDim.x * kWarps >= (unsigned)a.ntasks * (unsigned)a.batch) pwt_pdl_trigger();
     if (t_ >= (unsigned)a.ntasks * (unsigned)a.batch) return;
     const int img = t_ / a.ntasks, task = t_ - img * a.ntasks;
     const int strip = task % strips, band = task / strips;
@@ -516,10 +517,11 @@ int launch_fwd3n(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cu
     q->base += (unsigned)total + (unsigned)grid * kWarps;      // every warp makes exactly one failing pull
     TapsLH taps;
     for (int j = 0; j < 8; j++) taps.t[j] = (!HAAR && j < F) ? make_float2(f.L[F - 1 - j], f.H[F - 1 - j]) : make_float2(0.f, 0.f);
-    // plain launch: a fused kernel scheduled early next to its predecessor (programmatic dependent launch) ends up with
-    // an uneven CTA placement and runs up to 2x slower on 2048^2-4096^2 images (measured); its own early trigger still
-    // lets the small per-level kernels that follow it overlap their launch with its tail
-    k_fwd3<F, HAAR, MINB, PF, NRM><<<grid, 32 * kWarps, 0, st>>>(a, taps);
+    // programmatic dependent launch (the kernel triggers when its last wave of tasks starts): 3-level fwd+inv db2
+    // 0.0226 -> 0.0178 ms at 512^2, 0.0249 -> 0.0216 at 2048^2, 0.0612 -> 0.0567 at 4096^2, 0.198 -> 0.196 at 8192^2.
+    // Not for Haar: 4096^2 got slower (0.0502 -> 0.0594 ms) although 2048^2 and 8192^2 gained.
+    if (!HAAR && env_int("PWT_FUSED_PDL", 1)) pwt_launch_pdl(k_fwd3<F, HAAR, MINB, PF, NRM>, dim3(grid), 32 * kWarps, 0, st, a, taps);
+    else k_fwd3<F, HAAR, MINB, PF, NRM><<<grid, 32 * kWarps, 0, st>>>(a, taps);
     return 1;
 }
 
@@ -641,7 +643,6 @@ k_inv3(const __grid_constant__ Inv3Args a, const __grid_constant__ PwtFilters f)
     constexpr int WIN = HALF + (S1 - S0);
     constexpr int HW = S1;                               // 0 (haar) or 1 (F = 4, 6)
     static_assert(HW <= 1, "fused inverse supports a horizontal reach of one band sample");
-    pwt_pdl_trigger();
     pwt_pdl_wait();
     constexpr int OWN0 = (6 * S1 + 7) & ~7;              // image columns given up on each side of the 256 loaded
     constexpr int DT0 = S1 ? 2 : 0, DT1 = S1 ? 1 : -1;   // iterations before n0 / after n1-1
@@ -655,6 +656,8 @@ k_inv3(const __grid_constant__ Inv3Args a, const __grid_constant__ PwtFilters f)
     unsigned t_ = 0;
     if (lane == 0) t_ = atomicAdd(a.counter, 1u) - a.base;
     t_ = __shfl_sync(FULL, t_, 0);
+    // last wave of tasks (or none left): the next launch may start being scheduled into the slots that free up
+    if (t_ + gridDim.x * kWarps >= (unsigned)a.ntasks * (unsigned)a.batch) pwt_pdl_trigger();
     if (t_ >= (unsigned)a.ntasks * (unsigned)a.batch) return;
     const int img = t_ / a.ntasks, task = t_ - img * a.ntasks;
     const int strip = task % strips, band = task / strips;
@@ -887,7 +890,8 @@ int launch_inv3t(Inv3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cu
     a.counter = q->counter;
     a.base = q->base;
     q->base += (unsigned)total + (unsigned)grid * kWarps;
-    k_inv3<F, HAAR, MINB, THR><<<grid, 32 * kWarps, 0, st>>>(a, f);                    // plain launch: see the forward
+    if (!HAAR && env_int("PWT_FUSED_PDL", 1)) pwt_launch_pdl(k_inv3<F, HAAR, MINB, THR>, dim3(grid), 32 * kWarps, 0, st, a, f);
+    else k_inv3<F, HAAR, MINB, THR><<<grid, 32 * kWarps, 0, st>>>(a, f);
     return 1;
 }
 

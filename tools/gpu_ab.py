@@ -1,4 +1,5 @@
-"""Scratch A/B: time fwd / fwd+inv for the current env, and check against kernel mode 3 (bit-identical)."""
+"""Scratch A/B: time fwd / fwd+inv for the current env, and compare with kernel mode 3 (bit-identical when mode 3 runs the
+register kernels, i.e. widths that are a multiple of 128 -- or Haar; (1024, 520) db2 goes through the fast kernels: False)."""
 import sys, os, numpy as np
 sys.path.insert(0, ".")
 import pycudwt
