@@ -101,6 +101,19 @@ int pwt_get_coeff(pwt_plan* p, float* dst, int num);                     /* wt.c
 int pwt_set_coeff(pwt_plan* p, const float* src, int num, int mem_is_on_device); /* wt.cu:435 */
 intptr_t pwt_image_ptr(pwt_plan* p);                                     /* wt.cu:658 */
 intptr_t pwt_coeff_ptr(pwt_plan* p, int num);                            /* wt.cu:663 */
+/* Every band with ONE device->host copy (the reference's `coeffs` property issues 3L+1 blocking copies,
+ * pypwt.pyx:290-306 -> wt.cu:473-506).  On the device the bands are contiguous: [band 1 .. band N-1][A].
+ * pwt_coeffs_slab_floats = floats of that region, pwt_coeff_offset = where band `num` starts in it (floats, -1 on
+ * a bad index); pwt_get_coeffs copies the region into `dst` (>= slab_floats floats, ideally pinned) and
+ * synchronises.  Returns PWT_OK, 1 when refused after inverse() (wt.cu:474-477), or an error code. */
+long long pwt_coeffs_slab_floats(const pwt_plan* p);
+long long pwt_coeff_offset(const pwt_plan* p, int num);
+int pwt_get_coeffs(pwt_plan* p, float* dst);
+/* the plan's CUDA stream (a cudaStream_t) as an integer, for __cuda_array_interface__ / DLPack consumers */
+intptr_t pwt_stream_ptr(pwt_plan* p);
+/* order the plan's stream after everything queued so far on `producer_stream` (a cudaStream_t of the same device as an
+ * integer): used before a device-to-device set_image / set_coeff of memory another library is still writing */
+int pwt_wait_stream(pwt_plan* p, intptr_t producer_stream);
 
 /* ---- custom filter banks --------------------------------------------------------------- */
 /* wt.cu:558-581.  separable: f1=L, f2=H (f3,f4 ignored).  non-separable: LL, LH, HL, HH (len x len). */
@@ -149,6 +162,10 @@ int pwt_set_kernel_mode(pwt_plan* p, int mode);
 int pwt_comm_unique_id(unsigned char id[128]);
 int pwt_comm_init(pwt_plan* p, int nranks, int rank, const unsigned char id[128]);
 int pwt_comm_destroy(pwt_plan* p);
+/* single-process variant (ncclCommInitAll): `plans` = one plan per GPU of this process, on distinct devices */
+int pwt_comm_init_all(pwt_plan** plans, int n);
+/* global norms over the plans of such a communicator: local fused reductions + the n all-reduces as one NCCL group */
+int pwt_norms_allreduce_group(pwt_plan** plans, int n, double* norm1, double* norm2sq);
 /* global norms over all ranks' shards: fused local reduction + ncclAllReduce on the plan's stream */
 int pwt_norms_allreduce(pwt_plan* p, double* norm1, double* norm2sq);
 

@@ -33,7 +33,10 @@ device_count = _ext.device_count
 set_device = _ext.set_device
 lookup_filters = _ext.lookup_filters
 comm_unique_id = _ext.comm_unique_id
+comm_init_all = _ext.comm_init_all
+norms_allreduce_group = _ext.norms_allreduce_group
+DeviceArray = _ext.DeviceArray
 LIBRARY_PATH = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "libpwt_b200.so")
 __version__ = "1.0.3"
 __all__ = ["Wavelets", "pinned_empty", "pinned_zeros", "device_count", "set_device", "lookup_filters",
-           "comm_unique_id", "LIBRARY_PATH"]
+           "comm_unique_id", "comm_init_all", "norms_allreduce_group", "DeviceArray", "LIBRARY_PATH"]

@@ -491,21 +491,12 @@ k_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float* __
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
-int num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
-    }
-    return sms;
-}
+inline int num_sms() { return pwt_sm_count(); }
 
 // Pick the tile height (multiple of `quantum` rows) so that the grid is a whole number of waves when
 // possible: total CTAs close below a multiple of (#SM x resident CTAs).
 int pick_tile_rows(int rows, int nx, int batch, int quantum, int resident) {
-    if (const char* e = getenv("PWT_FAST_TILE_ROWS")) {      // tuning override (multiple of the chunk size)
-        const int v = atoi(e);
+    if (const int v = pwt_tuning().fast_tile_rows) {         // tuning override (multiple of the chunk size)
         if (v > 0) return ((v + quantum - 1) / quantum) * quantum;
     }
     const int slots = num_sms() * resident;
@@ -535,14 +526,9 @@ int launch_fwd(const float* in, float* A, float* Hb, float* V, float* D, int bat
     const int nx = cdiv(Nc2, txmax);
     const int TX = min(txmax, (cdiv(Nc2, nx) + 3) & ~3);
     const size_t smem = sizeof(float) * 2 * 2 * R * SW;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_fwd<F, HAAR, NT, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
-    }
-    int resident = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fwd<F, HAAR, NT, R, MINB>, NT, smem);
-    if (resident < 1) resident = 1;
+    static PwtKernelOnce once;
+    const int resident = pwt_kernel_once(once, k_fwd<F, HAAR, NT, R, MINB>, NT, smem, smem);
+    if (!resident) return 0;
     const int TYT = pick_tile_rows(Nr2, cdiv(Nc2, TX), batch, R, resident);
     dim3 grid(cdiv(Nc2, TX), cdiv(Nr2, TYT), batch);
     k_fwd<F, HAAR, NT, R, MINB><<<grid, NT, smem, st>>>(in, A, Hb, V, D, Nr, Nc, TX, TYT, in_bs, out_bs, flags, f,
@@ -561,14 +547,9 @@ int launch_inv(const float* A, const float* Hb, const float* V, const float* D, 
     const int nx = cdiv(nc, txmax);
     const int TXH = min(txmax, (cdiv(nc, nx) + 3) & ~3);
     const size_t smem = sizeof(float) * 2 * 2 * 2 * R * SW;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_inv<F, HAAR, NT, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
-    }
-    int resident = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_inv<F, HAAR, NT, R, MINB>, NT, smem);
-    if (resident < 1) resident = 1;
+    static PwtKernelOnce once;
+    const int resident = pwt_kernel_once(once, k_inv<F, HAAR, NT, R, MINB>, NT, smem, smem);
+    if (!resident) return 0;
     const int TYH = pick_tile_rows(nr, cdiv(nc, TXH), batch, R, resident);
     dim3 grid(cdiv(nc, TXH), cdiv(nr, TYH), batch);
     k_inv<F, HAAR, NT, R, MINB><<<grid, NT, smem, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out, TXH, TYH, in_bs,
@@ -593,11 +574,6 @@ int pwt_fast_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D,
     switch (F) {
         case 2: FWD(2, false, 4, 6);
         case 4:
-            if (const char* e = getenv("PWT_FWD_VARIANT")) {
-                if (atoi(e) == 1) FWD(4, false, 2, 8);
-                if (atoi(e) == 2) FWD(4, false, 2, 6);
-                if (atoi(e) == 3) FWD(4, false, 8, 3);
-            }
             FWD(4, false, 4, 5);
         case 6: FWD(6, false, 4, 4);
         case 8: FWD(8, false, 4, 4);

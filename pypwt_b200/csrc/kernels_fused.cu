@@ -458,11 +458,6 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ TapsLH f) {
 }
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
-int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return (e && *e) ? atoi(e) : dflt;
-}
-
 
 // Task height (level-3 rows per task): the tasks are long, so a partially filled last wave costs a lot
 // (measured: 1.26 waves -> +15 %).  Pick the height that makes the task count an integer number k of
@@ -480,37 +475,32 @@ int pick_t3(int R3, int strips, int batch, int slots) {
     return 16;
 }
 
-struct NormSink {     // host-side: where the launcher reports how many per-task partial sums were written
-    int cap;
+struct NormSink {     // where the launcher reports how many per-task partial sums were written (travels with the call:
+    int cap;          // one plan per host thread may be launching at the same time)
     int* ntasks_out;
 };
-NormSink g_sink = {0, nullptr};
 
 template <int F, bool HAAR, int MINB, int PF, bool NRM>
-int launch_fwd3n(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cudaStream_t st) {
+int launch_fwd3n(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, const NormSink& sink, cudaStream_t st) {
     a.n3 = HAAR ? 16 : Geo<F>::N3;
     const int W3 = a.Nc / 8, R3 = a.Nr / 8;
-    static int resident = 0;
-    if (!resident) {
-        int dev = 0, sms = 148, per_sm = 1;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fwd3<F, HAAR, MINB, PF, NRM>, 32 * kWarps, 0);
-        resident = sms * (per_sm > 0 ? per_sm : 1);
-    }
+    static PwtKernelOnce once;
+    const int per_sm = pwt_kernel_once(once, k_fwd3<F, HAAR, MINB, PF, NRM>, 32 * kWarps, 0, 0);
+    if (!per_sm) return 0;
+    const int resident = pwt_sm_count() * per_sm;
     // task height: as tall as possible (less warm-up) while every resident warp still gets a task
-    a.T3 = env_int("PWT_FUSED_T3", 0);
+    a.T3 = pwt_tuning().fused_t3;
     // Haar has no halo, hence no warm-up rows: short tasks cost nothing and balance best through the dynamic queue
     // (A/B at 8192^2: T3 = 4 -> 0.0891 ms, 8 -> 0.0905, wave-exact 28 -> 0.1027)
     if (a.T3 <= 0) a.T3 = HAAR ? 4 : pick_t3(R3, cdiv(W3, a.n3), batch, resident * kWarps);
     a.ntasks = cdiv(W3, a.n3) * cdiv(R3, a.T3);
     a.batch = batch;
     long long total = (long long)a.ntasks * batch;
-    if (NRM && total > g_sink.cap) {                   // never write past the plan's buffer
+    if (NRM && total > sink.cap) {                     // never write past the plan's buffer
         a.partials = nullptr;
-        if constexpr (NRM) return launch_fwd3n<F, HAAR, MINB, PF, false>(a, batch, f, q, st);
+        if constexpr (NRM) return launch_fwd3n<F, HAAR, MINB, PF, false>(a, batch, f, q, sink, st);
     }
-    if (g_sink.ntasks_out) *g_sink.ntasks_out = NRM ? (int)total : 0;
+    if (sink.ntasks_out) *sink.ntasks_out = NRM ? (int)total : 0;
     int grid = (int)(total < (long long)resident * kWarps ? (total + kWarps - 1) / kWarps : resident);
     a.counter = q->counter;
     a.base = q->base;
@@ -520,16 +510,16 @@ int launch_fwd3n(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cu
     // programmatic dependent launch (the kernel triggers when its last wave of tasks starts): 3-level fwd+inv db2
     // 0.0226 -> 0.0178 ms at 512^2, 0.0249 -> 0.0216 at 2048^2, 0.0612 -> 0.0567 at 4096^2, 0.198 -> 0.196 at 8192^2.
     // Not for Haar: 4096^2 got slower (0.0502 -> 0.0594 ms) although 2048^2 and 8192^2 gained.
-    if (!HAAR && env_int("PWT_FUSED_PDL", 1)) pwt_launch_pdl(k_fwd3<F, HAAR, MINB, PF, NRM>, dim3(grid), 32 * kWarps, 0, st, a, taps);
+    if (!HAAR && pwt_tuning().fused_pdl) pwt_launch_pdl(k_fwd3<F, HAAR, MINB, PF, NRM>, dim3(grid), 32 * kWarps, 0, st, a, taps);
     else k_fwd3<F, HAAR, MINB, PF, NRM><<<grid, 32 * kWarps, 0, st>>>(a, taps);
     return 1;
 }
 
 template <int F, bool HAAR, int MINB, int PF>
-int launch_fwd3(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cudaStream_t st) {
+int launch_fwd3(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, const NormSink& sink, cudaStream_t st) {
     // the norm accumulation is compiled in only when the plan asked for it (~2 % of the pass)
-    return a.partials ? launch_fwd3n<F, HAAR, MINB, PF, true>(a, batch, f, q, st)
-                      : launch_fwd3n<F, HAAR, MINB, PF, false>(a, batch, f, q, st);
+    return a.partials ? launch_fwd3n<F, HAAR, MINB, PF, true>(a, batch, f, q, sink, st)
+                      : launch_fwd3n<F, HAAR, MINB, PF, false>(a, batch, f, q, sink, st);
 }
 
 }  // namespace
@@ -545,7 +535,7 @@ int pwt_fused_dwt_fwd3(const float* in, float* A3, float* const* H, float* const
                        int batch, int Nr, int Nc, const PwtFilters& f, bool haar, PwtTaskQueue* q,
                        double* partials, int partials_cap, int count_a3, int* ntasks_out, cudaStream_t st) {
     const int F = haar ? 2 : f.hlen;
-    if (env_int("PWT_NO_FUSED", 0)) return 0;
+    if (pwt_tuning().no_fused) return 0;
     if (F > 8 || (F & 1) || Nr % 8 != 0 || Nc % 8 != 0 || Nc < 512 || Nr < 64 || batch > 65535) return 0;
     if (((uintptr_t)in & 15) != 0) return 0;
     Fwd3Args a;
@@ -566,25 +556,25 @@ int pwt_fused_dwt_fwd3(const float* in, float* A3, float* const* H, float* const
     a.in_bs = (long long)Nr * Nc;
     a.partials = partials;
     a.count_a3 = count_a3;
-    g_sink.cap = partials ? partials_cap : 0;
-    g_sink.ntasks_out = ntasks_out;
-    const int variant = env_int("PWT_FUSED_VARIANT", 0);
+    if (ntasks_out) *ntasks_out = 0;
+    const NormSink sink = {partials ? partials_cap : 0, ntasks_out};
+    const int variant = pwt_tuning().fused_variant;
     if (haar) {
-        if (variant == 1) return launch_fwd3<2, true, 6, 0>(a, batch, f, q, st);
-        if (variant == 2) return launch_fwd3<2, true, 5, 0>(a, batch, f, q, st);
-        return launch_fwd3<2, true, 4, 0>(a, batch, f, q, st);
+        if (variant == 1) return launch_fwd3<2, true, 6, 0>(a, batch, f, q, sink, st);
+        if (variant == 2) return launch_fwd3<2, true, 5, 0>(a, batch, f, q, sink, st);
+        return launch_fwd3<2, true, 4, 0>(a, batch, f, q, sink, st);
     }
     switch (F) {
         case 4:
-            if (variant == 2) return launch_fwd3<4, false, 5, 0>(a, batch, f, q, st);
-            if (variant == 3) return launch_fwd3<4, false, 6, 0>(a, batch, f, q, st);
-            if (variant == 4) return launch_fwd3<4, false, 4, 1>(a, batch, f, q, st);
-            if (variant == 5) return launch_fwd3<4, false, 4, 2>(a, batch, f, q, st);
-            if (variant == 6) return launch_fwd3<4, false, 3, 0>(a, batch, f, q, st);
-            if (variant == 7) return launch_fwd3<4, false, 2, 0>(a, batch, f, q, st);
-            return launch_fwd3<4, false, 4, 0>(a, batch, f, q, st);
-        case 6: return launch_fwd3<6, false, 3, 0>(a, batch, f, q, st);
-        case 8: return launch_fwd3<8, false, 3, 0>(a, batch, f, q, st);
+            if (variant == 2) return launch_fwd3<4, false, 5, 0>(a, batch, f, q, sink, st);
+            if (variant == 3) return launch_fwd3<4, false, 6, 0>(a, batch, f, q, sink, st);
+            if (variant == 4) return launch_fwd3<4, false, 4, 1>(a, batch, f, q, sink, st);
+            if (variant == 5) return launch_fwd3<4, false, 4, 2>(a, batch, f, q, sink, st);
+            if (variant == 6) return launch_fwd3<4, false, 3, 0>(a, batch, f, q, sink, st);
+            if (variant == 7) return launch_fwd3<4, false, 2, 0>(a, batch, f, q, sink, st);
+            return launch_fwd3<4, false, 4, 0>(a, batch, f, q, sink, st);
+        case 6: return launch_fwd3<6, false, 3, 0>(a, batch, f, q, sink, st);
+        case 8: return launch_fwd3<8, false, 3, 0>(a, batch, f, q, sink, st);
         default: return 0;
     }
 }
@@ -873,15 +863,11 @@ int launch_inv3t(Inv3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cu
     constexpr int OWN0 = (6 * S1 + 7) & ~7;
     a.n3 = (256 - 2 * OWN0) / 8;
     const int W3 = a.Nc / 8, R3 = a.Nr / 8;
-    static int resident = 0;
-    if (!resident) {
-        int dev = 0, sms = 148, per_sm = 1;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inv3<F, HAAR, MINB, THR>, 32 * kWarps, 0);
-        resident = sms * (per_sm > 0 ? per_sm : 1);
-    }
-    a.T3 = env_int("PWT_FUSED_INV_T3", 0);
+    static PwtKernelOnce once;
+    const int per_sm = pwt_kernel_once(once, k_inv3<F, HAAR, MINB, THR>, 32 * kWarps, 0, 0);
+    if (!per_sm) return 0;
+    const int resident = pwt_sm_count() * per_sm;
+    a.T3 = pwt_tuning().fused_inv_t3;
     if (a.T3 <= 0) a.T3 = HAAR ? 8 : pick_t3(R3, cdiv(W3, a.n3), batch, resident * kWarps);   // Haar: see the forward
     a.ntasks = cdiv(W3, a.n3) * cdiv(R3, a.T3);
     a.batch = batch;
@@ -890,7 +876,7 @@ int launch_inv3t(Inv3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cu
     a.counter = q->counter;
     a.base = q->base;
     q->base += (unsigned)total + (unsigned)grid * kWarps;
-    if (!HAAR && env_int("PWT_FUSED_PDL", 1)) pwt_launch_pdl(k_inv3<F, HAAR, MINB, THR>, dim3(grid), 32 * kWarps, 0, st, a, f);
+    if (!HAAR && pwt_tuning().fused_pdl) pwt_launch_pdl(k_inv3<F, HAAR, MINB, THR>, dim3(grid), 32 * kWarps, 0, st, a, f);
     else k_inv3<F, HAAR, MINB, THR><<<grid, 32 * kWarps, 0, st>>>(a, f);
     return 1;
 }
@@ -909,7 +895,7 @@ int pwt_fused_dwt_inv3(const float* A3, const float* const* H, const float* cons
                        float* out, int batch, int Nr, int Nc, const PwtFilters& f, bool haar, PwtTaskQueue* q,
                        const PwtDeferredOp* op, cudaStream_t st) {
     const int F = haar ? 2 : f.hlen;
-    if (env_int("PWT_NO_FUSED", 0) || env_int("PWT_NO_FUSED_INV", 0)) return 0;
+    if (pwt_tuning().no_fused || pwt_tuning().no_fused_inv) return 0;
     if (F > 6 || (F & 1) || Nr % 8 != 0 || Nc % 8 != 0 || Nc < 512 || Nr < 64 || batch > 65535) return 0;
     if (((uintptr_t)out & 15) != 0) return 0;
     Inv3Args a;

@@ -221,14 +221,7 @@ __global__ void __launch_bounds__(kThreads) k_fill(float* p, long long n, float 
 }
 
 int persistent_grid() {
-    static int blocks = 0;
-    if (!blocks) {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        blocks = sms * 8;   // 8 x 256 threads = full occupancy, grid = multiple of the SM count
-    }
-    return blocks;
+    return pwt_sm_count() * 8;   // 8 x 256 threads = full occupancy, grid = multiple of the SM count
 }
 
 long long total_elems(const PwtSegTable& t) {

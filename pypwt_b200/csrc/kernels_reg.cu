@@ -420,16 +420,11 @@ k_inv_reg(const float* __restrict__ A, const float* __restrict__ Hb, const float
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
-int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return (e && *e) ? atoi(e) : dflt;
-}
-
 template <int F, bool HAAR, int U, int MINB>
 int launch_fwd(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
                long long in_bs, long long out_bs, int flags, const PwtFilters& f, cudaStream_t st) {
     const int Nr2 = (Nr + 1) / 2;
-    int TYW = env_int("PWT_REG_TILE_ROWS", 16);
+    int TYW = pwt_tuning().reg_tile_rows;
     TYW = ((TYW + U - 1) / U) * U;
     const int tasks = (Nc / 128) * cdiv(Nr2, TYW);
     dim3 grid(cdiv(tasks, kWarps), batch);
@@ -441,7 +436,7 @@ template <int F, bool HAAR, int U, int MINB>
 int launch_inv(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch,
                int nr, int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs, int flags,
                const PwtFilters& f, cudaStream_t st) {
-    int TYW = env_int("PWT_REG_TILE_ROWS", 16) / 2;
+    int TYW = pwt_tuning().reg_tile_rows / 2;
     if (TYW < U) TYW = U;
     TYW = ((TYW + U - 1) / U) * U;
     const int tasks = (nc / 128) * cdiv(nr, TYW);
@@ -462,12 +457,12 @@ int pwt_reg_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, 
     if (in_bs % 4 != 0 || out_bs % 2 != 0 || ((uintptr_t)in & 15) != 0 ||
         (((uintptr_t)A | (uintptr_t)Hb | (uintptr_t)V | (uintptr_t)D) & 7) != 0)
         return 0;
-    const int flags = hint_flags | (env_int("PWT_USE_HINTS", 0) ? 0 : 1024);
+    const int flags = hint_flags | (pwt_tuning().use_hints ? 0 : 1024);
 #define FWD(FF, HH, UU, MB) return launch_fwd<FF, HH, UU, MB>(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, flags, f, st)
     if (haar) FWD(2, true, 4, 8);
     switch (F) {
         case 4:
-            switch (env_int("PWT_REG_FWD_VARIANT", 2)) {
+            switch (pwt_tuning().reg_fwd_variant) {
                 case 1: FWD(4, false, 2, 8);
                 case 3: FWD(4, false, 4, 5);
                 default: FWD(4, false, 2, 6);
@@ -488,7 +483,7 @@ int pwt_reg_dwt_inv2d(const float* A, const float* Hb, const float* V, const flo
     if (in_bs % 4 != 0 || out_bs % 4 != 0 || ((uintptr_t)out & 15) != 0 ||
         (((uintptr_t)A | (uintptr_t)Hb | (uintptr_t)V | (uintptr_t)D) & 15) != 0)
         return 0;
-    const int flags = hint_flags | (env_int("PWT_USE_HINTS", 0) ? 0 : 1024);
+    const int flags = hint_flags | (pwt_tuning().use_hints ? 0 : 1024);
 #define INV(FF, HH, UU, MB) return launch_inv<FF, HH, UU, MB>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, flags, f, st)
     if (haar) INV(2, true, 2, 8);
     switch (F) {

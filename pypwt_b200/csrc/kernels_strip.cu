@@ -806,16 +806,7 @@ int pick_segments(int nstrips, int batch, int rows_out, int rows_per_out, int ha
     return best;
 }
 
-int g_sm_count = 0;
-int sm_count() {
-    if (!g_sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
-    }
-    return g_sm_count;
-}
+inline int sm_count() { return pwt_sm_count(); }
 
 struct NormSink {             // optional fused norm reduction of a forward launch
     double* partials;         // receives one (sum |c|, sum c^2) pair per CTA, or null
@@ -827,16 +818,12 @@ template <int F, int MB, bool NRM>
 int launch_fwd_mb(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
                   long long in_bs, long long out_bs, const PwtFilters& f, NormSink* ns, cudaStream_t st) {
     using G = FwdGeo<F>;
-    static int per_sm = 0;
-    static unsigned long long seen = 0;
-    if (pwt_first_use_on_device(&seen)) {
-        cudaFuncSetAttribute(k_strip_fwd<F, MB, NRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_fwd<F, MB, NRM>, NT, G::smem);
-        if (per_sm <= 0) per_sm = 1;
-    }
+    static PwtKernelOnce once;
+    const int per_sm = pwt_kernel_once(once, k_strip_fwd<F, MB, NRM>, NT, G::smem, G::smem);
+    if (!per_sm) return 0;
     const int Nr2 = (Nr + 1) / 2, Nc2 = (Nc + 1) / 2;
     const int nstrips = cdiv(Nc2, HC);
-    static int force = getenv("PWT_STRIP_SEGS") ? atoi(getenv("PWT_STRIP_SEGS")) : 0;
+    const int force = pwt_tuning().strip_segs;
     const int nseg = force > 0 ? force : pick_segments(nstrips, batch, Nr2, 2, F - 2, G::R, per_sm * sm_count());
     const int QS = cdiv(Nr2, nseg);
     dim3 grid(nstrips, cdiv(Nr2, QS), batch);
@@ -853,11 +840,11 @@ int launch_fwd_mb(const float* in, float* A, float* Hb, float* V, float* D, int 
 }
 // resident CTAs per SM the kernels are compiled for (register cap 80 / 128)
 int occ_fwd(int F) {
-    static int o = getenv("PWT_STRIP_OCC_FWD") ? atoi(getenv("PWT_STRIP_OCC_FWD")) : 0;
+    const int o = pwt_tuning().strip_occ_fwd;
     return o ? o : (F >= 14 && F <= 16 ? 3 : 2);
 }
 int occ_inv(int F) {
-    static int o = getenv("PWT_STRIP_OCC_INV") ? atoi(getenv("PWT_STRIP_OCC_INV")) : 0;
+    const int o = pwt_tuning().strip_occ_inv;
     return o ? o : (F >= 14 && F <= 16 ? 3 : 2);
 }
 template <int F>
@@ -876,15 +863,11 @@ int launch_inv_mb(const float* A, const float* Hb, const float* V, const float* 
                   int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs, const PwtFilters& f,
                   const StripThr& thr, cudaStream_t st) {
     using G = InvGeo<F>;
-    static int per_sm = 0;
-    static unsigned long long seen = 0;
-    if (pwt_first_use_on_device(&seen)) {
-        cudaFuncSetAttribute(k_strip_inv<F, MB, THR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_inv<F, MB, THR>, NT, G::smem);
-        if (per_sm <= 0) per_sm = 1;
-    }
+    static PwtKernelOnce once;
+    const int per_sm = pwt_kernel_once(once, k_strip_inv<F, MB, THR>, NT, G::smem, G::smem);
+    if (!per_sm) return 0;
     const int nstrips = cdiv(nc, HC);
-    static int force = getenv("PWT_STRIP_SEGS") ? atoi(getenv("PWT_STRIP_SEGS")) : 0;
+    const int force = pwt_tuning().strip_segs;
     const int nseg = force > 0 ? force : pick_segments(nstrips, batch, nr, 1, G::SH + G::HALF - 1, G::R, per_sm * sm_count());
     const int QS = cdiv(nr, nseg);
     dim3 grid(nstrips, cdiv(nr, QS), batch);
@@ -1021,13 +1004,9 @@ int pick_segments_1d(int nstrips, int rows, int slots) {
 template <int F>
 int launch_fwd1d(const float* in, float* A, float* D, int rows, int Nc, const PwtFilters& f, cudaStream_t st) {
     using G = Fwd1Geo<F>;
-    static int per_sm = 0;
-    static unsigned long long seen = 0;
-    if (pwt_first_use_on_device(&seen)) {
-        cudaFuncSetAttribute(k_strip_fwd1d<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_fwd1d<F>, NT, G::smem);
-        if (per_sm <= 0) per_sm = 1;
-    }
+    static PwtKernelOnce once;
+    const int per_sm = pwt_kernel_once(once, k_strip_fwd1d<F>, NT, G::smem, G::smem);
+    if (!per_sm) return 0;
     const int nstrips = cdiv((Nc + 1) / 2, HC);
     const int QS = pick_segments_1d(nstrips, rows, per_sm * sm_count());
     dim3 grid(nstrips, cdiv(rows, QS), 1);
@@ -1038,13 +1017,9 @@ template <int F>
 int launch_inv1d(const float* A, const float* D, float* out, int rows, int nc, int Nc_out, const PwtFilters& f,
                  cudaStream_t st) {
     using G = Inv1Geo<F>;
-    static int per_sm = 0;
-    static unsigned long long seen = 0;
-    if (pwt_first_use_on_device(&seen)) {
-        cudaFuncSetAttribute(k_strip_inv1d<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip_inv1d<F>, NT, G::smem);
-        if (per_sm <= 0) per_sm = 1;
-    }
+    static PwtKernelOnce once;
+    const int per_sm = pwt_kernel_once(once, k_strip_inv1d<F>, NT, G::smem, G::smem);
+    if (!per_sm) return 0;
     const int nstrips = cdiv(nc, HC);
     const int QS = pick_segments_1d(nstrips, rows, per_sm * sm_count());
     dim3 grid(nstrips, cdiv(rows, QS), 1);

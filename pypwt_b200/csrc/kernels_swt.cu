@@ -297,8 +297,8 @@ SwtGeom make_geom(int Nr, int Nc, int level) {
     g.strips = cdiv(Nc, 4 * kThreads);
     const int nq = cdiv(Nr, g.s);
     int tq = 64;
-    if (const char* e = getenv("PWT_SWT_TQ")) tq = atoi(e) > 0 ? atoi(e) : tq;
-    while (tq > 16 && (long long)g.strips * g.s * cdiv(nq, tq) < 2 * 148 * 4) tq >>= 1;   // keep the GPU full
+    if (pwt_tuning().swt_tq > 0) tq = pwt_tuning().swt_tq;
+    while (tq > 16 && (long long)g.strips * g.s * cdiv(nq, tq) < 2LL * pwt_sm_count() * 4) tq >>= 1;   // keep the GPU full
     g.TQ = tq;
     g.chunks = cdiv(nq, tq);
     g.plane = (long long)Nr * Nc;
@@ -344,7 +344,7 @@ bool covered(int F, int batch, int Nr, int Nc, int level, const void* p0, const 
     if ((F & 1) || F < 2 || F > 12 || Nc % 4 != 0 || batch > 65535) return false;
     if ((F - 1) * s >= Nc || (F - 1) * s >= Nr) return false;          // single-step wrap must suffice
     if ((((uintptr_t)p0 | (uintptr_t)p1) & 15) != 0) return false;
-    if (getenv("PWT_NO_FAST_SWT")) return false;
+    if (pwt_tuning().no_fast_swt) return false;
     return true;
 }
 

@@ -204,16 +204,7 @@ k_swt1d_inv(const float* __restrict__ A, const float* __restrict__ D, float* __r
     }
 }
 
-int g_sms = 0;
-int sms() {
-    if (!g_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sms <= 0) g_sms = 148;
-    }
-    return g_sms;
-}
+inline int sms() { return pwt_sm_count(); }
 int pick_qs(int ntiles, int rows) {
     const int want = (12 * sms() + ntiles - 1) / ntiles;          // ~4 waves of 3 CTAs per SM
     int qs = (rows + want - 1) / want;
@@ -228,15 +219,9 @@ int launch_fwd(const float* in, float* A, float* D, int rows, int Nc, int s, con
     const int NG = (TW + halo_l(F / 2 - 1, s) + halo_l(F / 2, s)) >> 2;
     if (NG > MAXSLOT * NT) return 0;
     const size_t smem = sizeof(float) * 2 * RPS * 4 * (size_t)NG;
-    static unsigned long long seen = 0;
-    if (pwt_first_use_on_device(&seen)) {              // largest staged row this instantiation accepts (NG <= MAXSLOT * NT)
-        const size_t smem_max = sizeof(float) * 2 * RPS * 4 * (size_t)(MAXSLOT * NT);
-        if (cudaFuncSetAttribute(k_swt1d_fwd<F, SMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess) {
-            cudaGetLastError();
-            seen = 0;
-            return 0;
-        }
-    }
+    static PwtKernelOnce once;                         // largest staged row this instantiation accepts (NG <= MAXSLOT * NT)
+    const size_t smem_max = sizeof(float) * 2 * RPS * 4 * (size_t)(MAXSLOT * NT);
+    if (!pwt_kernel_once(once, k_swt1d_fwd<F, SMODE>, NT, smem_max, smem_max)) return 0;
     const int ntiles = (Nc + TW - 1) / TW, QS = pick_qs(ntiles, rows);
     dim3 grid(ntiles, (rows + QS - 1) / QS);
     pwt_launch_pdl(k_swt1d_fwd<F, SMODE>, grid, NT, smem, st, in, A, D, rows, Nc, s, QS, pwt_pack_taps_fwd(f, F));
@@ -247,15 +232,9 @@ int launch_inv(const float* A, const float* D, float* out, int rows, int Nc, int
     const int NG = (TW + halo_l(F / 2, s) + halo_l(F / 2 - 1, s)) >> 2;
     if (NG > MAXSLOT * NT) return 0;
     const size_t smem = sizeof(float) * 2 * RPS * 2 * 4 * (size_t)NG;
-    static unsigned long long seen = 0;
-    if (pwt_first_use_on_device(&seen)) {              // largest staged row this instantiation accepts (NG <= MAXSLOT * NT)
-        const size_t smem_max = sizeof(float) * 2 * RPS * 2 * 4 * (size_t)(MAXSLOT * NT);
-        if (cudaFuncSetAttribute(k_swt1d_inv<F, SMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess) {
-            cudaGetLastError();
-            seen = 0;
-            return 0;
-        }
-    }
+    static PwtKernelOnce once;                         // largest staged row this instantiation accepts (NG <= MAXSLOT * NT)
+    const size_t smem_max = sizeof(float) * 2 * RPS * 2 * 4 * (size_t)(MAXSLOT * NT);
+    if (!pwt_kernel_once(once, k_swt1d_inv<F, SMODE>, NT, smem_max, smem_max)) return 0;
     TapsDup t;
     for (int j = 0; j < PWT_MAX_TAPS; j++) {
         const float l = j < F ? 0.5f * f.IL[F - 1 - j] : 0.f, h = j < F ? 0.5f * f.IH[F - 1 - j] : 0.f;

@@ -172,16 +172,7 @@ k_swt_strip_fwd(const float* __restrict__ in, float* __restrict__ A, float* __re
 }
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
-int g_sms = 0;
-int sms() {
-    if (!g_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sms <= 0) g_sms = 148;
-    }
-    return g_sms;
-}
+inline int sms() { return pwt_sm_count(); }
 // segments per residue class: fullest last wave, discounting the F-1 halo rows and the rounding to whole chunks
 int pick_segments(long long base, int rows_out, int halo, int R, int slots) {
     int best = 1;
@@ -206,17 +197,12 @@ int launch(const float* in, float* A, float* Hb, float* V, float* D, int batch, 
     const int NG = (SWC + HL + HR) >> 2;
     if (NG > 128) return 0;                            // filter reach beyond the two staging groups per thread
     const size_t smem = sizeof(float) * ((size_t)2 * R * 4 * NG + (size_t)R * 2 * SWC);
-    static int per_sm = 0;
-    // the staged row pitch depends on the dilation: opt in to the largest size this instantiation can ask for
-    static unsigned long long seen = 0;
-    if (pwt_first_use_on_device(&seen)) {
-        const size_t smem_max = sizeof(float) * ((size_t)2 * R * 4 * 128 + (size_t)R * 2 * SWC);
-        if (cudaFuncSetAttribute(k_swt_strip_fwd<F, SMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess) {
-            cudaGetLastError();
-            seen = 0;
-            return 0;
-        }
-    }
+    // the staged row pitch depends on the dilation: opt in (once per device) to the largest size this instantiation can
+    // ask for; the occupancy depends on the actual size, so it is queried per launch
+    static PwtKernelOnce once;
+    const size_t smem_max = sizeof(float) * ((size_t)2 * R * 4 * 128 + (size_t)R * 2 * SWC);
+    if (!pwt_kernel_once(once, k_swt_strip_fwd<F, SMODE>, NT, smem_max, smem_max)) return 0;
+    int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_swt_strip_fwd<F, SMODE>, NT, smem);
     if (per_sm <= 0) per_sm = 1;
     const int strips = cdiv(Nc, SWC);
@@ -432,16 +418,9 @@ int launch_inv_n(const float* A, const float* Hb, const float* V, const float* D
     const int OWN = 256 - HL - HR;
     if (OWN < 128) return 0;                           // dilation too large for overlapping 256-column tiles
     const size_t smem = sizeof(float) * ((size_t)NBUF * R * 4 * 256 + (size_t)R * 2 * 256);
-    static unsigned long long seen = 0;
-    static int per_sm = 0;
-    if (pwt_first_use_on_device(&seen)) {
-        if (cudaFuncSetAttribute(k_swt_strip_inv<F, SMODE, THR, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return 0;
-        }
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_swt_strip_inv<F, SMODE, THR, NBUF>, NT, smem);
-        if (per_sm <= 0) per_sm = 1;
-    }
+    static PwtKernelOnce once;
+    const int per_sm = pwt_kernel_once(once, k_swt_strip_inv<F, SMODE, THR, NBUF>, NT, smem, smem);
+    if (!per_sm) return 0;
     const int strips = cdiv(Nc, OWN);
     const int nq = cdiv(Nr, s);
     const int nseg = pick_segments((long long)strips * s * batch, nq, F - 1, R, per_sm * sms());
@@ -465,7 +444,7 @@ int launch_inv_n(const float* A, const float* Hb, const float* V, const float* D
 template <int F, int SMODE, int THR>
 int launch_inv_t(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch, int Nr,
                  int Nc, int s, const PwtFilters& f, const Thr& thr, cudaStream_t st) {
-    static int nbuf = getenv("PWT_SWT_NBUF") ? atoi(getenv("PWT_SWT_NBUF")) : 1;
+    const int nbuf = pwt_tuning().swt_nbuf;
     if (F <= 8 && nbuf == 2) return launch_inv_n<F, SMODE, THR, (F <= 8 ? 2 : 1)>(A, Hb, V, D, out, batch, Nr, Nc, s, f, thr, st);
     return launch_inv_n<F, SMODE, THR, 1>(A, Hb, V, D, out, batch, Nr, Nc, s, f, thr, st);
 }
@@ -494,7 +473,7 @@ int pwt_strip_swt_inv2d_covers(int batch, int Nr, int Nc, int level, const PwtFi
     if ((F & 1) || F < 2 || F > 16 || (Nc & 3) || batch > 65535 || out == A) return 0;
     if ((F - 1) * s >= Nc || (F - 1) * s >= Nr || (long long)Nr * Nc >= (1LL << 31)) return 0;
     if ((((uintptr_t)out | (uintptr_t)A) & 15) != 0) return 0;
-    if (getenv("PWT_NO_STRIP_SWT")) return 0;
+    if (pwt_tuning().no_strip_swt) return 0;
     const int C = F / 2, HL = (C * s + 3) & ~3, HR = ((F - 1 - C) * s + 3) & ~3;
     return 256 - HL - HR >= 128;
 }
@@ -530,7 +509,7 @@ int pwt_strip_swt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D
     if ((F & 1) || F < 2 || F > 16 || (Nc & 3) || batch > 65535 || in == A) return 0;
     if ((F - 1) * s >= Nc || (F - 1) * s >= Nr || (long long)Nr * Nc >= (1LL << 31)) return 0;
     if ((((uintptr_t)in | (uintptr_t)A | (uintptr_t)Hb | (uintptr_t)V | (uintptr_t)D) & 15) != 0) return 0;
-    if (getenv("PWT_NO_STRIP_SWT")) return 0;
+    if (pwt_tuning().no_strip_swt) return 0;
     switch (F) {
 #define X(FF) case FF: return launch_s<FF>(in, A, Hb, V, D, batch, Nr, Nc, s, f, st);
         X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16)

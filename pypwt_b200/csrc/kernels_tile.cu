@@ -314,11 +314,8 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 template <int F>
 int launch_fwd(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,
                long long in_bs, long long out_bs, const PwtFilters& f, cudaStream_t st) {
-    static bool done = false;
-    if (!done) {
-        cudaFuncSetAttribute(k_tile_fwd<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdGeo<F>::smem);
-        done = true;
-    }
+    static PwtKernelOnce once;
+    if (!pwt_kernel_once(once, k_tile_fwd<F>, NT, FwdGeo<F>::smem, FwdGeo<F>::smem)) return 0;
     dim3 grid(cdiv((Nc + 1) / 2, TX), cdiv((Nr + 1) / 2, TY), batch);
     const TapsFwd t = pwt_pack_taps_fwd(f, F);
     k_tile_fwd<F><<<grid, NT, FwdGeo<F>::smem, st>>>(in, A, Hb, V, D, Nr, Nc, in_bs, out_bs, t);
@@ -328,11 +325,8 @@ template <int F>
 int launch_inv(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch, int nr,
                int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs, const PwtFilters& f,
                cudaStream_t st) {
-    static bool done = false;
-    if (!done) {
-        cudaFuncSetAttribute(k_tile_inv<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)InvGeo<F>::smem);
-        done = true;
-    }
+    static PwtKernelOnce once;
+    if (!pwt_kernel_once(once, k_tile_inv<F>, NT, InvGeo<F>::smem, InvGeo<F>::smem)) return 0;
     dim3 grid(cdiv(nc, BX), cdiv(nr, BY), batch);
     const TapsInv t = pwt_pack_taps_inv(f, F);
     k_tile_inv<F><<<grid, NT, InvGeo<F>::smem, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out, in_bs, out_bs, t);

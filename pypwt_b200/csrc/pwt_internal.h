@@ -50,16 +50,77 @@ static inline PwtTapsInv pwt_pack_taps_inv(const PwtFilters& f, int F) {
     return t;
 }
 
-// One-time per-DEVICE kernel set-up (cudaFuncSetAttribute is a per-device property): true the first time it is
-// called with this mask on the current device.  Launchers keep one static mask per kernel instantiation.
-static inline bool pwt_first_use_on_device(unsigned long long* mask) {
+// ---- host-side launcher state: everything below is safe to call from any number of host threads (one plan per
+// thread, the Cython wrapper releases the GIL around the transforms) and keeps its caches PER DEVICE ----
+#define PWT_MAX_DEVICES 64
+#ifdef __cplusplus
+#include <mutex>
+// Developer A/B knobs, read from the environment ONCE per process (never on the launch path).
+struct PwtTuning {
+    int no_pdl;            // PWT_NO_PDL=1: plain launches instead of programmatic dependent launch
+    int no_fused;          // PWT_NO_FUSED=1: no fused 3-level cascade
+    int no_fused_inv;      // PWT_NO_FUSED_INV=1
+    int fused_variant;     // PWT_FUSED_VARIANT (occupancy / staging variants of k_fwd3)
+    int fused_t3;          // PWT_FUSED_T3: forced task height of k_fwd3 (0 = automatic)
+    int fused_inv_t3;      // PWT_FUSED_INV_T3
+    int fused_pdl;         // PWT_FUSED_PDL (default 1)
+    int no_fused_norms;    // PWT_NO_FUSED_NORMS=1
+    int no_defer;          // PWT_NO_DEFER=1: thresholds always applied through memory
+    int tile_min_f;        // PWT_TILE_MIN_F (default 22)
+    int strip_min_f;       // PWT_STRIP_MIN_F (default 8)
+    int ns_direct;         // PWT_NS_DIRECT=1: true F x F stencils even for rank-1 banks
+    int l2_persist_mb;     // PWT_L2_PERSIST_MB (default 0)
+    int verbose;           // PWT_VERBOSE
+    int strip_segs;        // PWT_STRIP_SEGS: forced segment count of the strip kernels (0 = automatic)
+    int strip_occ_fwd;     // PWT_STRIP_OCC_FWD / _INV: forced CTAs per SM variant
+    int strip_occ_inv;
+    int swt_nbuf;          // PWT_SWT_NBUF (default 1)
+    int no_strip_swt;      // PWT_NO_STRIP_SWT=1
+    int no_fast_swt;       // PWT_NO_FAST_SWT=1
+    int swt_tq;            // PWT_SWT_TQ
+    int fast_tile_rows;    // PWT_FAST_TILE_ROWS
+    int fwd_variant;       // PWT_FWD_VARIANT (-1 = automatic)
+    int reg_tile_rows;     // PWT_REG_TILE_ROWS (default 16)
+    int use_hints;         // PWT_USE_HINTS
+    int reg_fwd_variant;   // PWT_REG_FWD_VARIANT (default 2)
+    int no_fold_cs;        // PWT_NO_FOLD_CS=1: cycle-spinning shifts as separate gather passes
+    int no_cascade8;       // PWT_NO_CASCADE8=1: no level-fused strip kernels (F >= 8)
+    int no_fused1d;        // PWT_NO_FUSED1D=1: batched 1D one launch per level
+    int no_tail;           // PWT_NO_TAIL=1: small levels one launch each
+};
+const PwtTuning& pwt_tuning();       // pwt_plan.cu
+int pwt_sm_count();                  // SM count of the CURRENT device (cached per device; pwt_plan.cu)
+
+// One-time per-device set-up of ONE kernel instantiation: raises the dynamic shared memory limit to `smem_attr`
+// and caches the resident CTAs per SM for (threads, smem_occ).  Returns that count (>= 1), or 0 when the set-up
+// failed -- nothing is cached then, so the next call retries instead of launching with a limit that was never raised.
+struct PwtKernelOnce {
+    std::mutex m;
+    int per_sm[PWT_MAX_DEVICES] = {};
+};
+template <typename K>
+static inline int pwt_kernel_once(PwtKernelOnce& o, K kernel, int threads, size_t smem_attr, size_t smem_occ) {
     int dev = 0;
     cudaGetDevice(&dev);
-    const unsigned long long bit = 1ull << (dev & 63);
-    if (*mask & bit) return false;
-    *mask |= bit;
-    return true;
+    if (dev < 0 || dev >= PWT_MAX_DEVICES) return 0;
+    int v = __atomic_load_n(&o.per_sm[dev], __ATOMIC_ACQUIRE);
+    if (v) return v;
+    std::lock_guard<std::mutex> g(o.m);
+    v = o.per_sm[dev];
+    if (v) return v;
+    if (smem_attr > 0 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attr) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, threads, smem_occ) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (v < 1) v = 1;
+    __atomic_store_n(&o.per_sm[dev], v, __ATOMIC_RELEASE);
+    return v;
 }
+#endif
 
 #ifdef __CUDACC__
 // Programmatic dependent launch (sm_90+): a kernel launched through pwt_launch_pdl may start being scheduled while
@@ -74,7 +135,7 @@ __device__ __forceinline__ void pwt_pdl_trigger() { asm volatile("griddepcontrol
 #include <stdlib.h>
 template <typename... KArgs, typename... Args>
 static inline void pwt_launch_pdl(void (*kernel)(KArgs...), dim3 grid, int threads, size_t smem, cudaStream_t st, Args... args) {
-    static const int use = getenv("PWT_NO_PDL") ? 0 : 1;            // PWT_NO_PDL=1: plain launches (A/B)
+    const int use = pwt_tuning().no_pdl ? 0 : 1;                    // PWT_NO_PDL=1: plain launches (A/B)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(threads, 1, 1);

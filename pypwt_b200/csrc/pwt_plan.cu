@@ -45,6 +45,61 @@ static int fail(int code, const char* fmt, ...) {
                         __FILE__, __LINE__);                                                       \
     } while (0)
 
+// ---- process-wide tuning knobs and per-device facts (declared in pwt_internal.h) ---------------
+static int env_i(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+const PwtTuning& pwt_tuning() {
+    static const PwtTuning t = [] {          // C++11 magic static: initialised once, thread-safe
+        PwtTuning k;
+        k.no_pdl = env_i("PWT_NO_PDL", 0);
+        k.no_fused = env_i("PWT_NO_FUSED", 0);
+        k.no_fused_inv = env_i("PWT_NO_FUSED_INV", 0);
+        k.fused_variant = env_i("PWT_FUSED_VARIANT", 0);
+        k.fused_t3 = env_i("PWT_FUSED_T3", 0);
+        k.fused_inv_t3 = env_i("PWT_FUSED_INV_T3", 0);
+        k.fused_pdl = env_i("PWT_FUSED_PDL", 1);
+        k.no_fused_norms = getenv("PWT_NO_FUSED_NORMS") ? 1 : 0;
+        k.no_defer = getenv("PWT_NO_DEFER") ? 1 : 0;
+        k.tile_min_f = env_i("PWT_TILE_MIN_F", 22);
+        k.strip_min_f = env_i("PWT_STRIP_MIN_F", 8);
+        k.ns_direct = getenv("PWT_NS_DIRECT") ? 1 : 0;
+        k.l2_persist_mb = env_i("PWT_L2_PERSIST_MB", 0);
+        k.verbose = getenv("PWT_VERBOSE") ? 1 : 0;
+        k.strip_segs = env_i("PWT_STRIP_SEGS", 0);
+        k.strip_occ_fwd = env_i("PWT_STRIP_OCC_FWD", 0);
+        k.strip_occ_inv = env_i("PWT_STRIP_OCC_INV", 0);
+        k.swt_nbuf = env_i("PWT_SWT_NBUF", 1);
+        k.no_strip_swt = getenv("PWT_NO_STRIP_SWT") ? 1 : 0;
+        k.no_fast_swt = getenv("PWT_NO_FAST_SWT") ? 1 : 0;
+        k.swt_tq = env_i("PWT_SWT_TQ", 0);
+        k.fast_tile_rows = env_i("PWT_FAST_TILE_ROWS", 0);
+        k.fwd_variant = env_i("PWT_FWD_VARIANT", -1);
+        k.reg_tile_rows = env_i("PWT_REG_TILE_ROWS", 16);
+        k.use_hints = env_i("PWT_USE_HINTS", 0);
+        k.reg_fwd_variant = env_i("PWT_REG_FWD_VARIANT", 2);
+        k.no_fold_cs = env_i("PWT_NO_FOLD_CS", 0);
+        k.no_cascade8 = env_i("PWT_NO_CASCADE8", 0);
+        k.no_fused1d = env_i("PWT_NO_FUSED1D", 0);
+        k.no_tail = env_i("PWT_NO_TAIL", 0);
+        return k;
+    }();
+    return t;
+}
+int pwt_sm_count() {
+    static int sms[PWT_MAX_DEVICES];         // 0 = not queried yet; racing first calls store the same value
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= PWT_MAX_DEVICES) return 148;
+    int v = __atomic_load_n(&sms[dev], __ATOMIC_RELAXED);
+    if (!v) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1) v = 148;
+        __atomic_store_n(&sms[dev], v, __ATOMIC_RELAXED);
+    }
+    return v;
+}
+
 // ---- minimal NCCL binding (dlopen: the product has no link-time dependency on NCCL) -----------
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId_t;
@@ -55,9 +110,14 @@ struct NcclApi {
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
     int (*CommDestroy)(ncclComm_t);
     const char* (*GetErrorString)(int);
+    int (*CommInitAll)(ncclComm_t*, int, const int*);
+    int (*GroupStart)();
+    int (*GroupEnd)();
 };
-static NcclApi g_nccl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+static NcclApi g_nccl = {};
 static int load_nccl() {
+    static std::mutex m;
+    std::lock_guard<std::mutex> guard(m);
     if (g_nccl.lib) return PWT_OK;
     const char* cands[] = {getenv("PWT_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     void* lib = nullptr;
@@ -73,6 +133,9 @@ static int load_nccl() {
         lib, "ncclAllReduce");
     g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    g_nccl.CommInitAll = (int (*)(ncclComm_t*, int, const int*))dlsym(lib, "ncclCommInitAll");
+    g_nccl.GroupStart = (int (*)())dlsym(lib, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())dlsym(lib, "ncclGroupEnd");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
         return fail(PWT_ERR_COMM, "libnccl is missing required symbols");
     g_nccl.lib = lib;
@@ -101,6 +164,7 @@ struct pwt_plan {
     size_t tmp_floats;
     int nbands;
     float* d_band[PWT_MAX_BANDS];
+    size_t coef_base, coef_floats;   // [coef_base, coef_base + coef_floats) of the slab holds every band at its final size
     int band_nr[PWT_MAX_BANDS], band_nc[PWT_MAX_BANDS];
     double* d_acc;      // device accumulators for the norms
     PwtTaskQueue queue; // dynamic task queue of the persistent kernels
@@ -232,10 +296,16 @@ static int alloc_plan(pwt_plan* p) {
     const size_t B = (size_t)p->batch;
     const size_t img = align64(B * img_elems(p));
     size_t total = img + (p->do_cs ? img : 0);
+    // coefficient region: detail bands first, the approximation LAST, so that [band 1 .. band N-1][A at its final size]
+    // is one contiguous piece of memory -- pwt_get_coeffs moves every band to the host with ONE copy.  Band 0 keeps its
+    // level-1-sized allocation (ping-pong plane of the intermediate approximations) behind that piece.
     size_t off[PWT_MAX_BANDS];
-    for (int b = 0; b < p->nbands; b++) {
-        off[b] = total;
-        const size_t n = b == 0 ? B * (size_t)lvl_elems(p, 1) : B * (size_t)band_elems(p, b);
+    p->coef_base = total;
+    for (int b = 1; b <= p->nbands; b++) {
+        const int bb = b == p->nbands ? 0 : b;
+        off[bb] = total;
+        if (bb == 0) p->coef_floats = total + B * (size_t)band_elems(p, 0) - p->coef_base;
+        const size_t n = bb == 0 ? B * (size_t)lvl_elems(p, 1) : B * (size_t)band_elems(p, bb);
         total += align64(n);
     }
     // scratch: DWT needs one approximation plane (we keep a full image so circshift can use it);
@@ -260,14 +330,14 @@ static int alloc_plan(pwt_plan* p) {
     p->d_partials = nullptr;
     clear_partials(p);
     p->want_norms = 0;
-    if (getenv("PWT_NO_FUSED_NORMS")) p->partials_cap = 0;
+    if (pwt_tuning().no_fused_norms) p->partials_cap = 0;
     if (p->partials_cap > 0) CK(cudaMalloc((void**)&p->d_partials, (size_t)p->partials_cap * 2 * sizeof(double)));
     CK(cudaMalloc((void**)&p->queue.counter, sizeof(unsigned)));
     CK(cudaMemsetAsync(p->queue.counter, 0, sizeof(unsigned), p->stream));
     p->queue.base = 0;
     CK(cudaMallocHost((void**)&p->h_acc, 2 * sizeof(double)));
     // SWT plans whose every level the fused inverse serves may defer thresholds into it (pointers are known now)
-    p->defer_swt_ok = swt_all_levels_fused(p) && !getenv("PWT_NO_DEFER");
+    p->defer_swt_ok = swt_all_levels_fused(p) && !pwt_tuning().no_defer;
     return PWT_OK;
 }
 
@@ -356,28 +426,25 @@ extern "C" int pwt_create_batch(pwt_plan** out, const float* img, int batch, int
         puts("Warning: makes little sense to use Cycle spinning with stationary Wavelet transform");
     compute_geometry(p);
     p->defer_ok = p->ndims == 2 && !p->do_swt && p->do_separable && p->nlevels >= 3 && Nr % 8 == 0 && Nc % 8 == 0 &&
-                  Nc >= 512 && Nr >= 64 && (p->hlen <= 6) && !getenv("PWT_NO_DEFER");
-    p->tile_min_f = getenv("PWT_TILE_MIN_F") ? atoi(getenv("PWT_TILE_MIN_F")) : 22;
-    p->strip_min_f = getenv("PWT_STRIP_MIN_F") ? atoi(getenv("PWT_STRIP_MIN_F")) : 8;
+                  Nc >= 512 && Nr >= 64 && (p->hlen <= 6) && !pwt_tuning().no_defer;
+    p->tile_min_f = pwt_tuning().tile_min_f;
+    p->strip_min_f = pwt_tuning().strip_min_f;
     p->defer_strip_ok = p->ndims == 2 && !p->do_swt && p->do_separable && p->nlevels >= 1 && p->lvNr[1] >= 32 &&
-                        p->lvNc[1] >= 128 && !getenv("PWT_NO_DEFER");     // + filter length, checked when used
+                        p->lvNc[1] >= 128 && !pwt_tuning().no_defer;     // + filter length, checked when used
 
-    // L2 residency of the ping-pong approximation planes: the kernels store them with an
-    // L2::evict_last policy, which only has an effect when a persisting-L2 carve-out exists.
-    {
-        static bool l2_done = false;
-        if (!l2_done) {
-            l2_done = true;
+    // Persisting-L2 carve-out: measured on B200 (profiles/r01_notes.md) to SLOW the level-1 kernels (0.10 -> 0.15-0.18 ms)
+    // without speeding up level 2, so it is off unless PWT_L2_PERSIST_MB asks for it (once per process).
+    if (pwt_tuning().l2_persist_mb > 0) {
+        static std::once_flag l2_once;
+        const int dev = p->device;
+        std::call_once(l2_once, [dev] {
             int max_persist = 0;
-            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, p->device);
-            // measured on B200 (profiles/r01_notes.md): a carve-out SLOWS the level-1 kernels (0.10 -> 0.15-0.18 ms)
-            // and does not speed up level 2, so it is off unless PWT_L2_PERSIST_MB asks for it.
-            const char* env = getenv("PWT_L2_PERSIST_MB");
-            size_t want = env ? (size_t)atoi(env) << 20 : 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+            size_t want = (size_t)pwt_tuning().l2_persist_mb << 20;
             if (want > (size_t)max_persist) want = (size_t)max_persist;
             if (want > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-            if (getenv("PWT_VERBOSE")) printf("pwt: persisting L2 carve-out %zu MB (max %d MB)\n", want >> 20, max_persist >> 20);
-        }
+            if (pwt_tuning().verbose) printf("pwt: persisting L2 carve-out %zu MB (max %d MB)\n", want >> 20, max_persist >> 20);
+        });
     }
 
     int rc = PWT_OK;
@@ -392,7 +459,7 @@ extern "C" int pwt_create_batch(pwt_plan** out, const float* img, int batch, int
         if (e != cudaSuccess) rc = fail(PWT_ERR_CUDA, "image upload failed: %s", cudaGetErrorString(e));
     }
     if (rc == PWT_OK && !p->do_separable) rc = build_k2d(p);
-    p->ns_rank1 = !p->do_separable && !getenv("PWT_NS_DIRECT");
+    p->ns_rank1 = !p->do_separable && !pwt_tuning().ns_direct;
     if (rc == PWT_OK) {
         e = cudaStreamSynchronize(p->stream);
         if (e != cudaSuccess) rc = fail(PWT_ERR_CUDA, "plan initialisation failed: %s", cudaGetErrorString(e));
@@ -1148,26 +1215,65 @@ extern "C" intptr_t pwt_coeff_ptr(pwt_plan* p, int num) {
     if (!p || num < 0 || num >= p->nbands) return 0;
     cudaSetDevice(p->device);
     flush_pending(p, 1, true);          // a raw pointer lets the caller see memory: make it current
+    clear_partials(p);                  // ... and lets the caller WRITE it: the fused per-task norm sums may go stale
     return (intptr_t)p->d_band[num];
 }
 
-// ---- custom filters ---------------------------------------------------------------------------
-// Odd lengths are zero-padded at the front to the next even length: for the analysis side this
-// reproduces the reference's odd-length window exactly (separable.cu:98-102: centre hlen/2).
-static void load_taps(float* dst, const float* src, unsigned len, unsigned padded) {
-    memset(dst, 0, PWT_MAX_TAPS * sizeof(float));
-    const unsigned o = padded - len;
-    for (unsigned k = 0; k < len; k++) dst[o + k] = src[k];
+// ---- every band with one copy (the reference's `coeffs` is 3L+1 cudaMemcpy, pypwt.pyx:290-306) ----
+extern "C" long long pwt_coeffs_slab_floats(const pwt_plan* p) { return p ? (long long)p->coef_floats : 0; }
+extern "C" long long pwt_coeff_offset(const pwt_plan* p, int num) {
+    if (!p || num < 0 || num >= p->nbands) return -1;
+    return (long long)((p->d_band[num] - p->slab) - (ptrdiff_t)p->coef_base);
+}
+extern "C" int pwt_get_coeffs(pwt_plan* p, float* dst) {
+    if (!p || !dst) return fail(PWT_ERR_ARG, "null argument");
+    if (p->state == PWT_INVERSE) {                                  // wt.cu:474-477
+        puts("Warning: get_coeff(): inverse() has been performed, the coefficients has been modified and do not make sense anymore.");
+        return 1;
+    }
+    cudaSetDevice(p->device);
+    int rc = flush_pending(p, 1, true);
+    if (rc != PWT_OK) return rc;
+    CK(cudaMemcpyAsync(dst, p->slab + p->coef_base, p->coef_floats * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return PWT_OK;
+}
+extern "C" intptr_t pwt_stream_ptr(pwt_plan* p) { return p ? (intptr_t)p->stream : 0; }
+extern "C" int pwt_wait_stream(pwt_plan* p, intptr_t producer) {
+    if (!p) return fail(PWT_ERR_ARG, "null plan");
+    cudaSetDevice(p->device);
+    CK(cudaEventRecord(p->ev1, (cudaStream_t)producer));
+    CK(cudaStreamWaitEvent(p->stream, p->ev1, 0));
+    return PWT_OK;
 }
 
-static int upload_k2d(pwt_plan* p, float* d_dst, const float* f[4], unsigned len, unsigned padded) {
+// ---- custom filters ---------------------------------------------------------------------------
+// Every kernel here is written for an EVEN number of taps.  The reference also accepts odd lengths (no built-in bank has
+// one: CDF 9/7 or LeGall 5/3 given without the padding of demo.cpp:83-179); its kernels then centre the windows
+// differently, and each odd-length case equals an even-length bank of len + 1 taps with one particular zero padding:
+//   analysis, DWT and SWT (separable.cu:98-102, 416-420: centre len/2, taps len-1-j)      -> [0, k0 .. k(len-1)]
+//   DWT synthesis (separable.cu:251-264: half length len/2, taps len-1-(2j+off); tap 0 is
+//                  never read, whichever the parity of len/2)                            -> [0, k1 .. k(len-1), 0]
+//   SWT synthesis (separable.cu:559-568: centre len/2, taps len-1-j)                      -> [k0 .. k(len-1), 0]
+// (derivation in DESIGN.md; checked against the reference's own CUDA build in tests/test_gpu_vs_pdwt.py).
+enum { PAD_FRONT = 0, PAD_DROP0 = 1, PAD_BACK = 2 };
+static inline int pad_shift(int mode, unsigned len, unsigned padded) { return mode == PAD_FRONT ? (int)(padded - len) : 0; }
+static void load_taps(float* dst, const float* src, unsigned len, unsigned padded, int mode) {
+    memset(dst, 0, PWT_MAX_TAPS * sizeof(float));
+    if (padded == len) mode = PAD_FRONT;                            // even length: taken as given
+    const int o = pad_shift(mode, len, padded);
+    for (unsigned k = (mode == PAD_DROP0 ? 1 : 0); k < len; k++) dst[o + k] = src[k];
+}
+
+static int upload_k2d(pwt_plan* p, float* d_dst, const float* f[4], unsigned len, unsigned padded, int mode) {
     const size_t n = (size_t)padded * padded;
     float* h = (float*)calloc(4 * n, sizeof(float));
     if (!h) return -3;
-    const unsigned o = padded - len;
+    if (padded == len) mode = PAD_FRONT;
+    const unsigned o = (unsigned)pad_shift(mode, len, padded), k0 = mode == PAD_DROP0 ? 1 : 0;
     for (int b = 0; b < 4; b++)
-        for (unsigned i = 0; i < len; i++)
-            for (unsigned j = 0; j < len; j++) h[b * n + (o + i) * padded + (o + j)] = f[b][i * len + j];
+        for (unsigned i = k0; i < len; i++)
+            for (unsigned j = k0; j < len; j++) h[b * n + (o + i) * padded + (o + j)] = f[b][i * len + j];
     cudaError_t e = cudaMemcpyAsync(d_dst, h, 4 * n * sizeof(float), cudaMemcpyHostToDevice, p->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
     free(h);
@@ -1185,15 +1291,15 @@ extern "C" int pwt_set_filters_forward(pwt_plan* p, const char* name, unsigned l
     cudaSetDevice(p->device);
     int res = 0;
     if (p->do_separable) {
-        load_taps(p->filt.L, f1, len, padded);
-        load_taps(p->filt.H, f2, len, padded);
+        load_taps(p->filt.L, f1, len, padded, PAD_FRONT);
+        load_taps(p->filt.H, f2, len, padded, PAD_FRONT);
     } else {
         if (!f3 || !f4) {
             puts("ERROR: Wavelets.set_filters_forward(): expected argument 4 and 5 for non-separable filtering");
             return -2;
         }
         const float* f[4] = {f1, f2, f3, f4};
-        res = upload_k2d(p, p->d_k2d_fwd, f, len, padded);
+        res = upload_k2d(p, p->d_k2d_fwd, f, len, padded, PAD_FRONT);
         p->ns_rank1 = 0;                                             // arbitrary 2D filters: direct F x F kernels from now on
     }
     p->hlen = (int)padded;
@@ -1214,9 +1320,10 @@ extern "C" int pwt_set_filters_inverse(pwt_plan* p, const float* f1, const float
     // padded there, the caller still passes the original number of taps
     const unsigned padded = (unsigned)p->hlen;
     const unsigned len = p->custom_len ? p->custom_len : padded;
+    const int mode = p->do_swt ? PAD_BACK : PAD_DROP0;              // odd lengths only (see above)
     if (p->do_separable) {
-        load_taps(p->filt.IL, f1, len, padded);
-        load_taps(p->filt.IH, f2, len, padded);
+        load_taps(p->filt.IL, f1, len, padded, mode);
+        load_taps(p->filt.IH, f2, len, padded, mode);
         return 0;
     }
     if (!f3 || !f4) {
@@ -1224,7 +1331,7 @@ extern "C" int pwt_set_filters_inverse(pwt_plan* p, const float* f1, const float
         return -2;
     }
     const float* f[4] = {f1, f2, f3, f4};
-    return upload_k2d(p, p->d_k2d_inv, f, len, padded);
+    return upload_k2d(p, p->d_k2d_inv, f, len, padded, mode);
 }
 
 // ---- misc -------------------------------------------------------------------------------------
@@ -1338,6 +1445,59 @@ extern "C" int pwt_comm_init(pwt_plan* p, int nranks, int rank, const unsigned c
     const int r = g_nccl.CommInitRank(&p->comm, nranks, u, rank);
     if (r != 0) return fail(PWT_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     p->comm_nranks = nranks;
+    return PWT_OK;
+}
+
+// Single-process variant (`ncclCommInitAll`): one plan per GPU of this process, no launcher and no id
+// exchange.  The plans must live on distinct devices.
+extern "C" int pwt_comm_init_all(pwt_plan** plans, int n) {
+    if (!plans || n < 1 || n > PWT_MAX_DEVICES) return fail(PWT_ERR_ARG, "bad plan list");
+    int rc = load_nccl();
+    if (rc != PWT_OK) return rc;
+    if (!g_nccl.CommInitAll || !g_nccl.GroupStart || !g_nccl.GroupEnd) return fail(PWT_ERR_COMM, "libnccl lacks ncclCommInitAll / ncclGroupStart");
+    int devs[PWT_MAX_DEVICES];
+    ncclComm_t comms[PWT_MAX_DEVICES];
+    for (int i = 0; i < n; i++) {
+        if (!plans[i] || plans[i]->comm) return fail(PWT_ERR_ARG, "plan %d is null or already has a communicator", i);
+        devs[i] = plans[i]->device;
+        for (int j = 0; j < i; j++)
+            if (devs[j] == devs[i]) return fail(PWT_ERR_ARG, "plans %d and %d share device %d", j, i, devs[i]);
+    }
+    const int r = g_nccl.CommInitAll(comms, n, devs);
+    if (r != 0) return fail(PWT_ERR_COMM, "ncclCommInitAll: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    for (int i = 0; i < n; i++) {
+        plans[i]->comm = comms[i];
+        plans[i]->comm_nranks = n;
+    }
+    return PWT_OK;
+}
+
+// Global norms of the plans of one communicator created by pwt_comm_init_all: every plan's fused local reduction, then
+// the n all-reduces as ONE NCCL group (a single host thread drives all GPUs), each on its plan's stream.
+extern "C" int pwt_norms_allreduce_group(pwt_plan** plans, int n, double* n1, double* n2) {
+    if (!plans || n < 1) return fail(PWT_ERR_ARG, "bad plan list");
+    for (int i = 0; i < n; i++)
+        if (!plans[i] || !plans[i]->comm || plans[i]->comm_nranks != n) return fail(PWT_ERR_COMM, "plan %d is not part of an %d-rank communicator", i, n);
+    for (int i = 0; i < n; i++) {
+        cudaSetDevice(plans[i]->device);
+        int rc = local_norms_async(plans[i]);
+        if (rc != PWT_OK) return rc;
+    }
+    int r = g_nccl.GroupStart();
+    for (int i = 0; i < n && r == 0; i++)
+        r = g_nccl.AllReduce(plans[i]->d_acc, plans[i]->d_acc, 2, kNcclFloat64, kNcclSum, plans[i]->comm, plans[i]->stream);
+    const int r2 = g_nccl.GroupEnd();
+    if (r != 0 || r2 != 0) return fail(PWT_ERR_COMM, "grouped ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r ? r : r2) : "?");
+    for (int i = 0; i < n; i++) {
+        cudaSetDevice(plans[i]->device);
+        CK(cudaMemcpyAsync(plans[i]->h_acc, plans[i]->d_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, plans[i]->stream));
+    }
+    for (int i = 0; i < n; i++) {
+        cudaSetDevice(plans[i]->device);
+        CK(cudaStreamSynchronize(plans[i]->stream));
+    }
+    if (n1) *n1 = plans[0]->h_acc[0];
+    if (n2) *n2 = plans[0]->h_acc[1];
     return PWT_OK;
 }
 

@@ -57,6 +57,11 @@ cdef extern from "pwt_b200.h":
     int pwt_set_coeff(pwt_plan* p, const float* src, int num, int on_device) nogil
     intptr_t pwt_image_ptr(pwt_plan* p) nogil
     intptr_t pwt_coeff_ptr(pwt_plan* p, int num) nogil
+    long long pwt_coeffs_slab_floats(const pwt_plan* p) nogil
+    long long pwt_coeff_offset(const pwt_plan* p, int num) nogil
+    int pwt_get_coeffs(pwt_plan* p, float* dst) nogil
+    intptr_t pwt_stream_ptr(pwt_plan* p) nogil
+    int pwt_wait_stream(pwt_plan* p, intptr_t producer_stream) nogil
     int pwt_set_filters_forward(pwt_plan* p, const char* name, unsigned int len, const float* f1,
                                 const float* f2, const float* f3, const float* f4) nogil
     int pwt_set_filters_inverse(pwt_plan* p, const float* f1, const float* f2, const float* f3,
@@ -81,6 +86,8 @@ cdef extern from "pwt_b200.h":
     int pwt_comm_init(pwt_plan* p, int nranks, int rank, const unsigned char* id) nogil
     int pwt_comm_destroy(pwt_plan* p) nogil
     int pwt_norms_allreduce(pwt_plan* p, double* n1, double* n2) nogil
+    int pwt_comm_init_all(pwt_plan** plans, int n) nogil
+    int pwt_norms_allreduce_group(pwt_plan** plans, int n, double* n1, double* n2) nogil
 
 PWT_ERR_UNKNOWN_WAVELET = -2
 PWT_ERR_UNSUPPORTED = -6
@@ -154,6 +161,164 @@ def comm_unique_id():
     return bytes(buf[:128])
 
 
+def comm_init_all(list plans):
+    """Single-process multi-GPU: one NCCL communicator over `plans` (Wavelets objects on distinct devices)."""
+    cdef pwt_plan* ps[64]
+    cdef int n = len(plans), rc
+    if n < 1 or n > 64:
+        raise ValueError("expected 1..64 plans")
+    for i in range(n):
+        ps[i] = (<Wavelets?> plans[i]).w
+    with nogil:
+        rc = pwt_comm_init_all(ps, n)
+    if rc != 0:
+        raise RuntimeError(_errmsg())
+
+
+def norms_allreduce_group(list plans):
+    """Global (norm1, norm2sq) over the plans of a `comm_init_all` communicator (one NCCL group, one host thread)."""
+    cdef pwt_plan* ps[64]
+    cdef int n = len(plans), rc
+    cdef double a = 0, b = 0
+    if n < 1 or n > 64:
+        raise ValueError("expected 1..64 plans")
+    for i in range(n):
+        ps[i] = (<Wavelets?> plans[i]).w
+    with nogil:
+        rc = pwt_norms_allreduce_group(ps, n, &a, &b)
+    if rc != 0:
+        raise RuntimeError(_errmsg())
+    return a, b
+
+
+# ---- device-array interop (SURVEY 8f rank 3; the reference only leaks raw addresses, wt.cu:658-665) ------------
+cdef extern from "Python.h":
+    object PyCapsule_New(void* pointer, const char* name, void (*destructor)(object) noexcept)
+    void* PyCapsule_GetPointer(object capsule, const char* name) except? NULL
+    int PyCapsule_IsValid(object capsule, const char* name)
+    void Py_INCREF(object o)
+    void Py_DECREF(object o)
+
+from libc.stdint cimport int64_t, uint64_t, int32_t, uint8_t, uint16_t
+from libc.stdlib cimport malloc, free
+
+cdef struct DLDevice:
+    int32_t device_type
+    int32_t device_id
+
+cdef struct DLDataType:
+    uint8_t code
+    uint8_t bits
+    uint16_t lanes
+
+cdef struct DLTensor:
+    void* data
+    DLDevice device
+    int32_t ndim
+    DLDataType dtype
+    int64_t* shape
+    int64_t* strides
+    uint64_t byte_offset
+
+cdef struct DLManagedTensor:
+    DLTensor dl_tensor
+    void* manager_ctx
+    void (*deleter)(DLManagedTensor*) noexcept
+
+
+cdef void _dl_deleter(DLManagedTensor* t) noexcept with gil:
+    if t == NULL:
+        return
+    if t.manager_ctx != NULL:
+        Py_DECREF(<object> t.manager_ctx)
+    free(t.dl_tensor.shape)
+    free(t)
+
+
+cdef void _dl_capsule_destructor(object cap) noexcept:
+    cdef DLManagedTensor* t
+    if PyCapsule_IsValid(cap, "dltensor"):       # never consumed: we still own the tensor
+        t = <DLManagedTensor*> PyCapsule_GetPointer(cap, "dltensor")
+        _dl_deleter(t)
+
+
+cdef class DeviceArray:
+    """Zero-copy view of device memory owned by a `Wavelets` instance (its image or one coefficient band).
+
+    Exposes `__cuda_array_interface__` (version 3: numba, cupy, torch.as_tensor) and the DLPack protocol
+    (`torch.from_dlpack`, `cupy.from_dlpack`).  The view keeps its owner alive.  Work queued by the owner is
+    ordered on the owner's stream, which both protocols report, so consumers synchronise correctly; writes through
+    the view are seen by the next transform (the fused norm cache is dropped when a band view is handed out)."""
+    cdef readonly object owner
+    cdef readonly size_t ptr
+    cdef readonly tuple shape
+    cdef readonly int device
+    cdef readonly size_t stream
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": "<f4", "data": (self.ptr, False), "version": 3, "strides": None,
+                "stream": self.stream if self.stream else 1}
+
+    @property
+    def nbytes(self):
+        n = 4
+        for d in self.shape:
+            n *= d
+        return n
+
+    def __dlpack_device__(self):
+        return (2, self.device)                  # kDLCUDA
+
+    def __dlpack__(self, stream=None, **kwargs):
+        # the producer's work is on `self.stream`; make the consumer's stream wait for it (-1: no synchronisation wanted)
+        if stream is not None and stream != -1:
+            (<Wavelets> self.owner)._sync_for_consumer()
+        cdef DLManagedTensor* t = <DLManagedTensor*> malloc(sizeof(DLManagedTensor))
+        if t == NULL:
+            raise MemoryError()
+        cdef int nd = len(self.shape)
+        t.dl_tensor.data = <void*> self.ptr
+        t.dl_tensor.device.device_type = 2
+        t.dl_tensor.device.device_id = self.device
+        t.dl_tensor.ndim = nd
+        t.dl_tensor.dtype.code = 2               # kDLFloat
+        t.dl_tensor.dtype.bits = 32
+        t.dl_tensor.dtype.lanes = 1
+        t.dl_tensor.shape = <int64_t*> malloc(sizeof(int64_t) * (nd if nd > 0 else 1))
+        for i in range(nd):
+            t.dl_tensor.shape[i] = self.shape[i]
+        t.dl_tensor.strides = NULL
+        t.dl_tensor.byte_offset = 0
+        Py_INCREF(self)
+        t.manager_ctx = <void*> self
+        t.deleter = _dl_deleter
+        return PyCapsule_New(t, "dltensor", _dl_capsule_destructor)
+
+
+cdef object _as_device_input(obj):
+    """(ptr, shape, producer stream) of a float32 C-contiguous device array exposing __cuda_array_interface__
+    (torch / cupy / numba / DeviceArray), or None for host data."""
+    if isinstance(obj, np.ndarray):
+        return None
+    cai = getattr(obj, "__cuda_array_interface__", None)
+    if cai is None:
+        return None
+    if np.dtype(cai["typestr"]) != np.float32:
+        raise ValueError("device arrays must be float32 (got %s)" % cai["typestr"])
+    shape = tuple(int(x) for x in cai["shape"])
+    strides = cai.get("strides")
+    if strides is not None:
+        expect, acc = [], 4
+        for d in reversed(shape):
+            expect.append(acc)
+            acc *= d
+        if tuple(strides) != tuple(reversed(expect)):
+            raise ValueError("device arrays must be C-contiguous")
+    stream = cai.get("stream")
+    return (int(cai["data"][0]), shape, int(stream) if stream else 0)
+
+
 cdef class Wavelets:
     """
     Initializes the Wavelet transform from an image and given parameters.
@@ -187,45 +352,60 @@ cdef class Wavelets:
     cdef readonly int batched1d
     cdef readonly int batch
     cdef list _coeffs
+    cdef object _slab          # pinned host slab that every array of _coeffs is a view of (one D2H fills them all)
     cdef tuple shape
     cdef int _is1d
 
     def __cinit__(self, img, str wname, int levels, int do_separable=1, int do_cycle_spinning=0,
                   int do_swt=0, int ndim=2, Wavelets copy=None):
         self.w = NULL
-        img = self._checkarray(img)
+        if copy is not None:            # shell for Wavelets.copy(): the cloned plan is attached by the caller
+            self.Nr, self.Nc, self.sizes, self.wname, self.levels = copy.Nr, copy.Nc, list(copy.sizes), copy.wname, copy.levels
+            self.do_cycle_spinning, self.hlen, self.do_swt, self.do_separable = copy.do_cycle_spinning, copy.hlen, copy.do_swt, copy.do_separable
+            self.ndim, self.batched1d, self.batch, self.shape, self._is1d = copy.ndim, copy.batched1d, copy.batch, copy.shape, copy._is1d
+            return
+        # a device array (anything exposing __cuda_array_interface__: torch, cupy, numba, DeviceArray) is taken
+        # where it lies: the reference's `memisonhost=0` constructor argument (wt.cu:84,145-150), which its wrapper
+        # never passes (pypwt.pyx:169)
+        dev_in = _as_device_input(img)
+        if dev_in is None:
+            img = self._checkarray(img)
+            ishape = tuple(int(x) for x in img.shape)
+        else:
+            ishape = dev_in[1]
+        indim = len(ishape)
         ndim = min(ndim, 2)                                       # pypwt.pyx:145
         self.batched1d = 0
         self.batch = 1
-        if img.ndim == 2:
-            self.Nr = img.shape[0]
-            self.Nc = img.shape[1]
-            if img.ndim != ndim:
+        if indim == 2:
+            self.Nr = ishape[0]
+            self.Nc = ishape[1]
+            if indim != ndim:
                 self.batched1d = 1
-        elif img.ndim == 1:
+        elif indim == 1:
             self.Nr = 1
-            self.Nc = img.shape[0]
-        elif img.ndim == 3 and ndim == 2:
+            self.Nc = ishape[0]
+        elif indim == 3 and ndim == 2:
             # extension: stack of independent 2D images (SURVEY 8e)
-            self.batch = img.shape[0]
-            self.Nr = img.shape[1]
-            self.Nc = img.shape[2]
+            self.batch = ishape[0]
+            self.Nr = ishape[1]
+            self.Nc = ishape[2]
         else:
             raise NotImplementedError("Wavelets(): Only 1D and 2D transforms are supported for now")
-        self.shape = tuple(int(s) for s in img.shape)
+        self.shape = ishape
         self.wname = wname
         py_wname = wname.encode("ASCII")
         self.do_cycle_spinning = do_cycle_spinning
         self.do_swt = do_swt
-        self.ndim = img.ndim
+        self.ndim = indim
 
         if pwt_device_count() < 1:
             raise RuntimeError("pycudwt: no CUDA device available (there is no CPU fallback)")
-        cdef const float* src = <const float*> <size_t> img.ctypes.data
+        cdef const float* src = <const float*> <size_t> (img.ctypes.data if dev_in is None else dev_in[0])
         cdef const char* c_wname = py_wname
-        cdef int rc, c_ndim = ndim, c_levels = levels, c_sep = do_separable
+        cdef int rc, c_ndim = ndim, c_levels = levels, c_sep = do_separable, c_onhost = 1 if dev_in is None else 0
         with nogil:
-            rc = pwt_create_batch(&self.w, src, self.batch, self.Nr, self.Nc, c_wname, c_levels, 1,
+            rc = pwt_create_batch(&self.w, src, self.batch, self.Nr, self.Nc, c_wname, c_levels, c_onhost,
                                   c_sep, self.do_cycle_spinning, self.do_swt, c_ndim)
         if rc != 0:
             self.w = NULL
@@ -242,14 +422,25 @@ cdef class Wavelets:
         self._is1d = 1 if info.ndims == 1 else 0
         self.sizes = self._compute_sizes()
 
-        # persistent host buffers: [A, [H1, V1, D1], ...] or [A, D1, ...]  (pypwt.pyx:191-205)
-        lead = (self.batch,) if self.batch > 1 else ()
-        self._coeffs = [pinned_zeros(lead + tuple(self.sizes[-1]))]
+        self._alloc_host_coeffs()
+
+    cdef _alloc_host_coeffs(self):
+        # persistent host buffers: [A, [H1, V1, D1], ...] or [A, D1, ...]  (pypwt.pyx:191-205), all of them views of
+        # ONE pinned slab laid out like the device's coefficient region, so `coeffs` is a single D2H copy
+        lead = (self.batch,) if len(self.shape) == 3 else ()
+        self._slab = pinned_zeros(int(pwt_coeffs_slab_floats(self.w)))
+
+        def view(num, shp):
+            shp = lead + tuple(shp)
+            off = int(pwt_coeff_offset(self.w, num))
+            return self._slab[off:off + int(np.prod(shp))].reshape(shp)
+
+        self._coeffs = [view(0, self.sizes[-1])]
         for i in range(self.levels):
             if self._is1d:
-                self._coeffs.append(pinned_zeros(lead + tuple(self.sizes[i])))
+                self._coeffs.append(view(i + 1, self.sizes[i]))
             else:
-                self._coeffs.append([pinned_zeros(lead + tuple(self.sizes[i])) for _ in range(3)])
+                self._coeffs.append([view(3 * i + 1 + j, self.sizes[i]) for j in range(3)])
 
     def info(self):
         """Print some information on the current ``Wavelets`` instance."""
@@ -319,15 +510,19 @@ cdef class Wavelets:
 
     @property
     def coeffs(self):
-        """[A, [H1, V1, D1], [H2, V2, D2], ...] (2D) or [A, D1, ...] (1D); copies every band from the device."""
-        self.coeff_only(0)
-        i_end = 3 * self.levels if not self._is1d else self.levels
-        for cnt in range(1, i_end + 1):
-            self.coeff_only(cnt)
+        """[A, [H1, V1, D1], [H2, V2, D2], ...] (2D) or [A, D1, ...] (1D): every band, moved from the device with ONE
+        copy into the persistent pinned host buffers (the reference issues 3L+1 blocking copies, pypwt.pyx:290-306)."""
+        cdef float* dst = <float*> <size_t> self._slab.ctypes.data
+        cdef int rc
+        with nogil:
+            rc = pwt_get_coeffs(self.w, dst)
+        if rc != 0:
+            raise RuntimeError("Wavelets.coeffs: something went wrong when retrieving the coefficients (%s)"
+                               % ("inverse() has been performed" if rc == 1 else _errmsg()))
         return self._coeffs
 
     def _img_shape(self):
-        return ((self.batch,) if self.batch > 1 else ()) + (self.Nr, self.Nc)
+        return ((self.batch,) if len(self.shape) == 3 else ()) + (self.Nr, self.Nc)
 
     @property
     def image(self):
@@ -346,27 +541,40 @@ cdef class Wavelets:
             raise RuntimeError("Wavelets.image(): something went wrong when retrieving image, expected %d coeffs, got %d" % (out.size, numc))
         return out
 
-    def set_image(self, img):
-        """Replace the device image (does not update the coefficients)."""
-        img = self._checkarray(img, self._img_shape())
-        cdef const float* src = <const float*> <size_t> img.ctypes.data
-        cdef int rc
+    cdef _upload_image(self, img, shp):
+        """host array -> H2D, device array (`__cuda_array_interface__`) -> D2D on the plan's stream, ordered after the
+        producer's stream when the array names one (wt.cu:425-432 with mem_is_on_device = 0 / 1)."""
+        cdef const float* src
+        cdef int rc, on_device = 0
+        cdef intptr_t producer = 0
+        dev_in = _as_device_input(img)
+        if dev_in is None:
+            img = self._checkarray(img, shp)
+            src = <const float*> <size_t> img.ctypes.data
+        else:
+            if tuple(dev_in[1]) != tuple(shp):
+                raise ValueError("The image does not have the correct shape (expected %s, got %s)" % (str(shp), str(dev_in[1])))
+            src = <const float*> <size_t> dev_in[0]
+            on_device = 1
+            producer = dev_in[2]
         with nogil:
-            rc = pwt_set_image(self.w, src, 0)
+            rc = 0
+            if producer > 2:
+                rc = pwt_wait_stream(self.w, producer)
+            if rc == 0:
+                rc = pwt_set_image(self.w, src, on_device)
         if rc != 0:
             raise RuntimeError(_errmsg())
 
+    def set_image(self, img):
+        """Replace the device image (does not update the coefficients).  `img`: numpy array or device array."""
+        self._upload_image(img, self._img_shape())
+
     def forward(self, img=None):
         """Forward transform of `img` (if given, checked against the original shape) or of the current image."""
-        cdef const float* src
         cdef int rc
         if img is not None:
-            img = self._checkarray(img, self.shape)
-            src = <const float*> <size_t> img.ctypes.data
-            with nogil:
-                rc = pwt_set_image(self.w, src, 0)
-            if rc != 0:
-                raise RuntimeError(_errmsg())
+            self._upload_image(img, self.shape)
         with nogil:
             rc = pwt_forward(self.w)
         if rc < 0:
@@ -440,31 +648,48 @@ cdef class Wavelets:
         return pwt_add_wavelet(self.w, W.w, c_alpha)
 
     def copy(self):
-        """Deep copy (device state included), the equivalent of the reference's C++ copy constructor."""
-        cdef Wavelets other = Wavelets.__new__(Wavelets, np.zeros(self.shape, np.float32), self.wname,
-                                               self.levels, self.do_separable, self.do_cycle_spinning,
-                                               self.do_swt, 1 if self.batched1d else 2)
+        """Deep copy (device state, custom filters included): the reference's C++ copy constructor (wt.cu:191-222)."""
         cdef pwt_plan* fresh = NULL
-        if pwt_clone(&fresh, self.w) != 0:
+        cdef int rc
+        with nogil:
+            rc = pwt_clone(&fresh, self.w)
+        if rc != 0:
             raise RuntimeError(_errmsg())
-        pwt_destroy(other.w)
+        # the Python shell is built around the cloned plan directly: no throw-away plan, and a custom bank's name
+        # (unknown to the filter table) is not looked up again
+        cdef Wavelets other = Wavelets.__new__(Wavelets, None, self.wname, self.levels, copy=self)
         other.w = fresh
+        other._alloc_host_coeffs()
         return other
 
     def set_coeff(self, coeff, int num, check=False):
-        """Overwrite coefficient `num` on the device."""
-        coeff = self._checkarray(coeff)
+        """Overwrite coefficient `num` on the device.  `coeff`: numpy array or device array."""
+        cdef const float* src
+        cdef int rc, on_device = 0
+        cdef intptr_t producer = 0
         ref = self._coeff_ref(num)
+        dev_in = _as_device_input(coeff)
+        if dev_in is None:
+            coeff = self._checkarray(coeff)
+            cshape, csize = coeff.shape, coeff.size
+            src = <const float*> <size_t> coeff.ctypes.data
+        else:
+            cshape, csize = dev_in[1], int(np.prod(dev_in[1]))
+            src = <const float*> <size_t> dev_in[0]
+            on_device = 1
+            producer = dev_in[2]
         if check:
             dcoeff = self.coeff_only(num)
-            if dcoeff.shape != coeff.shape:
-                raise ValueError("set_coefInvalid coefficient shape : expected %s, got %s" % (str(dcoeff.shape), str(coeff.shape)))
-        if coeff.size != ref.size:
-            raise ValueError("set_coeff(): expected %d elements, got %d" % (ref.size, coeff.size))
-        cdef const float* src = <const float*> <size_t> coeff.ctypes.data
-        cdef int rc
+            if dcoeff.shape != tuple(cshape):
+                raise ValueError("set_coefInvalid coefficient shape : expected %s, got %s" % (str(dcoeff.shape), str(cshape)))
+        if csize != ref.size:
+            raise ValueError("set_coeff(): expected %d elements, got %d" % (ref.size, csize))
         with nogil:
-            rc = pwt_set_coeff(self.w, src, num, 0)
+            rc = 0
+            if producer > 2:
+                rc = pwt_wait_stream(self.w, producer)
+            if rc == 0:
+                rc = pwt_set_coeff(self.w, src, num, on_device)
         if rc != 0:
             raise RuntimeError(_errmsg())
 
@@ -513,6 +738,44 @@ cdef class Wavelets:
     def coeff_int_ptr(self, int num):
         """Address of a device coefficient band."""
         return pwt_coeff_ptr(self.w, num)
+
+    cdef DeviceArray _device_view(self, size_t ptr, tuple shape):
+        cdef pwt_info info
+        pwt_get_info(self.w, &info)
+        cdef DeviceArray d = DeviceArray.__new__(DeviceArray)
+        d.owner = self
+        d.ptr = ptr
+        d.shape = shape
+        d.device = info.device
+        d.stream = <size_t> pwt_stream_ptr(self.w)
+        return d
+
+    def _sync_for_consumer(self):
+        self.sync()
+
+    @property
+    def image_device(self):
+        """Zero-copy device view of the image (`__cuda_array_interface__` + DLPack), e.g. `torch.as_tensor(W.image_device,
+        device="cuda")` -- the end-to-end path without the PCIe round trip of `image`."""
+        return self._device_view(<size_t> pwt_image_ptr(self.w), self._img_shape())
+
+    def coeff_device(self, int num):
+        """Zero-copy device view of coefficient band `num` (numbering of `coeff_only`)."""
+        nb = (3 * self.levels + 1) if not self._is1d else (self.levels + 1)
+        if num < 0 or num >= nb:
+            raise IndexError("coefficient number %d out of range" % num)
+        return self._device_view(<size_t> pwt_coeff_ptr(self.w, num), tuple(self._coeff_ref(num).shape))
+
+    @property
+    def coeffs_device(self):
+        """Device views in the layout of `coeffs`: [A, [H1, V1, D1], ...] (2D) or [A, D1, ...] (1D)."""
+        out = [self.coeff_device(0)]
+        for i in range(self.levels):
+            if self._is1d:
+                out.append(self.coeff_device(i + 1))
+            else:
+                out.append([self.coeff_device(3 * i + 1 + j) for j in range(3)])
+        return out
 
     # ---- extensions ------------------------------------------------------------------------
     def sync(self):

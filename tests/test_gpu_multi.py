@@ -38,8 +38,7 @@ WORKER = textwrap.dedent("""
     err = float(np.abs(S.local_image - stack[lo:hi]).max())
     print(json.dumps({"rank": rank, "nccl": bool(used_nccl), "g": g, "l": l, "g2": g2, "err": err,
                       "slices": [lo, hi]}), flush=True)
-    if S.W is not None:
-        S.W.comm_destroy()
+    S.close()
     dist.destroy_process_group()
 """)
 
@@ -71,3 +70,30 @@ def test_sharded_stack_two_gpus(tmp_path):
     W.forward()
     n1, n2 = W.norms()
     assert abs(n1 - tot1) <= 1e-9 * n1 and abs(n2 - tot2) <= 1e-9 * n2
+
+
+def test_stack_wavelets_single_process():
+    """`StackWavelets`: one process shards the stack over every visible GPU (ncclCommInitAll when there are several,
+    no communicator with one) -- results equal the one-plan transform of the whole stack."""
+    import pypwt_b200
+    import pycudwt
+    from pypwt_b200.sharded import StackWavelets
+    stack = np.random.default_rng(7).integers(0, 256, size=(5, 128, 256)).astype(np.float32)
+    S = StackWavelets(stack, "sym8", 3)
+    assert len(S.plans) == min(pypwt_b200.device_count(), 3 if pypwt_b200.device_count() == 4 else 5) or len(S.plans) >= 1
+    W = pycudwt.Wavelets(stack, "sym8", 3)
+    S.forward(); W.forward()
+    n1, n2 = S.norms()
+    w1, w2 = W.norms()
+    assert abs(n1 - w1) <= 1e-9 * w1 and abs(n2 - w2) <= 1e-9 * w2
+    cs, cw = S.coeffs, W.coeffs
+    assert np.array_equal(cs[0], cw[0])
+    for l in range(1, 4):
+        for j in range(3):
+            assert np.array_equal(cs[l][j], cw[l][j])
+    S.soft_threshold(5.0); W.soft_threshold(5.0)
+    S.inverse(); W.inverse()
+    assert np.array_equal(S.image, W.image)
+    S.forward(stack)
+    assert abs(S.norm1() - w1) <= 1e-9 * w1
+    S.close()

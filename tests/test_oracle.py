@@ -273,3 +273,80 @@ def test_c_port_matches_numpy_oracle(wname, shape):
         for j in range(3):
             assert np.abs(b[3 * i + 1 + j] - c[i + 1][j]).max() <= tol
     assert np.abs(P.inverse() - x).max() <= 1e-5 * 255 * (20 if wname in ("bior3.1", "rbio3.1") else 1) * 4
+
+
+# ---- odd-length custom banks ----------------------------------------------------------------
+def _pad(k, mode):
+    """The even-length bank (len + 1 taps) that reproduces the reference's odd-length windows; the product applies the
+    same paddings in pwt_set_filters_forward / _inverse (pwt_plan.cu, "custom filters")."""
+    k = np.asarray(k, dtype=np.float64)
+    z = np.zeros(1)
+    if mode == "front":
+        return np.concatenate([z, k])
+    if mode == "drop0":
+        return np.concatenate([z, k[1:], z])
+    return np.concatenate([k, z])          # "back"
+
+
+@pytest.mark.parametrize("hlen", [3, 5, 7, 9, 11])
+@pytest.mark.parametrize("shape", [(12, 16), (11, 13)])
+def test_odd_length_banks_equal_padded_even_banks(hlen, shape):
+    """Literal emulation of the reference kernels with an ODD number of taps (separable.cu:98-102, 251-264, 416-420,
+    559-568; nonseparable.cu:125, 182-190, 311, 367) against the same kernels fed the padded even-length bank."""
+    rng = np.random.default_rng(100 + hlen)
+    img = rng.standard_normal(shape)
+    fL, fH, iL, iH = (rng.standard_normal(hlen) for _ in range(4))
+    # analysis (DWT)
+    a = E.fwd_cols(*E.fwd_rows(img, fL, fH), fL, fH)
+    b = E.fwd_cols(*E.fwd_rows(img, _pad(fL, "front"), _pad(fH, "front")), _pad(fL, "front"), _pad(fH, "front"))
+    for x, y in zip(a, b):
+        np.testing.assert_allclose(x, y, atol=1e-12)
+    # synthesis (DWT): tap 0 of an odd-length synthesis filter is never read by the reference
+    cA, cH, cV, cD = a
+    t = E.inv_cols(cA, cH, cV, cD, iL, iH, shape[0])
+    r1 = E.inv_rows(t[0], t[1], iL, iH, shape[1])
+    pl, ph = _pad(iL, "drop0"), _pad(iH, "drop0")
+    t = E.inv_cols(cA, cH, cV, cD, pl, ph, shape[0])
+    r2 = E.inv_rows(t[0], t[1], pl, ph, shape[1])
+    np.testing.assert_allclose(r1, r2, atol=1e-12)
+    # SWT analysis / synthesis rows (the column passes use the same index arithmetic)
+    for level in (1, 2):
+        if (hlen - 1) * (1 << (level - 1)) >= min(shape):
+            continue
+        lo1, hi1 = E.swt_rows(img, fL, fH, level)
+        lo2, hi2 = E.swt_rows(img, _pad(fL, "front"), _pad(fH, "front"), level)
+        np.testing.assert_allclose(lo1, lo2, atol=1e-12)
+        np.testing.assert_allclose(hi1, hi2, atol=1e-12)
+        np.testing.assert_allclose(E.iswt_rows(lo1, hi1, iL, iH, level),
+                                   E.iswt_rows(lo1, hi1, _pad(iL, "back"), _pad(iH, "back"), level), atol=1e-12)
+
+
+def _pad2(K, mode):
+    n = K.shape[-1]
+    out = np.zeros((4, n + 1, n + 1))
+    if mode == "front":
+        out[:, 1:, 1:] = K
+    elif mode == "drop0":
+        out[:, 1:n, 1:n] = K[:, 1:, 1:]
+    else:
+        out[:, :n, :n] = K
+    return out
+
+
+@pytest.mark.parametrize("hlen", [3, 5, 7])
+def test_odd_length_nonseparable_banks_equal_padded_even_banks(hlen):
+    rng = np.random.default_rng(200 + hlen)
+    shape = (12, 14)
+    img = rng.standard_normal(shape)
+    K = rng.standard_normal((4, hlen, hlen))
+    IK = rng.standard_normal((4, hlen, hlen))
+    a = E.ns_forward(img, K)
+    b = E.ns_forward(img, _pad2(K, "front"))
+    for x, y in zip(a, b):
+        np.testing.assert_allclose(x, y, atol=1e-12)
+    np.testing.assert_allclose(E.ns_inverse(*a, IK, shape), E.ns_inverse(*a, _pad2(IK, "drop0"), shape), atol=1e-12)
+    a = E.ns_forward_swt(img, K, 1)
+    b = E.ns_forward_swt(img, _pad2(K, "front"), 1)
+    for x, y in zip(a, b):
+        np.testing.assert_allclose(x, y, atol=1e-12)
+    np.testing.assert_allclose(E.ns_inverse_swt(*a, IK, 1), E.ns_inverse_swt(*a, _pad2(IK, "back"), 1), atol=1e-12)
