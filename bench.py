@@ -19,6 +19,11 @@ Keys of the JSON line (one line, rank 0):
   cpu_baseline the plain-C/OpenMP oracle port of the same transform timed on the host cores (bounded sample)
   pdwt_cuda    the reference's own CUDA kernels (oracle/_ref, recompiled for sm_100a) on the same GPU,
                same workload, device-resident -- reported beside, not part of `value`
+  c3_stack     BASELINE config 3 as a measurement: a FIXED 512 x 2048 x 2048 sym8 stack (strong scaling: 512/N slices
+               per rank), step = forward + global norm1/norm2sq (fused reduction + ncclAllReduce, INSIDE the CUDA-event
+               region) + soft threshold + inverse; aggregate Mpixel/s, us of the collective alone
+  host_link    pinned-memory copy bandwidth of this rank (H2D, D2H, both at once) and the NUMA placement of the rank:
+               names the link that bounds `e2e`
 --impl reference: the CPU path of the reference workflow (pywt-equivalent C/OpenMP restatement
 oracle/dwt_cpu.c; pywt itself is not installable here) on all host cores, same metric/config.
 """
@@ -80,6 +85,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def wait_first(self, timeout=8.0):
+        """nvidia-smi needs ~1 s to start: block until its first row arrived (bounded)."""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+        return len(self.rows)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -122,7 +134,19 @@ def cpu_cores():
     return dwt_cpu.threads()
 
 
+def cpu_use_all_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to every worker: the CPU arm sets its own thread count (every core this
+    process may run on), so that its value is the same at every N."""
+    from oracle import dwt_cpu
+    try:        # a rank pinned to its GPU's NUMA node (or confined by torchrun) takes every core of the box back
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+    except Exception:      # noqa: BLE001
+        pass
+    return dwt_cpu.set_threads()
+
+
 def time_cpu_port(budget_s=float(os.environ.get("PWT_BENCH_CPU_BUDGET", "10")), side=4096):
+    cpu_use_all_cores()
     img = synth((side, side), 99)
     cpu_port_fwd_inv(img)                  # warm up (page faults, thread pool)
     n, t0 = 0, time.perf_counter()
@@ -147,6 +171,7 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
+    cpu_use_all_cores()
     # bounded sample of the workload: one step = one SxS image on the host, S the largest of
     # 4096/2048/1024/512 for which warmup + K steps stay within ~2.5 minutes
     probe = synth((1024, 1024), 98)
@@ -218,8 +243,145 @@ def time_pdwt(img, steps, warmup):
         return {"unavailable": str(e)[:200]}
 
 
+def numa_pin(local):
+    """Bind this rank's host threads to the cores of its GPU's NUMA node (pinned buffers allocated afterwards are
+    first-touched there).  Returns what happened, for the JSON line."""
+    info = {"gpu": local}
+    try:
+        before = sorted(os.sched_getaffinity(0))
+        info["affinity_before"] = "%d cpus [%d..%d]" % (len(before), before[0], before[-1])
+        bus = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                                  # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        info["numa_node"] = node
+        info["numa_nodes"] = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])
+        if node >= 0:
+            cpus = set()
+            for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            try:
+                os.sched_setaffinity(0, cpus)
+            except OSError as e:                           # cpuset of the container does not include them
+                info["pin_error"] = str(e)
+            after = sorted(os.sched_getaffinity(0))
+            info["affinity_after"] = "%d cpus [%d..%d]" % (len(after), after[0], after[-1])
+            info["pinned_to_gpu_node"] = set(after) <= cpus
+    except Exception as e:      # noqa: BLE001
+        info["error"] = str(e)[:200]
+    return info
+
+
+def host_link_bandwidth(W, img, out, barrier, max_over_ranks, min_over_ranks):
+    """Pinned host <-> device copy bandwidth of this rank through the public API (set_image = H2D, image_into = D2H),
+    alone and with every rank copying at the same time: the PCIe / host-memory limit that bounds `e2e`."""
+    res = {}
+    nb = img.nbytes / 1e9
+    for name, fn in (("h2d", lambda: W.set_image(img)), ("d2h", lambda: W.image_into(out))):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            fn()
+        dt = time.perf_counter() - t0
+        res[name + "_gbs_all_ranks_at_once_min"] = min_over_ranks(4 * nb / dt)
+        res[name + "_gbs_all_ranks_at_once_max"] = max_over_ranks(4 * nb / dt)
+        barrier()
+    return res
+
+
+def run_c3(args, rank, world, local, dist, barrier, max_over_ranks):
+    """BASELINE config 3: fixed 512 x 2048 x 2048 fp32 sym8 stack, per-slice 2D DWT (3 levels), sharded over the ranks
+    (strong scaling), global norms all-reduced inside the step."""
+    import pypwt_b200
+    import pycudwt
+    S, side, wname, levels = args.c3_slices, 2048, "sym8", 3
+    per = -(-S // world)
+    lo, hi = min(rank * per, S), min((rank + 1) * per, S)
+    n_loc = hi - lo
+    res = {"workload": "%dx%dx%d fp32 %s %d-level per-slice 2D DWT: forward + global norm1/norm2sq + soft_threshold + inverse"
+                       % (S, side, side, wname, levels),
+           "scaling": "strong", "slices_per_rank": per}
+    if n_loc <= 0:
+        raise SystemExit("bench.py: c3 leg needs at least one slice per rank")
+    # synthetic stack generated on the device (8 GiB at N = 1: host generation would take longer than the whole bench)
+    try:
+        import torch
+        g = torch.Generator(device="cuda")
+        g.manual_seed(4321 + rank)
+        x = torch.empty((n_loc, side, side), device="cuda", dtype=torch.float32)
+        x.normal_(128.0, 50.0, generator=g)
+        torch.cuda.synchronize()
+        W = pycudwt.Wavelets(x, wname, levels)          # memisonhost = 0: device-to-device
+        W.sync()
+        del x
+        torch.cuda.empty_cache()
+        res["data"] = "synthetic, generated on the device (torch.normal), seed per rank"
+    except ImportError:
+        base = synth((min(n_loc, 8), side, side), 4321 + rank)
+        W = pycudwt.Wavelets(np.concatenate([base] * (-(-n_loc // base.shape[0])))[:n_loc], wname, levels)
+        res["data"] = "synthetic, 8 distinct slices tiled"
+    if world > 1:
+        uid = [pypwt_b200.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        W.comm_init(world, rank, uid[0])
+        norms = W.norms_allreduce
+    else:
+        norms = W.norms
+    beta = 5.0
+
+    def step():
+        W.forward()
+        n1, n2 = norms()            # global statistics: fused per-CTA partial sums + ncclAllReduce(2 x f64) on the plan's stream
+        W.soft_threshold(beta, 0, 1)
+        W.inverse()
+        return n1, n2
+
+    for _ in range(3):
+        n1, n2 = step()
+    W.sync(); barrier(); W.sync()
+    l0 = W.launch_count
+    steps = max(3, min(args.steps, 10))
+    W.timer_start()
+    for _ in range(steps):
+        n1, n2 = step()
+    ms = W.timer_stop()
+    W.sync(); barrier()
+    launches = W.launch_count - l0
+    ms = max_over_ranks(ms)
+    pix = float(S) * side * side
+    res.update({"value": pix * steps / (ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": ms / steps, "steps": steps,
+                "gpu_launches_per_step": launches / steps, "global_norm1": n1, "global_norm2sq": n2,
+                "roofline_frac_16B_per_px": (16.0 * pix / world) / (ms / steps * 1e-3) / 1e9 / measured_peak()[0]})
+    # the collective alone: global norms (local reduction + all-reduce + 16-byte D2H) against the local reduction alone
+    W.forward()
+    for fn, key in ((norms, "global_norms_us"), (W.norms, "local_norms_us")):
+        fn(); W.sync(); barrier()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            fn()
+        res[key] = max_over_ranks((time.perf_counter() - t0) / 20 * 1e6)
+    res["allreduce_us"] = max(0.0, res["global_norms_us"] - res["local_norms_us"]) if world > 1 else 0.0
+    res["how"] = ("CUDA events on the plan's stream around %d steps, barrier + synchronize on both sides, max over ranks; "
+                  "the all-reduce is enqueued on the same stream by pwt_norms_allreduce" % steps)
+    # forward + inverse alone (no norms, no threshold) for the 16 B/px roofline of the strip kernels
+    W.timer_start()
+    for _ in range(steps):
+        W.forward(); W.inverse()
+    ms2 = max_over_ranks(W.timer_stop())
+    res["fwd_inv_only_ms_per_step"] = ms2 / steps
+    res["fwd_inv_only_value"] = pix * steps / (ms2 * 1e-3) / 1e6
+    if world > 1:
+        W.comm_destroy()
+    del W
+    return res
+
+
 def run_ours(args):
     rank, world, local = dist_env()
+    pin = numa_pin(local)            # before any pinned allocation
     import pypwt_b200
     import pycudwt
 
@@ -237,13 +399,16 @@ def run_ours(args):
         if dist is not None:
             dist.barrier()
 
-    def max_over_ranks(x):
+    def max_over_ranks(x, op="MAX"):
         if dist is None:
             return x
         import torch
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
         return float(t.item())
+
+    def min_over_ranks(x):
+        return max_over_ranks(x, "MIN")
 
     B = args.batch
     shape = (SIDE, SIDE) if B == 1 else (B, SIDE, SIDE)
@@ -257,8 +422,16 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()      # runs through warm-up, the timed region and the per-kernel pass (all GPU-loaded)
-    for _ in range(max(args.warmup, 3)):
+        sampler.wait_first()
+    warm = 0
+    t_w = time.perf_counter()
+    # at least W (>= 3) warm-up steps, and at least 0.5 s of the same load so that nvidia-smi (20 ms period) has seen the
+    # clocks this workload settles at before the (possibly very short) timed region starts
+    while warm < max(args.warmup, 3) or time.perf_counter() - t_w < 0.5:
         W.forward(); W.inverse()
+        warm += 1
+        if warm % 50 == 0:
+            W.sync()
     W.sync()
     l0 = W.launch_count
     barrier(); W.sync()
@@ -273,11 +446,18 @@ def run_ours(args):
 
     # ---- per-kernel durations (same loop, every launch bracketed by events) --------------------
     W.profile_enable(1)
-    for _ in range(min(args.steps, 40)):
+    for _ in range(max(8, min(args.steps, 40))):
         W.forward(); W.inverse()
     recs = W.profile_read()
     W.profile_enable(0)
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < 0.3:           # same load a little longer: the sampler's last rows
+        for _ in range(50):
+            W.forward(); W.inverse()
+        W.sync()
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["how"] = "nvidia-smi -lms 20 from the first warm-up step to the end of the per-kernel pass (same fwd+inv load throughout)"
     by_tag = {}
     for tag, t in recs:
         by_tag.setdefault(tag, []).append(t)
@@ -357,6 +537,13 @@ def run_ours(args):
            "serial_value": world * pix * e2e_steps / dt_serial / 1e6,
            "max_abs_reconstruction_err": float(max(np.abs(out - img).max(), np.abs(out2 - img).max()))}
     del W2
+    host_link = host_link_bandwidth(W, img, out, barrier, max_over_ranks, min_over_ranks)
+    host_link["numa"] = pin
+    host_link["e2e_gbs_per_rank_per_direction"] = img.nbytes * e2e_steps / dt / 1e9
+    lim = min(host_link["h2d_gbs_all_ranks_at_once_min"], host_link["d2h_gbs_all_ranks_at_once_min"])
+    host_link["limiter"] = ("e2e moves %.1f GB/s per rank and direction; the pinned-copy bandwidth of the slowest rank with all "
+                            "%d ranks copying at once is %.1f GB/s: the host link (PCIe / host memory of the ranks' NUMA node), "
+                            "not the GPU, bounds e2e" % (host_link["e2e_gbs_per_rank_per_direction"], world, lim))
 
     # ---- multi-GPU: global norms through the fused reduction + NCCL all-reduce ------------------
     extra = {}
@@ -376,18 +563,22 @@ def run_ours(args):
         l1, l2 = W.norms()
         extra["global_norms"]["local_norm1_rank0"] = l1
         W.comm_destroy()
+    del W
+    if not args.no_c3:
+        c3 = run_c3(args, rank, world, local, dist, barrier, max_over_ranks)
+        extra["c3_stack"] = c3
 
     if rank == 0:
         cpu_v, cpu_s = time_cpu_port()
         pd = time_pdwt(np.asarray(img if B == 1 else img[0]), min(args.steps, 10), 2) if not args.no_pdwt else None
         line = {
             "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "8192x8192 fp32 db2 3-level separable DWT forward+inverse",
                        "per_gpu_batch": B, "l2": "inputs larger than L2 (256 MiB image + 256 MiB coefficients per image vs 126 MB L2); no flush",
                        "parallelism": "independent images per GPU, no data-path collective"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "host_link": host_link,
             "roofline": roof, "roofline_step": roof_step,
             "cpu_baseline": {"value": cpu_v, "unit": "Mpixel/s", "cores": cpu_cores(), "kind": "port", "sample": cpu_s},
             "pdwt_cuda": pd,
@@ -406,6 +597,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="8192^2 images per GPU per step")
     ap.add_argument("--no-pdwt", action="store_true", help="skip the side-by-side timing of the reference's CUDA build")
+    ap.add_argument("--no-c3", action="store_true", help="skip the sharded 512x2048x2048 sym8 stack leg (BASELINE config 3)")
+    ap.add_argument("--c3-slices", type=int, default=512, help="slices of the fixed C3 stack (strong scaling over the ranks)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

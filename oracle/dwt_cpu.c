@@ -33,6 +33,15 @@ int dwt_cpu_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the baseline sets its thread count itself */
+void dwt_cpu_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* analysis of `rows` signals of length N with stride (rs = row stride, es = element stride) */
 static void analysis(const float* in, float* lo, float* hi, int rows, int N, long rs_in, long es_in,
                      long rs_out, long es_out, const float* L, const float* H, int F) {

@@ -34,6 +34,19 @@ def threads():
     return _lib().dwt_cpu_threads()
 
 
+def set_threads(n=None):
+    """Use n OpenMP threads (default: every core this process may run on), whatever OMP_NUM_THREADS says --
+    torchrun exports OMP_NUM_THREADS=1 to its workers.  Returns the thread count now in effect."""
+    if n is None:
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+    lib = _lib()
+    lib.dwt_cpu_set_threads(int(n))
+    return lib.dwt_cpu_threads()
+
+
 class CpuDwt2:
     """Multi-level separable 2D DWT plan on the CPU (fp32), band layout of the reference."""
 

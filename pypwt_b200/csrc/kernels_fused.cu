@@ -119,7 +119,7 @@ struct Geo {
     static constexpr int N3 = (63 - O1 - 3 * F / 2 + 4) / 4;
 };
 
-template <int F, bool HAAR, int MINB, int PF, bool NRM>      // PF: 0 direct loads, 1 bulk-copy (TMA) ring, 2 cp.async ring; NRM: accumulate norms
+template <int F, bool HAAR, int MINB, int PF, bool NRM>      // PF: 0 direct loads pipelined in place, 1 bulk-copy (TMA) ring, 2 cp.async ring, 3 direct un-pipelined; NRM: accumulate norms
 __global__ void __launch_bounds__(32 * kWarps, MINB)
 k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ TapsLH f) {
     using G = Geo<F>;
@@ -131,10 +131,11 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ TapsLH f) {
     const int R3 = Nr >> 3;
     const int strips = (W3 + a.n3 - 1) / a.n3;
     // PF: per-warp ring of kStages x 8 input rows of HB + 128 + HB samples, filled by bulk copies
-    constexpr int HB = (PF && C > 0) ? 4 : 0;                // halo block (16 B aligned) on either side
+    constexpr bool RING = PF == 1 || PF == 2;
+    constexpr int HB = (RING && C > 0) ? 4 : 0;              // halo block (16 B aligned) on either side
     constexpr int ROWB = (128 + 2 * HB) * 4;                 // bytes per staged row
-    __shared__ __align__(128) float ring[PF ? kWarps * kStages * 8 * (128 + 2 * HB) : 1];
-    __shared__ __align__(8) unsigned long long mbars[PF ? kWarps * kStages : 1];
+    __shared__ __align__(128) float ring[RING ? kWarps * kStages * 8 * (128 + 2 * HB) : 1];
+    __shared__ __align__(8) unsigned long long mbars[RING ? kWarps * kStages : 1];
     const unsigned ring0 = smem_u32(ring) + warp * (kStages * 8 * ROWB);
     const unsigned mbar0 = smem_u32(mbars) + warp * (kStages * 8);
     unsigned uses = 0;                                       // stage uses so far: stage = uses % kStages, parity from uses / kStages
@@ -369,13 +370,39 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ TapsLH f) {
             if (len0 < 128 + 2 * HB) bulk_g2s(dst + len0 * 4, src, ROWB - len0 * 4, mb);
         }
     };
+    // Direct loads (PF == 0) are software-pipelined IN PLACE: the registers of input rows 0-3 are re-loaded with the
+    // next iteration's rows as soon as level-1 rows 0, 1 have consumed them, rows 4-7 after level-1 rows 2, 3 -- a warp
+    // always has four rows (2 KB) in flight while it computes, at no register cost (the ncu profile of the un-pipelined
+    // loop: long-scoreboard stall 6.7 per issue, issue slots 39 % busy at 16 warps per SM).  PF == 3: the un-pipelined
+    // loop (all eight rows requested at the top of the iteration), kept for the A/B.
+    float4 v[8];
+    float e[8][C > 0 ? C : 1];
+    auto load_rows4 = [&](int rb, int h) {                   // rows rb + 4h .. rb + 4h + 3 -> v[4h ..], e[4h ..]
+        if (rb >= 0 && rb + 8 <= Nr) {
+            const float* p = in + (long long)(rb + 4 * h) * Nc;
+#pragma unroll
+            for (int i = 0; i < 4; i++, p += Nc) {
+                v[4 * h + i] = ldg4(p + xcol);
+#pragma unroll
+                for (int c = 0; c < C; c++) e[4 * h + i][c] = __ldg(p + ecol[c]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float* p = in + (long long)wrap1_per(rb + 4 * h + i, Nr) * Nc;
+                v[4 * h + i] = ldg4(p + xcol);
+#pragma unroll
+                for (int c = 0; c < C; c++) e[4 * h + i][c] = __ldg(p + ecol[c]);
+            }
+        }
+    };
     auto iteration = [&](int n, bool store_ok) {
         // level-2 rows produced here: m0 = 2n + E - 1, m1 = 2n + E ; level-1 rows: k = 2*m0 + E - 1 .. 2*m1 + E
         const int m0 = 2 * n + E - 1;
         const int kbase = 2 * m0 + E - 1;                 // four level-1 rows kbase .. kbase+3
-        float4 v[8];
-        float e[8][C > 0 ? C : 1];
-        if (PF) {
+        const int rb_next = rbase_of(n + 1);
+        const bool more = n + 1 < n1;
+        if (PF == 1 || PF == 2) {
             const unsigned stage = uses % kStages, parity = (uses / kStages) & 1;
             const unsigned base = ring0 + stage * (8 * ROWB);
             if (PF == 1) mbar_wait(mbar0 + 8 * stage, parity);
@@ -390,13 +417,14 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ TapsLH f) {
             if (n + kStages < n1) issue_rows(n + kStages, stage);
             if (PF == 2) cp_async_commit();                   // (possibly empty) group: keeps the group count uniform
             uses++;
-        } else {
+        } else if (PF == 3) {
             load_rows8(rbase_of(n), v, e);
         }
 #pragma unroll
         for (int t = 0; t < 4; t++) {
             w1[FW - 2] = hpass1(v[2 * t], e[2 * t]);
             w1[FW - 1] = hpass1(v[2 * t + 1], e[2 * t + 1]);
+            if (PF == 0 && (t & 1) && more) load_rows4(rb_next, t >> 1);      // rows 4(t>>1) .. +3 are dead now
             const int k = kbase + t;
             float a0, a1;
             vstep1(k, store_ok && k >= 4 * n0 && k < 4 * n1, a0, a1);
@@ -434,12 +462,16 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ TapsLH f) {
     // incomplete window belongs to rows this task does not own, and the ownership tests inside
     // iteration() keep it from being stored.  J = ceil((3E + 4C - 3) / 4): 0 (haar), 2 (F=4), 4 (F=6), 6 (F=8).
     constexpr int J = HAAR ? 0 : (3 * E + 4 * C - 3 + 3) / 4;
-    if (PF) {
+    if (PF == 1 || PF == 2) {
 #pragma unroll
         for (int s = 0; s < kStages; s++) {
             if (n0 - J + s < n1) issue_rows(n0 - J + s, (uses + s) % kStages);
             if (PF == 2) cp_async_commit();
         }
+    }
+    if (PF == 0) {                                            // prologue of the in-place pipeline
+        load_rows4(rbase_of(n0 - J), 0);
+        load_rows4(rbase_of(n0 - J), 1);
     }
     for (int n = n0 - J; n < n1; n++) iteration(n, true);
     if (NRM) {             // fused norm reduction: warp shuffle, one pair of plain stores per task (no atomics, no memset)
@@ -561,6 +593,7 @@ int pwt_fused_dwt_fwd3(const float* in, float* A3, float* const* H, float* const
     const int variant = pwt_tuning().fused_variant;
     if (haar) {
         if (variant == 1) return launch_fwd3<2, true, 6, 0>(a, batch, f, q, sink, st);
+        if (variant == 8) return launch_fwd3<2, true, 4, 3>(a, batch, f, q, sink, st);
         if (variant == 2) return launch_fwd3<2, true, 5, 0>(a, batch, f, q, sink, st);
         return launch_fwd3<2, true, 4, 0>(a, batch, f, q, sink, st);
     }
@@ -572,6 +605,7 @@ int pwt_fused_dwt_fwd3(const float* in, float* A3, float* const* H, float* const
             if (variant == 5) return launch_fwd3<4, false, 4, 2>(a, batch, f, q, sink, st);
             if (variant == 6) return launch_fwd3<4, false, 3, 0>(a, batch, f, q, sink, st);
             if (variant == 7) return launch_fwd3<4, false, 2, 0>(a, batch, f, q, sink, st);
+            if (variant == 8) return launch_fwd3<4, false, 4, 3>(a, batch, f, q, sink, st);
             return launch_fwd3<4, false, 4, 0>(a, batch, f, q, sink, st);
         case 6: return launch_fwd3<6, false, 3, 0>(a, batch, f, q, sink, st);
         case 8: return launch_fwd3<8, false, 3, 0>(a, batch, f, q, sink, st);
