@@ -119,7 +119,7 @@ struct Geo {
     static constexpr int N3 = (63 - O1 - 3 * F / 2 + 4) / 4;
 };
 
-template <int F, bool HAAR, int MINB, int PF, bool NRM>      // PF: 0 direct loads pipelined in place, 1 bulk-copy (TMA) ring, 2 cp.async ring, 3 direct un-pipelined; NRM: accumulate norms
+template <int F, bool HAAR, int MINB, int PF, bool NRM>      // PF: 0 direct loads, 1 bulk-copy (TMA) ring, 2 cp.async ring, 3 direct loads pipelined in place; NRM: accumulate norms
 __global__ void __launch_bounds__(32 * kWarps, MINB)
 k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ TapsLH f) {
     using G = Geo<F>;
@@ -370,11 +370,14 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ TapsLH f) {
             if (len0 < 128 + 2 * HB) bulk_g2s(dst + len0 * 4, src, ROWB - len0 * 4, mb);
         }
     };
-    // Direct loads (PF == 0) are software-pipelined IN PLACE: the registers of input rows 0-3 are re-loaded with the
-    // next iteration's rows as soon as level-1 rows 0, 1 have consumed them, rows 4-7 after level-1 rows 2, 3 -- a warp
-    // always has four rows (2 KB) in flight while it computes, at no register cost (the ncu profile of the un-pipelined
-    // loop: long-scoreboard stall 6.7 per issue, issue slots 39 % busy at 16 warps per SM).  PF == 3: the un-pipelined
-    // loop (all eight rows requested at the top of the iteration), kept for the A/B.
+    // PF == 0 (default): all eight input rows of an iteration are requested at its top.
+    // PF == 3: the loads software-pipelined IN PLACE -- the registers of input rows 0-3 are re-loaded with the next
+    // iteration's rows as soon as level-1 rows 0, 1 have consumed them, rows 4-7 after level-1 rows 2, 3, so a warp
+    // always has four rows (2 KB) in flight while it computes, at no register cost (114 vs 108 registers, same 16 warps
+    // per SM).  Built because the ncu profile shows long-scoreboard stalls (6.7 per issue, issue slots 39 % busy);
+    // measured on B200 (profiles/r02_notes.md): 4096^2 forward 0.0266 vs 0.0275 ms, but 8192^2 forward 0.118 vs
+    // 0.096 ms back to back and 0.200 vs 0.198 ms per forward + inverse -- more requests in flight do not help a kernel
+    // that already runs at 85 % of the copy bandwidth, they disturb the DRAM access order.  Kept for the A/B only.
     float4 v[8];
     float e[8][C > 0 ? C : 1];
     auto load_rows4 = [&](int rb, int h) {                   // rows rb + 4h .. rb + 4h + 3 -> v[4h ..], e[4h ..]
@@ -417,14 +420,14 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ TapsLH f) {
             if (n + kStages < n1) issue_rows(n + kStages, stage);
             if (PF == 2) cp_async_commit();                   // (possibly empty) group: keeps the group count uniform
             uses++;
-        } else if (PF == 3) {
+        } else if (PF == 0) {
             load_rows8(rbase_of(n), v, e);
         }
 #pragma unroll
         for (int t = 0; t < 4; t++) {
             w1[FW - 2] = hpass1(v[2 * t], e[2 * t]);
             w1[FW - 1] = hpass1(v[2 * t + 1], e[2 * t + 1]);
-            if (PF == 0 && (t & 1) && more) load_rows4(rb_next, t >> 1);      // rows 4(t>>1) .. +3 are dead now
+            if (PF == 3 && (t & 1) && more) load_rows4(rb_next, t >> 1);      // rows 4(t>>1) .. +3 are dead now
             const int k = kbase + t;
             float a0, a1;
             vstep1(k, store_ok && k >= 4 * n0 && k < 4 * n1, a0, a1);
@@ -469,7 +472,7 @@ k_fwd3(const __grid_constant__ Fwd3Args a, const __grid_constant__ TapsLH f) {
             if (PF == 2) cp_async_commit();
         }
     }
-    if (PF == 0) {                                            // prologue of the in-place pipeline
+    if (PF == 3) {                                            // prologue of the in-place pipeline
         load_rows4(rbase_of(n0 - J), 0);
         load_rows4(rbase_of(n0 - J), 1);
     }
