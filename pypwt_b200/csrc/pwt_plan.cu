@@ -83,6 +83,8 @@ const PwtTuning& pwt_tuning() {
         k.no_cascade8 = env_i("PWT_NO_CASCADE8", 0);
         k.no_fused1d = env_i("PWT_NO_FUSED1D", 0);
         k.no_tail = env_i("PWT_NO_TAIL", 0);
+        k.group_mb = env_i("PWT_GROUP_MB", 0);
+        k.group_streams = env_i("PWT_GROUP_STREAMS", 4);
         return k;
     }();
     return t;
@@ -144,6 +146,7 @@ static int load_nccl() {
 enum { kNcclFloat64 = 8, kNcclSum = 0 };
 
 #define PWT_PROF_CAP 512
+#define PWT_GROUP_STREAMS_MAX 8
 // ---- the plan --------------------------------------------------------------------------------
 struct pwt_plan {
     int device;
@@ -151,6 +154,11 @@ struct pwt_plan {
     cudaEvent_t ev0, ev1;
     int batch, Nr, Nc, ndims, nlevels, hlen, do_swt, do_separable, do_cs;
     int state, shift_r, shift_c;
+    // cycle spinning of a 2D SWT plan: the a-trous transform commutes EXACTLY with circular shifts (period N, no
+    // decimation), so the shifts of wt.cu:242-246 / :303 are recorded instead of executed: the logical image is
+    // circshift(d_image, vs_img), every logical band circshift(d_band[b], vs_coef).  Thresholds, shrink and norms do not
+    // look at positions; whoever does (get/set of image or bands, raw pointers, add_wavelet, clone) materialises first.
+    int vs_img_r, vs_img_c, vs_coef_r, vs_coef_c;
     char wname[128];
     PwtFilters filt;
     float* d_k2d_fwd;   // non-separable analysis filters  [LL, LH, HL, HH], hlen*hlen each
@@ -193,12 +201,17 @@ struct pwt_plan {
     int prof_tag[PWT_PROF_CAP];
     ncclComm_t comm;
     int comm_nranks;
+    cudaStream_t gstream[PWT_GROUP_STREAMS_MAX];   // side streams of the slice groups (created on first use)
+    cudaEvent_t gev[PWT_GROUP_STREAMS_MAX + 1];
+    int gstreams;
 };
 
 // ---- deferred thresholds (see PwtDeferredOp) -------------------------------------------------
 // flush: apply the pending threshold to memory for levels >= first_level (1 = everything) and, if
 // with_app, to the approximation band; clears the pending state when everything was flushed.
 static int flush_pending(pwt_plan* p, int first_level, bool with_app);
+static int materialize_image(pwt_plan* p);     // recorded cycle-spinning shifts (2D SWT plans), see pwt_plan::vs_img_r
+static int materialize_coeffs(pwt_plan* p);
 // thresholds of this plan can be applied by the strip inverse while it stages the coefficients
 static inline bool strip_defer_capable(const pwt_plan* p) {
     return p->defer_strip_ok && p->kernel_mode == 0 && p->do_separable && p->hlen >= p->strip_min_f && p->hlen <= 40 &&
@@ -222,6 +235,49 @@ static inline long long band_elems(const pwt_plan* p, int b) {
     return (long long)p->band_nr[b] * p->band_nc[b];
 }
 static inline long long lvl_elems(const pwt_plan* p, int l) { return (long long)p->lvNr[l] * p->lvNc[l]; }
+
+// Slice groups of a batched 2D DWT whose levels run one launch each (F >= 8: no level fusion).  Level by level over
+// the whole stack, every intermediate approximation makes a round trip through HBM (21 B/px for three levels against
+// 16 compulsory).  Group by group -- all levels of G slices before the next G -- the intermediates of a group are a few
+// MiB that live in the 126 MB L2: written by level l, read back by level l + 1 while still resident, and overwritten by
+// the next group at the SAME scratch address before the dirty lines are evicted.  G: PWT_GROUP_MB MiB of image per
+// group (0 = off).  Returns 0 when grouping does not apply.  The scratch planes are d_tmp and the tail of band 0's
+// level-1-sized allocation; the final approximations sit at its head and must not overlap that tail.
+static inline int group_stream_count() {
+    const int S = pwt_tuning().group_streams;
+    return S < 1 ? 1 : (S > PWT_GROUP_STREAMS_MAX ? PWT_GROUP_STREAMS_MAX : S);
+}
+static int group_slices(const pwt_plan* p) {
+    const int mb = pwt_tuning().group_mb;
+    if (mb <= 0 || p->ndims != 2 || p->do_swt || p->batch < 2 || p->nlevels < 2 || p->kernel_mode == 1) return 0;
+    const long long img_bytes = img_elems(p) * 4;
+    if ((long long)p->batch * img_bytes <= (long long)mb << 20) return 0;          // the whole stack is one group
+    long long G = ((long long)mb << 20) / img_bytes;
+    if (G < 1) G = 1;
+    if (G >= p->batch) return 0;
+    const int S = group_stream_count();
+    if ((long long)(p->batch - S * G) * lvl_elems(p, 1) < (long long)p->batch * lvl_elems(p, p->nlevels)) return 0;
+    return (int)G;
+}
+// fork: the side streams wait for everything enqueued on the plan's stream; join: the plan's stream waits for them
+static int group_fork(pwt_plan* p, int S) {
+    while (p->gstreams < S) {
+        CK(cudaStreamCreateWithFlags(&p->gstream[p->gstreams], cudaStreamNonBlocking));
+        p->gstreams++;
+    }
+    for (int k = 0; k <= S; k++)
+        if (!p->gev[k]) CK(cudaEventCreateWithFlags(&p->gev[k], cudaEventDisableTiming));
+    CK(cudaEventRecord(p->gev[S], p->stream));
+    for (int k = 0; k < S; k++) CK(cudaStreamWaitEvent(p->gstream[k], p->gev[S], 0));
+    return PWT_OK;
+}
+static int group_join(pwt_plan* p, int S) {
+    for (int k = 0; k < S; k++) {
+        CK(cudaEventRecord(p->gev[k], p->gstream[k]));
+        CK(cudaStreamWaitEvent(p->stream, p->gev[k], 0));
+    }
+    return PWT_OK;
+}
 
 static int build_k2d(pwt_plan* p) {
     // nonseparable.cu:70-74: LL = lo(x)lo, LH = lo(x)hi, HL = hi(x)lo, HH = hi(x)hi with
@@ -327,6 +383,7 @@ static int alloc_plan(pwt_plan* p) {
     p->partials_cap = (p->ndims == 2 && !p->do_swt && p->nlevels >= 3 && p->Nr % 8 == 0 && p->Nc % 8 == 0)
                           ? pwt_fused_fwd3_max_tasks(p->batch, p->Nr, p->Nc) : 0;
     if (p->ndims == 2 && !p->do_swt) p->partials_cap += 32768;      // one pair per CTA of the strip forward launches
+    if (const int Gs = group_slices(p)) p->partials_cap += ((p->batch + Gs - 1) / Gs) * p->nlevels * 2048;   // ... of every group
     p->d_partials = nullptr;
     clear_partials(p);
     p->want_norms = 0;
@@ -359,6 +416,9 @@ extern "C" void pwt_destroy(pwt_plan* p) {
             if (p->prof_ev[i]) cudaEventDestroy(p->prof_ev[i]);
         free(p->prof_ev);
     }
+    for (int k = 0; k < p->gstreams; k++) cudaStreamDestroy(p->gstream[k]);
+    for (int k = 0; k <= PWT_GROUP_STREAMS_MAX; k++)
+        if (p->gev[k]) cudaEventDestroy(p->gev[k]);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -500,10 +560,16 @@ extern "C" int pwt_clone(pwt_plan** out, const pwt_plan* src) {
     p->launches = 0;
     p->prof_ev = nullptr;
     p->prof_on = p->prof_n = 0;
+    p->gstreams = 0;
+    memset(p->gstream, 0, sizeof(p->gstream));
+    memset(p->gev, 0, sizeof(p->gev));
     *out = nullptr;
     cudaSetDevice(src->device);
     flush_pending(const_cast<pwt_plan*>(src), 1, true);
     p->pend.op = -1;
+    materialize_image(const_cast<pwt_plan*>(src));
+    materialize_coeffs(const_cast<pwt_plan*>(src));
+    p->vs_img_r = p->vs_img_c = p->vs_coef_r = p->vs_coef_c = 0;
     cudaStreamSynchronize(src->stream);
     int rc = PWT_OK;
     cudaError_t e = cudaStreamCreate(&p->stream);
@@ -588,9 +654,35 @@ static int do_circshift(pwt_plan* p, int sr, int sc, int inplace) {
     return PWT_OK;
 }
 
+// recorded (lazy) cycle-spinning shifts, see pwt_plan::vs_img_r
+static inline bool lazy_cs(const pwt_plan* p) {
+    return p->do_cs && p->do_swt && p->ndims == 2 && !pwt_tuning().no_fold_cs;
+}
+static inline int modn(int a, int n) { a %= n; return a < 0 ? a + n : a; }
+static int materialize_image(pwt_plan* p) {
+    if (!(p->vs_img_r | p->vs_img_c)) return PWT_OK;
+    const int r = p->vs_img_r, c = p->vs_img_c;
+    p->vs_img_r = p->vs_img_c = 0;
+    return do_circshift(p, r, c, 1);
+}
+static int materialize_coeffs(pwt_plan* p) {
+    if (!(p->vs_coef_r | p->vs_coef_c)) return PWT_OK;
+    const int r = p->vs_coef_r, c = p->vs_coef_c;
+    p->vs_coef_r = p->vs_coef_c = 0;
+    const size_t n = (size_t)p->batch * img_elems(p);               // SWT: every band is image-sized
+    for (int b = 0; b < p->nbands; b++) {
+        p->launches += pwt_launch_circshift(p->d_band[b], p->d_tmp, p->batch, p->Nr, p->Nc, r, c, p->stream);
+        CK(cudaMemcpyAsync(p->d_band[b], p->d_tmp, n * sizeof(float), cudaMemcpyDeviceToDevice, p->stream));
+    }
+    CK_LAUNCH();
+    return PWT_OK;
+}
+
 extern "C" int pwt_circshift(pwt_plan* p, int sr, int sc, int inplace) {
     if (!p) return fail(PWT_ERR_ARG, "null plan");
     cudaSetDevice(p->device);
+    int rc = materialize_image(p);
+    if (rc != PWT_OK) return rc;
     return do_circshift(p, sr, sc, inplace);
 }
 
@@ -648,8 +740,15 @@ extern "C" int pwt_forward(pwt_plan* p) {
     if (p->do_cs) {                                                 // wt.cu:242-246
         p->shift_r = rand() % p->Nr;
         p->shift_c = rand() % p->Nc;
-        int rc = do_circshift(p, p->shift_r, p->shift_c, 1);
-        if (rc != PWT_OK) return rc;
+        if (lazy_cs(p)) {                                           // recorded: the bands come out shifted by the same amount
+            p->vs_img_r = modn(p->vs_img_r + p->shift_r, p->Nr);
+            p->vs_img_c = modn(p->vs_img_c + p->shift_c, p->Nc);
+            p->vs_coef_r = p->vs_img_r;
+            p->vs_coef_c = p->vs_img_c;
+        } else {
+            int rc = do_circshift(p, p->shift_r, p->shift_c, 1);
+            if (rc != PWT_OK) return rc;
+        }
     }
     const int L = p->nlevels, B = p->batch;
     const bool haar = is_haar(p);
@@ -707,10 +806,25 @@ extern "C" int pwt_forward(pwt_plan* p) {
                 if (ntasks > 0) { p->norm_lvl_mask = 7u; p->norm_a = (L == 3); }
             }
         }
+        // slice groups (see group_slices): all levels of Gs slices, then the next Gs; one group = the whole stack otherwise
+        const int Gs = l_first == 1 ? group_slices(p) : 0;
+        bool nrm_lost = false;                                     // a grouped launch ran without its norm reduction
+        const int GS = group_stream_count();
+        if (Gs) {
+            int rc = group_fork(p, GS);
+            if (rc != PWT_OK) return rc;
+        }
+        for (int b0 = 0; b0 < B; b0 += (Gs ? Gs : B)) {
+        const int nb = Gs ? (B - b0 < Gs ? B - b0 : Gs) : B;
+        const int gk = Gs ? (b0 / Gs) % GS : 0;                    // side stream / scratch set of this group
+        if (Gs) {
+            src = p->d_image + (long long)b0 * img_elems(p);
+            st = p->gstream[gk];
+        }
         for (int l = l_first; l <= L; l++) {
-            float* Hb = p->d_band[3 * (l - 1) + sH];
-            float* V = p->d_band[3 * (l - 1) + sV];
-            float* D = p->d_band[3 * (l - 1) + 3];
+            float* Hb = p->d_band[3 * (l - 1) + sH] + (long long)b0 * lvl_elems(p, l);
+            float* V = p->d_band[3 * (l - 1) + sV] + (long long)b0 * lvl_elems(p, l);
+            float* D = p->d_band[3 * (l - 1) + 3] + (long long)b0 * lvl_elems(p, l);
             prof_begin(p, 100 * l + 1);
             if (p->do_swt) {
                 float* dstA = approx_dst(p, l, p->d_tmp + 2 * plane);
@@ -724,7 +838,12 @@ extern "C" int pwt_forward(pwt_plan* p) {
                     p->launches += pwt_launch_ns_swt_fwd2d(src, dstA, Hb, V, D, B, p->Nr, p->Nc, l, p->d_k2d_fwd, p->hlen, st);
                 src = dstA;
             } else {
-                float* dstA = approx_dst(p, l, p->d_tmp);
+                // grouped: the last level writes the group's slices of the final A, the others a scratch plane that every
+                // group re-uses (d_tmp / the tail of band 0's allocation, alternating like the ungrouped ping-pong)
+                float* dstA = !Gs ? approx_dst(p, l, p->d_tmp)
+                              : l == L ? p->d_band[0] + (long long)b0 * lvl_elems(p, L)
+                              : ((L - l) & 1) ? p->d_tmp + (long long)gk * Gs * lvl_elems(p, 1)
+                                              : p->d_band[0] + (long long)(B - (gk + 1) * Gs) * lvl_elems(p, 1);
                 const long long in_bs = lvl_elems(p, l - 1), out_bs = lvl_elems(p, l);
                 const int nr = p->lvNr[l - 1], nc = p->lvNc[l - 1];
                 if (sep) {
@@ -732,33 +851,41 @@ extern "C" int pwt_forward(pwt_plan* p) {
                     const int hints = (l < L ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l > 1 ? PWT_HINT_IN_FROM_PREV : 0);
                     if (!haar && ((p->kernel_mode == 0 && p->hlen >= p->strip_min_f && nr >= 64 && nc >= 256) || p->kernel_mode == 4)) {
                         // norms requested after an earlier forward: the strip kernel reduces |c|, c^2 of what it stores
-                        const bool nrm = p->want_norms && p->d_partials && p->do_separable && p->kernel_mode == 0 && l <= 32;
+                        const bool nrm = p->want_norms && p->d_partials && p->do_separable && p->kernel_mode == 0 && l <= 32 && !nrm_lost;
                         int wr = 0;
-                        n = pwt_strip_dwt_fwd2d_norms(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt,
+                        n = pwt_strip_dwt_fwd2d_norms(src, dstA, Hb, V, D, nb, nr, nc, in_bs, out_bs, p->filt,
                                                       nrm ? p->d_partials + 2 * (size_t)p->partials_n : nullptr,
                                                       p->partials_cap - p->partials_n, l == L, &wr, st);
                         if (n && wr > 0) {
                             p->partials_n += wr;
                             p->norm_lvl_mask |= 1u << (l - 1);
                             if (l == L) p->norm_a = 1;
+                        } else if (Gs && nrm) {
+                            nrm_lost = true;                        // the level is only partly covered: full reduction later
                         }
                     }
                     if (!n && (p->kernel_mode == 0 || p->kernel_mode == 3))
-                        n = pwt_reg_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, hints, st);
+                        n = pwt_reg_dwt_fwd2d(src, dstA, Hb, V, D, nb, nr, nc, in_bs, out_bs, p->filt, haar, hints, st);
                     if (!n && p->kernel_mode != 1 && !haar && p->hlen >= p->tile_min_f && nr >= 64 && nc >= 64)
-                        n = pwt_tile_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, st);
+                        n = pwt_tile_dwt_fwd2d(src, dstA, Hb, V, D, nb, nr, nc, in_bs, out_bs, p->filt, st);
                     if (!n && p->kernel_mode != 1)
-                        n = pwt_fast_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar,
+                        n = pwt_fast_dwt_fwd2d(src, dstA, Hb, V, D, nb, nr, nc, in_bs, out_bs, p->filt, haar,
                                                (l < L ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l > 1 ? PWT_HINT_IN_FROM_PREV : 0), st);
-                    if (!n) n = pwt_launch_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, st);
+                    if (!n) n = pwt_launch_dwt_fwd2d(src, dstA, Hb, V, D, nb, nr, nc, in_bs, out_bs, p->filt, haar, st);
                     p->launches += n;
                 } else {
-                    p->launches += pwt_launch_ns_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->d_k2d_fwd, p->hlen, st);
+                    p->launches += pwt_launch_ns_fwd2d(src, dstA, Hb, V, D, nb, nr, nc, in_bs, out_bs, p->d_k2d_fwd, p->hlen, st);
                 }
                 src = dstA;
             }
             prof_end(p);
         }
+        }
+        if (Gs) {
+            int rc = group_join(p, GS);
+            if (rc != PWT_OK) return rc;
+        }
+        if (nrm_lost) clear_partials(p);
     }
     CK_LAUNCH();
     p->state = PWT_FORWARD;
@@ -833,6 +960,27 @@ extern "C" int pwt_inverse(pwt_plan* p) {
             if (rc != PWT_OK) return rc;
             fop.app = 0;
         }
+        // slice groups (see group_slices): levels L..1 of Gs slices, then the next Gs; not when the fused cascade serves
+        // levels 3..1 (no intermediates to keep resident there)
+        const bool cascade3 = !p->do_swt && sep && p->kernel_mode == 0 && (haar || p->hlen < p->strip_min_f) && L >= 3;
+        const int Gs = cascade3 ? 0 : group_slices(p);
+        if (Gs && p->pend.op >= 0 && !strip_defer) {               // (the per-level flush below is written for one group)
+            int rc = flush_pending(p, 1, true);
+            if (rc != PWT_OK) return rc;
+        }
+        const int GS = group_stream_count();
+        if (Gs) {
+            int rc = group_fork(p, GS);
+            if (rc != PWT_OK) return rc;
+        }
+        for (int b0 = 0; b0 < B; b0 += (Gs ? Gs : B)) {
+        const int nb = Gs ? (B - b0 < Gs ? B - b0 : Gs) : B;
+        const int gk = Gs ? (b0 / Gs) % GS : 0;
+        if (Gs) {
+            cur = p->d_band[0] + (long long)b0 * lvl_elems(p, L);
+            st = p->gstream[gk];
+        }
+        int pong = 0;
         for (int l = L; l >= 1; l--) {
             if (l == 3 && p->pend.op >= 0 && !p->do_swt && !strip_defer && !cascade_ok) {
                 int rc = flush_pending(p, 1, L == 3);
@@ -862,9 +1010,9 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                     if (rc != PWT_OK) return rc;
                 }
             }
-            const float* Hb = p->d_band[3 * (l - 1) + sH];
-            const float* V = p->d_band[3 * (l - 1) + sV];
-            const float* D = p->d_band[3 * (l - 1) + 3];
+            const float* Hb = p->d_band[3 * (l - 1) + sH] + (long long)b0 * lvl_elems(p, l);
+            const float* V = p->d_band[3 * (l - 1) + sV] + (long long)b0 * lvl_elems(p, l);
+            const float* D = p->d_band[3 * (l - 1) + 3] + (long long)b0 * lvl_elems(p, l);
             prof_begin(p, 100 * l + 2);
             if (p->do_swt) {
                 float* alt = p->d_tmp + 2 * plane;
@@ -893,7 +1041,10 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                     p->launches += pwt_launch_ns_swt_inv2d(cur, Hb, V, D, dst, B, p->Nr, p->Nc, l, p->d_k2d_inv, p->hlen, st);
                 cur = dst;
             } else {
-                float* dst = (l == 1) ? p->d_image : (cur == p->d_band[0] ? p->d_tmp : p->d_band[0]);
+                float* dst = !Gs ? ((l == 1) ? p->d_image : (cur == p->d_band[0] ? p->d_tmp : p->d_band[0]))
+                             : l == 1 ? p->d_image + (long long)b0 * img_elems(p)
+                             : (pong++ & 1) ? p->d_band[0] + (long long)(B - (gk + 1) * Gs) * lvl_elems(p, 1)
+                                            : p->d_tmp + (long long)gk * Gs * lvl_elems(p, 1);
                 const long long in_bs = lvl_elems(p, l), out_bs = lvl_elems(p, l - 1);
                 const int nr = p->lvNr[l], nc = p->lvNc[l], Nro = p->lvNr[l - 1], Nco = p->lvNc[l - 1];
                 if (sep) {
@@ -901,10 +1052,10 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                     const int hints = (l > 1 ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l < L ? PWT_HINT_IN_FROM_PREV : 0);
                     if (!haar && ((p->kernel_mode == 0 && p->hlen >= p->strip_min_f && nr >= 32 && nc >= 128) || p->kernel_mode == 4)) {
                         if (strip_defer && l <= strip_lmax)
-                            n = pwt_strip_dwt_inv2d_thr(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, p->pend.op,
+                            n = pwt_strip_dwt_inv2d_thr(cur, Hb, V, D, dst, nb, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, p->pend.op,
                                                         p->pend.beta[l - 1], l == L && p->pend.app, p->pend.beta_app, st);
                         else
-                            n = pwt_strip_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, st);
+                            n = pwt_strip_dwt_inv2d(cur, Hb, V, D, dst, nb, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, st);
                     }
                     if (!n && strip_defer && l <= strip_lmax) {      // declined after all: apply the rest through memory
                         int rc = flush_pending(p, 1, l == L);
@@ -912,28 +1063,38 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                         strip_defer = false;
                     }
                     if (!n && (p->kernel_mode == 0 || p->kernel_mode == 3))
-                        n = pwt_reg_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, hints, st);
+                        n = pwt_reg_dwt_inv2d(cur, Hb, V, D, dst, nb, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, hints, st);
                     if (!n && p->kernel_mode != 1 && !haar && p->hlen >= p->tile_min_f && nr >= 32 && nc >= 32)
-                        n = pwt_tile_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, st);
+                        n = pwt_tile_dwt_inv2d(cur, Hb, V, D, dst, nb, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, st);
                     if (!n && p->kernel_mode != 1)
-                        n = pwt_fast_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar,
+                        n = pwt_fast_dwt_inv2d(cur, Hb, V, D, dst, nb, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar,
                                                (l > 1 ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l < L ? PWT_HINT_IN_FROM_PREV : 0), st);
-                    if (!n) n = pwt_launch_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, st);
+                    if (!n) n = pwt_launch_dwt_inv2d(cur, Hb, V, D, dst, nb, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, st);
                     p->launches += n;
                 } else {
-                    p->launches += pwt_launch_ns_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->d_k2d_inv, p->hlen, st);
+                    p->launches += pwt_launch_ns_inv2d(cur, Hb, V, D, dst, nb, nr, nc, Nro, Nco, in_bs, out_bs, p->d_k2d_inv, p->hlen, st);
                 }
                 cur = dst;
             }
             prof_end(p);
+        }
+        }
+        if (Gs) {
+            int rc = group_join(p, GS);
+            if (rc != PWT_OK) return rc;
         }
         if (strip_defer) p->pend.op = -1;                           // consumed by the strip inverse launches
     }
     CK_LAUNCH();
     if (p->do_swt) p->pend.op = -1;                                 // consumed by the fused SWT inverse (or flushed above)
     if (p->do_cs) {                                                 // wt.cu:303
-        int rc = do_circshift(p, -p->shift_r, -p->shift_c, 1);
-        if (rc != PWT_OK) return rc;
+        if (lazy_cs(p)) {                                           // normally (0, 0): the two shifts cancel
+            p->vs_img_r = modn(p->vs_coef_r - p->shift_r, p->Nr);
+            p->vs_img_c = modn(p->vs_coef_c - p->shift_c, p->Nc);
+        } else {
+            int rc = do_circshift(p, -p->shift_r, -p->shift_c, 1);
+            if (rc != PWT_OK) return rc;
+        }
     }
     clear_partials(p);
     p->state = PWT_INVERSE;
@@ -1140,6 +1301,10 @@ extern "C" int pwt_add_wavelet(pwt_plan* d, const pwt_plan* s, float alpha) {
     }
     cudaSetDevice(d->device);
     if (flush_pending(d, 1, true) != PWT_OK || flush_pending(const_cast<pwt_plan*>(s), 1, true) != PWT_OK) return PWT_ERR_CUDA;
+    if (materialize_coeffs(d) != PWT_OK) return PWT_ERR_CUDA;
+    cudaSetDevice(s->device);
+    if (materialize_coeffs(const_cast<pwt_plan*>(s)) != PWT_OK) return PWT_ERR_CUDA;
+    cudaSetDevice(d->device);
     cudaStreamSynchronize(s->stream);   // the source's pending work must be visible
     PwtSegTable td, ts;
     td.nseg = ts.nseg = 0;
@@ -1159,6 +1324,7 @@ extern "C" int pwt_get_image(pwt_plan* p, float* dst) {
     if (!p || !dst) return 0;
     cudaSetDevice(p->device);
     const size_t n = (size_t)p->batch * img_elems(p);
+    if (materialize_image(p) != PWT_OK) return 0;
     if (cudaMemcpyAsync(dst, p->d_image, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream) != cudaSuccess ||
         cudaStreamSynchronize(p->stream) != cudaSuccess) {
         fail(PWT_ERR_CUDA, "get_image failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1171,6 +1337,7 @@ extern "C" int pwt_set_image(pwt_plan* p, const float* img, int on_device) {
     if (!p || !img) return fail(PWT_ERR_ARG, "null argument");
     cudaSetDevice(p->device);
     const size_t n = (size_t)p->batch * img_elems(p);
+    p->vs_img_r = p->vs_img_c = 0;                                  // a new image: nothing recorded against it
     CK(cudaMemcpyAsync(p->d_image, img, n * sizeof(float),
                        on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, p->stream));
     if (!on_device) CK(cudaStreamSynchronize(p->stream));   // the host buffer may be reused by the caller
@@ -1185,7 +1352,7 @@ extern "C" int pwt_get_coeff(pwt_plan* p, float* dst, int num) {
         return 0;
     }
     cudaSetDevice(p->device);
-    if (flush_pending(p, 1, true) != PWT_OK) return 0;
+    if (flush_pending(p, 1, true) != PWT_OK || materialize_coeffs(p) != PWT_OK) return 0;
     const size_t n = (size_t)p->batch * band_elems(p, num);
     if (cudaMemcpyAsync(dst, p->d_band[num], n * sizeof(float), cudaMemcpyDeviceToHost, p->stream) != cudaSuccess ||
         cudaStreamSynchronize(p->stream) != cudaSuccess) {
@@ -1203,6 +1370,10 @@ extern "C" int pwt_set_coeff(pwt_plan* p, const float* src, int num, int on_devi
         if (rc0 != PWT_OK) return rc0;
     }
     clear_partials(p);
+    {
+        int rc1 = materialize_coeffs(p);
+        if (rc1 != PWT_OK) return rc1;
+    }
     const size_t n = (size_t)p->batch * band_elems(p, num);
     CK(cudaMemcpyAsync(p->d_band[num], src, n * sizeof(float),
                        on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, p->stream));
@@ -1210,11 +1381,19 @@ extern "C" int pwt_set_coeff(pwt_plan* p, const float* src, int num, int on_devi
     return PWT_OK;                                                  // state untouched (wt.cu:465)
 }
 
-extern "C" intptr_t pwt_image_ptr(pwt_plan* p) { return p ? (intptr_t)p->d_image : 0; }
+extern "C" intptr_t pwt_image_ptr(pwt_plan* p) {
+    if (!p) return 0;
+    if (p->vs_img_r | p->vs_img_c) {
+        cudaSetDevice(p->device);
+        materialize_image(p);
+    }
+    return (intptr_t)p->d_image;
+}
 extern "C" intptr_t pwt_coeff_ptr(pwt_plan* p, int num) {
     if (!p || num < 0 || num >= p->nbands) return 0;
     cudaSetDevice(p->device);
     flush_pending(p, 1, true);          // a raw pointer lets the caller see memory: make it current
+    materialize_coeffs(p);
     clear_partials(p);                  // ... and lets the caller WRITE it: the fused per-task norm sums may go stale
     return (intptr_t)p->d_band[num];
 }
@@ -1233,6 +1412,7 @@ extern "C" int pwt_get_coeffs(pwt_plan* p, float* dst) {
     }
     cudaSetDevice(p->device);
     int rc = flush_pending(p, 1, true);
+    if (rc == PWT_OK) rc = materialize_coeffs(p);
     if (rc != PWT_OK) return rc;
     CK(cudaMemcpyAsync(dst, p->slab + p->coef_base, p->coef_floats * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
