@@ -87,8 +87,6 @@ struct PwtTuning {
     int no_cascade8;       // PWT_NO_CASCADE8=1: no level-fused strip kernels (F >= 8)
     int no_fused1d;        // PWT_NO_FUSED1D=1: batched 1D one launch per level
     int no_tail;           // PWT_NO_TAIL=1: small levels one launch each
-    int group_mb;          // PWT_GROUP_MB (default 0 = off): MiB of image per slice group of a batched per-level DWT
-    int group_streams;     // PWT_GROUP_STREAMS (default 4): side streams the groups are spread over
 };
 const PwtTuning& pwt_tuning();       // pwt_plan.cu
 int pwt_sm_count();                  // SM count of the CURRENT device (cached per device; pwt_plan.cu)

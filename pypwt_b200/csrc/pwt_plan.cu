@@ -83,8 +83,6 @@ const PwtTuning& pwt_tuning() {
         k.no_cascade8 = env_i("PWT_NO_CASCADE8", 0);
         k.no_fused1d = env_i("PWT_NO_FUSED1D", 0);
         k.no_tail = env_i("PWT_NO_TAIL", 0);
-        k.group_mb = env_i("PWT_GROUP_MB", 0);
-        k.group_streams = env_i("PWT_GROUP_STREAMS", 4);
         return k;
     }();
     return t;
@@ -146,7 +144,6 @@ static int load_nccl() {
 enum { kNcclFloat64 = 8, kNcclSum = 0 };
 
 #define PWT_PROF_CAP 512
-#define PWT_GROUP_STREAMS_MAX 8
 // ---- the plan --------------------------------------------------------------------------------
 struct pwt_plan {
     int device;
@@ -201,9 +198,6 @@ struct pwt_plan {
     int prof_tag[PWT_PROF_CAP];
     ncclComm_t comm;
     int comm_nranks;
-    cudaStream_t gstream[PWT_GROUP_STREAMS_MAX];   // side streams of the slice groups (created on first use)
-    cudaEvent_t gev[PWT_GROUP_STREAMS_MAX + 1];
-    int gstreams;
 };
 
 // ---- deferred thresholds (see PwtDeferredOp) -------------------------------------------------
@@ -235,49 +229,6 @@ static inline long long band_elems(const pwt_plan* p, int b) {
     return (long long)p->band_nr[b] * p->band_nc[b];
 }
 static inline long long lvl_elems(const pwt_plan* p, int l) { return (long long)p->lvNr[l] * p->lvNc[l]; }
-
-// Slice groups of a batched 2D DWT whose levels run one launch each (F >= 8: no level fusion).  Level by level over
-// the whole stack, every intermediate approximation makes a round trip through HBM (21 B/px for three levels against
-// 16 compulsory).  Group by group -- all levels of G slices before the next G -- the intermediates of a group are a few
-// MiB that live in the 126 MB L2: written by level l, read back by level l + 1 while still resident, and overwritten by
-// the next group at the SAME scratch address before the dirty lines are evicted.  G: PWT_GROUP_MB MiB of image per
-// group (0 = off).  Returns 0 when grouping does not apply.  The scratch planes are d_tmp and the tail of band 0's
-// level-1-sized allocation; the final approximations sit at its head and must not overlap that tail.
-static inline int group_stream_count() {
-    const int S = pwt_tuning().group_streams;
-    return S < 1 ? 1 : (S > PWT_GROUP_STREAMS_MAX ? PWT_GROUP_STREAMS_MAX : S);
-}
-static int group_slices(const pwt_plan* p) {
-    const int mb = pwt_tuning().group_mb;
-    if (mb <= 0 || p->ndims != 2 || p->do_swt || p->batch < 2 || p->nlevels < 2 || p->kernel_mode == 1) return 0;
-    const long long img_bytes = img_elems(p) * 4;
-    if ((long long)p->batch * img_bytes <= (long long)mb << 20) return 0;          // the whole stack is one group
-    long long G = ((long long)mb << 20) / img_bytes;
-    if (G < 1) G = 1;
-    if (G >= p->batch) return 0;
-    const int S = group_stream_count();
-    if ((long long)(p->batch - S * G) * lvl_elems(p, 1) < (long long)p->batch * lvl_elems(p, p->nlevels)) return 0;
-    return (int)G;
-}
-// fork: the side streams wait for everything enqueued on the plan's stream; join: the plan's stream waits for them
-static int group_fork(pwt_plan* p, int S) {
-    while (p->gstreams < S) {
-        CK(cudaStreamCreateWithFlags(&p->gstream[p->gstreams], cudaStreamNonBlocking));
-        p->gstreams++;
-    }
-    for (int k = 0; k <= S; k++)
-        if (!p->gev[k]) CK(cudaEventCreateWithFlags(&p->gev[k], cudaEventDisableTiming));
-    CK(cudaEventRecord(p->gev[S], p->stream));
-    for (int k = 0; k < S; k++) CK(cudaStreamWaitEvent(p->gstream[k], p->gev[S], 0));
-    return PWT_OK;
-}
-static int group_join(pwt_plan* p, int S) {
-    for (int k = 0; k < S; k++) {
-        CK(cudaEventRecord(p->gev[k], p->gstream[k]));
-        CK(cudaStreamWaitEvent(p->stream, p->gev[k], 0));
-    }
-    return PWT_OK;
-}
 
 static int build_k2d(pwt_plan* p) {
     // nonseparable.cu:70-74: LL = lo(x)lo, LH = lo(x)hi, HL = hi(x)lo, HH = hi(x)hi with
@@ -383,7 +334,6 @@ static int alloc_plan(pwt_plan* p) {
     p->partials_cap = (p->ndims == 2 && !p->do_swt && p->nlevels >= 3 && p->Nr % 8 == 0 && p->Nc % 8 == 0)
                           ? pwt_fused_fwd3_max_tasks(p->batch, p->Nr, p->Nc) : 0;
     if (p->ndims == 2 && !p->do_swt) p->partials_cap += 32768;      // one pair per CTA of the strip forward launches
-    if (const int Gs = group_slices(p)) p->partials_cap += ((p->batch + Gs - 1) / Gs) * p->nlevels * 2048;   // ... of every group
     p->d_partials = nullptr;
     clear_partials(p);
     p->want_norms = 0;
@@ -416,9 +366,6 @@ extern "C" void pwt_destroy(pwt_plan* p) {
             if (p->prof_ev[i]) cudaEventDestroy(p->prof_ev[i]);
         free(p->prof_ev);
     }
-    for (int k = 0; k < p->gstreams; k++) cudaStreamDestroy(p->gstream[k]);
-    for (int k = 0; k <= PWT_GROUP_STREAMS_MAX; k++)
-        if (p->gev[k]) cudaEventDestroy(p->gev[k]);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -560,9 +507,6 @@ extern "C" int pwt_clone(pwt_plan** out, const pwt_plan* src) {
     p->launches = 0;
     p->prof_ev = nullptr;
     p->prof_on = p->prof_n = 0;
-    p->gstreams = 0;
-    memset(p->gstream, 0, sizeof(p->gstream));
-    memset(p->gev, 0, sizeof(p->gev));
     *out = nullptr;
     cudaSetDevice(src->device);
     flush_pending(const_cast<pwt_plan*>(src), 1, true);
@@ -806,25 +750,10 @@ extern "C" int pwt_forward(pwt_plan* p) {
                 if (ntasks > 0) { p->norm_lvl_mask = 7u; p->norm_a = (L == 3); }
             }
         }
-        // slice groups (see group_slices): all levels of Gs slices, then the next Gs; one group = the whole stack otherwise
-        const int Gs = l_first == 1 ? group_slices(p) : 0;
-        bool nrm_lost = false;                                     // a grouped launch ran without its norm reduction
-        const int GS = group_stream_count();
-        if (Gs) {
-            int rc = group_fork(p, GS);
-            if (rc != PWT_OK) return rc;
-        }
-        for (int b0 = 0; b0 < B; b0 += (Gs ? Gs : B)) {
-        const int nb = Gs ? (B - b0 < Gs ? B - b0 : Gs) : B;
-        const int gk = Gs ? (b0 / Gs) % GS : 0;                    // side stream / scratch set of this group
-        if (Gs) {
-            src = p->d_image + (long long)b0 * img_elems(p);
-            st = p->gstream[gk];
-        }
         for (int l = l_first; l <= L; l++) {
-            float* Hb = p->d_band[3 * (l - 1) + sH] + (long long)b0 * lvl_elems(p, l);
-            float* V = p->d_band[3 * (l - 1) + sV] + (long long)b0 * lvl_elems(p, l);
-            float* D = p->d_band[3 * (l - 1) + 3] + (long long)b0 * lvl_elems(p, l);
+            float* Hb = p->d_band[3 * (l - 1) + sH];
+            float* V = p->d_band[3 * (l - 1) + sV];
+            float* D = p->d_band[3 * (l - 1) + 3];
             prof_begin(p, 100 * l + 1);
             if (p->do_swt) {
                 float* dstA = approx_dst(p, l, p->d_tmp + 2 * plane);
@@ -838,12 +767,7 @@ extern "C" int pwt_forward(pwt_plan* p) {
                     p->launches += pwt_launch_ns_swt_fwd2d(src, dstA, Hb, V, D, B, p->Nr, p->Nc, l, p->d_k2d_fwd, p->hlen, st);
                 src = dstA;
             } else {
-                // grouped: the last level writes the group's slices of the final A, the others a scratch plane that every
-                // group re-uses (d_tmp / the tail of band 0's allocation, alternating like the ungrouped ping-pong)
-                float* dstA = !Gs ? approx_dst(p, l, p->d_tmp)
-                              : l == L ? p->d_band[0] + (long long)b0 * lvl_elems(p, L)
-                              : ((L - l) & 1) ? p->d_tmp + (long long)gk * Gs * lvl_elems(p, 1)
-                                              : p->d_band[0] + (long long)(B - (gk + 1) * Gs) * lvl_elems(p, 1);
+                float* dstA = approx_dst(p, l, p->d_tmp);
                 const long long in_bs = lvl_elems(p, l - 1), out_bs = lvl_elems(p, l);
                 const int nr = p->lvNr[l - 1], nc = p->lvNc[l - 1];
                 if (sep) {
@@ -851,41 +775,33 @@ extern "C" int pwt_forward(pwt_plan* p) {
                     const int hints = (l < L ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l > 1 ? PWT_HINT_IN_FROM_PREV : 0);
                     if (!haar && ((p->kernel_mode == 0 && p->hlen >= p->strip_min_f && nr >= 64 && nc >= 256) || p->kernel_mode == 4)) {
                         // norms requested after an earlier forward: the strip kernel reduces |c|, c^2 of what it stores
-                        const bool nrm = p->want_norms && p->d_partials && p->do_separable && p->kernel_mode == 0 && l <= 32 && !nrm_lost;
+                        const bool nrm = p->want_norms && p->d_partials && p->do_separable && p->kernel_mode == 0 && l <= 32;
                         int wr = 0;
-                        n = pwt_strip_dwt_fwd2d_norms(src, dstA, Hb, V, D, nb, nr, nc, in_bs, out_bs, p->filt,
+                        n = pwt_strip_dwt_fwd2d_norms(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt,
                                                       nrm ? p->d_partials + 2 * (size_t)p->partials_n : nullptr,
                                                       p->partials_cap - p->partials_n, l == L, &wr, st);
                         if (n && wr > 0) {
                             p->partials_n += wr;
                             p->norm_lvl_mask |= 1u << (l - 1);
                             if (l == L) p->norm_a = 1;
-                        } else if (Gs && nrm) {
-                            nrm_lost = true;                        // the level is only partly covered: full reduction later
                         }
                     }
                     if (!n && (p->kernel_mode == 0 || p->kernel_mode == 3))
-                        n = pwt_reg_dwt_fwd2d(src, dstA, Hb, V, D, nb, nr, nc, in_bs, out_bs, p->filt, haar, hints, st);
+                        n = pwt_reg_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, hints, st);
                     if (!n && p->kernel_mode != 1 && !haar && p->hlen >= p->tile_min_f && nr >= 64 && nc >= 64)
-                        n = pwt_tile_dwt_fwd2d(src, dstA, Hb, V, D, nb, nr, nc, in_bs, out_bs, p->filt, st);
+                        n = pwt_tile_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, st);
                     if (!n && p->kernel_mode != 1)
-                        n = pwt_fast_dwt_fwd2d(src, dstA, Hb, V, D, nb, nr, nc, in_bs, out_bs, p->filt, haar,
+                        n = pwt_fast_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar,
                                                (l < L ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l > 1 ? PWT_HINT_IN_FROM_PREV : 0), st);
-                    if (!n) n = pwt_launch_dwt_fwd2d(src, dstA, Hb, V, D, nb, nr, nc, in_bs, out_bs, p->filt, haar, st);
+                    if (!n) n = pwt_launch_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, st);
                     p->launches += n;
                 } else {
-                    p->launches += pwt_launch_ns_fwd2d(src, dstA, Hb, V, D, nb, nr, nc, in_bs, out_bs, p->d_k2d_fwd, p->hlen, st);
+                    p->launches += pwt_launch_ns_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->d_k2d_fwd, p->hlen, st);
                 }
                 src = dstA;
             }
             prof_end(p);
         }
-        }
-        if (Gs) {
-            int rc = group_join(p, GS);
-            if (rc != PWT_OK) return rc;
-        }
-        if (nrm_lost) clear_partials(p);
     }
     CK_LAUNCH();
     p->state = PWT_FORWARD;
@@ -960,27 +876,6 @@ extern "C" int pwt_inverse(pwt_plan* p) {
             if (rc != PWT_OK) return rc;
             fop.app = 0;
         }
-        // slice groups (see group_slices): levels L..1 of Gs slices, then the next Gs; not when the fused cascade serves
-        // levels 3..1 (no intermediates to keep resident there)
-        const bool cascade3 = !p->do_swt && sep && p->kernel_mode == 0 && (haar || p->hlen < p->strip_min_f) && L >= 3;
-        const int Gs = cascade3 ? 0 : group_slices(p);
-        if (Gs && p->pend.op >= 0 && !strip_defer) {               // (the per-level flush below is written for one group)
-            int rc = flush_pending(p, 1, true);
-            if (rc != PWT_OK) return rc;
-        }
-        const int GS = group_stream_count();
-        if (Gs) {
-            int rc = group_fork(p, GS);
-            if (rc != PWT_OK) return rc;
-        }
-        for (int b0 = 0; b0 < B; b0 += (Gs ? Gs : B)) {
-        const int nb = Gs ? (B - b0 < Gs ? B - b0 : Gs) : B;
-        const int gk = Gs ? (b0 / Gs) % GS : 0;
-        if (Gs) {
-            cur = p->d_band[0] + (long long)b0 * lvl_elems(p, L);
-            st = p->gstream[gk];
-        }
-        int pong = 0;
         for (int l = L; l >= 1; l--) {
             if (l == 3 && p->pend.op >= 0 && !p->do_swt && !strip_defer && !cascade_ok) {
                 int rc = flush_pending(p, 1, L == 3);
@@ -1010,9 +905,9 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                     if (rc != PWT_OK) return rc;
                 }
             }
-            const float* Hb = p->d_band[3 * (l - 1) + sH] + (long long)b0 * lvl_elems(p, l);
-            const float* V = p->d_band[3 * (l - 1) + sV] + (long long)b0 * lvl_elems(p, l);
-            const float* D = p->d_band[3 * (l - 1) + 3] + (long long)b0 * lvl_elems(p, l);
+            const float* Hb = p->d_band[3 * (l - 1) + sH];
+            const float* V = p->d_band[3 * (l - 1) + sV];
+            const float* D = p->d_band[3 * (l - 1) + 3];
             prof_begin(p, 100 * l + 2);
             if (p->do_swt) {
                 float* alt = p->d_tmp + 2 * plane;
@@ -1041,10 +936,7 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                     p->launches += pwt_launch_ns_swt_inv2d(cur, Hb, V, D, dst, B, p->Nr, p->Nc, l, p->d_k2d_inv, p->hlen, st);
                 cur = dst;
             } else {
-                float* dst = !Gs ? ((l == 1) ? p->d_image : (cur == p->d_band[0] ? p->d_tmp : p->d_band[0]))
-                             : l == 1 ? p->d_image + (long long)b0 * img_elems(p)
-                             : (pong++ & 1) ? p->d_band[0] + (long long)(B - (gk + 1) * Gs) * lvl_elems(p, 1)
-                                            : p->d_tmp + (long long)gk * Gs * lvl_elems(p, 1);
+                float* dst = (l == 1) ? p->d_image : (cur == p->d_band[0] ? p->d_tmp : p->d_band[0]);
                 const long long in_bs = lvl_elems(p, l), out_bs = lvl_elems(p, l - 1);
                 const int nr = p->lvNr[l], nc = p->lvNc[l], Nro = p->lvNr[l - 1], Nco = p->lvNc[l - 1];
                 if (sep) {
@@ -1052,10 +944,10 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                     const int hints = (l > 1 ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l < L ? PWT_HINT_IN_FROM_PREV : 0);
                     if (!haar && ((p->kernel_mode == 0 && p->hlen >= p->strip_min_f && nr >= 32 && nc >= 128) || p->kernel_mode == 4)) {
                         if (strip_defer && l <= strip_lmax)
-                            n = pwt_strip_dwt_inv2d_thr(cur, Hb, V, D, dst, nb, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, p->pend.op,
+                            n = pwt_strip_dwt_inv2d_thr(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, p->pend.op,
                                                         p->pend.beta[l - 1], l == L && p->pend.app, p->pend.beta_app, st);
                         else
-                            n = pwt_strip_dwt_inv2d(cur, Hb, V, D, dst, nb, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, st);
+                            n = pwt_strip_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, st);
                     }
                     if (!n && strip_defer && l <= strip_lmax) {      // declined after all: apply the rest through memory
                         int rc = flush_pending(p, 1, l == L);
@@ -1063,25 +955,20 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                         strip_defer = false;
                     }
                     if (!n && (p->kernel_mode == 0 || p->kernel_mode == 3))
-                        n = pwt_reg_dwt_inv2d(cur, Hb, V, D, dst, nb, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, hints, st);
+                        n = pwt_reg_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, hints, st);
                     if (!n && p->kernel_mode != 1 && !haar && p->hlen >= p->tile_min_f && nr >= 32 && nc >= 32)
-                        n = pwt_tile_dwt_inv2d(cur, Hb, V, D, dst, nb, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, st);
+                        n = pwt_tile_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, st);
                     if (!n && p->kernel_mode != 1)
-                        n = pwt_fast_dwt_inv2d(cur, Hb, V, D, dst, nb, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar,
+                        n = pwt_fast_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar,
                                                (l > 1 ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l < L ? PWT_HINT_IN_FROM_PREV : 0), st);
-                    if (!n) n = pwt_launch_dwt_inv2d(cur, Hb, V, D, dst, nb, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, st);
+                    if (!n) n = pwt_launch_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, st);
                     p->launches += n;
                 } else {
-                    p->launches += pwt_launch_ns_inv2d(cur, Hb, V, D, dst, nb, nr, nc, Nro, Nco, in_bs, out_bs, p->d_k2d_inv, p->hlen, st);
+                    p->launches += pwt_launch_ns_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->d_k2d_inv, p->hlen, st);
                 }
                 cur = dst;
             }
             prof_end(p);
-        }
-        }
-        if (Gs) {
-            int rc = group_join(p, GS);
-            if (rc != PWT_OK) return rc;
         }
         if (strip_defer) p->pend.op = -1;                           // consumed by the strip inverse launches
     }
