@@ -296,6 +296,12 @@ int pwt_strip_dwt_inv1d(const float* A, const float* D, float* out, int rows, in
 // Haar, batched 1D, width multiple of 8: flat streaming butterfly.  Return 0 when not covered.
 int pwt_haar_fwd1d_flat(const float* in, float* A, float* D, int rows, int Nc, cudaStream_t st);
 int pwt_haar_inv1d_flat(const float* A, const float* D, float* out, int rows, int nc, int Nc_out, cudaStream_t st);
+// kernels_row1d.cu : batched 1D DWT / IDWT, every level in ONE launch (rows staged once in shared memory).  D[l] = detail
+// band of level l + 1.  Return 0 when not covered (row too long for a CTA's shared memory, odd filter length).
+int pwt_row_dwt_fwd1d_all(const float* in, float* A, float* const* D, int rows, int Nc, int L, const PwtFilters& f,
+                          cudaStream_t st);
+int pwt_row_dwt_inv1d_all(const float* A, float* const* D, float* out, int rows, int Nc, int L, const PwtFilters& f,
+                          cudaStream_t st);
 // kernels_swt1d.cu : batched 1D a-trous level from a staged shared-memory row.  Return 0 when not covered.
 int pwt_fast_swt_fwd1d(const float* in, float* A, float* D, int rows, int Nc, int level, const PwtFilters& f,
                        cudaStream_t st);

@@ -705,7 +705,20 @@ extern "C" int pwt_forward(pwt_plan* p) {
     const float* src = p->d_image;
     if (p->ndims == 1) {
         const int rows = B * p->Nr;
-        for (int l = 1; l <= L; l++) {
+        int l_first = 1;
+        // every level in one launch, the rows staged once in shared memory (kernels_row1d.cu)
+        if (!p->do_swt && p->kernel_mode == 0 && !pwt_tuning().no_fused1d) {
+            float* Ds[PWT_MAX_LEVELS];
+            for (int l = 1; l <= L; l++) Ds[l - 1] = p->d_band[l];
+            prof_begin(p, 100 * L + 21);
+            const int n = pwt_row_dwt_fwd1d_all(src, p->d_band[0], Ds, rows, p->Nc, L, p->filt, st);
+            if (n) {
+                prof_end(p);
+                p->launches += n;
+                l_first = L + 1;
+            }
+        }
+        for (int l = l_first; l <= L; l++) {
             float* dstA = approx_dst(p, l, p->d_tmp);
             prof_begin(p, 100 * l + 1);
             if (p->do_swt) {
@@ -826,7 +839,19 @@ extern "C" int pwt_inverse(pwt_plan* p) {
     const float* cur = p->d_band[0];
     if (p->ndims == 1) {
         const int rows = B * p->Nr;
-        for (int l = L; l >= 1; l--) {
+        int l_top = L;
+        if (!p->do_swt && p->kernel_mode == 0 && !pwt_tuning().no_fused1d) {      // every level in one launch
+            float* Ds[PWT_MAX_LEVELS];
+            for (int l = 1; l <= L; l++) Ds[l - 1] = p->d_band[l];
+            prof_begin(p, 100 * L + 22);
+            const int n = pwt_row_dwt_inv1d_all(cur, Ds, p->d_image, rows, p->Nc, L, p->filt, st);
+            if (n) {
+                prof_end(p);
+                p->launches += n;
+                l_top = 0;
+            }
+        }
+        for (int l = l_top; l >= 1; l--) {
             float* dst = (l == 1) ? p->d_image : (cur == p->d_band[0] ? p->d_tmp : p->d_band[0]);
             prof_begin(p, 100 * l + 2);
             if (p->do_swt) {

@@ -742,6 +742,28 @@ def test_strip_kernels_1d_against_oracle(wname, batched):
     assert_close(W.image, Wo.image, SCALE, "strip idwt1d " + wname)
 
 
+ROWS1D_WAVELETS = [w for w in ALL if len(O.filters(w)[0]) % 2 == 0]
+
+
+@pytest.mark.parametrize("batched", [0, 1, 2])
+@pytest.mark.parametrize("wname", ROWS1D_WAVELETS)
+def test_fused_rows_1d_against_oracle(wname, batched):
+    """Batched 1D DWT / IDWT, every level in ONE launch per direction (kernels_row1d.cu; the auto choice): odd and
+    even widths, the maximum level count, a row that fills a CTA's shared memory, against the oracle."""
+    data = [synth_image((1, 4099), seed=43)[0], synth_image((37, 1000), seed=41), synth_image((3, 16384), seed=45)][batched]
+    W = _W(data, wname, 999, ndim=1)
+    Wo = O.OracleWavelets(data, wname, 999, ndim=1)
+    assert W.levels == Wo.levels
+    n0 = W.launch_count
+    W.forward(); Wo.forward()
+    assert W.launch_count - n0 == 1, "forward took %d launches" % (W.launch_count - n0)
+    compare_coeffs(W, Wo, SCALE, "rows dwt1d " + wname)
+    n0 = W.launch_count
+    W.inverse(); Wo.inverse()
+    assert W.launch_count - n0 == 1
+    assert_close(W.image, Wo.image, SCALE, "rows idwt1d " + wname)
+
+
 @pytest.mark.parametrize("shape", [(64, 1024), (5, 8192), (3, 136), (4096,)])
 @pytest.mark.parametrize("wname", ["haar", "db2", "sym8", "db20"])
 def test_fast_1d_kernels_agree_with_generic(wname, shape):
