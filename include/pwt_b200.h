@@ -169,6 +169,36 @@ int pwt_norms_allreduce_group(pwt_plan** plans, int n, double* norm1, double* no
 /* global norms over all ranks' shards: fused local reduction + ncclAllReduce on the plan's stream */
 int pwt_norms_allreduce(pwt_plan* p, double* norm1, double* norm2sq);
 
+/* ---- double precision ------------------------------------------------------ */
+/* The reference's DOUBLEPRECISION build (pdwt/src/filters.h:16-30 `DTYPE double`, pdwt/Makefile:36-39 libpdwtd.so):
+ * the same class (wt.h:20-76) with double samples and the filter table at full precision.  One entry point per
+ * method, same argument meaning, return codes and band numbering as the float functions above; `batch` stacked
+ * images like pwt_create_batch.  Non-separable plans use the rank-1 identity of the built-in banks (separable kernels,
+ * reference slot order).  Not carried over: custom filter banks, add_wavelet, group_soft / proj_linf, NCCL norms. */
+typedef struct pwt64_plan pwt64_plan;
+int pwt64_create(pwt64_plan** out, const double* img, int batch, int Nr, int Nc, const char* wname, int levels,
+                 int memisonhost, int do_separable, int do_cycle_spinning, int do_swt, int ndim);   /* wt.cu:84-185 */
+void pwt64_destroy(pwt64_plan* p);                                                                  /* wt.cu:226-233 */
+int pwt64_get_info(const pwt64_plan* p, pwt_info* info);
+int pwt64_band_shape(const pwt64_plan* p, int num, int* nr, int* nc);
+int pwt64_forward(pwt64_plan* p);                                                                   /* wt.cu:236-269 */
+int pwt64_inverse(pwt64_plan* p);                                                                   /* wt.cu:271-305 */
+int pwt64_soft_threshold(pwt64_plan* p, double beta, int do_thresh_appcoeffs, int normalize);       /* wt.cu:308 */
+int pwt64_hard_threshold(pwt64_plan* p, double beta, int do_thresh_appcoeffs, int normalize);       /* wt.cu:318 */
+int pwt64_shrink(pwt64_plan* p, double beta, int do_thresh_appcoeffs);                              /* wt.cu:340 */
+int pwt64_norms(pwt64_plan* p, double* norm1, double* norm2sq);                                     /* wt.cu:368-416 */
+int pwt64_get_image(pwt64_plan* p, double* dst);                                                    /* wt.cu:419 */
+int pwt64_set_image(pwt64_plan* p, const double* img, int mem_is_on_device);                        /* wt.cu:425 */
+int pwt64_get_coeff(pwt64_plan* p, double* dst, int num);                                           /* wt.cu:473 */
+int pwt64_set_coeff(pwt64_plan* p, const double* src, int num, int mem_is_on_device);               /* wt.cu:435 */
+intptr_t pwt64_image_ptr(pwt64_plan* p);                                                            /* wt.cu:658 */
+intptr_t pwt64_coeff_ptr(pwt64_plan* p, int num);                                                   /* wt.cu:663 */
+int pwt64_sync(pwt64_plan* p);
+int pwt64_timer_start(pwt64_plan* p);
+int pwt64_timer_stop(pwt64_plan* p, float* ms);
+long long pwt64_launch_count(const pwt64_plan* p);
+int pwt64_lookup_filters(const char* wname, double* L, double* H, double* IL, double* IH);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,17 +78,18 @@ def band_sizes(Nr, Nc, levels, do_swt, ndim):
 # ----------------------------------------------------------------------------
 # filters (filters.cpp; relations checked bit-exactly by tools/gen_filter_table.py)
 # ----------------------------------------------------------------------------
-def filters(wname, dtype=np.float64):
-    """Return (L, H, IL, IH), each first rounded to fp32 like the reference's DTYPE table."""
+def filters(wname, dtype=np.float64, table_dtype=np.float32):
+    """Return (L, H, IL, IH), each first rounded to fp32 like the reference's DTYPE table
+    (table_dtype=np.float64: the DOUBLEPRECISION build's table, filters.h:16-30)."""
     key = wname.lower()
     if key in HAAR_ALIASES:
         key = "haar"
     if key not in _TABLE:
         raise ValueError("unknown wavelet %r" % wname)
     e = _TABLE[key]
-    L = np.asarray(e["dec_lo"], np.float64).astype(np.float32)
-    IL = L[::-1].copy() if e["orthogonal"] else np.asarray(e["rec_lo"], np.float64).astype(np.float32)
-    sign = np.where(np.arange(L.size) % 2 == 0, 1.0, -1.0).astype(np.float32)
+    L = np.asarray(e["dec_lo"], np.float64).astype(table_dtype)
+    IL = L[::-1].copy() if e["orthogonal"] else np.asarray(e["rec_lo"], np.float64).astype(table_dtype)
+    sign = np.where(np.arange(L.size) % 2 == 0, 1.0, -1.0).astype(table_dtype)
     H = -sign * IL
     IH = sign * L
     return tuple(np.asarray(f, dtype) for f in (L, H, IL, IH))
@@ -239,26 +240,26 @@ def proj_linf(v, beta):
     return np.copysign(np.minimum(np.abs(v), beta), v)
 
 
-def beta_schedule(beta, levels, normalize):
+def beta_schedule(beta, levels, normalize, ft=np.float32):
     """Per-level thresholds for the detail bands (common.cu:239-247):
-    cumulative fp32 `beta /= SQRT_2` (fp32 / double -> fp32)."""
-    b = np.float32(beta)
+    cumulative DTYPE `beta /= SQRT_2` (fp32 / double -> fp32 in the default build)."""
+    b = ft(beta)
     out = []
     for _ in range(levels):
         if normalize > 0:
-            b = np.float32(np.float64(b) / SQRT_2)
+            b = ft(np.float64(b) / SQRT_2)
         out.append(b)
     return out
 
 
-def beta_appcoeffs(beta, levels, normalize):
+def beta_appcoeffs(beta, levels, normalize, ft=np.float32):
     """common.cu:230-235: beta / sqrt(2)^levels computed as /(1<<(L/2)) then /SQRT_2 if L odd."""
-    b = np.float32(beta)
+    b = ft(beta)
     if normalize > 0:
         n2 = levels // 2
-        b = np.float32(b / np.float32(1 << n2))
+        b = ft(b / ft(1 << n2))
         if n2 * 2 != levels:
-            b = np.float32(np.float64(b) / SQRT_2)
+            b = ft(np.float64(b) / SQRT_2)
     return b
 
 
@@ -310,8 +311,11 @@ class OracleWavelets:
     W_INIT, W_FORWARD, W_INVERSE = 0, 1, 2
 
     def __init__(self, img, wname, levels, do_separable=1, do_cycle_spinning=0, do_swt=0, ndim=2,
-                 dtype=np.float64, rng=None):
-        img = np.ascontiguousarray(img, dtype=np.float32)
+                 dtype=np.float64, rng=None, double_build=False):
+        # double_build: the reference compiled with DOUBLEPRECISION (filters.h:16-30): DTYPE = double for the samples,
+        # the filter table and the thresholds
+        self._ft = np.float64 if double_build else np.float32
+        img = np.ascontiguousarray(img, dtype=self._ft)
         ndim = min(ndim, 2)
         self.batched1d = 0
         if img.ndim == 2:
@@ -334,7 +338,7 @@ class OracleWavelets:
         self._haar = (wname.lower() in HAAR_ALIASES) and not self.do_swt      # wt.cu:248,255
         if self.do_swt and wname.lower() != "haar" and wname.lower() in HAAR_ALIASES:
             raise ValueError("unknown wavelet %r for SWT (separable.cu:24-28)" % wname)
-        self.L, self.H, self.IL, self.IH = filters(wname, dtype)
+        self.L, self.H, self.IL, self.IH = filters(wname, dtype, self._ft)
         self.hlen = 2 if self._haar else self.L.size
         levels = max(int(levels), 1)                                             # wt.cu:111-114
         self.levels = min(levels, max_level(self.Nr, self.Nc, self.hlen, self._ndims))  # wt.cu:156-165
@@ -367,7 +371,7 @@ class OracleWavelets:
 
     # -- transforms ----------------------------------------------------------
     def set_image(self, img):
-        img = np.ascontiguousarray(img, dtype=np.float32)
+        img = np.ascontiguousarray(img, dtype=self._ft)
         if img.shape != (self.Nr, self.Nc):
             raise ValueError("wrong shape")
         self._image = img.astype(self.dtype)
@@ -375,7 +379,7 @@ class OracleWavelets:
 
     def forward(self, img=None):
         if img is not None:
-            img = np.ascontiguousarray(img, dtype=np.float32)
+            img = np.ascontiguousarray(img, dtype=self._ft)
             if img.shape != self.shape:
                 raise ValueError("wrong shape")
             self._image = img.reshape(self.Nr, self.Nc).astype(self.dtype)
@@ -445,9 +449,9 @@ class OracleWavelets:
         if self.state == self.W_INVERSE:                                         # wt.cu:309,319
             return
         if app:
-            b = np.float32(beta) if app_unscaled else beta_appcoeffs(beta, self.levels, normalize)
+            b = self._ft(beta) if app_unscaled else beta_appcoeffs(beta, self.levels, normalize, self._ft)
             self._c[0] = fn(self._c[0], self.dtype(b))
-        for i, b in enumerate(beta_schedule(beta, self.levels, normalize)):
+        for i, b in enumerate(beta_schedule(beta, self.levels, normalize, self._ft)):
             for s in self._detail_slots(i):
                 self._c[s] = fn(self._c[s], self.dtype(b))
 
@@ -464,7 +468,7 @@ class OracleWavelets:
     def shrink(self, beta, do_threshold_appcoeffs=1):
         if self.state == self.W_INVERSE:
             return
-        f = self.dtype(np.float32(1.0) / (np.float32(1.0) + np.float32(beta)))  # common.cu:355
+        f = self.dtype(self._ft(1.0) / (self._ft(1.0) + self._ft(beta)))  # common.cu:355
         start = 0 if do_threshold_appcoeffs else 1
         for s in range(start, len(self._c)):
             self._c[s] = self._c[s] * f
@@ -507,26 +511,26 @@ class OracleWavelets:
         return 0
 
     def set_coeff(self, coeff, num):
-        self._c[num] = np.ascontiguousarray(coeff, np.float32).reshape(self._c[num].shape).astype(self.dtype)
+        self._c[num] = np.ascontiguousarray(coeff, self._ft).reshape(self._c[num].shape).astype(self.dtype)
 
     # -- read-back -----------------------------------------------------------
     @property
     def image(self):
-        return np.asarray(self._image, np.float32).reshape(self.Nr, self.Nc)
+        return np.asarray(self._image, self._ft).reshape(self.Nr, self.Nc)
 
     def coeff_only(self, num):
         if self.state == self.W_INVERSE:                                         # wt.cu:474-477 + pyx:284
             raise RuntimeError("coefficients were consumed by inverse()")
-        return np.asarray(self._c[num], np.float32)
+        return np.asarray(self._c[num], self._ft)
 
     @property
     def coeffs(self):
         if self.state == self.W_INVERSE:
             raise RuntimeError("coefficients were consumed by inverse()")
-        out = [np.asarray(self._c[0], np.float32)]
+        out = [np.asarray(self._c[0], self._ft)]
         for i in range(self.levels):
             if self._ndims == 2:
-                out.append([np.asarray(self._c[3 * i + 1 + j], np.float32) for j in range(3)])
+                out.append([np.asarray(self._c[3 * i + 1 + j], self._ft) for j in range(3)])
             else:
-                out.append(np.asarray(self._c[i + 1], np.float32))
+                out.append(np.asarray(self._c[i + 1], self._ft))
         return out

@@ -32,26 +32,35 @@ __device__ __forceinline__ int wrap_per(int i, int N) {
     return i < 0 ? i + N : i;
 }
 
+// ---- precision helpers: the separable kernels below are templates over the sample type (float: the reference's
+// build; double: its DOUBLEPRECISION build, filters.h:16-30 -- SURVEY 8f rank 4) -------------------------------
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
+template <typename T> __device__ __forceinline__ T sqrt_half();
+template <> __device__ __forceinline__ float sqrt_half<float>() { return 0.70710678118654746f; }
+template <> __device__ __forceinline__ double sqrt_half<double>() { return 0.70710678118654752440; }
+
 // =========================================================================================
 // separable DWT, forward, fused row+column pass
 // =========================================================================================
 constexpr int GTX = 32;   // output columns per tile
 constexpr int GTY = 16;   // output rows per tile
 
-template <bool HAAR>
+template <typename T, bool HAAR>
 __global__ void __launch_bounds__(kThreads)
-k_dwt_fwd2d(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ Hb,
-            float* __restrict__ V, float* __restrict__ D, int Nr, int Nc, long long in_bs,
-            long long out_bs, const __grid_constant__ PwtFilters f) {
-    extern __shared__ float sm[];
+k_dwt_fwd2d(const T* __restrict__ in, T* __restrict__ A, T* __restrict__ Hb,
+            T* __restrict__ V, T* __restrict__ D, int Nr, int Nc, long long in_bs,
+            long long out_bs, const __grid_constant__ PwtFiltersT<T> f) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    T* sm = reinterpret_cast<T*>(sm_raw);
     const int F = f.hlen;
     const int c = (F - 1) / 2;
     const int IH = 2 * GTY + F - 2, IW = 2 * GTX + F - 2;
     const int IWp = IW | 1;                       // odd pitch: the stride-2 row pass stays conflict-light
     int* colidx = reinterpret_cast<int*>(sm);     // IW entries, padded to a multiple of 4
-    float* s_in = sm + ((IW + 4) & ~3);
-    float* s_lo = s_in + IH * IWp;
-    float* s_hi = s_lo + IH * GTX;
+    T* s_in = sm + ((IW + 4) & ~3);
+    T* s_lo = s_in + IH * IWp;
+    T* s_hi = s_lo + IH * GTX;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Nr2 = (Nr + 1) >> 1, Nc2 = (Nc + 1) >> 1;
@@ -62,23 +71,23 @@ k_dwt_fwd2d(const float* __restrict__ in, float* __restrict__ A, float* __restri
     for (int i = tid; i < IW; i += kThreads) colidx[i] = wrap_dwt(2 * kx0 - c + i, Nc);
     __syncthreads();
     for (int r = warp; r < IH; r += kWarps) {
-        const float* row = in + (long long)wrap_dwt(2 * ky0 - c + r, Nr) * Nc;
+        const T* row = in + (long long)wrap_dwt(2 * ky0 - c + r, Nr) * Nc;
         for (int cc = lane; cc < IW; cc += 32) s_in[r * IWp + cc] = __ldg(row + colidx[cc]);
     }
     __syncthreads();
     // row pass (lane = output column)
     for (int r = warp; r < IH; r += kWarps) {
-        const float* p = s_in + r * IWp + 2 * lane;
-        float lo, hi;
+        const T* p = s_in + r * IWp + 2 * lane;
+        T lo, hi;
         if (HAAR) {
             lo = p[0] + p[1];
             hi = p[0] - p[1];
         } else {
-            lo = 0.f, hi = 0.f;
+            lo = T(0), hi = T(0);
             for (int j = 0; j < F; j++) {
-                const float v = p[j];
-                lo = fmaf(v, f.L[F - 1 - j], lo);
-                hi = fmaf(v, f.H[F - 1 - j], hi);
+                const T v = p[j];
+                lo = fma_t(v, f.L[F - 1 - j], lo);
+                hi = fma_t(v, f.H[F - 1 - j], hi);
             }
         }
         s_lo[r * GTX + lane] = lo;
@@ -87,23 +96,23 @@ k_dwt_fwd2d(const float* __restrict__ in, float* __restrict__ A, float* __restri
     __syncthreads();
     // column pass
     for (int y = warp; y < GTY; y += kWarps) {
-        float a, h, v, d;
-        const float* pl = s_lo + (2 * y) * GTX + lane;
-        const float* ph = s_hi + (2 * y) * GTX + lane;
+        T a, h, v, d;
+        const T* pl = s_lo + (2 * y) * GTX + lane;
+        const T* ph = s_hi + (2 * y) * GTX + lane;
         if (HAAR) {
-            a = 0.5f * (pl[0] + pl[GTX]);
-            h = 0.5f * (pl[0] - pl[GTX]);
-            v = 0.5f * (ph[0] + ph[GTX]);
-            d = 0.5f * (ph[0] - ph[GTX]);
+            a = T(0.5) * (pl[0] + pl[GTX]);
+            h = T(0.5) * (pl[0] - pl[GTX]);
+            v = T(0.5) * (ph[0] + ph[GTX]);
+            d = T(0.5) * (ph[0] - ph[GTX]);
         } else {
-            a = h = v = d = 0.f;
+            a = h = v = d = T(0);
             for (int j = 0; j < F; j++) {
-                const float l = pl[j * GTX], g = ph[j * GTX];
-                const float tl = f.L[F - 1 - j], th = f.H[F - 1 - j];
-                a = fmaf(l, tl, a);
-                h = fmaf(l, th, h);
-                v = fmaf(g, tl, v);
-                d = fmaf(g, th, d);
+                const T l = pl[j * GTX], g = ph[j * GTX];
+                const T tl = f.L[F - 1 - j], th = f.H[F - 1 - j];
+                a = fma_t(l, tl, a);
+                h = fma_t(l, th, h);
+                v = fma_t(g, tl, v);
+                d = fma_t(g, th, d);
             }
         }
         const int ky = ky0 + y, kx = kx0 + lane;
@@ -123,33 +132,34 @@ k_dwt_fwd2d(const float* __restrict__ in, float* __restrict__ A, float* __restri
 constexpr int GOX = 64;   // output columns per tile
 constexpr int GOY = 32;   // output rows per tile
 
-template <bool HAAR>
+template <typename T, bool HAAR>
 __global__ void __launch_bounds__(kThreads)
-k_dwt_inv2d(const float* __restrict__ A, const float* __restrict__ Hb, const float* __restrict__ V,
-            const float* __restrict__ D, float* __restrict__ out, int nr, int nc, int Nr_out,
-            int Nc_out, long long in_bs, long long out_bs, const __grid_constant__ PwtFilters f) {
-    extern __shared__ float sm[];
+k_dwt_inv2d(const T* __restrict__ A, const T* __restrict__ Hb, const T* __restrict__ V,
+            const T* __restrict__ D, T* __restrict__ out, int nr, int nc, int Nr_out,
+            int Nc_out, long long in_bs, long long out_bs, const __grid_constant__ PwtFiltersT<T> f) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    T* sm = reinterpret_cast<T*>(sm_raw);
     const int F = f.hlen;
     const int p = F / 2 - 1, hl = (p + 1) >> 1, half = F / 2;
     const int BH = GOY / 2 + 2 * hl, BW = GOX / 2 + 2 * hl;
     const int BWp = BW | 1;
     int* colidx = reinterpret_cast<int*>(sm);
-    float* s_b = sm + ((BW + 4) & ~3);            // 4 band tiles [4][BH][BWp]
-    float* s_t = s_b + 4 * BH * BWp;              // t1, t2 : [2][GOY][BWp]
+    T* s_b = sm + ((BW + 4) & ~3);            // 4 band tiles [4][BH][BWp]
+    T* s_t = s_b + 4 * BH * BWp;              // t1, t2 : [2][GOY][BWp]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n0x = blockIdx.x * GOX, n0y = blockIdx.y * GOY;
     const int kx_start = n0x / 2 - hl, ky_start = n0y / 2 - hl;
     const long long ib = blockIdx.z * in_bs;
     out += blockIdx.z * out_bs;
-    const float* bands[4] = {A + ib, Hb + ib, V + ib, D + ib};
+    const T* bands[4] = {A + ib, Hb + ib, V + ib, D + ib};
 
     for (int i = tid; i < BW; i += kThreads) colidx[i] = wrap_per(kx_start + i, nc);
     __syncthreads();
     for (int r = warp; r < 4 * BH; r += kWarps) {
         const int b = r / BH, rr = r - b * BH;
-        const float* row = bands[b] + (long long)wrap_per(ky_start + rr, nr) * nc;
-        float* dst = s_b + (b * BH + rr) * BWp;
+        const T* row = bands[b] + (long long)wrap_per(ky_start + rr, nr) * nc;
+        T* dst = s_b + (b * BH + rr) * BWp;
         for (int cc = lane; cc < BW; cc += 32) dst[cc] = __ldg(row + colidx[cc]);
     }
     __syncthreads();
@@ -159,23 +169,23 @@ k_dwt_inv2d(const float* __restrict__ A, const float* __restrict__ Hb, const flo
         const int b = y & 1;
         const int kb = (y >> 1) + ((b + p) >> 1) + hl;   // local row of tap j = 0
         const int t0 = (b + p) & 1;
-        float t1, t2;
-        const float* pa = s_b + (0 * BH + kb) * BWp + x;
-        const float* ph = s_b + (1 * BH + kb) * BWp + x;
-        const float* pv = s_b + (2 * BH + kb) * BWp + x;
-        const float* pd = s_b + (3 * BH + kb) * BWp + x;
+        T t1, t2;
+        const T* pa = s_b + (0 * BH + kb) * BWp + x;
+        const T* ph = s_b + (1 * BH + kb) * BWp + x;
+        const T* pv = s_b + (2 * BH + kb) * BWp + x;
+        const T* pd = s_b + (3 * BH + kb) * BWp + x;
         if (HAAR) {
             t1 = b ? pa[0] - ph[0] : pa[0] + ph[0];
             t2 = b ? pv[0] - pd[0] : pv[0] + pd[0];
         } else {
-            t1 = t2 = 0.f;
+            t1 = t2 = T(0);
             for (int j = 0; j < half; j++) {
-                const float tl = f.IL[2 * j + t0], th = f.IH[2 * j + t0];
+                const T tl = f.IL[2 * j + t0], th = f.IH[2 * j + t0];
                 const int o = -j * BWp;
-                t1 = fmaf(pa[o], tl, t1);
-                t1 = fmaf(ph[o], th, t1);
-                t2 = fmaf(pv[o], tl, t2);
-                t2 = fmaf(pd[o], th, t2);
+                t1 = fma_t(pa[o], tl, t1);
+                t1 = fma_t(ph[o], th, t1);
+                t2 = fma_t(pv[o], tl, t2);
+                t2 = fma_t(pd[o], th, t2);
             }
         }
         s_t[y * BWp + x] = t1;
@@ -188,16 +198,16 @@ k_dwt_inv2d(const float* __restrict__ A, const float* __restrict__ Hb, const flo
         const int b = x & 1;
         const int kb = (x >> 1) + ((b + p) >> 1) + hl;
         const int t0 = (b + p) & 1;
-        const float* p1 = s_t + y * BWp + kb;
-        const float* p2 = s_t + (GOY + y) * BWp + kb;
-        float r;
+        const T* p1 = s_t + y * BWp + kb;
+        const T* p2 = s_t + (GOY + y) * BWp + kb;
+        T r;
         if (HAAR) {
-            r = 0.5f * (b ? p1[0] - p2[0] : p1[0] + p2[0]);
+            r = T(0.5) * (b ? p1[0] - p2[0] : p1[0] + p2[0]);
         } else {
-            r = 0.f;
+            r = T(0);
             for (int j = 0; j < half; j++) {
-                r = fmaf(p1[-j], f.IL[2 * j + t0], r);
-                r = fmaf(p2[-j], f.IH[2 * j + t0], r);
+                r = fma_t(p1[-j], f.IL[2 * j + t0], r);
+                r = fma_t(p2[-j], f.IH[2 * j + t0], r);
             }
         }
         const int gy = n0y + y, gx = n0x + x;
@@ -210,29 +220,30 @@ k_dwt_inv2d(const float* __restrict__ A, const float* __restrict__ Hb, const flo
 // =========================================================================================
 constexpr int G1X = 256;  // outputs per block (forward) / coefficient columns per block (inverse)
 
-template <bool HAAR>
+template <typename T, bool HAAR>
 __global__ void __launch_bounds__(kThreads)
-k_dwt_fwd1d(const float* __restrict__ in, float* __restrict__ A, float* __restrict__ D, int rows,
-            int Nc, const __grid_constant__ PwtFilters f) {
-    extern __shared__ float sm[];
+k_dwt_fwd1d(const T* __restrict__ in, T* __restrict__ A, T* __restrict__ D, int rows,
+            int Nc, const __grid_constant__ PwtFiltersT<T> f) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    T* sm = reinterpret_cast<T*>(sm_raw);
     const int F = f.hlen, c = (F - 1) / 2;
     const int IW = 2 * G1X + F - 2;
     const int Nc2 = (Nc + 1) >> 1;
     const int kx0 = blockIdx.x * G1X, tid = threadIdx.x;
     for (int row = blockIdx.y; row < rows; row += gridDim.y) {
-        const float* src = in + (long long)row * Nc;
+        const T* src = in + (long long)row * Nc;
         for (int i = tid; i < IW; i += kThreads) sm[i] = __ldg(src + wrap_dwt(2 * kx0 - c + i, Nc));
         __syncthreads();
-        const float* p = sm + 2 * tid;
-        float lo, hi;
+        const T* p = sm + 2 * tid;
+        T lo, hi;
         if (HAAR) {
-            lo = 0.70710678118654746f * (p[0] + p[1]);
-            hi = 0.70710678118654746f * (p[0] - p[1]);
+            lo = sqrt_half<T>() * (p[0] + p[1]);
+            hi = sqrt_half<T>() * (p[0] - p[1]);
         } else {
-            lo = hi = 0.f;
+            lo = hi = T(0);
             for (int j = 0; j < F; j++) {
-                lo = fmaf(p[j], f.L[F - 1 - j], lo);
-                hi = fmaf(p[j], f.H[F - 1 - j], hi);
+                lo = fma_t(p[j], f.L[F - 1 - j], lo);
+                hi = fma_t(p[j], f.H[F - 1 - j], hi);
             }
         }
         if (kx0 + tid < Nc2) {
@@ -243,15 +254,16 @@ k_dwt_fwd1d(const float* __restrict__ in, float* __restrict__ A, float* __restri
     }
 }
 
-template <bool HAAR>
+template <typename T, bool HAAR>
 __global__ void __launch_bounds__(kThreads)
-k_dwt_inv1d(const float* __restrict__ A, const float* __restrict__ D, float* __restrict__ out,
-            int rows, int nc, int Nc_out, const __grid_constant__ PwtFilters f) {
-    extern __shared__ float sm[];
+k_dwt_inv1d(const T* __restrict__ A, const T* __restrict__ D, T* __restrict__ out,
+            int rows, int nc, int Nc_out, const __grid_constant__ PwtFiltersT<T> f) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    T* sm = reinterpret_cast<T*>(sm_raw);
     const int F = f.hlen, p = F / 2 - 1, hl = (p + 1) >> 1, half = F / 2;
     const int BW = G1X + 2 * hl;
-    float* s_a = sm;
-    float* s_d = sm + BW;
+    T* s_a = sm;
+    T* s_d = sm + BW;
     const int k0 = blockIdx.x * G1X - hl, tid = threadIdx.x;
     for (int row = blockIdx.y; row < rows; row += gridDim.y) {
         for (int i = tid; i < BW; i += kThreads) {
@@ -263,14 +275,14 @@ k_dwt_inv1d(const float* __restrict__ A, const float* __restrict__ D, float* __r
 #pragma unroll
         for (int b = 0; b < 2; b++) {
             const int kb = tid + ((b + p) >> 1) + hl, t0 = (b + p) & 1;
-            float r;
+            T r;
             if (HAAR) {
-                r = 0.70710678118654746f * (b ? s_a[kb] - s_d[kb] : s_a[kb] + s_d[kb]);
+                r = sqrt_half<T>() * (b ? s_a[kb] - s_d[kb] : s_a[kb] + s_d[kb]);
             } else {
-                r = 0.f;
+                r = T(0);
                 for (int j = 0; j < half; j++) {
-                    r = fmaf(s_a[kb - j], f.IL[2 * j + t0], r);
-                    r = fmaf(s_d[kb - j], f.IH[2 * j + t0], r);
+                    r = fma_t(s_a[kb - j], f.IL[2 * j + t0], r);
+                    r = fma_t(s_d[kb - j], f.IH[2 * j + t0], r);
                 }
             }
             const int n = 2 * (blockIdx.x * G1X + tid) + b;
@@ -286,33 +298,33 @@ k_dwt_inv1d(const float* __restrict__ A, const float* __restrict__ D, float* __r
 // for small dilations lives in kernels_fast.cu.
 // =========================================================================================
 // rows pass.  FWD: (in) -> (lo, hi) with analysis taps.  INV: (a, d) -> out with synthesis taps / 2.
-template <bool INV>
+template <typename T, bool INV>
 __global__ void __launch_bounds__(kThreads)
-k_swt_rows(const float* __restrict__ in0, const float* __restrict__ in1, float* __restrict__ out0,
-           float* __restrict__ out1, long long rows, int Nc, int s,
-           const __grid_constant__ PwtFilters f) {
+k_swt_rows(const T* __restrict__ in0, const T* __restrict__ in1, T* __restrict__ out0,
+           T* __restrict__ out1, long long rows, int Nc, int s,
+           const __grid_constant__ PwtFiltersT<T> f) {
     const int F = f.hlen;
     const int c = INV ? F / 2 : (F - 1) / 2;
     const int x = blockIdx.x * kThreads + threadIdx.x;
     if (x >= Nc) return;
     for (long long row = blockIdx.y; row < rows; row += gridDim.y) {
-        const float* p0 = in0 + row * Nc;
+        const T* p0 = in0 + row * Nc;
         if (!INV) {
-            float lo = 0.f, hi = 0.f;
+            T lo = T(0), hi = T(0);
             for (int j = 0; j < F; j++) {
-                const float v = __ldg(p0 + wrap_per(x + (j - c) * s, Nc));
-                lo = fmaf(v, f.L[F - 1 - j], lo);
-                hi = fmaf(v, f.H[F - 1 - j], hi);
+                const T v = __ldg(p0 + wrap_per(x + (j - c) * s, Nc));
+                lo = fma_t(v, f.L[F - 1 - j], lo);
+                hi = fma_t(v, f.H[F - 1 - j], hi);
             }
             out0[row * Nc + x] = lo;
             out1[row * Nc + x] = hi;
         } else {
-            const float* p1 = in1 + row * Nc;
-            float r1 = 0.f, r2 = 0.f;
+            const T* p1 = in1 + row * Nc;
+            T r1 = T(0), r2 = T(0);
             for (int j = 0; j < F; j++) {
                 const int xx = wrap_per(x + (j - c) * s, Nc);
-                r1 = fmaf(__ldg(p0 + xx), 0.5f * f.IL[F - 1 - j], r1);
-                r2 = fmaf(__ldg(p1 + xx), 0.5f * f.IH[F - 1 - j], r2);
+                r1 = fma_t(__ldg(p0 + xx), T(0.5) * f.IL[F - 1 - j], r1);
+                r2 = fma_t(__ldg(p1 + xx), T(0.5) * f.IH[F - 1 - j], r2);
             }
             out0[row * Nc + x] = r1 + r2;
         }
@@ -320,12 +332,12 @@ k_swt_rows(const float* __restrict__ in0, const float* __restrict__ in1, float* 
 }
 
 // columns pass.  FWD: (lo, hi) -> (A, H, V, D).  INV: (A, H, V, D) -> (t1, t2).
-template <bool INV>
+template <typename T, bool INV>
 __global__ void __launch_bounds__(kThreads)
-k_swt_cols(const float* __restrict__ i0, const float* __restrict__ i1, const float* __restrict__ i2,
-           const float* __restrict__ i3, float* __restrict__ o0, float* __restrict__ o1,
-           float* __restrict__ o2, float* __restrict__ o3, int Nr, int Nc, int s,
-           const __grid_constant__ PwtFilters f) {
+k_swt_cols(const T* __restrict__ i0, const T* __restrict__ i1, const T* __restrict__ i2,
+           const T* __restrict__ i3, T* __restrict__ o0, T* __restrict__ o1,
+           T* __restrict__ o2, T* __restrict__ o3, int Nr, int Nc, int s,
+           const __grid_constant__ PwtFiltersT<T> f) {
     const int F = f.hlen;
     const int c = INV ? F / 2 : (F - 1) / 2;
     const int x = blockIdx.x * kThreads + threadIdx.x;
@@ -334,29 +346,29 @@ k_swt_cols(const float* __restrict__ i0, const float* __restrict__ i1, const flo
     for (int y = blockIdx.y; y < Nr; y += gridDim.y) {
         const long long o = pb + (long long)y * Nc + x;
         if (!INV) {
-            float a = 0.f, h = 0.f, v = 0.f, d = 0.f;
+            T a = T(0), h = T(0), v = T(0), d = T(0);
             for (int j = 0; j < F; j++) {
                 const long long q = pb + (long long)wrap_per(y + (j - c) * s, Nr) * Nc + x;
-                const float l = __ldg(i0 + q), g = __ldg(i1 + q);
-                const float tl = f.L[F - 1 - j], th = f.H[F - 1 - j];
-                a = fmaf(l, tl, a);
-                h = fmaf(l, th, h);
-                v = fmaf(g, tl, v);
-                d = fmaf(g, th, d);
+                const T l = __ldg(i0 + q), g = __ldg(i1 + q);
+                const T tl = f.L[F - 1 - j], th = f.H[F - 1 - j];
+                a = fma_t(l, tl, a);
+                h = fma_t(l, th, h);
+                v = fma_t(g, tl, v);
+                d = fma_t(g, th, d);
             }
             o0[o] = a;
             o1[o] = h;
             o2[o] = v;
             o3[o] = d;
         } else {
-            float ra = 0.f, rh = 0.f, rv = 0.f, rd = 0.f;
+            T ra = T(0), rh = T(0), rv = T(0), rd = T(0);
             for (int j = 0; j < F; j++) {
                 const long long q = pb + (long long)wrap_per(y + (j - c) * s, Nr) * Nc + x;
-                const float tl = 0.5f * f.IL[F - 1 - j], th = 0.5f * f.IH[F - 1 - j];
-                ra = fmaf(__ldg(i0 + q), tl, ra);
-                rh = fmaf(__ldg(i1 + q), th, rh);
-                rv = fmaf(__ldg(i2 + q), tl, rv);
-                rd = fmaf(__ldg(i3 + q), th, rd);
+                const T tl = T(0.5) * f.IL[F - 1 - j], th = T(0.5) * f.IH[F - 1 - j];
+                ra = fma_t(__ldg(i0 + q), tl, ra);
+                rh = fma_t(__ldg(i1 + q), th, rh);
+                rv = fma_t(__ldg(i2 + q), tl, rv);
+                rd = fma_t(__ldg(i3 + q), th, rd);
             }
             o0[o] = ra + rh;
             o1[o] = rv + rd;
@@ -535,118 +547,178 @@ inline void set_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
-// =========================================================================================
-// launchers
-// =========================================================================================
-int pwt_launch_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr,
-                         int Nc, long long in_bs, long long out_bs, const PwtFilters& f, bool haar,
+namespace {
+template <typename T>
+static int launch_dwt_fwd2d_t(const T* in, T* A, T* Hb, T* V, T* D, int batch, int Nr,
+                         int Nc, long long in_bs, long long out_bs, const PwtFiltersT<T>& f, bool haar,
                          cudaStream_t st) {
     const int F = haar ? 2 : f.hlen;
-    PwtFilters ff = f;
+    PwtFiltersT<T> ff = f;
     ff.hlen = F;
     const int IH = 2 * GTY + F - 2, IW = 2 * GTX + F - 2, IWp = IW | 1;
-    const size_t smem = sizeof(float) * (size_t)(((IW + 4) & ~3) + IH * IWp + 2 * IH * GTX);
+    const size_t smem = sizeof(T) * (size_t)(((IW + 4) & ~3) + IH * IWp + 2 * IH * GTX);
     dim3 grid(cdiv((Nc + 1) / 2, GTX), cdiv((Nr + 1) / 2, GTY), batch);
     if (haar) {
-        set_smem(k_dwt_fwd2d<true>, smem);
-        k_dwt_fwd2d<true><<<grid, kThreads, smem, st>>>(in, A, Hb, V, D, Nr, Nc, in_bs, out_bs, ff);
+        set_smem(k_dwt_fwd2d<T, true>, smem);
+        k_dwt_fwd2d<T, true><<<grid, kThreads, smem, st>>>(in, A, Hb, V, D, Nr, Nc, in_bs, out_bs, ff);
     } else {
-        set_smem(k_dwt_fwd2d<false>, smem);
-        k_dwt_fwd2d<false><<<grid, kThreads, smem, st>>>(in, A, Hb, V, D, Nr, Nc, in_bs, out_bs, ff);
+        set_smem(k_dwt_fwd2d<T, false>, smem);
+        k_dwt_fwd2d<T, false><<<grid, kThreads, smem, st>>>(in, A, Hb, V, D, Nr, Nc, in_bs, out_bs, ff);
     }
     return 1;
 }
 
-int pwt_launch_dwt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out,
+template <typename T>
+static int launch_dwt_inv2d_t(const T* A, const T* Hb, const T* V, const T* D, T* out,
                          int batch, int nr, int nc, int Nr_out, int Nc_out, long long in_bs,
-                         long long out_bs, const PwtFilters& f, bool haar, cudaStream_t st) {
+                         long long out_bs, const PwtFiltersT<T>& f, bool haar, cudaStream_t st) {
     const int F = haar ? 2 : f.hlen;
-    PwtFilters ff = f;
+    PwtFiltersT<T> ff = f;
     ff.hlen = F;
     const int p = F / 2 - 1, hl = (p + 1) >> 1;
     const int BH = GOY / 2 + 2 * hl, BW = GOX / 2 + 2 * hl, BWp = BW | 1;
-    const size_t smem = sizeof(float) * (size_t)(((BW + 4) & ~3) + 4 * BH * BWp + 2 * GOY * BWp);
+    const size_t smem = sizeof(T) * (size_t)(((BW + 4) & ~3) + 4 * BH * BWp + 2 * GOY * BWp);
     dim3 grid(cdiv(Nc_out, GOX), cdiv(Nr_out, GOY), batch);
     if (haar) {
-        set_smem(k_dwt_inv2d<true>, smem);
-        k_dwt_inv2d<true><<<grid, kThreads, smem, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out,
+        set_smem(k_dwt_inv2d<T, true>, smem);
+        k_dwt_inv2d<T, true><<<grid, kThreads, smem, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out,
                                                         in_bs, out_bs, ff);
     } else {
-        set_smem(k_dwt_inv2d<false>, smem);
-        k_dwt_inv2d<false><<<grid, kThreads, smem, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out,
+        set_smem(k_dwt_inv2d<T, false>, smem);
+        k_dwt_inv2d<T, false><<<grid, kThreads, smem, st>>>(A, Hb, V, D, out, nr, nc, Nr_out, Nc_out,
                                                          in_bs, out_bs, ff);
     }
     return 1;
 }
 
-int pwt_launch_dwt_fwd1d(const float* in, float* A, float* D, int rows, int Nc, const PwtFilters& f,
+template <typename T>
+static int launch_dwt_fwd1d_t(const T* in, T* A, T* D, int rows, int Nc, const PwtFiltersT<T>& f,
                          bool haar, cudaStream_t st) {
     const int F = haar ? 2 : f.hlen;
-    PwtFilters ff = f;
+    PwtFiltersT<T> ff = f;
     ff.hlen = F;
-    const size_t smem = sizeof(float) * (size_t)(2 * G1X + F - 2);
+    const size_t smem = sizeof(T) * (size_t)(2 * G1X + F - 2);
     dim3 grid(cdiv((Nc + 1) / 2, G1X), clamp_grid_y(rows), 1);
     if (haar)
-        k_dwt_fwd1d<true><<<grid, kThreads, smem, st>>>(in, A, D, rows, Nc, ff);
+        k_dwt_fwd1d<T, true><<<grid, kThreads, smem, st>>>(in, A, D, rows, Nc, ff);
     else
-        k_dwt_fwd1d<false><<<grid, kThreads, smem, st>>>(in, A, D, rows, Nc, ff);
+        k_dwt_fwd1d<T, false><<<grid, kThreads, smem, st>>>(in, A, D, rows, Nc, ff);
     return 1;
 }
 
-int pwt_launch_dwt_inv1d(const float* A, const float* D, float* out, int rows, int nc, int Nc_out,
-                         const PwtFilters& f, bool haar, cudaStream_t st) {
+template <typename T>
+static int launch_dwt_inv1d_t(const T* A, const T* D, T* out, int rows, int nc, int Nc_out,
+                         const PwtFiltersT<T>& f, bool haar, cudaStream_t st) {
     const int F = haar ? 2 : f.hlen;
-    PwtFilters ff = f;
+    PwtFiltersT<T> ff = f;
     ff.hlen = F;
     const int hl = (F / 2) >> 1;
-    const size_t smem = sizeof(float) * (size_t)(2 * (G1X + 2 * hl));
+    const size_t smem = sizeof(T) * (size_t)(2 * (G1X + 2 * hl));
     dim3 grid(cdiv(cdiv(Nc_out, 2), G1X), clamp_grid_y(rows), 1);
     if (haar)
-        k_dwt_inv1d<true><<<grid, kThreads, smem, st>>>(A, D, out, rows, nc, Nc_out, ff);
+        k_dwt_inv1d<T, true><<<grid, kThreads, smem, st>>>(A, D, out, rows, nc, Nc_out, ff);
     else
-        k_dwt_inv1d<false><<<grid, kThreads, smem, st>>>(A, D, out, rows, nc, Nc_out, ff);
+        k_dwt_inv1d<T, false><<<grid, kThreads, smem, st>>>(A, D, out, rows, nc, Nc_out, ff);
     return 1;
 }
 
-int pwt_launch_swt_fwd1d(const float* in, float* A, float* D, int rows, int Nc, int level,
-                         const PwtFilters& f, cudaStream_t st) {
+template <typename T>
+static int launch_swt_fwd1d_t(const T* in, T* A, T* D, int rows, int Nc, int level,
+                         const PwtFiltersT<T>& f, cudaStream_t st) {
     dim3 grid(cdiv(Nc, kThreads), clamp_grid_y(rows), 1);
-    k_swt_rows<false><<<grid, kThreads, 0, st>>>(in, nullptr, A, D, rows, Nc, 1 << (level - 1), f);
+    k_swt_rows<T, false><<<grid, kThreads, 0, st>>>(in, nullptr, A, D, rows, Nc, 1 << (level - 1), f);
     return 1;
 }
 
-int pwt_launch_swt_inv1d(const float* A, const float* D, float* out, int rows, int Nc, int level,
-                         const PwtFilters& f, cudaStream_t st) {
+template <typename T>
+static int launch_swt_inv1d_t(const T* A, const T* D, T* out, int rows, int Nc, int level,
+                         const PwtFiltersT<T>& f, cudaStream_t st) {
     dim3 grid(cdiv(Nc, kThreads), clamp_grid_y(rows), 1);
-    k_swt_rows<true><<<grid, kThreads, 0, st>>>(A, D, out, nullptr, rows, Nc, 1 << (level - 1), f);
+    k_swt_rows<T, true><<<grid, kThreads, 0, st>>>(A, D, out, nullptr, rows, Nc, 1 << (level - 1), f);
     return 1;
 }
 
-int pwt_launch_swt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, float* tmp,
-                         int batch, int Nr, int Nc, int level, const PwtFilters& f, cudaStream_t st) {
+template <typename T>
+static int launch_swt_fwd2d_t(const T* in, T* A, T* Hb, T* V, T* D, T* tmp,
+                         int batch, int Nr, int Nc, int level, const PwtFiltersT<T>& f, cudaStream_t st) {
     const long long plane = (long long)batch * Nr * Nc;
-    float* lo = tmp;
-    float* hi = tmp + plane;
+    T* lo = tmp;
+    T* hi = tmp + plane;
     const int s = 1 << (level - 1);
     dim3 g1(cdiv(Nc, kThreads), clamp_grid_y((long long)batch * Nr), 1);
-    k_swt_rows<false><<<g1, kThreads, 0, st>>>(in, nullptr, lo, hi, (long long)batch * Nr, Nc, s, f);
+    k_swt_rows<T, false><<<g1, kThreads, 0, st>>>(in, nullptr, lo, hi, (long long)batch * Nr, Nc, s, f);
     dim3 g2(cdiv(Nc, kThreads), clamp_grid_y(Nr), batch);
-    k_swt_cols<false><<<g2, kThreads, 0, st>>>(lo, hi, nullptr, nullptr, A, Hb, V, D, Nr, Nc, s, f);
+    k_swt_cols<T, false><<<g2, kThreads, 0, st>>>(lo, hi, nullptr, nullptr, A, Hb, V, D, Nr, Nc, s, f);
     return 2;
 }
 
-int pwt_launch_swt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out,
-                         float* tmp, int batch, int Nr, int Nc, int level, const PwtFilters& f,
+template <typename T>
+static int launch_swt_inv2d_t(const T* A, const T* Hb, const T* V, const T* D, T* out,
+                         T* tmp, int batch, int Nr, int Nc, int level, const PwtFiltersT<T>& f,
                          cudaStream_t st) {
     const long long plane = (long long)batch * Nr * Nc;
-    float* t1 = tmp;
-    float* t2 = tmp + plane;
+    T* t1 = tmp;
+    T* t2 = tmp + plane;
     const int s = 1 << (level - 1);
     dim3 g2(cdiv(Nc, kThreads), clamp_grid_y(Nr), batch);
-    k_swt_cols<true><<<g2, kThreads, 0, st>>>(A, Hb, V, D, t1, t2, nullptr, nullptr, Nr, Nc, s, f);
+    k_swt_cols<T, true><<<g2, kThreads, 0, st>>>(A, Hb, V, D, t1, t2, nullptr, nullptr, Nr, Nc, s, f);
     dim3 g1(cdiv(Nc, kThreads), clamp_grid_y((long long)batch * Nr), 1);
-    k_swt_rows<true><<<g1, kThreads, 0, st>>>(t1, t2, out, nullptr, (long long)batch * Nr, Nc, s, f);
+    k_swt_rows<T, true><<<g1, kThreads, 0, st>>>(t1, t2, out, nullptr, (long long)batch * Nr, Nc, s, f);
     return 2;
+}
+
+}  // namespace
+
+// =========================================================================================
+// launchers (float: the product path's fallback family; double: the fp64 plans of pwt_plan64.cu)
+// =========================================================================================
+int pwt_launch_dwt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc, long long in_bs, long long out_bs, const PwtFilters& f, bool haar, cudaStream_t st) {
+    return launch_dwt_fwd2d_t<float>(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, f, haar, st);
+}
+int pwt_launch_dwt_fwd2d_f64(const double* in, double* A, double* Hb, double* V, double* D, int batch, int Nr, int Nc, long long in_bs, long long out_bs, const PwtFilters64& f, bool haar, cudaStream_t st) {
+    return launch_dwt_fwd2d_t<double>(in, A, Hb, V, D, batch, Nr, Nc, in_bs, out_bs, f, haar, st);
+}
+int pwt_launch_dwt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch, int nr, int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs, const PwtFilters& f, bool haar, cudaStream_t st) {
+    return launch_dwt_inv2d_t<float>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, haar, st);
+}
+int pwt_launch_dwt_inv2d_f64(const double* A, const double* Hb, const double* V, const double* D, double* out, int batch, int nr, int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs, const PwtFilters64& f, bool haar, cudaStream_t st) {
+    return launch_dwt_inv2d_t<double>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, haar, st);
+}
+int pwt_launch_dwt_fwd1d(const float* in, float* A, float* D, int rows, int Nc, const PwtFilters& f, bool haar, cudaStream_t st) {
+    return launch_dwt_fwd1d_t<float>(in, A, D, rows, Nc, f, haar, st);
+}
+int pwt_launch_dwt_fwd1d_f64(const double* in, double* A, double* D, int rows, int Nc, const PwtFilters64& f, bool haar, cudaStream_t st) {
+    return launch_dwt_fwd1d_t<double>(in, A, D, rows, Nc, f, haar, st);
+}
+int pwt_launch_dwt_inv1d(const float* A, const float* D, float* out, int rows, int nc, int Nc_out, const PwtFilters& f, bool haar, cudaStream_t st) {
+    return launch_dwt_inv1d_t<float>(A, D, out, rows, nc, Nc_out, f, haar, st);
+}
+int pwt_launch_dwt_inv1d_f64(const double* A, const double* D, double* out, int rows, int nc, int Nc_out, const PwtFilters64& f, bool haar, cudaStream_t st) {
+    return launch_dwt_inv1d_t<double>(A, D, out, rows, nc, Nc_out, f, haar, st);
+}
+int pwt_launch_swt_fwd1d(const float* in, float* A, float* D, int rows, int Nc, int level, const PwtFilters& f, cudaStream_t st) {
+    return launch_swt_fwd1d_t<float>(in, A, D, rows, Nc, level, f, st);
+}
+int pwt_launch_swt_fwd1d_f64(const double* in, double* A, double* D, int rows, int Nc, int level, const PwtFilters64& f, cudaStream_t st) {
+    return launch_swt_fwd1d_t<double>(in, A, D, rows, Nc, level, f, st);
+}
+int pwt_launch_swt_inv1d(const float* A, const float* D, float* out, int rows, int Nc, int level, const PwtFilters& f, cudaStream_t st) {
+    return launch_swt_inv1d_t<float>(A, D, out, rows, Nc, level, f, st);
+}
+int pwt_launch_swt_inv1d_f64(const double* A, const double* D, double* out, int rows, int Nc, int level, const PwtFilters64& f, cudaStream_t st) {
+    return launch_swt_inv1d_t<double>(A, D, out, rows, Nc, level, f, st);
+}
+int pwt_launch_swt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, float* tmp, int batch, int Nr, int Nc, int level, const PwtFilters& f, cudaStream_t st) {
+    return launch_swt_fwd2d_t<float>(in, A, Hb, V, D, tmp, batch, Nr, Nc, level, f, st);
+}
+int pwt_launch_swt_fwd2d_f64(const double* in, double* A, double* Hb, double* V, double* D, double* tmp, int batch, int Nr, int Nc, int level, const PwtFilters64& f, cudaStream_t st) {
+    return launch_swt_fwd2d_t<double>(in, A, Hb, V, D, tmp, batch, Nr, Nc, level, f, st);
+}
+int pwt_launch_swt_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, float* tmp, int batch, int Nr, int Nc, int level, const PwtFilters& f, cudaStream_t st) {
+    return launch_swt_inv2d_t<float>(A, Hb, V, D, out, tmp, batch, Nr, Nc, level, f, st);
+}
+int pwt_launch_swt_inv2d_f64(const double* A, const double* Hb, const double* V, const double* D, double* out, double* tmp, int batch, int Nr, int Nc, int level, const PwtFilters64& f, cudaStream_t st) {
+    return launch_swt_inv2d_t<double>(A, Hb, V, D, out, tmp, batch, Nr, Nc, level, f, st);
 }
 
 int pwt_launch_ns_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr,

@@ -10,13 +10,16 @@
 
 // 1D filter bank, passed BY VALUE to kernels (lands in the constant bank as kernel
 // parameters, so every instance has its own filters -- fixes reference quirk Q4).
-struct PwtFilters {
-    float L[PWT_MAX_TAPS];    // analysis low-pass   (dec_lo)
-    float H[PWT_MAX_TAPS];    // analysis high-pass  (dec_hi)
-    float IL[PWT_MAX_TAPS];   // synthesis low-pass  (rec_lo)
-    float IH[PWT_MAX_TAPS];   // synthesis high-pass (rec_hi)
+template <typename T>
+struct PwtFiltersT {
+    T L[PWT_MAX_TAPS];        // analysis low-pass   (dec_lo)
+    T H[PWT_MAX_TAPS];        // analysis high-pass  (dec_hi)
+    T IL[PWT_MAX_TAPS];       // synthesis low-pass  (rec_lo)
+    T IH[PWT_MAX_TAPS];       // synthesis high-pass (rec_hi)
     int hlen;
 };
+using PwtFilters = PwtFiltersT<float>;
+using PwtFilters64 = PwtFiltersT<double>;   // the reference's DOUBLEPRECISION build (filters.h:16-30): taps not rounded to fp32
 
 // Taps packed for the 2-wide FMA of sm_100 (FFMA2: one sample times a pair of taps).  FFMA2 issues at half the
 // rate of FFMA with the same FMA-pipe throughput (tools/bench/fma2bench.cu): it halves the issue slots the
@@ -194,6 +197,24 @@ int pwt_launch_swt_fwd1d(const float* in, float* A, float* D, int rows, int Nc, 
                          const PwtFilters& f, cudaStream_t st);
 int pwt_launch_swt_inv1d(const float* A, const float* D, float* out, int rows, int Nc, int level,
                          const PwtFilters& f, cudaStream_t st);
+// the same kernels instantiated for double (pwt_plan64.cu)
+int pwt_launch_dwt_fwd2d_f64(const double* in, double* A, double* Hb, double* V, double* D, int batch, int Nr,
+                             int Nc, long long in_bs, long long out_bs, const PwtFilters64& f, bool haar, cudaStream_t st);
+int pwt_launch_dwt_inv2d_f64(const double* A, const double* Hb, const double* V, const double* D, double* out,
+                             int batch, int nr, int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs,
+                             const PwtFilters64& f, bool haar, cudaStream_t st);
+int pwt_launch_dwt_fwd1d_f64(const double* in, double* A, double* D, int rows, int Nc, const PwtFilters64& f, bool haar,
+                             cudaStream_t st);
+int pwt_launch_dwt_inv1d_f64(const double* A, const double* D, double* out, int rows, int nc, int Nc_out,
+                             const PwtFilters64& f, bool haar, cudaStream_t st);
+int pwt_launch_swt_fwd2d_f64(const double* in, double* A, double* Hb, double* V, double* D, double* tmp, int batch, int Nr,
+                             int Nc, int level, const PwtFilters64& f, cudaStream_t st);
+int pwt_launch_swt_inv2d_f64(const double* A, const double* Hb, const double* V, const double* D, double* out, double* tmp,
+                             int batch, int Nr, int Nc, int level, const PwtFilters64& f, cudaStream_t st);
+int pwt_launch_swt_fwd1d_f64(const double* in, double* A, double* D, int rows, int Nc, int level, const PwtFilters64& f,
+                             cudaStream_t st);
+int pwt_launch_swt_inv1d_f64(const double* A, const double* D, double* out, int rows, int Nc, int level,
+                             const PwtFilters64& f, cudaStream_t st);
 // non-separable (true 2D stencils).  k2d = device array of 4*hlen*hlen taps: LL, LH, HL, HH.
 int pwt_launch_ns_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr,
                         int Nc, long long in_bs, long long out_bs, const float* k2d, int hlen,

@@ -30,6 +30,10 @@ static int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+int pwt_set_error(int code, const char* msg) {       // for the other translation units (pwt_plan64.cu, pwt_vol.cu)
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
 #define CK(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \

@@ -89,6 +89,30 @@ cdef extern from "pwt_b200.h":
     int pwt_comm_init_all(pwt_plan** plans, int n) nogil
     int pwt_norms_allreduce_group(pwt_plan** plans, int n, double* n1, double* n2) nogil
 
+    # double precision (the reference's DOUBLEPRECISION build, filters.h:16-30)
+    ctypedef struct pwt64_plan:
+        pass
+    int pwt64_create(pwt64_plan** out, const double* img, int batch, int Nr, int Nc, const char* wname, int levels,
+                     int memisonhost, int do_separable, int do_cycle_spinning, int do_swt, int ndim) nogil
+    void pwt64_destroy(pwt64_plan* p) nogil
+    int pwt64_get_info(const pwt64_plan* p, pwt_info* info) nogil
+    int pwt64_band_shape(const pwt64_plan* p, int num, int* nr, int* nc) nogil
+    int pwt64_forward(pwt64_plan* p) nogil
+    int pwt64_inverse(pwt64_plan* p) nogil
+    int pwt64_soft_threshold(pwt64_plan* p, double beta, int app, int normalize) nogil
+    int pwt64_hard_threshold(pwt64_plan* p, double beta, int app, int normalize) nogil
+    int pwt64_shrink(pwt64_plan* p, double beta, int app) nogil
+    int pwt64_norms(pwt64_plan* p, double* n1, double* n2) nogil
+    int pwt64_get_image(pwt64_plan* p, double* dst) nogil
+    int pwt64_set_image(pwt64_plan* p, const double* img, int on_device) nogil
+    int pwt64_get_coeff(pwt64_plan* p, double* dst, int num) nogil
+    int pwt64_set_coeff(pwt64_plan* p, const double* src, int num, int on_device) nogil
+    int pwt64_sync(pwt64_plan* p) nogil
+    int pwt64_timer_start(pwt64_plan* p) nogil
+    int pwt64_timer_stop(pwt64_plan* p, float* ms) nogil
+    long long pwt64_launch_count(const pwt64_plan* p) nogil
+    int pwt64_lookup_filters(const char* wname, double* L, double* H, double* IL, double* IH) nogil
+
 PWT_ERR_UNKNOWN_WAVELET = -2
 PWT_ERR_UNSUPPORTED = -6
 PWT_ERR_TOO_SMALL = -7
@@ -874,3 +898,225 @@ cdef class Wavelets:
     def version(cls):
         """Version string of the library this is a drop-in for."""
         return pwt_version().decode("ASCII")
+
+
+def lookup_filters64(str wname):
+    """(L, H, IL, IH) of a built-in bank at the table's full (double) precision."""
+    cdef double L[40]
+    cdef double H[40]
+    cdef double IL[40]
+    cdef double IH[40]
+    b = wname.encode("ASCII")
+    cdef int hlen = pwt64_lookup_filters(b, L, H, IL, IH)
+    if hlen < 0:
+        raise ValueError("unknown wavelet name '%s'" % wname)
+    return (np.array([L[k] for k in range(hlen)], dtype=np.float64), np.array([H[k] for k in range(hlen)], dtype=np.float64),
+            np.array([IL[k] for k in range(hlen)], dtype=np.float64), np.array([IH[k] for k in range(hlen)], dtype=np.float64))
+
+
+cdef class Wavelets64:
+    """Double-precision counterpart of `Wavelets`: the reference's DOUBLEPRECISION build (libpdwtd.so,
+    pdwt/src/filters.h:16-30), which its Python wrapper cannot reach.  Same constructor arguments and attribute /
+    method names (pypwt.pyx:64-118); images and coefficients are float64.  Not carried over: custom filter banks,
+    add_wavelet, device-array interop."""
+    cdef pwt64_plan* w
+    cdef readonly int Nr
+    cdef readonly int Nc
+    cdef readonly list sizes
+    cdef readonly str wname
+    cdef readonly int levels
+    cdef readonly int do_cycle_spinning
+    cdef readonly int hlen
+    cdef readonly int do_swt
+    cdef readonly int do_separable
+    cdef readonly int ndim
+    cdef readonly int batched1d
+    cdef readonly int batch
+    cdef tuple shape
+    cdef int _is1d
+    cdef int _nbands
+
+    def __cinit__(self, img, str wname, int levels, int do_separable=1, int do_cycle_spinning=0, int do_swt=0, int ndim=2):
+        self.w = NULL
+        img = np.ascontiguousarray(img, dtype=np.float64)
+        ishape = tuple(int(x) for x in img.shape)
+        indim = len(ishape)
+        ndim = min(ndim, 2)
+        self.batched1d = 0
+        self.batch = 1
+        if indim == 2:
+            self.Nr, self.Nc = ishape
+            if indim != ndim:
+                self.batched1d = 1
+        elif indim == 1:
+            self.Nr, self.Nc = 1, ishape[0]
+        elif indim == 3 and ndim == 2:
+            self.batch, self.Nr, self.Nc = ishape
+        else:
+            raise NotImplementedError("Wavelets64(): Only 1D and 2D transforms are supported for now")
+        self.shape = ishape
+        self.wname = wname
+        self.do_cycle_spinning = do_cycle_spinning
+        self.do_swt = do_swt
+        self.ndim = indim
+        if pwt_device_count() < 1:
+            raise RuntimeError("pycudwt: no CUDA device available (there is no CPU fallback)")
+        py_wname = wname.encode("ASCII")
+        cdef const double* src = <const double*> <size_t> img.ctypes.data
+        cdef const char* c_wname = py_wname
+        cdef int rc, c_ndim = ndim, c_levels = levels, c_sep = do_separable
+        with nogil:
+            rc = pwt64_create(&self.w, src, self.batch, self.Nr, self.Nc, c_wname, c_levels, 1, c_sep,
+                              self.do_cycle_spinning, self.do_swt, c_ndim)
+        if rc != 0:
+            self.w = NULL
+            msg = _errmsg()
+            if rc in (PWT_ERR_UNKNOWN_WAVELET, PWT_ERR_TOO_SMALL, PWT_ERR_UNSUPPORTED, -1):
+                raise ValueError(msg)
+            raise RuntimeError(msg)
+        cdef pwt_info info
+        pwt64_get_info(self.w, &info)
+        self.levels = info.nlevels
+        self.hlen = info.hlen
+        self.do_separable = info.do_separable
+        self._is1d = 1 if info.ndims == 1 else 0
+        self._nbands = info.nbands
+        cdef int nr = 0, nc = 0
+        per = 1 if self._is1d else 3
+        self.sizes = []
+        for i in range(self.levels):
+            pwt64_band_shape(self.w, per * i + 1, &nr, &nc)
+            self.sizes.append((nr, nc))
+
+    def _band(self, int num, shp):
+        lead = (self.batch,) if len(self.shape) == 3 else ()
+        out = np.empty(lead + tuple(shp), dtype=np.float64)
+        cdef double* dst = <double*> <size_t> out.ctypes.data
+        cdef int n
+        with nogil:
+            n = pwt64_get_coeff(self.w, dst, num)
+        if n == 0:
+            raise RuntimeError("Wavelets64.coeffs: the coefficients were consumed by inverse()")
+        return out
+
+    @property
+    def coeffs(self):
+        """[A, [H1, V1, D1], ...] (2D) or [A, D1, ...] (1D / batched 1D), float64, level 1 = finest (pypwt.pyx:261-306)."""
+        res = [self._band(0, self.sizes[-1])]
+        for i in range(self.levels):
+            if self._is1d:
+                res.append(self._band(i + 1, self.sizes[i]))
+            else:
+                res.append([self._band(3 * i + 1 + j, self.sizes[i]) for j in range(3)])
+        return res
+
+    @property
+    def image(self):
+        out = np.empty(self.shape, dtype=np.float64)
+        cdef double* dst = <double*> <size_t> out.ctypes.data
+        cdef int n
+        with nogil:
+            n = pwt64_get_image(self.w, dst)
+        if n == 0:
+            raise RuntimeError(_errmsg())
+        return out
+
+    def set_image(self, img):
+        img = np.ascontiguousarray(img, dtype=np.float64)
+        if tuple(img.shape) != self.shape:
+            raise ValueError("Wavelets64.set_image(): shape mismatch %s != %s" % (img.shape, self.shape))
+        cdef const double* src = <const double*> <size_t> img.ctypes.data
+        cdef int rc
+        with nogil:
+            rc = pwt64_set_image(self.w, src, 0)
+        if rc != 0:
+            raise RuntimeError(_errmsg())
+
+    def set_coeff(self, arr, int num):
+        cdef int nr = 0, nc = 0
+        if num < 0 or num >= self._nbands:
+            raise ValueError("Wavelets64.set_coeff(): band %d out of range" % num)
+        pwt64_band_shape(self.w, num, &nr, &nc)
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        if arr.size != self.batch * nr * nc:
+            raise ValueError("Wavelets64.set_coeff(): band %d holds %d values, got %d" % (num, self.batch * nr * nc, arr.size))
+        cdef const double* src = <const double*> <size_t> arr.ctypes.data
+        cdef int rc
+        with nogil:
+            rc = pwt64_set_coeff(self.w, src, num, 0)
+        if rc != 0:
+            raise RuntimeError(_errmsg())
+
+    def forward(self, img=None):
+        if img is not None:
+            self.set_image(img)
+        cdef int rc
+        with nogil:
+            rc = pwt64_forward(self.w)
+        if rc != 0:
+            raise RuntimeError(_errmsg())
+
+    def inverse(self):
+        cdef int rc
+        with nogil:
+            rc = pwt64_inverse(self.w)
+        if rc < 0:
+            raise RuntimeError(_errmsg())
+
+    def soft_threshold(self, double beta, int do_threshold_appcoeffs=0, int normalize=0):
+        if pwt64_soft_threshold(self.w, beta, do_threshold_appcoeffs, normalize) < 0:
+            raise RuntimeError(_errmsg())
+
+    def hard_threshold(self, double beta, int do_threshold_appcoeffs=0, int normalize=0):
+        if pwt64_hard_threshold(self.w, beta, do_threshold_appcoeffs, normalize) < 0:
+            raise RuntimeError(_errmsg())
+
+    def shrink(self, double beta, int do_threshold_appcoeffs=1):
+        if pwt64_shrink(self.w, beta, do_threshold_appcoeffs) < 0:
+            raise RuntimeError(_errmsg())
+
+    def norms(self):
+        cdef double a = 0, b = 0
+        cdef int rc
+        with nogil:
+            rc = pwt64_norms(self.w, &a, &b)
+        if rc != 0:
+            raise RuntimeError(_errmsg())
+        return a, b
+
+    def norm1(self):
+        return self.norms()[0]
+
+    def norm2sq(self):
+        return self.norms()[1]
+
+    def sync(self):
+        pwt64_sync(self.w)
+
+    def timer_start(self):
+        if pwt64_timer_start(self.w) != 0:
+            raise RuntimeError(_errmsg())
+
+    def timer_stop(self):
+        cdef float ms = 0
+        cdef int rc
+        with nogil:
+            rc = pwt64_timer_stop(self.w, &ms)
+        if rc != 0:
+            raise RuntimeError(_errmsg())
+        return ms
+
+    @property
+    def launch_count(self):
+        return int(pwt64_launch_count(self.w))
+
+    @property
+    def current_shift(self):
+        cdef pwt_info info
+        pwt64_get_info(self.w, &info)
+        return (info.shift_r, info.shift_c)
+
+    def __dealloc__(self):
+        if self.w is not NULL:
+            pwt64_destroy(self.w)
+            self.w = NULL
