@@ -199,6 +199,33 @@ int pwt64_timer_stop(pwt64_plan* p, float* ms);
 long long pwt64_launch_count(const pwt64_plan* p);
 int pwt64_lookup_filters(const char* wname, double* L, double* H, double* IL, double* IH);
 
+/* ---- volumetric (3D) separable DWT ------------------------------------------ */
+/* The reference stops at 2D ("3D is not handled", pdwt/README.md:29; pypwt.pyx:155-156 raises on 3D input).  Same
+ * conventions carried to volumes [Nz][Ny][Nx]: periodisation (separable.cu:98-102), ceil halving per axis (utils.cu:24),
+ * level clip over the smallest axis (wt.cu:156-165); x is filtered first, then y, then z.  Bands of level l (1 = finest)
+ * are indexed b = 4 dz + 2 dy + dx, d = 1 meaning the high-pass along that axis: b = 1..7 are pywt.wavedecn's
+ * 'aad','ada','add','daa','dad','dda','ddd'; the approximation is (level = nlevels, b = 0). */
+typedef struct pwt3_plan pwt3_plan;
+int pwt3_create(pwt3_plan** out, const float* vol, int Nz, int Ny, int Nx, const char* wname, int levels, int memisonhost);
+void pwt3_destroy(pwt3_plan* p);
+int pwt3_levels(const pwt3_plan* p);
+int pwt3_band_shape(const pwt3_plan* p, int level, int* nz, int* ny, int* nx);
+int pwt3_forward(pwt3_plan* p);
+int pwt3_inverse(pwt3_plan* p);                                   /* returns 1 if refused (already inverted) */
+int pwt3_soft_threshold(pwt3_plan* p, float beta, int do_thresh_appcoeffs);   /* common.cu:13-22 on every detail band */
+int pwt3_hard_threshold(pwt3_plan* p, float beta, int do_thresh_appcoeffs);   /* common.cu:56-64 */
+int pwt3_norms(pwt3_plan* p, double* norm1, double* norm2sq);
+int pwt3_get_image(pwt3_plan* p, float* dst);
+int pwt3_set_image(pwt3_plan* p, const float* vol, int mem_is_on_device);
+int pwt3_get_coeff(pwt3_plan* p, float* dst, int level, int b);
+int pwt3_set_coeff(pwt3_plan* p, const float* src, int level, int b, int mem_is_on_device);
+intptr_t pwt3_coeff_ptr(pwt3_plan* p, int level, int b);
+intptr_t pwt3_image_ptr(pwt3_plan* p);
+int pwt3_sync(pwt3_plan* p);
+int pwt3_timer_start(pwt3_plan* p);
+int pwt3_timer_stop(pwt3_plan* p, float* ms);
+long long pwt3_launch_count(const pwt3_plan* p);
+
 #ifdef __cplusplus
 }
 #endif

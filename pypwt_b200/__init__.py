@@ -28,6 +28,8 @@ if "PWT_NCCL_LIB" not in _os.environ:
 
 Wavelets = _ext.Wavelets
 Wavelets64 = _ext.Wavelets64
+Wavelets3D = _ext.Wavelets3D
+VOLUME_BAND_KEYS = _ext.VOLUME_BAND_KEYS
 lookup_filters64 = _ext.lookup_filters64
 pinned_empty = _ext.pinned_empty
 pinned_zeros = _ext.pinned_zeros
@@ -40,5 +42,5 @@ norms_allreduce_group = _ext.norms_allreduce_group
 DeviceArray = _ext.DeviceArray
 LIBRARY_PATH = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "libpwt_b200.so")
 __version__ = "1.0.3"
-__all__ = ["Wavelets", "Wavelets64", "lookup_filters64", "pinned_empty", "pinned_zeros", "device_count", "set_device", "lookup_filters",
+__all__ = ["Wavelets", "Wavelets64", "Wavelets3D", "VOLUME_BAND_KEYS", "lookup_filters64", "pinned_empty", "pinned_zeros", "device_count", "set_device", "lookup_filters",
            "comm_unique_id", "comm_init_all", "norms_allreduce_group", "DeviceArray", "LIBRARY_PATH"]

@@ -317,6 +317,12 @@ int pwt_strip_dwt_inv1d(const float* A, const float* D, float* out, int rows, in
 // Haar, batched 1D, width multiple of 8: flat streaming butterfly.  Return 0 when not covered.
 int pwt_haar_fwd1d_flat(const float* in, float* A, float* D, int rows, int Nc, cudaStream_t st);
 int pwt_haar_inv1d_flat(const float* A, const float* D, float* out, int rows, int nc, int Nc_out, cudaStream_t st);
+// pwt_plan.cu : one separable 2D level over a stack with the automatic kernel choice (for pwt_vol.cu)
+int pwt_level_fwd2d(const float* src, float* A, float* Hb, float* V, float* D, int batch, int nr, int nc, long long in_bs,
+                    long long out_bs, const PwtFilters& f, bool haar, cudaStream_t st);
+int pwt_level_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* dst, int batch, int nr, int nc,
+                    int Nro, int Nco, long long in_bs, long long out_bs, const PwtFilters& f, bool haar, cudaStream_t st);
+int pwt_set_error(int code, const char* msg);
 // kernels_row1d.cu : batched 1D DWT / IDWT, every level in ONE launch (rows staged once in shared memory).  D[l] = detail
 // band of level l + 1.  Return 0 when not covered (row too long for a CTA's shared memory, odd filter length).
 int pwt_row_dwt_fwd1d_all(const float* in, float* A, float* const* D, int rows, int Nc, int L, const PwtFilters& f,

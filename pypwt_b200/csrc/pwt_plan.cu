@@ -825,6 +825,36 @@ extern "C" int pwt_forward(pwt_plan* p) {
     return PWT_OK;
 }
 
+// One separable 2D level over a stack of planes with the automatic kernel choice of pwt_forward / pwt_inverse (strip
+// kernels for F >= 8 on large planes, register kernels, tile / shared-memory kernels, generic).  Used by the volumetric
+// plans (pwt_vol.cu), whose x-y passes are batched 2D levels.  Returns the number of launches.
+int pwt_level_fwd2d(const float* src, float* A, float* Hb, float* V, float* D, int batch, int nr, int nc, long long in_bs,
+                    long long out_bs, const PwtFilters& f, bool haar, cudaStream_t st) {
+    const PwtTuning& k = pwt_tuning();
+    int n = 0;
+    if (!haar && f.hlen >= k.strip_min_f && nr >= 64 && nc >= 256)
+        n = pwt_strip_dwt_fwd2d(src, A, Hb, V, D, batch, nr, nc, in_bs, out_bs, f, st);
+    if (!n) n = pwt_reg_dwt_fwd2d(src, A, Hb, V, D, batch, nr, nc, in_bs, out_bs, f, haar, 0, st);
+    if (!n && !haar && f.hlen >= k.tile_min_f && nr >= 64 && nc >= 64)
+        n = pwt_tile_dwt_fwd2d(src, A, Hb, V, D, batch, nr, nc, in_bs, out_bs, f, st);
+    if (!n) n = pwt_fast_dwt_fwd2d(src, A, Hb, V, D, batch, nr, nc, in_bs, out_bs, f, haar, 0, st);
+    if (!n) n = pwt_launch_dwt_fwd2d(src, A, Hb, V, D, batch, nr, nc, in_bs, out_bs, f, haar, st);
+    return n;
+}
+int pwt_level_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* dst, int batch, int nr, int nc,
+                    int Nro, int Nco, long long in_bs, long long out_bs, const PwtFilters& f, bool haar, cudaStream_t st) {
+    const PwtTuning& k = pwt_tuning();
+    int n = 0;
+    if (!haar && f.hlen >= k.strip_min_f && nr >= 32 && nc >= 128)
+        n = pwt_strip_dwt_inv2d(A, Hb, V, D, dst, batch, nr, nc, Nro, Nco, in_bs, out_bs, f, st);
+    if (!n) n = pwt_reg_dwt_inv2d(A, Hb, V, D, dst, batch, nr, nc, Nro, Nco, in_bs, out_bs, f, haar, 0, st);
+    if (!n && !haar && f.hlen >= k.tile_min_f && nr >= 32 && nc >= 32)
+        n = pwt_tile_dwt_inv2d(A, Hb, V, D, dst, batch, nr, nc, Nro, Nco, in_bs, out_bs, f, st);
+    if (!n) n = pwt_fast_dwt_inv2d(A, Hb, V, D, dst, batch, nr, nc, Nro, Nco, in_bs, out_bs, f, haar, 0, st);
+    if (!n) n = pwt_launch_dwt_inv2d(A, Hb, V, D, dst, batch, nr, nc, Nro, Nco, in_bs, out_bs, f, haar, st);
+    return n;
+}
+
 // ---- inverse ----------------------------------------------------------------------------------
 extern "C" int pwt_inverse(pwt_plan* p) {
     if (!p) return fail(PWT_ERR_ARG, "null plan");

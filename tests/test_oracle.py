@@ -350,3 +350,57 @@ def test_odd_length_nonseparable_banks_equal_padded_even_banks(hlen):
     for x, y in zip(a, b):
         np.testing.assert_allclose(x, y, atol=1e-12)
     np.testing.assert_allclose(E.ns_inverse_swt(*a, IK, 1), E.ns_inverse_swt(*a, _pad2(IK, "back"), 1), atol=1e-12)
+
+
+def test_volume_oracle_properties():
+    """oracle/dwt3_oracle.py (composition of the pinned 1D closed forms): perfect reconstruction for even and odd sizes,
+    energy preservation for orthogonal banks on even sizes, and consistency with the 2D oracle on a volume that is
+    constant along z."""
+    from oracle import dwt3_oracle as D
+    rng = np.random.default_rng(0)
+    for shp in ((40, 44, 48), (31, 37, 43)):
+        v = rng.standard_normal(shp).astype(np.float32)
+        for wn in ("haar", "db2", "bior2.4"):
+            W = D.OracleWavelets3D(v, wn, 2)
+            W.forward()
+            if shp[0] % 4 == 0 and wn != "bior2.4":
+                assert abs(W.norm2sq() / (v.astype(np.float64) ** 2).sum() - 1) < 1e-6
+            assert set(W.coeffs[1]) == set(D.KEYS)
+            W.inverse()
+            assert np.abs(W.image - v).max() < 2e-6
+    sl = rng.standard_normal((16, 24)).astype(np.float32)
+    W = D.OracleWavelets3D(np.repeat(sl[None], 8, axis=0), "db2", 1)
+    W.forward()
+    W2 = O.OracleWavelets(sl, "db2", 1)
+    W2.forward()
+    assert np.abs(W.coeffs[0][0] - np.sqrt(2) * W2.coeffs[0]).max() < 1e-5
+    assert np.abs(W.coeffs[1]["ada"][0] - np.sqrt(2) * W2.coeffs[1][0]).max() < 1e-5
+    assert np.abs(W.coeffs[1]["aad"][0] - np.sqrt(2) * W2.coeffs[1][1]).max() < 1e-5
+    assert np.abs(W.coeffs[1]["daa"]).max() < 1e-5
+    try:
+        import pywt
+    except ImportError:
+        return
+    v = rng.standard_normal((32, 40, 48)).astype(np.float32)
+    W = D.OracleWavelets3D(v, "db3", 2)
+    W.forward()
+    ref = pywt.wavedecn(v.astype(np.float64), "db3", mode="periodization", level=2)
+    assert np.abs(W.coeffs[0] - ref[0]).max() < 1e-5
+    for lev in (1, 2):
+        for k in D.KEYS:
+            assert np.abs(W.coeffs[lev][k] - ref[-lev][k]).max() < 1e-5
+
+
+def test_double_build_oracle():
+    """double_build=True (the DOUBLEPRECISION build): samples, table and thresholds stay float64."""
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((64, 80))
+    W = O.OracleWavelets(x, "db4", 3, double_build=True)
+    W.forward()
+    assert W.coeffs[0].dtype == np.float64 and W.coeffs[1][0].dtype == np.float64
+    W.soft_threshold(0.0)
+    W.inverse()
+    assert np.abs(W.image - x).max() < 1e-9            # limited by the table's own precision (SURVEY 8a a14)
+    W32 = O.OracleWavelets(x, "db4", 3)
+    W32.forward(); W32.inverse()
+    assert np.abs(W32.image - x).max() > 1e-9          # fp32-rounded samples and taps
