@@ -285,6 +285,265 @@ k_row_inv(const float* __restrict__ A, float* __restrict__ out, const __grid_con
     }
 }
 
+// =====================================================================================================
+// Batched 1D stationary (a trous) transform, every level in one launch (reference: w_forward_swt_separable_1d
+// separable.cu:519-537, w_inverse_swt_separable_1d :653-672: one launch per level, 12 B/px each; here 4 + 4 (L + 1) B/px
+// per direction).  A row is staged once; level l filters it with dilation s = 2^(l-1) and period N (no odd
+// extension): out[g] = sum_j f[F-1-j] * in[(g + (j - c) s) mod N], c = F/2 - 1 (analysis), c = F/2 and taps / 2
+// (synthesis, separable.cu:553-626).  The approximation ping-pongs between two shared rows, detail rows go to / come
+// from global memory.  4 adjacent outputs per thread: dilations that are multiples of 4 read one aligned 128-bit
+// group per tap, s = 1 and s = 2 read the contiguous window once; wrap-around per 128-bit group (N % 4 == 0).
+// =====================================================================================================
+struct SwtLevels {
+    float* D[PWT_MAX_LEVELS];
+    int L;
+};
+struct TapsDup1d {                // synthesis taps halved and duplicated: l[j] = (IL[F-1-j] / 2, same), h likewise
+    float2 l[PWT_MAX_TAPS];
+    float2 h[PWT_MAX_TAPS];
+};
+__device__ __forceinline__ int wrapq(int q, int nq) {          // -nq <= q < 2 nq
+    if (q < 0) q += nq;
+    else if (q >= nq) q -= nq;
+    return q;
+}
+
+template <int F, int SM>
+__device__ __forceinline__ void swt_fwd_level(const float* __restrict__ cur, float* __restrict__ nxt, int pitch, float* __restrict__ Dg,
+                                              float* __restrict__ Ag, bool last, int nr, int N, int s, const PwtTapsFwd& tp, int tid) {
+    constexpr int C = F / 2 - 1;
+    const int nq = N >> 2;
+    const int tb = log2_ceil_cap(nq), T = 1 << tb;
+    for (int r = tid >> tb; r < nr; r += NT >> tb) {
+        const float* crow = cur + r * pitch;
+        for (int g4 = tid & (T - 1); g4 < nq; g4 += T) {
+            float2 p0 = make_float2(0.f, 0.f), p1 = p0, p2 = p0, p3 = p0;
+            if (SM == 0) {
+                const int sq = s >> 2;
+                int q = mod_pos(g4 - C * sq, nq);
+#pragma unroll
+                for (int j = 0; j < F; j++) {
+                    const float4 x = lds4(crow, q);
+                    p0 = fma2s(x.x, tp.t[j], p0);
+                    p1 = fma2s(x.y, tp.t[j], p1);
+                    p2 = fma2s(x.z, tp.t[j], p2);
+                    p3 = fma2s(x.w, tp.t[j], p3);
+                    q += sq;
+                    if (q >= nq) q -= nq;
+                }
+            } else {
+                constexpr int S = SM;
+                constexpr int OFF = (4 - (C * S) % 4) % 4;              // the window starts OFF floats into its first group
+                constexpr int NV = (OFF + 4 + (F - 1) * S + 3) / 4;
+                int q = mod_pos(g4 - (C * S + OFF) / 4, nq);
+                float w[4 * NV];
+#pragma unroll
+                for (int k = 0; k < NV; k++) {
+                    const float4 x = lds4(crow, q);
+                    w[4 * k] = x.x; w[4 * k + 1] = x.y; w[4 * k + 2] = x.z; w[4 * k + 3] = x.w;
+                    q = q + 1 == nq ? 0 : q + 1;
+                }
+#pragma unroll
+                for (int j = 0; j < F; j++) {
+                    p0 = fma2s(w[OFF + j * S], tp.t[j], p0);
+                    p1 = fma2s(w[OFF + 1 + j * S], tp.t[j], p1);
+                    p2 = fma2s(w[OFF + 2 + j * S], tp.t[j], p2);
+                    p3 = fma2s(w[OFF + 3 + j * S], tp.t[j], p3);
+                }
+            }
+            const size_t o = (size_t)r * N + 4 * g4;
+            stg_cs(reinterpret_cast<float4*>(Dg + o), make_float4(p0.y, p1.y, p2.y, p3.y));
+            const float4 lo = make_float4(p0.x, p1.x, p2.x, p3.x);
+            if (last) stg_cs(reinterpret_cast<float4*>(Ag + o), lo);
+            else sts4(nxt + r * pitch, g4, lo);
+        }
+    }
+}
+
+template <int F>
+__global__ void __launch_bounds__(NT)
+k_row_swt_fwd(const float* __restrict__ in, float* __restrict__ A, const __grid_constant__ SwtLevels lv,
+              const __grid_constant__ PwtTapsFwd tp, int rows, int N, int R, int pitch) {
+    extern __shared__ __align__(16) float sm[];
+    float* buf0 = sm;
+    float* buf1 = sm + (size_t)R * pitch;
+    const int tid = threadIdx.x, L = lv.L;
+    const int ngroups = (rows + R - 1) / R;
+    pwt_pdl_wait();
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int r0 = g * R, nr = rows - r0 < R ? rows - r0 : R;
+        if (g + (int)gridDim.x >= ngroups) pwt_pdl_trigger();
+        stage_rows(buf0, pitch, 0, in + (size_t)r0 * N, nr, N, tid);
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncthreads();
+        float* cur = buf0;
+        float* nxt = buf1;
+        for (int l = 1; l <= L; l++) {
+            float* Dg = lv.D[l - 1] + (size_t)r0 * N;
+            float* Ag = A + (size_t)r0 * N;
+            if (l == 1) swt_fwd_level<F, 1>(cur, nxt, pitch, Dg, Ag, l == L, nr, N, 1, tp, tid);
+            else if (l == 2) swt_fwd_level<F, 2>(cur, nxt, pitch, Dg, Ag, l == L, nr, N, 2, tp, tid);
+            else swt_fwd_level<F, 0>(cur, nxt, pitch, Dg, Ag, l == L, nr, N, 1 << (l - 1), tp, tid);
+            __syncthreads();
+            float* t = cur; cur = nxt; nxt = t;
+        }
+    }
+}
+
+template <int F, int SM>
+__device__ __forceinline__ void swt_inv_level(const float* __restrict__ ca, const float* __restrict__ cd, float* __restrict__ na, int pitch,
+                                              float* __restrict__ Og, bool final, int nr, int N, int s, const TapsDup1d& tp, int tid) {
+    constexpr int C = F / 2;
+    const int nq = N >> 2;
+    const int tb = log2_ceil_cap(nq), T = 1 << tb;
+    for (int r = tid >> tb; r < nr; r += NT >> tb) {
+        const float* arow = ca + r * pitch;
+        const float* drow = cd + r * pitch;
+        for (int g4 = tid & (T - 1); g4 < nq; g4 += T) {
+            float2 e01 = make_float2(0.f, 0.f), e23 = e01;             // outputs 4 g4 .. 4 g4 + 3
+            if (SM == 0) {
+                const int sq = s >> 2;
+                int q = mod_pos(g4 - C * sq, nq);
+#pragma unroll
+                for (int j = 0; j < F; j++) {
+                    const float4 x = lds4(arow, q), y = lds4(drow, q);
+                    e01 = __ffma2_rn(make_float2(x.x, x.y), tp.l[j], e01);
+                    e23 = __ffma2_rn(make_float2(x.z, x.w), tp.l[j], e23);
+                    e01 = __ffma2_rn(make_float2(y.x, y.y), tp.h[j], e01);
+                    e23 = __ffma2_rn(make_float2(y.z, y.w), tp.h[j], e23);
+                    q += sq;
+                    if (q >= nq) q -= nq;
+                }
+            } else {
+                constexpr int S = SM;
+                constexpr int OFF = (4 - (C * S) % 4) % 4;
+                constexpr int NV = (OFF + 4 + (F - 1) * S + 3) / 4;
+                int q = mod_pos(g4 - (C * S + OFF) / 4, nq);
+                float wa[4 * NV], wd[4 * NV];
+#pragma unroll
+                for (int k = 0; k < NV; k++) {
+                    const float4 x = lds4(arow, q), y = lds4(drow, q);
+                    wa[4 * k] = x.x; wa[4 * k + 1] = x.y; wa[4 * k + 2] = x.z; wa[4 * k + 3] = x.w;
+                    wd[4 * k] = y.x; wd[4 * k + 1] = y.y; wd[4 * k + 2] = y.z; wd[4 * k + 3] = y.w;
+                    q = q + 1 == nq ? 0 : q + 1;
+                }
+#pragma unroll
+                for (int j = 0; j < F; j++) {
+                    e01 = __ffma2_rn(make_float2(wa[OFF + j * S], wa[OFF + 1 + j * S]), tp.l[j], e01);
+                    e23 = __ffma2_rn(make_float2(wa[OFF + 2 + j * S], wa[OFF + 3 + j * S]), tp.l[j], e23);
+                    e01 = __ffma2_rn(make_float2(wd[OFF + j * S], wd[OFF + 1 + j * S]), tp.h[j], e01);
+                    e23 = __ffma2_rn(make_float2(wd[OFF + 2 + j * S], wd[OFF + 3 + j * S]), tp.h[j], e23);
+                }
+            }
+            const float4 o = make_float4(e01.x, e01.y, e23.x, e23.y);
+            if (final) stg_cs(reinterpret_cast<float4*>(Og + (size_t)r * N + 4 * g4), o);
+            else sts4(na + r * pitch, g4, o);
+        }
+    }
+}
+
+// shared layout: [R x pitch : a][R x pitch : a'][R x pitch : details of the level being synthesised]
+template <int F>
+__global__ void __launch_bounds__(NT)
+k_row_swt_inv(const float* __restrict__ A, float* __restrict__ out, const __grid_constant__ SwtLevels lv,
+              const __grid_constant__ TapsDup1d tp, int rows, int N, int R, int pitch) {
+    extern __shared__ __align__(16) float sm[];
+    float* bufA = sm;
+    float* bufB = sm + (size_t)R * pitch;
+    float* bufD = sm + (size_t)2 * R * pitch;
+    const int tid = threadIdx.x, L = lv.L;
+    const int ngroups = (rows + R - 1) / R;
+    pwt_pdl_wait();
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int r0 = g * R, nr = rows - r0 < R ? rows - r0 : R;
+        if (g + (int)gridDim.x >= ngroups) pwt_pdl_trigger();
+        stage_rows(bufA, pitch, 0, A + (size_t)r0 * N, nr, N, tid);
+        float* cur = bufA;
+        float* nxt = bufB;
+        for (int l = L; l >= 1; l--) {
+            stage_rows(bufD, pitch, 0, lv.D[l - 1] + (size_t)r0 * N, nr, N, tid);
+            cp_async_commit();
+            cp_async_wait_all();
+            __syncthreads();
+            float* Og = out + (size_t)r0 * N;
+            if (l == 1) swt_inv_level<F, 1>(cur, bufD, nxt, pitch, Og, true, nr, N, 1, tp, tid);
+            else if (l == 2) swt_inv_level<F, 2>(cur, bufD, nxt, pitch, Og, false, nr, N, 2, tp, tid);
+            else swt_inv_level<F, 0>(cur, bufD, nxt, pitch, Og, false, nr, N, 1 << (l - 1), tp, tid);
+            __syncthreads();
+            float* t = cur; cur = nxt; nxt = t;
+        }
+    }
+}
+
+// rows per CTA and launch geometry of the a-trous rows kernels (nbuf shared rows per staged row)
+struct SwtPlan1d {
+    int R, pitch, grid, ok;
+    size_t smem;
+};
+inline SwtPlan1d make_swt_plan(int rows, int N, int L, int F, int nbuf) {
+    SwtPlan1d pl = {};
+    if ((N & 3) || N < 8 || L < 1 || L > 30) return pl;
+    if ((long long)(F - 1) * (1LL << (L - 1)) >= N) return pl;         // one wrap must cover the reach (always true after level clipping)
+    pl.pitch = N + 8;
+    const size_t per_row = sizeof(float) * (size_t)nbuf * pl.pitch;
+    const size_t budget = (nbuf == 2 ? 72 : 104) * 1024;              // 3 / 2 CTAs per SM
+    int R = (int)(budget / per_row);
+    if (R < 1) {
+        if (per_row > 200 * 1024) return pl;
+        R = 1;
+    }
+    const int want = (4096 + N - 1) / N;
+    if (R > want) R = want;
+    if (R > rows) R = rows;
+    pl.R = R < 1 ? 1 : R;
+    pl.smem = per_row * pl.R;
+    const int ngroups = (rows + pl.R - 1) / pl.R;
+    int per_sm = (int)((220 * 1024) / (pl.smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+    const int cap = pwt_sm_count() * per_sm;
+    pl.grid = ngroups < cap ? ngroups : cap;
+    pl.ok = 1;
+    return pl;
+}
+template <int F>
+int launch_row_swt_fwd(const float* in, float* A, float* const* D, int rows, int N, int L, const PwtFilters& f, cudaStream_t st) {
+    const SwtPlan1d pl = make_swt_plan(rows, N, L, F, 2);
+    if (!pl.ok || ((((uintptr_t)in) | ((uintptr_t)A)) & 15)) return 0;
+    SwtLevels lv = {};
+    lv.L = L;
+    for (int l = 0; l < L; l++) {
+        if (((uintptr_t)D[l]) & 15) return 0;
+        lv.D[l] = D[l];
+    }
+    static PwtKernelOnce once;
+    if (!pwt_kernel_once(once, k_row_swt_fwd<F>, NT, 200 * 1024, 72 * 1024)) return 0;
+    const PwtTapsFwd t = pwt_pack_taps_fwd(f, F);
+    pwt_launch_pdl(k_row_swt_fwd<F>, dim3((unsigned)pl.grid), NT, pl.smem, st, in, A, lv, t, rows, N, pl.R, pl.pitch);
+    return 1;
+}
+template <int F>
+int launch_row_swt_inv(const float* A, float* const* D, float* out, int rows, int N, int L, const PwtFilters& f, cudaStream_t st) {
+    const SwtPlan1d pl = make_swt_plan(rows, N, L, F, 3);
+    if (!pl.ok || ((((uintptr_t)out) | ((uintptr_t)A)) & 15)) return 0;
+    SwtLevels lv = {};
+    lv.L = L;
+    for (int l = 0; l < L; l++) {
+        if (((uintptr_t)D[l]) & 15) return 0;
+        lv.D[l] = D[l];
+    }
+    static PwtKernelOnce once;
+    if (!pwt_kernel_once(once, k_row_swt_inv<F>, NT, 200 * 1024, 104 * 1024)) return 0;
+    TapsDup1d t;
+    for (int j = 0; j < PWT_MAX_TAPS; j++) {
+        const float l = j < F ? 0.5f * f.IL[F - 1 - j] : 0.f, h = j < F ? 0.5f * f.IH[F - 1 - j] : 0.f;
+        t.l[j] = make_float2(l, l);
+        t.h[j] = make_float2(h, h);
+    }
+    pwt_launch_pdl(k_row_swt_inv<F>, dim3((unsigned)pl.grid), NT, pl.smem, st, A, out, lv, t, rows, N, pl.R, pl.pitch);
+    return 1;
+}
+
 struct Plan1d {
     RowLevels lv;
     int R, S0, S1, SD;
@@ -365,6 +624,7 @@ int launch_row_inv(const float* A, float* const* D, float* out, int rows, int Nc
 }
 }  // namespace
 
+#define PWT_ROWSWT_CASES(X) X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20)
 #define PWT_ROW1D_CASES(X) X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20) X(22) X(24) X(26) X(28) X(30) X(32) X(34) X(36) X(38) X(40)
 
 // D[l]: detail band of level l + 1 (rows x ceil(Nc / 2^(l+1))); A: rows x n[L].  Returns 0 when not covered.
@@ -382,6 +642,27 @@ int pwt_row_dwt_inv1d_all(const float* A, float* const* D, float* out, int rows,
     switch (f.hlen) {
 #define X(FF) case FF: return launch_row_inv<FF>(A, D, out, rows, Nc, L, f, st);
         PWT_ROW1D_CASES(X)
+#undef X
+        default: return 0;
+    }
+}
+
+// batched 1D a-trous transform, every level in one launch.  D[l]: detail band of level l + 1 (rows x Nc).  Return 0 when
+// not covered (width not a multiple of 4, row too long for a CTA's shared memory, filter longer than 20 taps at s = 2).
+int pwt_row_swt_fwd1d_all(const float* in, float* A, float* const* D, int rows, int Nc, int L, const PwtFilters& f, cudaStream_t st) {
+    if (rows < 1 || L < 1 || L > PWT_MAX_LEVELS || (long long)rows * Nc >= (1LL << 40)) return 0;
+    switch (f.hlen) {
+#define X(FF) case FF: return launch_row_swt_fwd<FF>(in, A, D, rows, Nc, L, f, st);
+        PWT_ROWSWT_CASES(X)
+#undef X
+        default: return 0;
+    }
+}
+int pwt_row_swt_inv1d_all(const float* A, float* const* D, float* out, int rows, int Nc, int L, const PwtFilters& f, cudaStream_t st) {
+    if (rows < 1 || L < 1 || L > PWT_MAX_LEVELS || (long long)rows * Nc >= (1LL << 40)) return 0;
+    switch (f.hlen) {
+#define X(FF) case FF: return launch_row_swt_inv<FF>(A, D, out, rows, Nc, L, f, st);
+        PWT_ROWSWT_CASES(X)
 #undef X
         default: return 0;
     }

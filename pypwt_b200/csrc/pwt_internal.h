@@ -327,6 +327,10 @@ int pwt_set_error(int code, const char* msg);
 // band of level l + 1.  Return 0 when not covered (row too long for a CTA's shared memory, odd filter length).
 int pwt_row_dwt_fwd1d_all(const float* in, float* A, float* const* D, int rows, int Nc, int L, const PwtFilters& f,
                           cudaStream_t st);
+int pwt_row_swt_fwd1d_all(const float* in, float* A, float* const* D, int rows, int Nc, int L, const PwtFilters& f,
+                          cudaStream_t st);
+int pwt_row_swt_inv1d_all(const float* A, float* const* D, float* out, int rows, int Nc, int L, const PwtFilters& f,
+                          cudaStream_t st);
 int pwt_row_dwt_inv1d_all(const float* A, float* const* D, float* out, int rows, int Nc, int L, const PwtFilters& f,
                           cudaStream_t st);
 // kernels_swt1d.cu : batched 1D a-trous level from a staged shared-memory row.  Return 0 when not covered.

@@ -711,11 +711,12 @@ extern "C" int pwt_forward(pwt_plan* p) {
         const int rows = B * p->Nr;
         int l_first = 1;
         // every level in one launch, the rows staged once in shared memory (kernels_row1d.cu)
-        if (!p->do_swt && p->kernel_mode == 0 && !pwt_tuning().no_fused1d) {
+        if (p->kernel_mode == 0 && !pwt_tuning().no_fused1d) {
             float* Ds[PWT_MAX_LEVELS];
             for (int l = 1; l <= L; l++) Ds[l - 1] = p->d_band[l];
             prof_begin(p, 100 * L + 21);
-            const int n = pwt_row_dwt_fwd1d_all(src, p->d_band[0], Ds, rows, p->Nc, L, p->filt, st);
+            const int n = p->do_swt ? pwt_row_swt_fwd1d_all(src, p->d_band[0], Ds, rows, p->Nc, L, p->filt, st)
+                                    : pwt_row_dwt_fwd1d_all(src, p->d_band[0], Ds, rows, p->Nc, L, p->filt, st);
             if (n) {
                 prof_end(p);
                 p->launches += n;
@@ -874,11 +875,12 @@ extern "C" int pwt_inverse(pwt_plan* p) {
     if (p->ndims == 1) {
         const int rows = B * p->Nr;
         int l_top = L;
-        if (!p->do_swt && p->kernel_mode == 0 && !pwt_tuning().no_fused1d) {      // every level in one launch
+        if (p->kernel_mode == 0 && !pwt_tuning().no_fused1d) {                    // every level in one launch
             float* Ds[PWT_MAX_LEVELS];
             for (int l = 1; l <= L; l++) Ds[l - 1] = p->d_band[l];
             prof_begin(p, 100 * L + 22);
-            const int n = pwt_row_dwt_inv1d_all(cur, Ds, p->d_image, rows, p->Nc, L, p->filt, st);
+            const int n = p->do_swt ? pwt_row_swt_inv1d_all(cur, Ds, p->d_image, rows, p->Nc, L, p->filt, st)
+                                    : pwt_row_dwt_inv1d_all(cur, Ds, p->d_image, rows, p->Nc, L, p->filt, st);
             if (n) {
                 prof_end(p);
                 p->launches += n;

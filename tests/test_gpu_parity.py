@@ -764,6 +764,29 @@ def test_fused_rows_1d_against_oracle(wname, batched):
     assert_close(W.image, Wo.image, SCALE, "rows idwt1d " + wname)
 
 
+ROWSSWT_WAVELETS = [w for w in ALL if w not in O.HAAR_ALIASES or w == "haar"]
+ROWSSWT_WAVELETS = [w for w in ROWSSWT_WAVELETS if len(O.filters(w)[0]) % 2 == 0 and len(O.filters(w)[0]) <= 20]
+
+
+@pytest.mark.parametrize("batched", [0, 1])
+@pytest.mark.parametrize("wname", ROWSSWT_WAVELETS)
+def test_fused_rows_swt_1d_against_oracle(wname, batched):
+    """Batched 1D a-trous transform, every level in ONE launch per direction (kernels_row1d.cu; the auto choice for
+    widths that are multiples of 4 and filters up to 20 taps), at the maximum level count, against the oracle."""
+    data = synth_image((21, 1000), seed=51) if batched else synth_image((1, 4100), seed=53)[0]
+    W = _W(data, wname, 999, ndim=1, do_swt=1)
+    Wo = O.OracleWavelets(data, wname, 999, ndim=1, do_swt=1)
+    assert W.levels == Wo.levels
+    n0 = W.launch_count
+    W.forward(); Wo.forward()
+    assert W.launch_count - n0 == 1, "forward took %d launches" % (W.launch_count - n0)
+    compare_coeffs(W, Wo, SCALE, "rows swt1d " + wname)
+    n0 = W.launch_count
+    W.inverse(); Wo.inverse()
+    assert W.launch_count - n0 == 1
+    assert_close(W.image, Wo.image, SCALE, "rows iswt1d " + wname)
+
+
 @pytest.mark.parametrize("shape", [(64, 1024), (5, 8192), (3, 136), (4096,)])
 @pytest.mark.parametrize("wname", ["haar", "db2", "sym8", "db20"])
 def test_fast_1d_kernels_agree_with_generic(wname, shape):
