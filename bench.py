@@ -22,6 +22,8 @@ Keys of the JSON line (one line, rank 0):
   c3_stack     BASELINE config 3 as a measurement: a FIXED 512 x 2048 x 2048 sym8 stack (strong scaling: 512/N slices
                per rank), step = forward + global norm1/norm2sq (fused reduction + ncclAllReduce, INSIDE the CUDA-event
                region) + soft threshold + inverse; aggregate Mpixel/s, us of the collective alone
+  other_configs  (N = 1) the other BASELINE configurations in short: C2 4096^2, C4 SWT + cycle spinning + hard threshold,
+               batched 1D DWT / SWT, two C5 filter lengths -- ms, Mpixel/s, fraction of their own HBM roofline
   host_link    pinned-memory copy bandwidth of this rank (H2D, D2H, both at once) and the NUMA placement of the rank:
                names the link that bounds `e2e`
 --impl reference: the CPU path of the reference workflow (pywt-equivalent C/OpenMP restatement
@@ -379,6 +381,50 @@ def run_c3(args, rank, world, local, dist, barrier, max_over_ranks):
     return res
 
 
+def run_other_configs(peak):
+    """The remaining BASELINE configurations in short (N = 1 only; device-resident, CUDA events on the plan's stream, median
+    of 3 x 10): C2 (4096^2 haar / db2 L3), C4 (SWT db4 L4 8192^2, cycle spinning + hard threshold), batched 1D DWT / SWT."""
+    import pycudwt
+    out = {}
+
+    def t(W, fn, reps=10):
+        for _ in range(3):
+            fn(W)
+        W.sync()
+        ts = []
+        for _ in range(3):
+            W.timer_start()
+            for _ in range(reps):
+                fn(W)
+            ts.append(W.timer_stop() / reps)
+        return sorted(ts)[1]
+
+    def fi(W):
+        W.forward(); W.inverse()
+
+    def den(W):
+        W.forward(); W.hard_threshold(20.0); W.inverse()
+
+    def add(key, shape, wname, levels, bpp, fn=fi, **kw):
+        img = synth(shape, 77)
+        W = pycudwt.Wavelets(img, wname, levels, **kw)
+        ms = t(W, fn)
+        l0 = W.launch_count
+        fn(W)
+        out[key] = {"ms": ms, "Mpixel/s": img.size / ms / 1e3, "bytes_per_px": bpp, "launches": int(W.launch_count - l0),
+                    "roofline_frac": bpp * img.size / (ms * 1e-3) / 1e9 / peak}
+        del W
+
+    add("C2 4096^2 haar L3 fwd+inv", (4096, 4096), "haar", 3, 16)
+    add("C2 4096^2 db2 L3 fwd+inv", (4096, 4096), "db2", 3, 16)
+    add("C4 8192^2 swt db4 L4 fwd+hard+inv, cycle spinning", (8192, 8192), "db4", 4, 2 * (3 * 4 + 2) * 4, fn=den, do_swt=1, do_cycle_spinning=1)
+    add("1D 8192x8192 db2 L3 fwd+inv", (8192, 8192), "db2", 3, 16, ndim=1)
+    add("1D 8192x8192 swt db2 L3 fwd+inv", (8192, 8192), "db2", 3, 2 * (3 + 2) * 4, ndim=1, do_swt=1)
+    add("C5 8192^2 sym8 L5 fwd+inv", (8192, 8192), "sym8", 5, 16)
+    add("C5 8192^2 db20 L5 fwd+inv (FMA-bound)", (8192, 8192), "db20", 5, 16)
+    return out
+
+
 def run_ours(args):
     rank, world, local = dist_env()
     pin = numa_pin(local)            # before any pinned allocation
@@ -568,6 +614,8 @@ def run_ours(args):
         c3 = run_c3(args, rank, world, local, dist, barrier, max_over_ranks)
         extra["c3_stack"] = c3
 
+    if rank == 0 and world == 1 and not args.no_other:
+        extra["other_configs"] = run_other_configs(measured_peak()[0])
     if rank == 0:
         cpu_v, cpu_s = time_cpu_port()
         pd = time_pdwt(np.asarray(img if B == 1 else img[0]), min(args.steps, 10), 2) if not args.no_pdwt else None
@@ -598,6 +646,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1, help="8192^2 images per GPU per step")
     ap.add_argument("--no-pdwt", action="store_true", help="skip the side-by-side timing of the reference's CUDA build")
     ap.add_argument("--no-c3", action="store_true", help="skip the sharded 512x2048x2048 sym8 stack leg (BASELINE config 3)")
+    ap.add_argument("--no-other", action="store_true", help="skip the short legs of the other BASELINE configurations (N = 1)")
     ap.add_argument("--c3-slices", type=int, default=512, help="slices of the fixed C3 stack (strong scaling over the ranks)")
     args = ap.parse_args()
     if args.impl == "reference":
