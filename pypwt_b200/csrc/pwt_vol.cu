@@ -150,6 +150,149 @@ k_vol_z_inv(const float* __restrict__ lo, const float* __restrict__ hi, float* _
     }
 }
 
+// ---- z pass with a sliding register window (planes that are multiples of 4 floats) -----
+// (compile-time F = 2 .. 20.)  A thread owns 4 adjacent columns and a run of KS consecutive outputs: the F input rows of an output live in a rotating
+// window of F float4 registers, each new output loads TWO new rows (analysis) / ONE new row of each band (synthesis)
+// instead of re-reading F (F/2 + 1) rows through L1/L2.  The rotation is unrolled over its period so that every window
+// index is static.  The four sub-volumes of a level go in ONE launch (blockIdx.y).
+struct ZJobs {
+    const float* a[4];     // analysis: input sub-volume;  synthesis: low-pass band
+    const float* b[4];     // synthesis: high-pass band
+    float* o0[4];          // analysis: low-pass output;   synthesis: output sub-volume
+    float* o1[4];          // analysis: high-pass output
+};
+template <int F>
+__global__ void __launch_bounds__(128)
+k_vol_z_fwd_win(const __grid_constant__ ZJobs jb, int Nz, long long P, int KS, const __grid_constant__ PwtTapsFwd tp) {
+    constexpr int C = F / 2 - 1;
+    const float* __restrict__ in = jb.a[blockIdx.y];
+    float* __restrict__ lo = jb.o0[blockIdx.y];
+    float* __restrict__ hi = jb.o1[blockIdx.y];
+    const int Nz2 = (Nz + 1) >> 1;
+    const long long PV = P >> 2;
+    const int nseg = (Nz2 + KS - 1) / KS;
+    pwt_pdl_wait();
+    for (long long i = blockIdx.x * 128LL + threadIdx.x; i < PV * nseg; i += gridDim.x * 128LL) {
+        const int seg = (int)(i / PV);
+        const long long p = (i - (long long)seg * PV) << 2;
+        const int k0 = seg * KS, kend = min(k0 + KS, Nz2);
+        float4 w[F];
+#pragma unroll
+        for (int j = 0; j < F - 2; j++) w[j] = __ldg(reinterpret_cast<const float4*>(in + (long long)wrap_dwt(2 * k0 - C + j, Nz) * P + p));
+        for (int kb = k0; kb < kend; kb += F / 2) {
+#pragma unroll
+            for (int u = 0; u < F / 2; u++) {
+                const int k = kb + u;
+                if (k < kend) {
+                    w[(F - 2 + 2 * u) % F] = __ldg(reinterpret_cast<const float4*>(in + (long long)wrap_dwt(2 * k - C + F - 2, Nz) * P + p));
+                    w[(F - 1 + 2 * u) % F] = __ldg(reinterpret_cast<const float4*>(in + (long long)wrap_dwt(2 * k - C + F - 1, Nz) * P + p));
+                    float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+                    for (int j = 0; j < F; j++) {
+                        const float4 x = w[(j + 2 * u) % F];
+                        a0 = fma2s(x.x, tp.t[j], a0);
+                        a1 = fma2s(x.y, tp.t[j], a1);
+                        a2 = fma2s(x.z, tp.t[j], a2);
+                        a3 = fma2s(x.w, tp.t[j], a3);
+                    }
+                    __stcs(reinterpret_cast<float4*>(lo + (long long)k * P + p), make_float4(a0.x, a1.x, a2.x, a3.x));
+                    __stcs(reinterpret_cast<float4*>(hi + (long long)k * P + p), make_float4(a0.y, a1.y, a2.y, a3.y));
+                }
+            }
+        }
+    }
+}
+// synthesis: output pair j (rows 2j, 2j + 1) = sum_w a[j - S1 + w] * l[w] + d[j - S1 + w] * h[w], (even, odd) tap pairs
+template <int F>
+__global__ void __launch_bounds__(128)
+k_vol_z_inv_win(const __grid_constant__ ZJobs jb, int nz2, int Nz_out, long long P, int KS, const __grid_constant__ PwtTapsInv tp) {
+    constexpr int S1 = (F / 2) >> 1, W = F / 2 + 1;
+    const float* __restrict__ lo = jb.a[blockIdx.y];
+    const float* __restrict__ hi = jb.b[blockIdx.y];
+    float* __restrict__ out = jb.o0[blockIdx.y];
+    const long long PV = P >> 2;
+    const int nseg = (nz2 + KS - 1) / KS;
+    pwt_pdl_wait();
+    for (long long i = blockIdx.x * 128LL + threadIdx.x; i < PV * nseg; i += gridDim.x * 128LL) {
+        const int seg = (int)(i / PV);
+        const long long p = (i - (long long)seg * PV) << 2;
+        const int j0 = seg * KS, jend = min(j0 + KS, nz2);
+        float4 wa[W], wd[W];
+#pragma unroll
+        for (int w = 0; w < W - 1; w++) {
+            const long long row = (long long)wrap_per(j0 - S1 + w, nz2) * P + p;
+            wa[w] = __ldg(reinterpret_cast<const float4*>(lo + row));
+            wd[w] = __ldg(reinterpret_cast<const float4*>(hi + row));
+        }
+        for (int jb0 = j0; jb0 < jend; jb0 += W) {
+#pragma unroll
+            for (int u = 0; u < W; u++) {
+                const int j = jb0 + u;
+                if (j < jend) {
+                    const long long row = (long long)wrap_per(j - S1 + W - 1, nz2) * P + p;
+                    wa[(W - 1 + u) % W] = __ldg(reinterpret_cast<const float4*>(lo + row));
+                    wd[(W - 1 + u) % W] = __ldg(reinterpret_cast<const float4*>(hi + row));
+                    float2 e0 = make_float2(0.f, 0.f), e1 = e0, e2 = e0, e3 = e0;   // (row 2j, row 2j + 1) of the 4 columns
+#pragma unroll
+                    for (int w = 0; w < W; w++) {
+                        const float4 a = wa[(w + u) % W], d = wd[(w + u) % W];
+                        e0 = fma2s(a.x, tp.l[w], e0); e0 = fma2s(d.x, tp.h[w], e0);
+                        e1 = fma2s(a.y, tp.l[w], e1); e1 = fma2s(d.y, tp.h[w], e1);
+                        e2 = fma2s(a.z, tp.l[w], e2); e2 = fma2s(d.z, tp.h[w], e2);
+                        e3 = fma2s(a.w, tp.l[w], e3); e3 = fma2s(d.w, tp.h[w], e3);
+                    }
+                    __stcs(reinterpret_cast<float4*>(out + (long long)(2 * j) * P + p), make_float4(e0.x, e1.x, e2.x, e3.x));
+                    if (2 * j + 1 < Nz_out)
+                        __stcs(reinterpret_cast<float4*>(out + (long long)(2 * j + 1) * P + p), make_float4(e0.y, e1.y, e2.y, e3.y));
+                }
+            }
+        }
+    }
+}
+// outputs per thread run: long enough to amortise the F - 2 preloaded rows, short enough to fill the GPU
+inline int pick_ks(int n_out, long long PV, int period) {
+    const long long want_threads = 4LL * 148 * 1024;
+    long long nseg = (want_threads + 4 * PV - 1) / (4 * PV);
+    if (nseg < 1) nseg = 1;
+    int ks = (int)((n_out + nseg - 1) / nseg);
+    if (ks < 4 * period) ks = 4 * period;
+    ks = ((ks + period - 1) / period) * period;
+    return ks;
+}
+#define PWT_VOLZ_CASES(X) X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20)
+// all four sub-volumes of a level in one launch; returns 0 when the window kernels do not cover the configuration
+int launch_z_fwd4(const ZJobs& jb, int Nz, long long P, const PwtFilters& f, cudaStream_t st) {
+    if ((P & 3) || f.hlen < 2 || f.hlen > 20 || (f.hlen & 1)) return 0;
+    for (int q = 0; q < 4; q++)
+        if ((((uintptr_t)jb.a[q]) | ((uintptr_t)jb.o0[q]) | ((uintptr_t)jb.o1[q])) & 15) return 0;
+    const int Nz2 = (Nz + 1) >> 1;
+    const PwtTapsFwd t = pwt_pack_taps_fwd(f, f.hlen);
+    const int KS = pick_ks(Nz2, P >> 2, f.hlen / 2);
+    const long long items = (P >> 2) * ((Nz2 + KS - 1) / KS);
+    const dim3 grid((unsigned)((items + 127) / 128 < 65535 * 16 ? (items + 127) / 128 : 65535 * 16), 4);
+    switch (f.hlen) {
+#define X(FF) case FF: pwt_launch_pdl(k_vol_z_fwd_win<FF>, grid, 128, 0, st, jb, Nz, P, KS, t); return 1;
+        PWT_VOLZ_CASES(X)
+#undef X
+    }
+    return 0;
+}
+int launch_z_inv4(const ZJobs& jb, int nz2, int Nz_out, long long P, const PwtFilters& f, cudaStream_t st) {
+    if ((P & 3) || f.hlen < 2 || f.hlen > 20 || (f.hlen & 1)) return 0;
+    for (int q = 0; q < 4; q++)
+        if ((((uintptr_t)jb.a[q]) | ((uintptr_t)jb.b[q]) | ((uintptr_t)jb.o0[q])) & 15) return 0;
+    const PwtTapsInv t = pwt_pack_taps_inv(f, f.hlen);
+    const int KS = pick_ks(nz2, P >> 2, f.hlen / 2 + 1);
+    const long long items = (P >> 2) * ((nz2 + KS - 1) / KS);
+    const dim3 grid((unsigned)((items + 127) / 128 < 65535 * 16 ? (items + 127) / 128 : 65535 * 16), 4);
+    switch (f.hlen) {
+#define X(FF) case FF: pwt_launch_pdl(k_vol_z_inv_win<FF>, grid, 128, 0, st, jb, nz2, Nz_out, P, KS, t); return 1;
+        PWT_VOLZ_CASES(X)
+#undef X
+    }
+    return 0;
+}
+
 inline unsigned grid_for(long long items) {
     long long g = (items + 255) / 256;
     const long long cap = (long long)pwt_sm_count() * 32;
@@ -323,10 +466,17 @@ extern "C" int pwt3_forward(pwt3_plan* p) {
         // (2) z: band b = 4 dz + 2 dy + dx.  a -> (0, 4), V (dx) -> (1, 5), H (dy) -> (2, 6), D -> (3, 7)
         float* dstA = l == L ? p->d_A : p->d_app[l & 1];
         float** B = p->d_band[l - 1];
-        p->launches += launch_z_fwd(p->d_sub[0], dstA, B[4], nz, P, p->filt, p->haar, st);
-        p->launches += launch_z_fwd(p->d_sub[2], B[1], B[5], nz, P, p->filt, p->haar, st);
-        p->launches += launch_z_fwd(p->d_sub[1], B[2], B[6], nz, P, p->filt, p->haar, st);
-        p->launches += launch_z_fwd(p->d_sub[3], B[3], B[7], nz, P, p->filt, p->haar, st);
+        ZJobs jb = {};
+        const int sub_of[4] = {0, 2, 1, 3};                         // job q reads a, V, H, D
+        for (int q = 0; q < 4; q++) {
+            jb.a[q] = p->d_sub[sub_of[q]];
+            jb.o0[q] = q == 0 ? dstA : B[q];
+            jb.o1[q] = B[4 + q];
+        }
+        int n = launch_z_fwd4(jb, nz, P, p->filt, st);
+        if (!n)
+            for (int q = 0; q < 4; q++) n += launch_z_fwd(jb.a[q], jb.o0[q], jb.o1[q], nz, P, p->filt, p->haar, st);
+        p->launches += n;
         src = dstA;
     }
     CKV(cudaGetLastError());
@@ -348,10 +498,17 @@ extern "C" int pwt3_inverse(pwt3_plan* p) {
         const int nz = p->lz[l - 1], ny = p->ly[l - 1], nx = p->lx[l - 1];
         const long long P = (long long)p->ly[l] * p->lx[l];
         float** B = p->d_band[l - 1];
-        p->launches += launch_z_inv(cur, B[4], p->d_sub[0], p->lz[l], nz, P, p->filt, p->haar, st);
-        p->launches += launch_z_inv(B[1], B[5], p->d_sub[2], p->lz[l], nz, P, p->filt, p->haar, st);
-        p->launches += launch_z_inv(B[2], B[6], p->d_sub[1], p->lz[l], nz, P, p->filt, p->haar, st);
-        p->launches += launch_z_inv(B[3], B[7], p->d_sub[3], p->lz[l], nz, P, p->filt, p->haar, st);
+        ZJobs jb = {};
+        const int sub_of[4] = {0, 2, 1, 3};
+        for (int q = 0; q < 4; q++) {
+            jb.a[q] = q == 0 ? cur : B[q];
+            jb.b[q] = B[4 + q];
+            jb.o0[q] = p->d_sub[sub_of[q]];
+        }
+        int n = launch_z_inv4(jb, p->lz[l], nz, P, p->filt, st);
+        if (!n)
+            for (int q = 0; q < 4; q++) n += launch_z_inv(jb.a[q], jb.b[q], jb.o0[q], p->lz[l], nz, P, p->filt, p->haar, st);
+        p->launches += n;
         float* dst = l == 1 ? p->d_image : p->d_app[(l - 1) & 1];
         p->launches += pwt_level_inv2d(p->d_sub[0], p->d_sub[1], p->d_sub[2], p->d_sub[3], dst, nz, p->ly[l], p->lx[l], ny, nx, P,
                                        (long long)ny * nx, p->filt, p->haar, st);

@@ -423,6 +423,25 @@ def test_generic_kernels_agree_with_auto(wname):
     assert_close(A.image, G.image, 255.0, "auto vs generic inverse")
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(do_swt=1), dict(ndim=1), dict(do_separable=0)])
+@pytest.mark.parametrize("wname", ["haar", "db2", "db4", "sym8", "db12", "bior2.6"])
+def test_kernel_mode_2_against_oracle(wname, kw):
+    """Kernel mode 2 (shared-memory `fast` kernels + generic, no register-resident / strip families): the family the
+    auto mode only reaches as a fallback, forced here and compared with the oracle (odd sizes included)."""
+    for shape in ((512, 768), (203, 177)):
+        img = synth_image(shape, seed=19)
+        try:
+            Wo = O.OracleWavelets(img, wname, 3, **kw)
+        except ValueError:
+            continue
+        W = _W(img, wname, 3, **kw)
+        W.set_kernel_mode(2)
+        W.forward(); Wo.forward()
+        compare_coeffs(W, Wo, SCALE, "mode 2 " + wname)
+        W.inverse(); Wo.inverse()
+        assert_close(W.image.reshape(Wo.image.shape), Wo.image, SCALE, "mode 2 inverse " + wname)
+
+
 @pytest.mark.parametrize("shape", [(512, 1024), (1024, 512), (2048, 2048), (3, 512, 512)])
 @pytest.mark.parametrize("wname", ["haar", "db2", "db3", "coif1"])
 def test_fused_cascade_is_bit_identical_to_per_level_kernels(wname, shape):
