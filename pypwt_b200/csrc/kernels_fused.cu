@@ -545,7 +545,7 @@ int launch_fwd3n(Fwd3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, co
     // programmatic dependent launch (the kernel triggers when its last wave of tasks starts): 3-level fwd+inv db2
     // 0.0226 -> 0.0178 ms at 512^2, 0.0249 -> 0.0216 at 2048^2, 0.0612 -> 0.0567 at 4096^2, 0.198 -> 0.196 at 8192^2.
     // Not for Haar: 4096^2 got slower (0.0502 -> 0.0594 ms) although 2048^2 and 8192^2 gained.
-    if (!HAAR && pwt_tuning().fused_pdl) pwt_launch_pdl(k_fwd3<F, HAAR, MINB, PF, NRM>, dim3(grid), 32 * kWarps, 0, st, a, taps);
+    if (!HAAR && (pwt_tuning().fused_pdl & 1)) pwt_launch_pdl(k_fwd3<F, HAAR, MINB, PF, NRM>, dim3(grid), 32 * kWarps, 0, st, a, taps);
     else k_fwd3<F, HAAR, MINB, PF, NRM><<<grid, 32 * kWarps, 0, st>>>(a, taps);
     return 1;
 }
@@ -622,6 +622,7 @@ int pwt_fused_dwt_fwd3(const float* in, float* A3, float* const* H, float* const
 namespace {
 
 struct Inv3Args {
+    int plain;                     // host only: launch without the programmatic-dependent-launch attribute
     const float* A3;
     const float* H[3];     // index 0 = level 1 (finest)
     const float* V[3];
@@ -913,7 +914,7 @@ int launch_inv3t(Inv3Args a, int batch, const PwtFilters& f, PwtTaskQueue* q, cu
     a.counter = q->counter;
     a.base = q->base;
     q->base += (unsigned)total + (unsigned)grid * kWarps;
-    if (!HAAR && pwt_tuning().fused_pdl) pwt_launch_pdl(k_inv3<F, HAAR, MINB, THR>, dim3(grid), 32 * kWarps, 0, st, a, f);
+    if (!HAAR && !a.plain && (pwt_tuning().fused_pdl & 2)) pwt_launch_pdl(k_inv3<F, HAAR, MINB, THR>, dim3(grid), 32 * kWarps, 0, st, a, f);
     else k_inv3<F, HAAR, MINB, THR><<<grid, 32 * kWarps, 0, st>>>(a, f);
     return 1;
 }
@@ -930,12 +931,13 @@ int launch_inv3(const Inv3Args& a, int batch, const PwtFilters& f, PwtTaskQueue*
 // Levels 3..1 of the inverse transform in one launch.  H/V/D[0] = level 1 (finest).
 int pwt_fused_dwt_inv3(const float* A3, const float* const* H, const float* const* V, const float* const* D,
                        float* out, int batch, int Nr, int Nc, const PwtFilters& f, bool haar, PwtTaskQueue* q,
-                       const PwtDeferredOp* op, cudaStream_t st) {
+                       const PwtDeferredOp* op, int plain_launch, cudaStream_t st) {
     const int F = haar ? 2 : f.hlen;
     if (pwt_tuning().no_fused || pwt_tuning().no_fused_inv) return 0;
     if (F > 6 || (F & 1) || Nr % 8 != 0 || Nc % 8 != 0 || Nc < 512 || Nr < 64 || batch > 65535) return 0;
     if (((uintptr_t)out & 15) != 0) return 0;
     Inv3Args a;
+    a.plain = plain_launch;
     a.A3 = A3;
     a.out = out;
     for (int l = 0; l < 3; l++) {

@@ -89,7 +89,7 @@ struct PwtTuning {
     int no_fold_cs;        // PWT_NO_FOLD_CS=1: cycle-spinning shifts as separate gather passes
     int no_cascade8;       // PWT_NO_CASCADE8=1: no level-fused strip kernels (F >= 8)
     int no_fused1d;        // PWT_NO_FUSED1D=1: batched 1D one launch per level
-    int no_tail;           // PWT_NO_TAIL=1: small levels one launch each
+    int tail_strip;        // PWT_TAIL_STRIP (default 1): levels >= 4 of short-filter transforms run the strip kernels
 };
 const PwtTuning& pwt_tuning();       // pwt_plan.cu
 int pwt_sm_count();                  // SM count of the CURRENT device (cached per device; pwt_plan.cu)
@@ -285,7 +285,7 @@ struct PwtDeferredOp {
 };
 int pwt_fused_dwt_inv3(const float* A3, const float* const* H, const float* const* V, const float* const* D,
                        float* out, int batch, int Nr, int Nc, const PwtFilters& f, bool haar, PwtTaskQueue* q,
-                       const PwtDeferredOp* op, cudaStream_t st);
+                       const PwtDeferredOp* op, int plain_launch, cudaStream_t st);
 
 // kernels_swt.cu : fused (row + column) a-trous level in registers.  Return 0 when not covered.
 int pwt_fast_swt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc,

@@ -63,7 +63,7 @@ const PwtTuning& pwt_tuning() {
         k.fused_variant = env_i("PWT_FUSED_VARIANT", 0);
         k.fused_t3 = env_i("PWT_FUSED_T3", 0);
         k.fused_inv_t3 = env_i("PWT_FUSED_INV_T3", 0);
-        k.fused_pdl = env_i("PWT_FUSED_PDL", 1);
+        k.fused_pdl = env_i("PWT_FUSED_PDL", 3);
         k.no_fused_norms = getenv("PWT_NO_FUSED_NORMS") ? 1 : 0;
         k.no_defer = getenv("PWT_NO_DEFER") ? 1 : 0;
         k.tile_min_f = env_i("PWT_TILE_MIN_F", 22);
@@ -86,7 +86,7 @@ const PwtTuning& pwt_tuning() {
         k.no_fold_cs = env_i("PWT_NO_FOLD_CS", 0);
         k.no_cascade8 = env_i("PWT_NO_CASCADE8", 0);
         k.no_fused1d = env_i("PWT_NO_FUSED1D", 0);
-        k.no_tail = env_i("PWT_NO_TAIL", 0);
+        k.tail_strip = env_i("PWT_TAIL_STRIP", 1);
         return k;
     }();
     return t;
@@ -791,7 +791,10 @@ extern "C" int pwt_forward(pwt_plan* p) {
                 if (sep) {
                     int n = 0;
                     const int hints = (l < L ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l > 1 ? PWT_HINT_IN_FROM_PREV : 0);
-                    if (!haar && ((p->kernel_mode == 0 && p->hlen >= p->strip_min_f && nr >= 64 && nc >= 256) || p->kernel_mode == 4)) {
+                    // F >= 8 always; shorter filters on the small planes that follow the fused cascade (levels >= 4: the
+                    // register kernels need 9-11 us per launch there, the strip kernels 3-4)
+                    const bool tail = l >= 4 && p->hlen >= 4 && pwt_tuning().tail_strip && (p->kernel_mode == 0 || p->kernel_mode == 3);
+                    if (!haar && ((((p->kernel_mode == 0 && p->hlen >= p->strip_min_f) || tail) && nr >= 64 && nc >= 256) || p->kernel_mode == 4)) {
                         // norms requested after an earlier forward: the strip kernel reduces |c|, c^2 of what it stores
                         const bool nrm = p->want_norms && p->d_partials && p->do_separable && p->kernel_mode == 0 && l <= 32;
                         int wr = 0;
@@ -952,8 +955,11 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                     p->queue.base = 0;
                 }
                 prof_begin(p, 100 * 3 + 2 + 10);      // tag 312: fused levels 3..1
+                // F = 6 behind a strip launch of level 4: launched plainly -- started early by programmatic dependent launch,
+                // its persistent CTAs get placed unevenly next to the draining strip kernel (8192^2 db3 L5: 0.346 vs 0.255 ms)
+                const int plain = L > 3 && p->hlen == 6 && pwt_tuning().tail_strip;
                 const int n = pwt_fused_dwt_inv3(cur, Hs, Vs, Ds, p->d_image, B, p->Nr, p->Nc, p->filt, haar, &p->queue,
-                                                 p->pend.op >= 0 ? &fop : nullptr, st);
+                                                 p->pend.op >= 0 ? &fop : nullptr, plain, st);
                 if (n) {
                     prof_end(p);
                     p->launches += n;
@@ -1003,7 +1009,8 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                 if (sep) {
                     int n = 0;
                     const int hints = (l > 1 ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l < L ? PWT_HINT_IN_FROM_PREV : 0);
-                    if (!haar && ((p->kernel_mode == 0 && p->hlen >= p->strip_min_f && nr >= 32 && nc >= 128) || p->kernel_mode == 4)) {
+                    const bool tail = l >= 4 && p->hlen >= 4 && pwt_tuning().tail_strip && (p->kernel_mode == 0 || p->kernel_mode == 3);
+                    if (!haar && ((((p->kernel_mode == 0 && p->hlen >= p->strip_min_f) || tail) && nr >= 32 && nc >= 128) || p->kernel_mode == 4)) {
                         if (strip_defer && l <= strip_lmax)
                             n = pwt_strip_dwt_inv2d_thr(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, p->pend.op,
                                                         p->pend.beta[l - 1], l == L && p->pend.app, p->pend.beta_app, st);
