@@ -326,6 +326,60 @@ def test_cycle_spinning():
     assert len(seen) > 1
 
 
+def test_recorded_cycle_spinning_shifts_of_swt_plans():
+    """2D SWT plans record the cycle-spinning shifts instead of executing them (the a-trous transform commutes with
+    circular shifts) and materialise them when positions are observed.  Every observable sequence must equal the
+    reference's (wt.cu:242-246,303): image / coefficients read between forward and inverse, two forwards in a row
+    (the shifts accumulate, inverse() undoes only the last), set_coeff on shifted bands, copy(), add_wavelet."""
+    img = synth_image((96, 128), seed=21)
+
+    # (1) read everything between forward and inverse
+    W = _W(img, "db2", 2, do_swt=1, do_cycle_spinning=1)
+    W.forward()
+    s1 = W.current_shift
+    Wo = O.OracleWavelets(img, "db2", 2, do_swt=1, do_cycle_spinning=1, rng=_FixedRand(list(s1)))
+    Wo.forward()
+    assert np.array_equal(W.image, np.roll(img, s1, axis=(0, 1)))
+    compare_coeffs(W, Wo, 255.0, "swt cs, coefficients read")
+    W.hard_threshold(5.0); Wo.hard_threshold(5.0)
+    W.inverse(); Wo.inverse()
+    assert_close(W.image, Wo.image, 255.0, "swt cs, after reads")
+    # (2) nothing read in between (the fast path), thresholds and norms only
+    W.forward(img)
+    s2 = W.current_shift
+    Wo = O.OracleWavelets(img, "db2", 2, do_swt=1, do_cycle_spinning=1, rng=_FixedRand(list(s2)))
+    Wo.forward()
+    W.soft_threshold(3.0, 1, 1); Wo.soft_threshold(3.0, 1, 1)
+    assert abs(W.norm1() - Wo.norm1()) <= 1e-5 * Wo.norm1()
+    W.inverse(); Wo.inverse()
+    assert_close(W.image, Wo.image, 255.0, "swt cs, fast path")
+    # (3) two forwards in a row: the image is shifted twice, inverse() shifts back once
+    W.set_image(img)
+    W.forward(); a = W.current_shift
+    W.forward(); b = W.current_shift
+    Wo = O.OracleWavelets(img, "db2", 2, do_swt=1, do_cycle_spinning=1, rng=_FixedRand(list(a) + list(b)))
+    Wo.forward(); Wo.forward()
+    compare_coeffs(W, Wo, 255.0, "swt cs, two forwards")
+    W.inverse(); Wo.inverse()
+    assert_close(W.image, Wo.image, 255.0, "swt cs, two forwards, inverse")
+    assert_close(W.image, np.roll(img, a, axis=(0, 1)), 255.0 * 4, "one shift left")
+    # (4) set_coeff on a plan with a recorded shift, copy(), add_wavelet
+    W.set_image(img)
+    W.forward(); s4 = W.current_shift
+    Wo = O.OracleWavelets(img, "db2", 2, do_swt=1, do_cycle_spinning=1, rng=_FixedRand(list(s4)))
+    Wo.forward()
+    z = np.zeros((96, 128), np.float32)
+    W.set_coeff(z, 3); Wo.set_coeff(z, 3)
+    C = W.copy()
+    compare_coeffs(C, Wo, 255.0, "swt cs, copy")
+    assert W.add_wavelet(C, 1.0) == 0
+    assert_close(W.coeffs[0], 2.0 * np.asarray(Wo.coeffs[0]), 255.0, "swt cs, add_wavelet")
+    W.inverse()
+    C.inverse(); Wo.inverse()
+    assert_close(C.image, Wo.image, 255.0, "swt cs, copy, inverse")
+    assert_close(W.image, 2.0 * np.asarray(Wo.image), 255.0, "swt cs, sum, inverse")
+
+
 def test_cycle_spinning_rand_sequence():
     """In a fresh process the shifts follow the unseeded libc rand() sequence, row first then column
     (1804289383 % Nr, 846930886 % Nc, ...), exactly like the reference (quirk Q7)."""
