@@ -516,7 +516,10 @@ def run_ours(args):
     alg_bytes = 8.0 * pix
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as fh:
+        tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+        if not os.path.exists(tpath):
+            tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        with open(tpath) as fh:
             traffic = json.load(fh).get("k_fwd3" if fused else "k_fwd_reg", {}).get("dram_bytes_per_launch")
     except Exception:
         pass
@@ -524,7 +527,7 @@ def run_ours(args):
             "achieved": alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None, "peak": peak, "unit": "GB/s",
             "frac": (alg_bytes / (k_ms * 1e-3) / 1e9 / peak) if k_ms else None, "traffic": traffic,
             "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch at the 8192^2 "
-                              "workload (profiles/r01_ncu_traffic.json)" if traffic else None,
+                              "workload (profiles/%s)" % os.path.basename(tpath) if traffic else None,
             "algorithmic_bytes": alg_bytes,
             "peak_source": peak_src, "kernel_ms": k_ms,
             "kernel_ms_by_level": {{1: "fwd", 2: "inv", 11: "fwd1-", 12: "inv1-"}.get(t % 100, "k") + str(t // 100): round(v, 5) for t, v in sorted(avg.items())},

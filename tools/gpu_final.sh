@@ -1,14 +1,14 @@
 # Round-end artifact capture (run on the GPU box through gpurun): bench line, ncu launch list, ncu --set full
 # of the two fused kernels and of the long-filter kernels, configuration sweep.  Outputs under gpurun_out/final/.
 set -x
-O=gpurun_out/final
+O=${PWT_FINAL_DIR:-gpurun_out/final}
 mkdir -p $O
 for what in "$@"; do
 case $what in
 bench) python bench.py 2>&1 | grep -v "^Warn\|^Forc" | tail -1 > $O/bench.json; cut -c1-400 $O/bench.json ;;
 ref) python bench.py --impl reference --steps 5 --warmup 1 2>&1 | tail -1 > $O/bench_reference.json; cut -c1-300 $O/bench_reference.json ;;
-launches) ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 1 --no-pdwt > $O/ncu_bench.log 2>&1; grep -c . $O/launches.csv ;;
-ncufused) ncu --set full --clock-control none --import-source on -k regex:"k_fwd3|k_inv3" -s 12 -c 2 -f -o $O/prof_fused python bench.py --steps 2 --warmup 1 --no-pdwt > $O/ncu_fused.log 2>&1; tail -1 $O/ncu_fused.log
+launches) ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 1 --no-pdwt --no-c3 --no-other > $O/ncu_bench.log 2>&1; grep -c . $O/launches.csv ;;
+ncufused) ncu --set full --clock-control none --import-source on -k regex:"k_fwd3|k_inv3" -s 12 -c 2 -f -o $O/prof_fused python bench.py --steps 2 --warmup 1 --no-pdwt --no-c3 --no-other > $O/ncu_fused.log 2>&1; tail -1 $O/ncu_fused.log
   python tools/ncu_summary.py $O/ncu_fused_summary.csv $O/prof_fused.ncu-rep; for i in 0 1; do python tools/ncu_mix.py $O/prof_fused.ncu-rep $i > $O/ncu_fused_mix$i.txt; done; rm -f $O/prof_fused.ncu-rep ;;
 nculong) for w in db4 sym8 db20; do ncu --set full --clock-control none --import-source on -k regex:"k_strip" -s 4 -c 2 -f -o $O/prof_$w python tools/gpu_one.py $w > $O/ncu_$w.log 2>&1; tail -1 $O/ncu_$w.log; done
   python tools/ncu_summary.py $O/ncu_strip_summary.csv $O/prof_db4.ncu-rep $O/prof_sym8.ncu-rep $O/prof_db20.ncu-rep
