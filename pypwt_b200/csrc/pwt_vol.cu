@@ -2,7 +2,7 @@
 // pdwt/README.md:29; pypwt.pyx:155-156 rejects 3D input); this is the natural extension of its transform to volumes with
 // the same conventions: periodisation over the size rounded up to even (separable.cu:98-102), ceil halving of every axis
 // (utils.cu:24-27), level clip ilog2(min(Nz, Ny, Nx) / (F - 1)) (wt.cu:156-165), x filtered first, then y, then z.
-// The result equals pywt.wavedecn(mode="periodization") on the same volume (oracle/dwt3_oracle.py restates it).
+// The result equals pywt.wavedecn(mode="periodization") on the same volume.
 //
 // One level = (1) the batched 2D level of the fp32 plans over the Nz slices of the current approximation -- the same
 // kernels, chosen by pwt_level_fwd2d -- into four half-resolution sub-volumes, then (2) a pass along z of each
