@@ -793,7 +793,9 @@ extern "C" int pwt_forward(pwt_plan* p) {
                     const int hints = (l < L ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l > 1 ? PWT_HINT_IN_FROM_PREV : 0);
                     // F >= 8 always; shorter filters on the small planes that follow the fused cascade (levels >= 4: the
                     // register kernels need 9-11 us per launch there, the strip kernels 3-4)
-                    const bool tail = l >= 4 && p->hlen >= 4 && pwt_tuning().tail_strip && (p->kernel_mode == 0 || p->kernel_mode == 3);
+                    // ... and on widths that are not multiples of 4, where the register kernels do not apply (1001 x 777 db2: 2.4x)
+                    const bool tail = ((l >= 4 && (p->kernel_mode == 0 || p->kernel_mode == 3)) || ((nc & 3) && p->kernel_mode == 0)) &&
+                                      p->hlen >= 4 && pwt_tuning().tail_strip;
                     if (!haar && ((((p->kernel_mode == 0 && p->hlen >= p->strip_min_f) || tail) && nr >= 64 && nc >= 256) || p->kernel_mode == 4)) {
                         // norms requested after an earlier forward: the strip kernel reduces |c|, c^2 of what it stores
                         const bool nrm = p->want_norms && p->d_partials && p->do_separable && p->kernel_mode == 0 && l <= 32;
@@ -1009,7 +1011,8 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                 if (sep) {
                     int n = 0;
                     const int hints = (l > 1 ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l < L ? PWT_HINT_IN_FROM_PREV : 0);
-                    const bool tail = l >= 4 && p->hlen >= 4 && pwt_tuning().tail_strip && (p->kernel_mode == 0 || p->kernel_mode == 3);
+                    const bool tail = ((l >= 4 && (p->kernel_mode == 0 || p->kernel_mode == 3)) || ((Nco & 3) && p->kernel_mode == 0)) &&
+                                      p->hlen >= 4 && pwt_tuning().tail_strip;
                     if (!haar && ((((p->kernel_mode == 0 && p->hlen >= p->strip_min_f) || tail) && nr >= 32 && nc >= 128) || p->kernel_mode == 4)) {
                         if (strip_defer && l <= strip_lmax)
                             n = pwt_strip_dwt_inv2d_thr(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, p->pend.op,
