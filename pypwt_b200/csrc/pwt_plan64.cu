@@ -2,8 +2,8 @@
 // pdwt/Makefile:36-39 libpdwtd.so), which its Python wrapper never reaches.  Same class surface as
 // the fp32 plan -- wt.h:42-75 with DTYPE = double -- behind `pwt64_*` entry points (include/pwt_b200.h).
 //
-// Kernels: the separable tile kernels of kernels_generic.cu instantiated for double (fused row + column pass per
-// level, polyphase synthesis, a-trous passes), taps at the table's full precision.  The roofline doubles per pixel
+// Kernels: 2D DWT levels with F = 4 .. 20 run the two-pass streaming kernels below; everything else (Haar, longer filters,
+// batched 1D, a-trous) the separable tile kernels of kernels_generic.cu instantiated for double.  Taps at the table's full precision.  The roofline doubles per pixel
 // (16 B forward, 16 B inverse); the specialised fp32 families (register cascade, strip kernels) are not instantiated
 // for double -- measured numbers in profiles/r02_notes.md.  Non-separable mode uses the rank-1 identity (the four
 // F x F banks are outer products of the 1D bank): separable kernels, detail slots 1 and 2 swapped like the reference
@@ -92,6 +92,283 @@ k64_circshift(const double* __restrict__ in, double* __restrict__ out, int Nr, i
         out[pb + i] = in[pb + (long long)ys * Nc + xs];
     }
 }
+
+// ---- two-pass separable kernels for double, compile-time F = 4 .. 20 --------------------------------------------
+// The generic tile kernels (kernels_generic.cu) reach 0.12-0.21 of the fp64 roofline: every tap is a 64-bit shared-memory
+// read.  These run a level as two streaming passes instead -- rows (threads along x, 4 output pairs per thread from one
+// window of F + 6 samples read through L1), then columns (a thread owns 2 adjacent columns and a run of consecutive
+// outputs; the F input rows live in a rotating register window, two new rows per output) -- 32 instead of 16 B per
+// level-input pixel and direction, but at streaming speed.  Same arithmetic order as the reference (taps ascending).
+__device__ __forceinline__ int wrap_dwt64(int i, int N) {
+    const int Ne = N + (N & 1);
+    i %= Ne;
+    if (i < 0) i += Ne;
+    return i >= N ? N - 1 : i;
+}
+__device__ __forceinline__ int wrap_per64(int i, int N) {
+    i %= N;
+    return i < 0 ? i + N : i;
+}
+// rows, analysis: in [rows][Nc] -> lo, hi [rows][Nc2]
+template <int F>
+__global__ void __launch_bounds__(256)
+k64_rows_fwd(const double* __restrict__ in, double* __restrict__ lo, double* __restrict__ hi, long long rows, int Nc,
+             const __grid_constant__ PwtFilters64 f) {
+    constexpr int C = F / 2 - 1, NP = 4, W = F + 2 * (NP - 1);
+    const int Nc2 = (Nc + 1) >> 1, nch = (Nc2 + NP - 1) / NP;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < rows * nch; i += gridDim.x * 256LL) {
+        const long long r = i / nch;
+        const int k0 = (int)(i - r * nch) * NP, x0 = 2 * k0 - C;
+        const double* row = in + r * Nc;
+        double w[W];
+        if (x0 >= 0 && x0 + W <= Nc) {
+#pragma unroll
+            for (int j = 0; j < W; j++) w[j] = __ldg(row + x0 + j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < W; j++) w[j] = __ldg(row + wrap_dwt64(x0 + j, Nc));
+        }
+        double a[NP], d[NP];
+#pragma unroll
+        for (int o = 0; o < NP; o++) a[o] = d[o] = 0.0;
+#pragma unroll
+        for (int j = 0; j < F; j++)
+#pragma unroll
+            for (int o = 0; o < NP; o++) {
+                a[o] = fma(w[2 * o + j], f.L[F - 1 - j], a[o]);
+                d[o] = fma(w[2 * o + j], f.H[F - 1 - j], d[o]);
+            }
+#pragma unroll
+        for (int o = 0; o < NP; o++)
+            if (k0 + o < Nc2) {
+                lo[r * Nc2 + k0 + o] = a[o];
+                hi[r * Nc2 + k0 + o] = d[o];
+            }
+    }
+}
+// rows, synthesis: t1, t2 [rows][nc] -> out [rows][Nc_out];  x[n] = sum_j IL[2j + t0] t1[kb - j] + IH[2j + t0] t2[kb - j]
+template <int F>
+__global__ void __launch_bounds__(256)
+k64_rows_inv(const double* __restrict__ t1, const double* __restrict__ t2, double* __restrict__ out, long long rows, int nc,
+             int Nc_out, const __grid_constant__ PwtFilters64 f) {
+    constexpr int P = F / 2 - 1, S1 = (P + 1) >> 1, HALF = F / 2, NP = 4, W = HALF + NP;   // pairs j0 .. j0 + 3 read bands j0 - S1' ..
+    const int nch = (nc + NP - 1) / NP;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < rows * nch; i += gridDim.x * 256LL) {
+        const long long r = i / nch;
+        const int j0 = (int)(i - r * nch) * NP;
+        // output n = 2 j + b reads k = j + ((b + P) >> 1) - jj, jj = 0 .. HALF - 1: k in [j + ((b+P)>>1) - HALF + 1, j + ((b+P)>>1)]
+        const int kmin = j0 + (P >> 1) - HALF + 1;                          // smallest band index any of the 8 outputs reads
+        const double* a = t1 + r * nc;
+        const double* d = t2 + r * nc;
+        double wa[W + 1], wd[W + 1];
+        if (kmin >= 0 && kmin + W + 1 <= nc) {
+#pragma unroll
+            for (int q = 0; q <= W; q++) { wa[q] = __ldg(a + kmin + q); wd[q] = __ldg(d + kmin + q); }
+        } else {
+#pragma unroll
+            for (int q = 0; q <= W; q++) { const int k = wrap_per64(kmin + q, nc); wa[q] = __ldg(a + k); wd[q] = __ldg(d + k); }
+        }
+#pragma unroll
+        for (int o = 0; o < NP; o++)
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                const int t0 = (b + P) & 1, kb = o + ((b + P) >> 1) - (P >> 1) + HALF - 1;   // index into the window
+                double x = 0.0;
+#pragma unroll
+                for (int jj = 0; jj < HALF; jj++) {
+                    x = fma(wa[kb - jj], f.IL[2 * jj + t0], x);
+                    x = fma(wd[kb - jj], f.IH[2 * jj + t0], x);
+                }
+                const int n = 2 * (j0 + o) + b;
+                if (j0 + o < nc && n < Nc_out) out[r * Nc_out + n] = x;
+            }
+    }
+}
+struct ColJobs64 {
+    const double* a[2];
+    const double* b[2];
+    double* o0[2];
+    double* o1[2];
+};
+// columns, analysis: plane [Nr][P] (batch stride in_bs) -> lo, hi [Nr2][P] (batch stride out_bs); blockIdx.y = job, z = image
+template <int F, int VEC>
+__global__ void __launch_bounds__(128)
+k64_cols_fwd(const __grid_constant__ ColJobs64 jb, int Nr, int P, long long in_bs, long long out_bs, int KS,
+             const __grid_constant__ PwtFilters64 f) {
+    constexpr int C = F / 2 - 1;
+    const double* __restrict__ in = jb.a[blockIdx.y] + blockIdx.z * in_bs;
+    double* __restrict__ lo = jb.o0[blockIdx.y] + blockIdx.z * out_bs;
+    double* __restrict__ hi = jb.o1[blockIdx.y] + blockIdx.z * out_bs;
+    const int Nr2 = (Nr + 1) >> 1, PV = P / VEC, nseg = (Nr2 + KS - 1) / KS;
+    for (long long i = blockIdx.x * 128LL + threadIdx.x; i < (long long)PV * nseg; i += gridDim.x * 128LL) {
+        const int seg = (int)(i / PV), p = (int)(i - (long long)seg * PV) * VEC;
+        const int k0 = seg * KS, kend = min(k0 + KS, Nr2);
+        double w[F][VEC];
+        auto ld = [&](int slot, int row) {
+            const double* q = in + (long long)wrap_dwt64(row, Nr) * P + p;
+            if (VEC == 2) { const double2 v = __ldg(reinterpret_cast<const double2*>(q)); w[slot][0] = v.x; w[slot][VEC - 1] = v.y; }
+            else w[slot][0] = __ldg(q);
+        };
+#pragma unroll
+        for (int j = 0; j < F - 2; j++) ld(j, 2 * k0 - C + j);
+        for (int kb = k0; kb < kend; kb += F / 2) {
+#pragma unroll
+            for (int u = 0; u < F / 2; u++) {
+                const int k = kb + u;
+                if (k < kend) {
+                    ld((F - 2 + 2 * u) % F, 2 * k - C + F - 2);
+                    ld((F - 1 + 2 * u) % F, 2 * k - C + F - 1);
+                    double a[VEC], d[VEC];
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) a[v] = d[v] = 0.0;
+#pragma unroll
+                    for (int j = 0; j < F; j++)
+#pragma unroll
+                        for (int v = 0; v < VEC; v++) {
+                            a[v] = fma(w[(j + 2 * u) % F][v], f.L[F - 1 - j], a[v]);
+                            d[v] = fma(w[(j + 2 * u) % F][v], f.H[F - 1 - j], d[v]);
+                        }
+                    double* ol = lo + (long long)k * P + p;
+                    double* oh = hi + (long long)k * P + p;
+                    if (VEC == 2) {
+                        *reinterpret_cast<double2*>(ol) = make_double2(a[0], a[VEC - 1]);
+                        *reinterpret_cast<double2*>(oh) = make_double2(d[0], d[VEC - 1]);
+                    } else {
+                        ol[0] = a[0];
+                        oh[0] = d[0];
+                    }
+                }
+            }
+        }
+    }
+}
+// columns, synthesis: lo, hi [nr2][P] -> out [Nr_out][P]: output pair j (rows 2j, 2j + 1) from band rows j - S1 .. j - S1 + F/2
+template <int F, int VEC>
+__global__ void __launch_bounds__(128)
+k64_cols_inv(const __grid_constant__ ColJobs64 jb, int nr2, int Nr_out, int P, long long in_bs, long long out_bs, int KS,
+             const __grid_constant__ PwtFilters64 f) {
+    constexpr int PP = F / 2 - 1, S1 = (PP + 1) >> 1, W = F / 2 + 1;
+    const double* __restrict__ lo = jb.a[blockIdx.y] + blockIdx.z * in_bs;
+    const double* __restrict__ hi = jb.b[blockIdx.y] + blockIdx.z * in_bs;
+    double* __restrict__ out = jb.o0[blockIdx.y] + blockIdx.z * out_bs;
+    const int PV = P / VEC, nseg = (nr2 + KS - 1) / KS;
+    for (long long i = blockIdx.x * 128LL + threadIdx.x; i < (long long)PV * nseg; i += gridDim.x * 128LL) {
+        const int seg = (int)(i / PV), p = (int)(i - (long long)seg * PV) * VEC;
+        const int j0 = seg * KS, jend = min(j0 + KS, nr2);
+        double wa[W][VEC], wd[W][VEC];
+        auto ld = [&](int slot, int row) {
+            const long long o = (long long)wrap_per64(row, nr2) * P + p;
+            if (VEC == 2) {
+                const double2 x = __ldg(reinterpret_cast<const double2*>(lo + o)), y = __ldg(reinterpret_cast<const double2*>(hi + o));
+                wa[slot][0] = x.x; wa[slot][VEC - 1] = x.y; wd[slot][0] = y.x; wd[slot][VEC - 1] = y.y;
+            } else {
+                wa[slot][0] = __ldg(lo + o);
+                wd[slot][0] = __ldg(hi + o);
+            }
+        };
+#pragma unroll
+        for (int w = 0; w < W - 1; w++) ld(w, j0 - S1 + w);
+        for (int jb0 = j0; jb0 < jend; jb0 += W) {
+#pragma unroll
+            for (int u = 0; u < W; u++) {
+                const int j = jb0 + u;
+                if (j < jend) {
+                    ld((W - 1 + u) % W, j - S1 + W - 1);
+                    // window position w holds band row j - S1 + w; output 2j + b uses taps 2 jj + t0 at row j + ((b+PP)>>1) - jj
+#pragma unroll
+                    for (int b = 0; b < 2; b++) {
+                        const int t0 = (b + PP) & 1, wb = ((b + PP) >> 1) + S1;
+                        double x[VEC];
+#pragma unroll
+                        for (int v = 0; v < VEC; v++) x[v] = 0.0;
+#pragma unroll
+                        for (int jj = 0; jj < F / 2; jj++)
+#pragma unroll
+                            for (int v = 0; v < VEC; v++) {
+                                x[v] = fma(wa[(wb - jj + u) % W][v], f.IL[2 * jj + t0], x[v]);
+                                x[v] = fma(wd[(wb - jj + u) % W][v], f.IH[2 * jj + t0], x[v]);
+                            }
+                        const int n = 2 * j + b;
+                        if (n < Nr_out) {
+                            double* o = out + (long long)n * P + p;
+                            if (VEC == 2) *reinterpret_cast<double2*>(o) = make_double2(x[0], x[VEC - 1]);
+                            else o[0] = x[0];
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+inline int pick_ks64(int n_out, int PV, int period, int jobs) {
+    const long long want_threads = 2LL * 148 * 1024;
+    long long nseg = (want_threads + (long long)jobs * PV - 1) / ((long long)jobs * PV);
+    if (nseg < 1) nseg = 1;
+    int ks = (int)((n_out + nseg - 1) / nseg);
+    if (ks < 4 * period) ks = 4 * period;
+    return ((ks + period - 1) / period) * period;
+}
+inline unsigned grid64(long long items, int threads) {
+    long long g = (items + threads - 1) / threads;
+    const long long cap = (long long)pwt_sm_count() * 64;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+#define PWT64_CASES(X) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20)
+// one 2D level, two passes; tmp holds 2 * batch * Nr * ceil(Nc / 2) doubles.  Returns the launches (0: not covered).
+int level_fwd2d_2pass(const double* in, double* A, double* Hb, double* V, double* D, double* tmp, int batch, int Nr, int Nc,
+                      long long in_bs, long long out_bs, const PwtFilters64& f, cudaStream_t st) {
+    const int F = f.hlen, Nc2 = (Nc + 1) >> 1, Nr2 = (Nr + 1) >> 1;
+    if (F < 4 || F > 20 || (F & 1) || in_bs != (long long)Nr * Nc || out_bs != (long long)Nr2 * Nc2) return 0;
+    const long long rows = (long long)batch * Nr, half = rows * Nc2;
+    double* lo = tmp;
+    double* hi = tmp + half;
+    ColJobs64 jb = {};
+    jb.a[0] = lo; jb.o0[0] = A; jb.o1[0] = Hb;
+    jb.a[1] = hi; jb.o0[1] = V; jb.o1[1] = D;
+    const bool vec = (Nc2 & 1) == 0 && ((((uintptr_t)lo) | ((uintptr_t)hi) | ((uintptr_t)A) | ((uintptr_t)Hb) | ((uintptr_t)V) | ((uintptr_t)D)) & 15) == 0 &&
+                     (((long long)Nr * Nc2) & 1) == 0 && (out_bs & 1) == 0;
+    const int PV = vec ? Nc2 / 2 : Nc2;
+    const int KS = pick_ks64(Nr2, PV * batch, F / 2, 2);
+    const dim3 gc(grid64((long long)PV * ((Nr2 + KS - 1) / KS), 128), 2, batch);
+    const unsigned gr = grid64(rows * ((Nc2 + 3) / 4), 256);
+    switch (F) {
+#define X(FF) case FF: k64_rows_fwd<FF><<<gr, 256, 0, st>>>(in, lo, hi, rows, Nc, f); \
+        if (vec) k64_cols_fwd<FF, 2><<<gc, 128, 0, st>>>(jb, Nr, Nc2, (long long)Nr * Nc2, out_bs, KS, f); \
+        else k64_cols_fwd<FF, 1><<<gc, 128, 0, st>>>(jb, Nr, Nc2, (long long)Nr * Nc2, out_bs, KS, f); \
+        return 2;
+        PWT64_CASES(X)
+#undef X
+    }
+    return 0;
+}
+int level_inv2d_2pass(const double* A, const double* Hb, const double* V, const double* D, double* out, double* tmp, int batch,
+                      int nr, int nc, int Nro, int Nco, long long in_bs, long long out_bs, const PwtFilters64& f, cudaStream_t st) {
+    const int F = f.hlen;
+    if (F < 4 || F > 20 || (F & 1) || in_bs != (long long)nr * nc || out_bs != (long long)Nro * Nco) return 0;
+    const long long rows = (long long)batch * Nro, half = rows * nc;
+    double* t1 = tmp;
+    double* t2 = tmp + half;
+    ColJobs64 jb = {};
+    jb.a[0] = A; jb.b[0] = Hb; jb.o0[0] = t1;
+    jb.a[1] = V; jb.b[1] = D; jb.o0[1] = t2;
+    const bool vec = (nc & 1) == 0 && ((((uintptr_t)t1) | ((uintptr_t)t2) | ((uintptr_t)A) | ((uintptr_t)Hb) | ((uintptr_t)V) | ((uintptr_t)D)) & 15) == 0 &&
+                     (in_bs & 1) == 0 && (((long long)Nro * nc) & 1) == 0;
+    const int PV = vec ? nc / 2 : nc;
+    const int KS = pick_ks64(nr, PV * batch, F / 2 + 1, 2);
+    const dim3 gc(grid64((long long)PV * ((nr + KS - 1) / KS), 128), 2, batch);
+    const unsigned gr = grid64(rows * ((nc + 3) / 4), 256);
+    switch (F) {
+#define X(FF) case FF: \
+        if (vec) k64_cols_inv<FF, 2><<<gc, 128, 0, st>>>(jb, nr, Nro, nc, in_bs, (long long)Nro * nc, KS, f); \
+        else k64_cols_inv<FF, 1><<<gc, 128, 0, st>>>(jb, nr, Nro, nc, in_bs, (long long)Nro * nc, KS, f); \
+        k64_rows_inv<FF><<<gr, 256, 0, st>>>(t1, t2, out, rows, nc, Nco, f); \
+        return 2;
+        PWT64_CASES(X)
+#undef X
+    }
+    return 0;
+}
+
 inline unsigned grid_for(long long n) {
     long long g = (n + 255) / 256;
     const long long cap = (long long)pwt_sm_count() * 16;
@@ -111,6 +388,7 @@ struct pwt64_plan {
     double* slab;
     double* d_image;
     double* d_tmp;       // DWT: one image-sized plane; 2D SWT: three
+    double* d_tmp2;      // 2D DWT: the two row-pass planes of the two-pass kernels (2 x Nr x ceil(Nc/2))
     int nbands;
     double* d_band[PWT_MAX_BANDS];
     int band_nr[PWT_MAX_BANDS], band_nc[PWT_MAX_BANDS];
@@ -232,6 +510,8 @@ extern "C" int pwt64_create(pwt64_plan** out, const double* img, int batch, int 
         }
         const size_t tmp_off = total;
         total += (p->do_swt && p->ndims == 2) ? 3 * img_n : img_n;
+        const size_t tmp2_off = total;
+        if (!p->do_swt && p->ndims == 2) total += align32(B * (size_t)p->Nr * (size_t)(p->Nc + 2));
         e = cudaMalloc((void**)&p->slab, total * sizeof(double));
         if (e == cudaSuccess) e = cudaMemsetAsync(p->slab, 0, total * sizeof(double), p->stream);
         if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_acc, 2 * sizeof(double));
@@ -241,6 +521,7 @@ extern "C" int pwt64_create(pwt64_plan** out, const double* img, int batch, int 
             p->d_image = p->slab;
             for (int b = 0; b < p->nbands; b++) p->d_band[b] = p->slab + off[b];
             p->d_tmp = p->slab + tmp_off;
+            p->d_tmp2 = (!p->do_swt && p->ndims == 2) ? p->slab + tmp2_off : nullptr;
         }
     }
     if (rc == PWT_OK && img) {
@@ -302,9 +583,13 @@ extern "C" int pwt64_forward(pwt64_plan* p) {
             double* D = p->d_band[3 * (l - 1) + 3];
             if (p->do_swt)
                 p->launches += pwt_launch_swt_fwd2d_f64(src, dstA, Hb, V, D, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
-            else
-                p->launches += pwt_launch_dwt_fwd2d_f64(src, dstA, Hb, V, D, B, p->lvNr[l - 1], p->lvNc[l - 1],
-                                                        lvl_elems(p, l - 1), lvl_elems(p, l), p->filt, haar, st);
+            else {
+                int n = haar ? 0 : level_fwd2d_2pass(src, dstA, Hb, V, D, p->d_tmp2, B, p->lvNr[l - 1], p->lvNc[l - 1],
+                                                     lvl_elems(p, l - 1), lvl_elems(p, l), p->filt, st);
+                if (!n) n = pwt_launch_dwt_fwd2d_f64(src, dstA, Hb, V, D, B, p->lvNr[l - 1], p->lvNc[l - 1],
+                                                     lvl_elems(p, l - 1), lvl_elems(p, l), p->filt, haar, st);
+                p->launches += n;
+            }
         }
         src = dstA;
     }
@@ -341,9 +626,13 @@ extern "C" int pwt64_inverse(pwt64_plan* p) {
             const double* D = p->d_band[3 * (l - 1) + 3];
             if (p->do_swt)
                 p->launches += pwt_launch_swt_inv2d_f64(cur, Hb, V, D, dst, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
-            else
-                p->launches += pwt_launch_dwt_inv2d_f64(cur, Hb, V, D, dst, B, p->lvNr[l], p->lvNc[l], p->lvNr[l - 1],
-                                                        p->lvNc[l - 1], lvl_elems(p, l), lvl_elems(p, l - 1), p->filt, haar, st);
+            else {
+                int n = haar ? 0 : level_inv2d_2pass(cur, Hb, V, D, dst, p->d_tmp2, B, p->lvNr[l], p->lvNc[l], p->lvNr[l - 1],
+                                                     p->lvNc[l - 1], lvl_elems(p, l), lvl_elems(p, l - 1), p->filt, st);
+                if (!n) n = pwt_launch_dwt_inv2d_f64(cur, Hb, V, D, dst, B, p->lvNr[l], p->lvNc[l], p->lvNr[l - 1],
+                                                     p->lvNc[l - 1], lvl_elems(p, l), lvl_elems(p, l - 1), p->filt, haar, st);
+                p->launches += n;
+            }
         }
         cur = dst;
     }
