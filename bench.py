@@ -208,7 +208,7 @@ def run_reference(args):
                                    "mode=periodization (pywt not installable here); host has %d cores" % (args.steps, side, side, os.cpu_count() or 0)},
         "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def time_pdwt(img, steps, warmup):
@@ -635,12 +635,30 @@ def run_ours(args):
             "pdwt_cuda": pd,
         }
         line.update(extra)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract goes to the process's original stdout; everything else the run prints (the C
+    library reproduces the reference's warnings with puts(), e.g. "makes little sense to use Cycle spinning with
+    stationary Wavelet transform" in the C4 leg) has been routed to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)          # keep the real stdout for the JSON line ...
+    os.dup2(2, 1)                 # ... and send every other write to fd 1 (Python prints, C puts) to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
