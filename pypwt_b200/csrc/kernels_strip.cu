@@ -884,6 +884,12 @@ template <int F>
 int launch_inv(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch, int nr,
                int nc, int Nr_out, int Nc_out, long long in_bs, long long out_bs, const PwtFilters& f, int thr_op,
                const StripThr& thr, cudaStream_t st) {
+    // F = 14: 3 CTAs per SM like the plain inverse (64 x 2048^2 db7 fwd+soft+inv 1.184 -> 1.150 ms); F = 16 spills at the
+    // 80-register cap with the threshold code and loses (1.23 -> 1.28 ms), so it stays at 2
+    if (F == 14 && occ_inv(F) == 3 && pwt_tuning().strip_thr_occ3) {
+        if (thr_op == PWT_OP_SOFT) return launch_inv_mb<F, (F == 14 ? 3 : 2), 1>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, thr, st);
+        if (thr_op == PWT_OP_HARD) return launch_inv_mb<F, (F == 14 ? 3 : 2), 2>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, thr, st);
+    }
     if (thr_op == PWT_OP_SOFT) return launch_inv_mb<F, 2, 1>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, thr, st);
     if (thr_op == PWT_OP_HARD) return launch_inv_mb<F, 2, 2>(A, Hb, V, D, out, batch, nr, nc, Nr_out, Nc_out, in_bs, out_bs, f, thr, st);
     if (F <= 16 && occ_inv(F) == 3)

@@ -89,6 +89,7 @@ struct PwtTuning {
     int no_fold_cs;        // PWT_NO_FOLD_CS=1: cycle-spinning shifts as separate gather passes
     int no_cascade8;       // PWT_NO_CASCADE8=1: no level-fused strip kernels (F >= 8)
     int no_fused1d;        // PWT_NO_FUSED1D=1: batched 1D one launch per level
+    int strip_thr_occ3;    // PWT_STRIP_THR_OCC3 (default 1): thresholding strip inverse at 3 CTAs/SM for F = 14
     int tail_strip;        // PWT_TAIL_STRIP (default 1): levels >= 4 of short-filter transforms run the strip kernels
 };
 const PwtTuning& pwt_tuning();       // pwt_plan.cu

@@ -87,6 +87,7 @@ const PwtTuning& pwt_tuning() {
         k.no_cascade8 = env_i("PWT_NO_CASCADE8", 0);
         k.no_fused1d = env_i("PWT_NO_FUSED1D", 0);
         k.tail_strip = env_i("PWT_TAIL_STRIP", 1);
+        k.strip_thr_occ3 = env_i("PWT_STRIP_THR_OCC3", 1);
         return k;
     }();
     return t;
