@@ -324,6 +324,12 @@ int pwt_level_fwd2d(const float* src, float* A, float* Hb, float* V, float* D, i
 int pwt_level_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* dst, int batch, int nr, int nc,
                     int Nro, int Nco, long long in_bs, long long out_bs, const PwtFilters& f, bool haar, cudaStream_t st);
 int pwt_set_error(int code, const char* msg);
+// kernels_swt2p.cu : 2D a-trous level as two streaming passes (any even F <= 40, any size): the fallback behind the fused
+// SWT kernels.  tmp holds 2 * batch * Nr * Nc floats.  Return 0 when not covered.
+int pwt_swt2p_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, float* tmp, int batch, int Nr, int Nc, int level,
+                    const PwtFilters& f, cudaStream_t st);
+int pwt_swt2p_inv2d(const float* A, const float* Hb, const float* V, const float* D, float* out, float* tmp, int batch, int Nr,
+                    int Nc, int level, const PwtFilters& f, cudaStream_t st);
 // kernels_row1d.cu : batched 1D DWT / IDWT, every level in ONE launch (rows staged once in shared memory).  D[l] = detail
 // band of level l + 1.  Return 0 when not covered (row too long for a CTA's shared memory, odd filter length).
 int pwt_row_dwt_fwd1d_all(const float* in, float* A, float* const* D, int rows, int Nc, int L, const PwtFilters& f,

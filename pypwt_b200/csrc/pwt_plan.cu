@@ -779,6 +779,7 @@ extern "C" int pwt_forward(pwt_plan* p) {
                 if (p->do_separable || ns_sep) {
                     int n = p->kernel_mode == 0 ? pwt_strip_swt_fwd2d(src, dstA, Hb, V, D, B, p->Nr, p->Nc, l, p->filt, st) : 0;
                     if (!n && p->kernel_mode != 1) n = pwt_fast_swt_fwd2d(src, dstA, Hb, V, D, B, p->Nr, p->Nc, l, p->filt, st);
+                    if (!n && p->kernel_mode != 1) n = pwt_swt2p_fwd2d(src, dstA, Hb, V, D, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
                     if (!n) n = pwt_launch_swt_fwd2d(src, dstA, Hb, V, D, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
                     p->launches += n;
                 }
@@ -999,6 +1000,7 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                             n = pwt_fast_swt_inv2d(cur, Hb, V, D, dst, B, p->Nr, p->Nc, l, p->filt, -1, 0.f, 0, 0.f, st);
                     }
                     if (!n && swt_defer) return fail(PWT_ERR_CUDA, "fused SWT inverse declined a level it had accepted");
+                    if (!n && p->kernel_mode != 1) n = pwt_swt2p_inv2d(cur, Hb, V, D, dst, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
                     if (!n) n = pwt_launch_swt_inv2d(cur, Hb, V, D, dst, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
                     p->launches += n;
                 }

@@ -595,6 +595,31 @@ def test_fused_swt_kernels_agree_with_generic(wname, shape):
     assert_close(A.image, img, 255.0, "swt roundtrip")
 
 
+@pytest.mark.parametrize("shape", [(256, 512), (201, 303), (130, 254), (2, 96, 132)])
+@pytest.mark.parametrize("wname", ["db2", "sym8", "db9", "db10", "coif4", "coif5", "db19", "db20"])
+def test_two_pass_swt_kernels_against_oracle(wname, shape):
+    """The streaming two-pass a-trous level (kernels_swt2p.cu: what the fused SWT kernels leave -- filters longer than
+    16 taps, widths that are not multiples of 4) against the generic kernels and the oracle, 4 levels (dilations 1..8,
+    periodic wrap inside the tile staging and inside the column walk), columns per thread 4 / 2 / 1 by width."""
+    img = synth_image(shape, seed=21, kind="smooth")
+    A = _W(img, wname, 4, do_swt=1); G = _W(img, wname, 4, do_swt=1)
+    G.set_kernel_mode(1)
+    A.forward(); G.forward()
+    assert A.levels == G.levels
+    for i in range(A.levels + 1):
+        for a, g in zip(A.coeffs[i] if i else [A.coeffs[0]], G.coeffs[i] if i else [G.coeffs[0]]):
+            assert_close(a, g, 255.0, "swt two-pass vs generic")
+    if len(shape) == 2:
+        Wo = O.OracleWavelets(img, wname, 4, do_swt=1)
+        Wo.forward()
+        compare_coeffs(A, Wo, 255.0, "swt two-pass vs oracle")
+        Wo.inverse()
+    A.inverse(); G.inverse()
+    assert_close(A.image, G.image, 255.0, "iswt two-pass vs generic")
+    if len(shape) == 2:
+        assert_close(A.image, Wo.image, 255.0, "iswt two-pass vs oracle")
+
+
 @pytest.mark.parametrize("wname", ["haar", "db2"])
 def test_full_size_roundtrip_properties(wname):
     """BASELINE metric size (8192^2, 3 levels): size-independent properties -- perfect reconstruction,
