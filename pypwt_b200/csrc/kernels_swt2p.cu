@@ -25,8 +25,9 @@ __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // ---- rows ------------------------------------------------------------------------------------------------------------
 constexpr int kTO = 2048;                                  // outputs per tile
 // analysis: out[g] = sum_j f[F-1-j] in[(g + (j - c) s) mod Nc], c = F/2 - 1  ->  lo, hi
+template <int F>
 __global__ void __launch_bounds__(256)
-k_swt2p_rows_fwd(const float* __restrict__ in, float* __restrict__ lo, float* __restrict__ hi, long long rows, int Nc, int s, int F,
+k_swt2p_rows_fwd(const float* __restrict__ in, float* __restrict__ lo, float* __restrict__ hi, long long rows, int Nc, int s,
                  const __grid_constant__ PwtTapsFwd tp) {
     extern __shared__ float sx[];
     const int c = F / 2 - 1, reach = (F - 1) * s, ntile = cdiv(Nc, kTO);
@@ -50,6 +51,7 @@ k_swt2p_rows_fwd(const float* __restrict__ in, float* __restrict__ lo, float* __
         __syncthreads();
         for (int o = threadIdx.x; o < nout; o += 256) {
             float2 p = make_float2(0.f, 0.f);
+#pragma unroll
             for (int j = 0; j < F; j++) p = fma2s(sx[o + j * s], tp.t[j], p);
             lo[r * Nc + g0 + o] = p.x;
             hi[r * Nc + g0 + o] = p.y;
@@ -61,9 +63,10 @@ k_swt2p_rows_fwd(const float* __restrict__ in, float* __restrict__ lo, float* __
 struct TapsHalf {
     float l[PWT_MAX_TAPS], h[PWT_MAX_TAPS];
 };
+template <int F>
 __global__ void __launch_bounds__(256)
 k_swt2p_rows_inv(const float* __restrict__ t1, const float* __restrict__ t2, float* __restrict__ out, long long rows, int Nc, int s,
-                 int F, const __grid_constant__ TapsHalf tp) {
+                 const __grid_constant__ TapsHalf tp) {
     extern __shared__ float sx[];
     const int c = F / 2, reach = (F - 1) * s, ntile = cdiv(Nc, kTO);
     float* sa = sx;
@@ -86,6 +89,7 @@ k_swt2p_rows_inv(const float* __restrict__ t1, const float* __restrict__ t2, flo
         __syncthreads();
         for (int o = threadIdx.x; o < nout; o += 256) {
             float x = 0.f;
+#pragma unroll
             for (int j = 0; j < F; j++) {
                 x = fmaf(sa[o + j * s], tp.l[j], x);
                 x = fmaf(sd[o + j * s], tp.h[j], x);
@@ -237,6 +241,22 @@ void launch_cols_inv(const ColJobs& jb, int batch, int Nr, int Nc, int s, const 
     const long long items = (long long)PV * cdiv(nqmax, KS) * s;
     pwt_launch_pdl(k_swt2p_cols_inv<F, VEC>, dim3(grid_for(items, 128), 2, batch), 128, 0, st, jb, Nr, Nc, s, KS, (long long)Nr * Nc, t);
 }
+template <int F>
+int launch_rows_fwd(const float* in, float* lo, float* hi, long long rows, int Nc, int s, size_t smem, const PwtTapsFwd& t, cudaStream_t st) {
+    static PwtKernelOnce once;
+    if (!pwt_kernel_once(once, k_swt2p_rows_fwd<F>, 256, 64 * 1024, smem)) return 0;
+    pwt_launch_pdl(k_swt2p_rows_fwd<F>, dim3(grid_for(rows * cdiv(Nc, kTO) * 256, 256)), 256, smem, st, in, lo, hi, rows, Nc, s, t);
+    return 1;
+}
+template <int F>
+bool prep_rows_inv(size_t smem) {
+    static PwtKernelOnce once;
+    return pwt_kernel_once(once, k_swt2p_rows_inv<F>, 256, 64 * 1024, smem);
+}
+template <int F>
+void launch_rows_inv(const float* t1, const float* t2, float* out, long long rows, int Nc, int s, size_t smem, const TapsHalf& t, cudaStream_t st) {
+    pwt_launch_pdl(k_swt2p_rows_inv<F>, dim3(grid_for(rows * cdiv(Nc, kTO) * 256, 256)), 256, smem, st, t1, t2, out, rows, Nc, s, t);
+}
 inline int vec_cap() {                                    // PWT_SWT2P_VEC: cap of the columns per thread (A/B)
     static const int v = [] { const char* e = getenv("PWT_SWT2P_VEC"); return e && *e ? atoi(e) : 4; }();
     return v;
@@ -259,9 +279,12 @@ int pwt_swt2p_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, fl
     float* hi = tmp + planeN;
     const PwtTapsFwd t = pwt_pack_taps_fwd(f, F);
     const size_t smem = sizeof(float) * (size_t)(kTO + reach);
-    static PwtKernelOnce once;
-    if (!pwt_kernel_once(once, k_swt2p_rows_fwd, 256, 64 * 1024, smem)) return 0;
-    pwt_launch_pdl(k_swt2p_rows_fwd, dim3(grid_for(rows * cdiv(Nc, kTO) * 256, 256)), 256, smem, st, in, lo, hi, rows, Nc, s, F, t);
+    switch (F) {
+#define X(FF) case FF: if (!launch_rows_fwd<FF>(in, lo, hi, rows, Nc, s, smem, t, st)) return 0; break;
+        PWT_SWT2P_CASES(X)
+#undef X
+        default: return 0;
+    }
     ColJobs jb = {};
     jb.a[0] = lo; jb.o0[0] = A; jb.o1[0] = Hb;
     jb.a[1] = hi; jb.o0[1] = V; jb.o1[1] = D;
@@ -292,8 +315,12 @@ int pwt_swt2p_inv2d(const float* A, const float* Hb, const float* V, const float
         t.h[j] = j < F ? 0.5f * f.IH[F - 1 - j] : 0.f;
     }
     const size_t smem = sizeof(float) * 2 * (size_t)(kTO + reach);
-    static PwtKernelOnce once;
-    if (!pwt_kernel_once(once, k_swt2p_rows_inv, 256, 64 * 1024, smem)) return 0;
+    switch (F) {
+#define X(FF) case FF: if (!prep_rows_inv<FF>(smem)) return 0; break;
+        PWT_SWT2P_CASES(X)
+#undef X
+        default: return 0;
+    }
     ColJobs jb = {};
     jb.a[0] = A; jb.b[0] = Hb; jb.o0[0] = t1;
     jb.a[1] = V; jb.b[1] = D; jb.o0[1] = t2;
@@ -308,6 +335,10 @@ int pwt_swt2p_inv2d(const float* A, const float* Hb, const float* V, const float
 #undef X
         default: return 0;
     }
-    pwt_launch_pdl(k_swt2p_rows_inv, dim3(grid_for(rows * cdiv(Nc, kTO) * 256, 256)), 256, smem, st, t1, t2, out, rows, Nc, s, F, t);
+    switch (F) {
+#define X(FF) case FF: launch_rows_inv<FF>(t1, t2, out, rows, Nc, s, smem, t, st); break;
+        PWT_SWT2P_CASES(X)
+#undef X
+    }
     return 2;
 }
