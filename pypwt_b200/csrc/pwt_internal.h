@@ -216,6 +216,11 @@ int pwt_launch_swt_fwd1d_f64(const double* in, double* A, double* D, int rows, i
                              cudaStream_t st);
 int pwt_launch_swt_inv1d_f64(const double* A, const double* D, double* out, int rows, int Nc, int level,
                              const PwtFilters64& f, cudaStream_t st);
+// kernels_f64_fused.cu : one double-precision 2D DWT level per launch, row and column pass fused (F = 4 .. 40).  0: not covered.
+int pwt64_fused_fwd2d(const double* in, double* A, double* Hb, double* V, double* D, int batch, int Nr, int Nc, long long in_bs,
+                      long long out_bs, const PwtFilters64& f, cudaStream_t st);
+int pwt64_fused_inv2d(const double* A, const double* Hb, const double* V, const double* D, double* out, int batch, int nr, int nc,
+                      int Nro, int Nco, long long in_bs, long long out_bs, const PwtFilters64& f, cudaStream_t st);
 // non-separable (true 2D stencils).  k2d = device array of 4*hlen*hlen taps: LL, LH, HL, HH.
 int pwt_launch_ns_fwd2d(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr,
                         int Nc, long long in_bs, long long out_bs, const float* k2d, int hlen,

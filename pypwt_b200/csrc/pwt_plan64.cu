@@ -619,8 +619,10 @@ extern "C" int pwt64_forward(pwt64_plan* p) {
             if (p->do_swt)
                 p->launches += pwt_launch_swt_fwd2d_f64(src, dstA, Hb, V, D, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
             else {
-                int n = haar ? 0 : level_fwd2d_2pass(src, dstA, Hb, V, D, p->d_tmp2, B, p->lvNr[l - 1], p->lvNc[l - 1],
-                                                     lvl_elems(p, l - 1), lvl_elems(p, l), p->filt, st);
+                int n = haar ? 0 : pwt64_fused_fwd2d(src, dstA, Hb, V, D, B, p->lvNr[l - 1], p->lvNc[l - 1], lvl_elems(p, l - 1),
+                                                     lvl_elems(p, l), p->filt, st);
+                if (!n && !haar) n = level_fwd2d_2pass(src, dstA, Hb, V, D, p->d_tmp2, B, p->lvNr[l - 1], p->lvNc[l - 1],
+                                                       lvl_elems(p, l - 1), lvl_elems(p, l), p->filt, st);
                 if (!n) n = pwt_launch_dwt_fwd2d_f64(src, dstA, Hb, V, D, B, p->lvNr[l - 1], p->lvNc[l - 1],
                                                      lvl_elems(p, l - 1), lvl_elems(p, l), p->filt, haar, st);
                 p->launches += n;
@@ -666,8 +668,10 @@ extern "C" int pwt64_inverse(pwt64_plan* p) {
             if (p->do_swt)
                 p->launches += pwt_launch_swt_inv2d_f64(cur, Hb, V, D, dst, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
             else {
-                int n = haar ? 0 : level_inv2d_2pass(cur, Hb, V, D, dst, p->d_tmp2, B, p->lvNr[l], p->lvNc[l], p->lvNr[l - 1],
-                                                     p->lvNc[l - 1], lvl_elems(p, l), lvl_elems(p, l - 1), p->filt, st);
+                int n = haar ? 0 : pwt64_fused_inv2d(cur, Hb, V, D, dst, B, p->lvNr[l], p->lvNc[l], p->lvNr[l - 1], p->lvNc[l - 1],
+                                                     lvl_elems(p, l), lvl_elems(p, l - 1), p->filt, st);
+                if (!n && !haar) n = level_inv2d_2pass(cur, Hb, V, D, dst, p->d_tmp2, B, p->lvNr[l], p->lvNc[l], p->lvNr[l - 1],
+                                                       p->lvNc[l - 1], lvl_elems(p, l), lvl_elems(p, l - 1), p->filt, st);
                 if (!n) n = pwt_launch_dwt_inv2d_f64(cur, Hb, V, D, dst, B, p->lvNr[l], p->lvNc[l], p->lvNr[l - 1],
                                                      p->lvNc[l - 1], lvl_elems(p, l), lvl_elems(p, l - 1), p->filt, haar, st);
                 p->launches += n;

@@ -160,3 +160,77 @@ def test_errors_f64():
         W.set_image(np.zeros((3, 3)))
     with pytest.raises(ValueError):
         W.set_coeff(np.zeros(5), 1)
+
+
+EVEN_BANKS_4_20 = ["db2", "db3", "db4", "db5", "sym6", "db7", "sym8", "db9", "db10", "bior2.2", "bior3.1", "rbio2.8", "bior6.8", "coif2", "coif3"]
+
+
+@pytest.mark.parametrize("shape", [(300, 520), (257, 1031), (2, 131, 258), (64, 64), (5, 7)])
+@pytest.mark.parametrize("wname", EVEN_BANKS_4_20)
+def test_fused_level_kernels_f64(wname, shape):
+    """kernels_f64_fused.cu (row + column pass of a level in one launch, F = 4 .. 20): several 128-column strips and row
+    segments, odd sizes in both directions (the repeated last sample of the analysis, the clipped last row / column of the
+    synthesis), a stack, a size smaller than the filter -- against the double-build oracle."""
+    img = _img(shape, 11)
+    imgs = img if img.ndim == 3 else img[None]
+    try:
+        Wos = [O.OracleWavelets(x, wname, 4, double_build=True) for x in imgs]
+    except ValueError:
+        pytest.skip("not a valid configuration")
+    W = _W64(img, wname, 4)
+    l0 = W.launch_count
+    W.forward()
+    assert W.levels == Wos[0].levels
+    if O.OracleWavelets(imgs[0], wname, 1, double_build=True).hlen <= 20:
+        assert W.launch_count - l0 == W.levels, "one launch per level expected (fused row + column pass)"
+    for Wo in Wos:
+        Wo.forward()
+    c = W.coeffs
+    for k, Wo in enumerate(Wos):
+        pick = (lambda a: a[k]) if img.ndim == 3 else (lambda a: a)
+        close(pick(c[0]), Wo.coeffs[0], "fused f64 A", wname=wname)
+        for i in range(1, len(c)):
+            for j in range(3):
+                close(pick(c[i][j]), Wo.coeffs[i][j], "fused f64 L%d b%d %s" % (i, j, wname), wname=wname)
+    W.inverse()
+    for k, Wo in enumerate(Wos):
+        Wo.inverse()
+        close(W.image[k] if img.ndim == 3 else W.image, Wo.image, "fused f64 inverse " + wname, wname=wname)
+
+
+def test_fused_level_kernels_f64_match_the_two_pass_kernels():
+    """Same process image, two library instances: PWT_F64_FUSED=0 selects the two-pass kernels.  The analysis keeps their
+    summation order (bit-identical bands); the synthesis runs rows before columns (fp64 rounding apart)."""
+    import os, subprocess, sys, tempfile
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import pypwt_b200
+rng = np.random.default_rng(5)
+out = {}
+for wn, shape in (("db2", (515, 770)), ("sym8", (384, 640)), ("db10", (3, 200, 300))):
+    img = rng.standard_normal(shape) * 40 + 100
+    W = pypwt_b200.Wavelets64(img, wn, 3)
+    W.forward()
+    c = W.coeffs
+    out[wn + "_A"] = c[0]
+    for i in range(1, len(c)):
+        for j in range(3): out["%%s_%%d_%%d" %% (wn, i, j)] = c[i][j]
+    W.inverse()
+    out[wn + "_img"] = W.image
+np.savez(sys.argv[1], **out)
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    with tempfile.TemporaryDirectory() as d:
+        for mode in ("1", "0"):
+            path = os.path.join(d, "m%s.npz" % mode)
+            env = dict(os.environ, PWT_F64_FUSED=mode)
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+            with np.load(path) as z:
+                res[mode] = {k: z[k] for k in z.files}
+    assert set(res["0"]) == set(res["1"]) and len(res["1"]) > 20
+    for k in res["1"]:
+        if k.endswith("_img"):
+            assert np.abs(res["1"][k] - res["0"][k]).max() <= 1e-12 * 255, k
+        else:
+            assert np.array_equal(res["1"][k], res["0"][k]), k
