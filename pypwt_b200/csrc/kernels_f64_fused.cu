@@ -4,16 +4,17 @@
 // round trip through HBM) and sit at the streaming limit for that traffic (8192^2 db2 3 levels fwd+inv 0.95 ms = 0.35 of
 // the 32 B/px roofline of the double-precision transform).  Here a CTA owns a strip of 128 half-resolution columns and
 // walks DOWN a segment of rows:
-//   analysis   R input rows of the strip (256 + F - 2 samples each) are staged with cp.async one chunk ahead; thread t
+//   analysis   the input rows of the strip (256 + F - 2 samples each) are staged with cp.async through a ring; thread t
 //              filters row n along x for its column (F/2 128-bit shared loads -> low-pass and high-pass sample), pushes the
 //              pair into two rotating register windows of F rows, and every second row emits A, H, V, D of its column
 //              (coalesced 8-byte stores).  Reference: w_kern_forward_pass1/2, separable.cu:98-197 with DTYPE = double.
-//   synthesis  R rows of the four bands (128 + F/2 columns each) are staged the same way; thread t synthesises along x the
+//   synthesis  the rows of the four bands (128 + F/2 columns each) are staged the same way; thread t synthesises along x the
 //              two output columns 2t, 2t + 1 of the two row planes (A, V -> low-pass plane; H, D -> high-pass plane), keeps
 //              F/2 + 1 rows of them in rotating register windows, and every band row emits two output rows (128-bit
 //              stores).  Reference: w_kern_inverse_pass1/2, separable.cu:252-361 (columns first there: same sums, the
 //              result differs by fp64 rounding only).
-// 16 B per level-input sample and direction.  The analysis keeps the summation order of the two-pass kernels exactly
+// 16 B per level-input sample and direction: 8192^2 3 levels fwd+inv db2 0.95 -> 0.52 ms (0.63 of the roofline; 0.75 is the
+// ceiling of one launch per level), sym8 1.33 -> 0.68, haar 0.94 -> 0.45.  The analysis keeps the summation order of the two-pass kernels exactly
 // (bit-identical results); rotations are unrolled over their period so every register index is static.
 #include <stdlib.h>
 
@@ -403,6 +404,91 @@ k64_fused_inv(const double* __restrict__ A, const double* __restrict__ Hb, const
     }
 }
 
+// ---- Haar (haar.cu:10-58 with DTYPE = double: the exact 1/2 butterfly, not the filter bank) ------------------------------
+// One thread per pair of adjacent band columns: 2 x 32 bytes in, 4 x 16 bytes out (analysis) and the converse.  VEC: sizes
+// and pointers allow 128-bit accesses; otherwise one band column per thread, scalar, with the odd-size rules (the analysis
+// repeats the last row / column, the synthesis drops the extra ones).
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+k64_haar_fwd(const double* __restrict__ in, double* __restrict__ A, double* __restrict__ Hb, double* __restrict__ V,
+             double* __restrict__ D, int Nr, int Nc, long long in_bs, long long out_bs) {
+    const int Nr2 = (Nr + 1) >> 1, Nc2 = (Nc + 1) >> 1, PV = VEC ? Nc2 >> 1 : Nc2;
+    in += blockIdx.z * in_bs;
+    const long long ob = blockIdx.z * out_bs;
+    pwt_pdl_wait();
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < (long long)Nr2 * PV; i += gridDim.x * 256LL) {
+        const int k = (int)(i / PV), p = (int)(i - (long long)k * PV);
+        const double* r0 = in + (long long)(2 * k) * Nc;
+        const double* r1 = in + (long long)min(2 * k + 1, Nr - 1) * Nc;
+        if (VEC) {
+            const double2 u0 = __ldcs(reinterpret_cast<const double2*>(r0 + 4 * p)), u1 = __ldcs(reinterpret_cast<const double2*>(r0 + 4 * p + 2));
+            const double2 l0 = __ldcs(reinterpret_cast<const double2*>(r1 + 4 * p)), l1 = __ldcs(reinterpret_cast<const double2*>(r1 + 4 * p + 2));
+            const double s0 = u0.x + l0.x, t0 = u0.y + l0.y, d0 = u0.x - l0.x, e0 = u0.y - l0.y;
+            const double s1 = u1.x + l1.x, t1 = u1.y + l1.y, d1 = u1.x - l1.x, e1 = u1.y - l1.y;
+            const long long o = ob + (long long)k * Nc2 + 2 * p;
+            *reinterpret_cast<double2*>(A + o) = make_double2(0.5 * (s0 + t0), 0.5 * (s1 + t1));
+            *reinterpret_cast<double2*>(V + o) = make_double2(0.5 * (s0 - t0), 0.5 * (s1 - t1));
+            *reinterpret_cast<double2*>(Hb + o) = make_double2(0.5 * (d0 + e0), 0.5 * (d1 + e1));
+            *reinterpret_cast<double2*>(D + o) = make_double2(0.5 * (d0 - e0), 0.5 * (d1 - e1));
+        } else {
+            const int c0 = 2 * p, c1 = min(2 * p + 1, Nc - 1);
+            const double a = r0[c0], b = r0[c1], c = r1[c0], d = r1[c1];
+            const long long o = ob + (long long)k * Nc2 + p;
+            A[o] = 0.5 * ((a + c) + (b + d));
+            V[o] = 0.5 * ((a + c) - (b + d));
+            Hb[o] = 0.5 * ((a - c) + (b - d));
+            D[o] = 0.5 * ((a - c) - (b - d));
+        }
+    }
+}
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+k64_haar_inv(const double* __restrict__ A, const double* __restrict__ Hb, const double* __restrict__ V,
+             const double* __restrict__ D, double* __restrict__ out, int nr, int nc, int Nro, int Nco, long long in_bs,
+             long long out_bs) {
+    const int PV = VEC ? nc >> 1 : nc;
+    const long long ib = blockIdx.z * in_bs;
+    out += blockIdx.z * out_bs;
+    pwt_pdl_wait();
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < (long long)nr * PV; i += gridDim.x * 256LL) {
+        const int j = (int)(i / PV), p = (int)(i - (long long)j * PV);
+        double* o0 = out + (long long)(2 * j) * Nco;
+        double* o1 = o0 + Nco;
+        const bool row1 = 2 * j + 1 < Nro;
+        if (VEC) {
+            const long long o = ib + (long long)j * nc + 2 * p;
+            const double2 a = __ldcs(reinterpret_cast<const double2*>(A + o)), b = __ldcs(reinterpret_cast<const double2*>(V + o));
+            const double2 c = __ldcs(reinterpret_cast<const double2*>(Hb + o)), d = __ldcs(reinterpret_cast<const double2*>(D + o));
+            const double s0 = a.x + c.x, t0 = b.x + d.x, u0 = a.x - c.x, v0 = b.x - d.x;
+            const double s1 = a.y + c.y, t1 = b.y + d.y, u1 = a.y - c.y, v1 = b.y - d.y;
+            *reinterpret_cast<double2*>(o0 + 4 * p) = make_double2(0.5 * (s0 + t0), 0.5 * (s0 - t0));
+            *reinterpret_cast<double2*>(o0 + 4 * p + 2) = make_double2(0.5 * (s1 + t1), 0.5 * (s1 - t1));
+            if (row1) {
+                *reinterpret_cast<double2*>(o1 + 4 * p) = make_double2(0.5 * (u0 + v0), 0.5 * (u0 - v0));
+                *reinterpret_cast<double2*>(o1 + 4 * p + 2) = make_double2(0.5 * (u1 + v1), 0.5 * (u1 - v1));
+            }
+        } else {
+            const long long o = ib + (long long)j * nc + p;
+            const double a = A[o], b = V[o], c = Hb[o], d = D[o];
+            const bool col1 = 2 * p + 1 < Nco;
+            o0[2 * p] = 0.5 * ((a + c) + (b + d));
+            if (col1) o0[2 * p + 1] = 0.5 * ((a + c) - (b + d));
+            if (row1) {
+                o1[2 * p] = 0.5 * ((a - c) + (b - d));
+                if (col1) o1[2 * p + 1] = 0.5 * ((a - c) - (b - d));
+            }
+        }
+    }
+}
+inline unsigned haar_grid(long long items) {
+    long long g = (items + 255) / 256;
+    const long long cap = (long long)pwt_sm_count() * 32;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+inline bool al16(const void* a, const void* b = nullptr, const void* c = nullptr, const void* d = nullptr, const void* e = nullptr) {
+    return ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)c) | ((uintptr_t)d) | ((uintptr_t)e)) & 15) == 0;
+}
+
 // Rows per segment: the grid (units x segments) should fill whole waves of the resident CTAs (cap); every segment
 // re-reads `halo` stream rows.  Cost model: waves x (rows a CTA streams).
 inline int pick_ks(int n_out, long long units, int cap, int rows_per_out, int halo, int min_ks) {
@@ -454,6 +540,25 @@ int launch_inv(const double* A, const double* Hb, const double* V, const double*
 
 #define PWT64F_CASES(X) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20) X(22) X(24) X(26) X(28) X(30) X(32) X(34) X(36) X(38) X(40)
 
+int pwt64_haar_fwd2d(const double* in, double* A, double* Hb, double* V, double* D, int batch, int Nr, int Nc, long long in_bs,
+                     long long out_bs, cudaStream_t st) {
+    if (!fused_enabled() || batch < 1 || batch > 65535 || Nr < 1 || Nc < 1) return 0;
+    const int Nr2 = (Nr + 1) >> 1, Nc2 = (Nc + 1) >> 1;
+    const bool vec = (Nc & 3) == 0 && al16(in, A, Hb, V, D) && (in_bs & 1) == 0 && (out_bs & 1) == 0;
+    const dim3 grid(haar_grid((long long)Nr2 * (vec ? Nc2 / 2 : Nc2)), 1, batch);
+    if (vec) pwt_launch_pdl(k64_haar_fwd<true>, grid, 256, 0, st, in, A, Hb, V, D, Nr, Nc, in_bs, out_bs);
+    else pwt_launch_pdl(k64_haar_fwd<false>, grid, 256, 0, st, in, A, Hb, V, D, Nr, Nc, in_bs, out_bs);
+    return 1;
+}
+int pwt64_haar_inv2d(const double* A, const double* Hb, const double* V, const double* D, double* out, int batch, int nr, int nc,
+                     int Nro, int Nco, long long in_bs, long long out_bs, cudaStream_t st) {
+    if (!fused_enabled() || batch < 1 || batch > 65535 || nr < 1 || nc < 1) return 0;
+    const bool vec = (nc & 1) == 0 && Nco == 2 * nc && al16(out, A, Hb, V, D) && (in_bs & 1) == 0 && (out_bs & 1) == 0;
+    const dim3 grid(haar_grid((long long)nr * (vec ? nc / 2 : nc)), 1, batch);
+    if (vec) pwt_launch_pdl(k64_haar_inv<true>, grid, 256, 0, st, A, Hb, V, D, out, nr, nc, Nro, Nco, in_bs, out_bs);
+    else pwt_launch_pdl(k64_haar_inv<false>, grid, 256, 0, st, A, Hb, V, D, out, nr, nc, Nro, Nco, in_bs, out_bs);
+    return 1;
+}
 // One analysis level, [batch] images of Nr x Nc -> four bands of ceil(Nr/2) x ceil(Nc/2).  Returns the launches (1), 0: not covered.
 int pwt64_fused_fwd2d(const double* in, double* A, double* Hb, double* V, double* D, int batch, int Nr, int Nc, long long in_bs,
                       long long out_bs, const PwtFilters64& f, cudaStream_t st) {

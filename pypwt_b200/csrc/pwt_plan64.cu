@@ -21,6 +21,11 @@
 int pwt_is_haar_alias(const char* wname);
 int pwt_fill_filters64(const char* wname, PwtFilters64* out);
 extern "C" const char* pwt_last_error(void);
+// kernels_f64_fused.cu: the Haar butterfly of a 2D level, one thread per pair of band columns (0: switched off)
+int pwt64_haar_fwd2d(const double* in, double* A, double* Hb, double* V, double* D, int batch, int Nr, int Nc, long long in_bs,
+                     long long out_bs, cudaStream_t st);
+int pwt64_haar_inv2d(const double* A, const double* Hb, const double* V, const double* D, double* out, int batch, int nr, int nc,
+                     int Nro, int Nco, long long in_bs, long long out_bs, cudaStream_t st);
 int pwt_set_error(int code, const char* msg);      // pwt_plan.cu: stores the thread-local message, returns code
 
 namespace {
@@ -619,8 +624,9 @@ extern "C" int pwt64_forward(pwt64_plan* p) {
             if (p->do_swt)
                 p->launches += pwt_launch_swt_fwd2d_f64(src, dstA, Hb, V, D, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
             else {
-                int n = haar ? 0 : pwt64_fused_fwd2d(src, dstA, Hb, V, D, B, p->lvNr[l - 1], p->lvNc[l - 1], lvl_elems(p, l - 1),
-                                                     lvl_elems(p, l), p->filt, st);
+                int n = haar ? pwt64_haar_fwd2d(src, dstA, Hb, V, D, B, p->lvNr[l - 1], p->lvNc[l - 1], lvl_elems(p, l - 1), lvl_elems(p, l), st)
+                             : pwt64_fused_fwd2d(src, dstA, Hb, V, D, B, p->lvNr[l - 1], p->lvNc[l - 1], lvl_elems(p, l - 1),
+                                                 lvl_elems(p, l), p->filt, st);
                 if (!n && !haar) n = level_fwd2d_2pass(src, dstA, Hb, V, D, p->d_tmp2, B, p->lvNr[l - 1], p->lvNc[l - 1],
                                                        lvl_elems(p, l - 1), lvl_elems(p, l), p->filt, st);
                 if (!n) n = pwt_launch_dwt_fwd2d_f64(src, dstA, Hb, V, D, B, p->lvNr[l - 1], p->lvNc[l - 1],
@@ -668,8 +674,10 @@ extern "C" int pwt64_inverse(pwt64_plan* p) {
             if (p->do_swt)
                 p->launches += pwt_launch_swt_inv2d_f64(cur, Hb, V, D, dst, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
             else {
-                int n = haar ? 0 : pwt64_fused_inv2d(cur, Hb, V, D, dst, B, p->lvNr[l], p->lvNc[l], p->lvNr[l - 1], p->lvNc[l - 1],
-                                                     lvl_elems(p, l), lvl_elems(p, l - 1), p->filt, st);
+                int n = haar ? pwt64_haar_inv2d(cur, Hb, V, D, dst, B, p->lvNr[l], p->lvNc[l], p->lvNr[l - 1], p->lvNc[l - 1],
+                                                lvl_elems(p, l), lvl_elems(p, l - 1), st)
+                             : pwt64_fused_inv2d(cur, Hb, V, D, dst, B, p->lvNr[l], p->lvNc[l], p->lvNr[l - 1], p->lvNc[l - 1],
+                                                 lvl_elems(p, l), lvl_elems(p, l - 1), p->filt, st);
                 if (!n && !haar) n = level_inv2d_2pass(cur, Hb, V, D, dst, p->d_tmp2, B, p->lvNr[l], p->lvNc[l], p->lvNr[l - 1],
                                                        p->lvNc[l - 1], lvl_elems(p, l), lvl_elems(p, l - 1), p->filt, st);
                 if (!n) n = pwt_launch_dwt_inv2d_f64(cur, Hb, V, D, dst, B, p->lvNr[l], p->lvNc[l], p->lvNr[l - 1],
