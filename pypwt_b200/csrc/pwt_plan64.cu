@@ -26,6 +26,11 @@ int pwt64_haar_fwd2d(const double* in, double* A, double* Hb, double* V, double*
                      long long out_bs, cudaStream_t st);
 int pwt64_haar_inv2d(const double* A, const double* Hb, const double* V, const double* D, double* out, int batch, int nr, int nc,
                      int Nro, int Nco, long long in_bs, long long out_bs, cudaStream_t st);
+// kernels_swt2p.cu instantiated for double: a 2D a-trous level as two streaming passes (0: not covered)
+int pwt_swt2p_fwd2d_f64(const double* in, double* A, double* Hb, double* V, double* D, double* tmp, int batch, int Nr, int Nc, int level,
+                        const PwtFilters64& f, cudaStream_t st);
+int pwt_swt2p_inv2d_f64(const double* A, const double* Hb, const double* V, const double* D, double* out, double* tmp, int batch, int Nr,
+                        int Nc, int level, const PwtFilters64& f, cudaStream_t st);
 int pwt_set_error(int code, const char* msg);      // pwt_plan.cu: stores the thread-local message, returns code
 
 namespace {
@@ -621,8 +626,11 @@ extern "C" int pwt64_forward(pwt64_plan* p) {
             double* Hb = p->d_band[3 * (l - 1) + sH];
             double* V = p->d_band[3 * (l - 1) + sV];
             double* D = p->d_band[3 * (l - 1) + 3];
-            if (p->do_swt)
-                p->launches += pwt_launch_swt_fwd2d_f64(src, dstA, Hb, V, D, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
+            if (p->do_swt) {
+                int n = pwt_swt2p_fwd2d_f64(src, dstA, Hb, V, D, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
+                if (!n) n = pwt_launch_swt_fwd2d_f64(src, dstA, Hb, V, D, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
+                p->launches += n;
+            }
             else {
                 int n = haar ? pwt64_haar_fwd2d(src, dstA, Hb, V, D, B, p->lvNr[l - 1], p->lvNc[l - 1], lvl_elems(p, l - 1), lvl_elems(p, l), st)
                              : pwt64_fused_fwd2d(src, dstA, Hb, V, D, B, p->lvNr[l - 1], p->lvNc[l - 1], lvl_elems(p, l - 1),
@@ -671,8 +679,11 @@ extern "C" int pwt64_inverse(pwt64_plan* p) {
             const double* Hb = p->d_band[3 * (l - 1) + sH];
             const double* V = p->d_band[3 * (l - 1) + sV];
             const double* D = p->d_band[3 * (l - 1) + 3];
-            if (p->do_swt)
-                p->launches += pwt_launch_swt_inv2d_f64(cur, Hb, V, D, dst, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
+            if (p->do_swt) {
+                int n = pwt_swt2p_inv2d_f64(cur, Hb, V, D, dst, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
+                if (!n) n = pwt_launch_swt_inv2d_f64(cur, Hb, V, D, dst, p->d_tmp, B, p->Nr, p->Nc, l, p->filt, st);
+                p->launches += n;
+            }
             else {
                 int n = haar ? pwt64_haar_inv2d(cur, Hb, V, D, dst, B, p->lvNr[l], p->lvNc[l], p->lvNr[l - 1], p->lvNc[l - 1],
                                                 lvl_elems(p, l), lvl_elems(p, l - 1), st)
