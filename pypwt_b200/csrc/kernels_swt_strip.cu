@@ -470,7 +470,7 @@ int pwt_strip_swt_inv2d_covers(int batch, int Nr, int Nc, int level, const PwtFi
     const int F = f.hlen;
     if (level < 1 || level > 16) return 0;
     const int s = 1 << (level - 1);
-    if ((F & 1) || F < 2 || F > 16 || (Nc & 3) || batch > 65535 || out == A) return 0;
+    if ((F & 1) || F < 2 || F > 20 || (Nc & 3) || batch > 65535 || out == A) return 0;
     if ((F - 1) * s >= Nc || (F - 1) * s >= Nr || (long long)Nr * Nc >= (1LL << 31)) return 0;
     if ((((uintptr_t)out | (uintptr_t)A) & 15) != 0) return 0;
     if (pwt_tuning().no_strip_swt) return 0;
@@ -494,7 +494,7 @@ int pwt_strip_swt_inv2d(const float* A, const float* Hb, const float* V, const f
     thr.app = app;
     switch (F) {
 #define X(FF) case FF: return launch_inv<FF>(A, Hb, V, D, out, batch, Nr, Nc, s, f, thr_op, thr, st);
-        X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16)
+        X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20)
 #undef X
         default: return 0;
     }
@@ -506,13 +506,13 @@ int pwt_strip_swt_fwd2d(const float* in, float* A, float* Hb, float* V, float* D
     const int F = f.hlen;
     if (level < 1 || level > 16) return 0;
     const int s = 1 << (level - 1);
-    if ((F & 1) || F < 2 || F > 16 || (Nc & 3) || batch > 65535 || in == A) return 0;
+    if ((F & 1) || F < 2 || F > 20 || (Nc & 3) || batch > 65535 || in == A) return 0;
     if ((F - 1) * s >= Nc || (F - 1) * s >= Nr || (long long)Nr * Nc >= (1LL << 31)) return 0;
     if ((((uintptr_t)in | (uintptr_t)A | (uintptr_t)Hb | (uintptr_t)V | (uintptr_t)D) & 15) != 0) return 0;
     if (pwt_tuning().no_strip_swt) return 0;
     switch (F) {
 #define X(FF) case FF: return launch_s<FF>(in, A, Hb, V, D, batch, Nr, Nc, s, f, st);
-        X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16)
+        X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20)
 #undef X
         default: return 0;
     }

@@ -702,7 +702,7 @@ def test_fused_norms_batched():
 @pytest.mark.parametrize("op,app,normalize", [("soft_threshold", 0, 0), ("soft_threshold", 1, 1),
                                               ("hard_threshold", 0, 1), ("hard_threshold", 1, 0)])
 @pytest.mark.parametrize("wname,shape", [("haar", (256, 512)), ("db2", (200, 300 * 4)), ("db4", (256, 2048)),
-                                         ("db6", (2, 96, 640))])
+                                         ("db6", (2, 96, 640)), ("db10", (256, 1024)), ("coif3", (130, 512))])
 def test_swt_deferred_threshold_is_unobservable(wname, shape, op, app, normalize):
     """SWT plans served by the fused inverse record soft/hard thresholds and apply them while the
     inverse loads each band (once per coefficient).  Same contract as the decimated transform: the
