@@ -21,6 +21,10 @@
 
 int pwt_is_haar_alias(const char* wname);
 int pwt_fill_filters(const char* wname, PwtFilters* out);
+// kernels_vol_fused.cu: one level, x + y + z in one launch (F = 4, 6); bands[b], b = 4 dz + 2 dy + dx.  0: not covered
+int pwt_vol_fused_fwd(const float* in, float* const* bands, int Nz, int Ny, int Nx, const PwtFilters& f, cudaStream_t st);
+int pwt_vol_fused_inv(const float* const* bands, float* out, int nz2, int ny2, int nx2, int Nz, int Ny, int Nx, const PwtFilters& f,
+                      cudaStream_t st);
 
 namespace {
 int failv(int code, const char* fmt, ...) {
@@ -460,6 +464,17 @@ extern "C" int pwt3_forward(pwt3_plan* p) {
     for (int l = 1; l <= L; l++) {
         const int nz = p->lz[l - 1], ny = p->ly[l - 1], nx = p->lx[l - 1];
         const long long P = (long long)p->ly[l] * p->lx[l];
+        if (!p->haar) {                                             // x, y and z in one launch (short filters)
+            float* fb[8];
+            fb[0] = l == L ? p->d_A : p->d_app[l & 1];
+            for (int b = 1; b < 8; b++) fb[b] = p->d_band[l - 1][b];
+            const int nf = pwt_vol_fused_fwd(src, fb, nz, ny, nx, p->filt, st);
+            if (nf) {
+                p->launches += nf;
+                src = fb[0];
+                continue;
+            }
+        }
         // (1) x then y on every slice: a = (Lx, Ly), H = (Lx, Hy), V = (Hx, Ly), D = (Hx, Hy)   [separable.cu:165-174]
         p->launches += pwt_level_fwd2d(src, p->d_sub[0], p->d_sub[1], p->d_sub[2], p->d_sub[3], nz, ny, nx, (long long)ny * nx, P,
                                        p->filt, p->haar, st);
@@ -498,6 +513,18 @@ extern "C" int pwt3_inverse(pwt3_plan* p) {
         const int nz = p->lz[l - 1], ny = p->ly[l - 1], nx = p->lx[l - 1];
         const long long P = (long long)p->ly[l] * p->lx[l];
         float** B = p->d_band[l - 1];
+        if (!p->haar) {                                             // z, y and x in one launch (short filters)
+            const float* fb[8];
+            fb[0] = cur;
+            for (int b = 1; b < 8; b++) fb[b] = B[b];
+            float* fdst = l == 1 ? p->d_image : p->d_app[(l - 1) & 1];
+            const int nf = pwt_vol_fused_inv(fb, fdst, p->lz[l], p->ly[l], p->lx[l], nz, ny, nx, p->filt, st);
+            if (nf) {
+                p->launches += nf;
+                cur = fdst;
+                continue;
+            }
+        }
         ZJobs jb = {};
         const int sub_of[4] = {0, 2, 1, 3};
         for (int q = 0; q < 4; q++) {

@@ -59,6 +59,29 @@ def test_dwt3_idwt3(wname, shape):
     close(W.image, vol, "reconstruction " + wname, scale=255.0 * 4)
 
 
+@pytest.mark.parametrize("shape", [(70, 130, 160), (37, 101, 96), (16, 72, 320), (66, 64, 200), (5, 9, 88)])
+@pytest.mark.parametrize("wname", ["db2", "db3", "bior2.2", "sym2", "coif1", "rbio1.3"])
+def test_fused_level_kernels_3d(wname, shape):
+    """kernels_vol_fused.cu (x + y + z of a level in one launch, F = 4 and 6): several tiles with overhang, several z segments,
+    odd heights and depths (the repeated last row / slice of the analysis, the clipped last one of the synthesis), widths where
+    only the first level (or only the analysis: Nx % 4 == 0 but Nx % 8 != 0) takes the fused kernels."""
+    vol = _vol(shape, 9)
+    try:
+        Wo = D.OracleWavelets3D(vol, wname, 2)
+    except ValueError:
+        pytest.skip("volume too small for this filter")
+    W = _W3(vol, wname, 2)
+    assert W.levels == Wo.levels
+    l0 = W.launch_count
+    W.forward(); Wo.forward()
+    if shape[2] % 4 == 0 and shape[2] >= 80 and shape[1] >= 8:
+        assert W.launch_count - l0 < 2 * W.levels, "the first level at least is one fused launch"
+    compare(W, Wo, "fused dwt3 " + wname)
+    W.inverse(); Wo.inverse()
+    close(W.image, Wo.image, "fused idwt3 " + wname)
+    close(W.image, vol, "reconstruction " + wname, scale=255.0 * 4)
+
+
 def test_thresholds_norms_state_3d():
     vol = _vol((48, 64, 80), 5)
     for op in ("soft_threshold", "hard_threshold"):
