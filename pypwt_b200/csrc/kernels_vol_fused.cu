@@ -1,4 +1,4 @@
-// Volumetric DWT level with the x, y and z passes FUSED in one launch (short filters: F = 4, 6).
+// Volumetric DWT level with the x, y and z passes FUSED in one launch (short filters: F = 2, 4, 6).
 //
 // The volumetric plan ran a level as a batched 2D launch over the slices plus a z pass over the four sub-volumes: 16 B per
 // voxel and direction against 8 compulsory, at the streaming limit for that traffic (512^3 db2, 3 levels, fwd+inv 0.82 ms =
@@ -197,7 +197,7 @@ template <int F>
 __global__ void __launch_bounds__(NT, 2)
 k_vol3_inv(const __grid_constant__ VolBandsIn bands, float* __restrict__ out, int nz2, int ny2, int nx2, int Nz, int Ny, int Nx,
            int tiles_x, int KS, const __grid_constant__ PwtTapsInv tp) {
-    static_assert(F == 4 || F == 6, "three window positions");
+    static_assert(F == 2 || F == 4 || F == 6, "three window positions (F = 2: the launcher shifts its single position to w = 1)");
     extern __shared__ __align__(16) float sm[];
     float* raw = sm;                                       // [8 bands][NRB][PXB]
     float* up = sm + 8 * NRB * PXB;                        // [2 dz + dy][NRB][TX]: x-synthesised planes
@@ -367,8 +367,12 @@ int launch_inv(const VolBandsIn& bands, float* out, int nz2, int ny2, int nx2, i
     const int KS = pick_ks(nz2, (long long)tiles_x * tiles_y, per_sm * pwt_sm_count(), 1, 2, 6);
     const int nseg = (nz2 + KS - 1) / KS;
     if (nseg > 65535) return 0;
-    pwt_launch_pdl(k_vol3_inv<F>, dim3(tiles_x * tiles_y, nseg), NT, kInvSmem, st, bands, out, nz2, ny2, nx2, Nz, Ny, Nx, tiles_x, KS,
-                   pwt_pack_taps_inv(f, F));
+    PwtTapsInv t = pwt_pack_taps_inv(f, F);
+    if (F == 2) {                                          // S1 = 0: the window of pair j is band sample j alone -> position w = 1
+        t.l[1] = t.l[0]; t.h[1] = t.h[0];
+        t.l[0] = t.h[0] = make_float2(0.f, 0.f);
+    }
+    pwt_launch_pdl(k_vol3_inv<F>, dim3(tiles_x * tiles_y, nseg), NT, kInvSmem, st, bands, out, nz2, ny2, nx2, Nz, Ny, Nx, tiles_x, KS, t);
     return 1;
 }
 }  // namespace
@@ -380,6 +384,7 @@ int pwt_vol_fused_fwd(const float* in, float* const* bands, int Nz, int Ny, int 
     VolBands vb;
     for (int b = 0; b < 8; b++) vb.b[b] = bands[b];
     switch (f.hlen) {
+        case 2: return launch_fwd<2>(in, vb, Nz, Ny, Nx, f, st);
         case 4: return launch_fwd<4>(in, vb, Nz, Ny, Nx, f, st);
         case 6: return launch_fwd<6>(in, vb, Nz, Ny, Nx, f, st);
     }
@@ -397,6 +402,7 @@ int pwt_vol_fused_inv(const float* const* bands, float* out, int nz2, int ny2, i
         vb.b[b] = bands[b];
     }
     switch (f.hlen) {
+        case 2: return launch_inv<2>(vb, out, nz2, ny2, nx2, Nz, Ny, Nx, f, st);
         case 4: return launch_inv<4>(vb, out, nz2, ny2, nx2, Nz, Ny, Nx, f, st);
         case 6: return launch_inv<6>(vb, out, nz2, ny2, nx2, Nz, Ny, Nx, f, st);
     }

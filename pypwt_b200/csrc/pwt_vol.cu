@@ -464,7 +464,7 @@ extern "C" int pwt3_forward(pwt3_plan* p) {
     for (int l = 1; l <= L; l++) {
         const int nz = p->lz[l - 1], ny = p->ly[l - 1], nx = p->lx[l - 1];
         const long long P = (long long)p->ly[l] * p->lx[l];
-        if (!p->haar) {                                             // x, y and z in one launch (short filters)
+        {                                                           // x, y and z in one launch (short filters; Haar as a 2-tap bank)
             float* fb[8];
             fb[0] = l == L ? p->d_A : p->d_app[l & 1];
             for (int b = 1; b < 8; b++) fb[b] = p->d_band[l - 1][b];
@@ -513,7 +513,7 @@ extern "C" int pwt3_inverse(pwt3_plan* p) {
         const int nz = p->lz[l - 1], ny = p->ly[l - 1], nx = p->lx[l - 1];
         const long long P = (long long)p->ly[l] * p->lx[l];
         float** B = p->d_band[l - 1];
-        if (!p->haar) {                                             // z, y and x in one launch (short filters)
+        {                                                           // z, y and x in one launch (short filters; Haar as a 2-tap bank)
             const float* fb[8];
             fb[0] = cur;
             for (int b = 1; b < 8; b++) fb[b] = B[b];
