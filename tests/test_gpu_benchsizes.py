@@ -248,3 +248,37 @@ def test_batched_1d_8192_rows_vs_pdwt(wname):
 def test_batched_1d_swt_vs_pdwt():
     img = synth_image((2048, 8192), seed=66, kind="smooth")
     _side_by_side("1D swt db4 2048x8192 L3", img, "db4", 3, kw=dict(ndim=1, do_swt=1))
+
+
+# ---- maximum sizes ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("wname,levels", [("db2", 3), ("sym8", 2)])
+def test_largest_image_vs_pdwt(wname, levels):
+    """2^29 samples (16384 x 32768, 2 GiB): element offsets beyond 2^28 in every kernel family that serves large images
+    (fused cascade, strip kernels), beside the reference run on the same array."""
+    tile = synth_image((2048, 4096), seed=70 + levels, kind="smooth")
+    img = np.ascontiguousarray(np.tile(tile, (8, 8)))
+    assert img.shape == (16384, 32768)
+    _side_by_side("MAX %s 16384x32768 L%d" % (wname, levels), img, wname, levels)
+
+
+def test_image_size_limit_is_refused_cleanly():
+    """One image must hold fewer than 2^31 samples (32-bit element offsets inside an image): the C ABI refuses larger
+    ones with PWT_ERR_ARG and a message before anything is allocated; the largest accepted width still works in 1D."""
+    from pypwt_b200 import LIBRARY_PATH
+    lib = ctypes.CDLL(LIBRARY_PATH)
+    lib.pwt_last_error.restype = ctypes.c_char_p
+    for nr, nc in ((46341, 46341), (32768, 65536), (65536, 32768)):
+        h = ctypes.c_void_p()
+        rc = lib.pwt_create(ctypes.byref(h), None, nr, nc, b"db2", 1, 1, 1, 0, 0, 2)
+        assert rc != 0 and not h.value, (nr, nc)
+        assert b"2^31" in lib.pwt_last_error()
+    # a long 1D signal: 2^27 + 3 samples, odd length, 4 levels, against perfect reconstruction and energy conservation
+    n = 2 ** 27 + 3
+    x = np.sin(np.arange(n, dtype=np.float64) * 1e-3).astype(np.float32) * 100 + np.random.default_rng(3).standard_normal(n).astype(np.float32)
+    W = _mine().Wavelets(x, "db3", 4, ndim=1)
+    W.forward()
+    e = sum(float(np.square(np.asarray(c, np.float64)).sum()) for c in W.coeffs)
+    ex = float(np.square(x.astype(np.float64)).sum())
+    assert abs(e - ex) <= 2e-4 * ex                          # orthogonal bank; the odd-length extension adds one sample per level
+    W.inverse()
+    assert np.abs(W.image.ravel() - x).max() <= 1e-5 * 8 * np.abs(x).max()
