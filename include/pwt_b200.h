@@ -198,6 +198,10 @@ int pwt64_timer_start(pwt64_plan* p);
 int pwt64_timer_stop(pwt64_plan* p, float* ms);
 long long pwt64_launch_count(const pwt64_plan* p);
 int pwt64_lookup_filters(const char* wname, double* L, double* H, double* IL, double* IH);
+/* custom separable banks: Wavelets::set_filters_forward / set_filters_inverse wt.cu:558-600 in the DOUBLEPRECISION build
+ * (len <= 40 taps; odd lengths mapped like pwt_set_filters_*; non-separable plans -> -2) */
+int pwt64_set_filters_forward(pwt64_plan* p, const char* name, unsigned len, const double* lowpass, const double* highpass);
+int pwt64_set_filters_inverse(pwt64_plan* p, const double* lowpass, const double* highpass);
 
 /* ---- volumetric (3D) separable DWT ------------------------------------------ */
 /* The reference stops at 2D ("3D is not handled", pdwt/README.md:29; pypwt.pyx:155-156 raises on 3D input).  Same

@@ -423,6 +423,7 @@ struct pwt64_plan {
     cudaEvent_t ev0, ev1;
     int batch, Nr, Nc, ndims, nlevels, hlen, do_swt, do_separable, do_cs;
     int state, shift_r, shift_c;
+    int custom_len;      // taps given to pwt64_set_filters_forward (0: a built-in bank); a custom 2-tap bank is NOT the Haar butterfly
     char wname[128];
     PwtFilters64 filt;
     int lvNr[PWT_MAX_LEVELS + 1], lvNc[PWT_MAX_LEVELS + 1];
@@ -439,7 +440,7 @@ struct pwt64_plan {
 };
 
 namespace {
-inline bool is_haar(const pwt64_plan* p) { return p->hlen == 2 && !p->do_swt; }
+inline bool is_haar(const pwt64_plan* p) { return p->hlen == 2 && !p->do_swt && !p->custom_len; }
 inline long long img_elems(const pwt64_plan* p) { return (long long)p->Nr * p->Nc; }
 inline long long lvl_elems(const pwt64_plan* p, int l) { return (long long)p->lvNr[l] * p->lvNc[l]; }
 inline long long band_elems(const pwt64_plan* p, int b) { return (long long)p->band_nr[b] * p->band_nc[b]; }
@@ -704,6 +705,55 @@ extern "C" int pwt64_inverse(pwt64_plan* p) {
         if (rc != PWT_OK) return rc;
     }
     p->state = PWT_INVERSE;
+    return PWT_OK;
+}
+
+// ---- custom filter banks (wt.cu:558-600 with DTYPE = double; separable banks) --------------------------------------
+// Odd lengths are mapped onto the windows the reference's kernels read (separable.cu:98-102, :252-264), like the fp32
+// plans do (pwt_plan.cu: load_taps): analysis taps padded in front, synthesis taps of the decimated transform with the first
+// tap dropped, of the stationary transform padded at the back.
+namespace {
+enum { PAD64_FRONT = 0, PAD64_DROP0 = 1, PAD64_BACK = 2 };
+void load_taps64(double* dst, const double* src, unsigned len, unsigned padded, int mode) {
+    memset(dst, 0, PWT_MAX_TAPS * sizeof(double));
+    if (padded == len) mode = PAD64_FRONT;
+    const unsigned o = mode == PAD64_FRONT ? padded - len : 0;
+    for (unsigned k = (mode == PAD64_DROP0 ? 1 : 0); k < len; k++) dst[o + k] = src[k];
+}
+}  // namespace
+extern "C" int pwt64_set_filters_forward(pwt64_plan* p, const char* name, unsigned len, const double* lo, const double* hi) {
+    if (!p || !lo || !hi || len < 2) return fail64(PWT_ERR_ARG, "bad argument");
+    const unsigned padded = len + (len & 1);
+    if (padded > PWT_MAX_TAPS) {                                    // wt.cu:560-563
+        printf("ERROR: Wavelets.set_filters_forward(): filter length (%d) exceeds the maximum size (%d)\n", len, PWT_MAX_TAPS);
+        return -1;
+    }
+    if (!p->do_separable) {
+        puts("ERROR: Wavelets.set_filters_forward(): the double-precision plans take separable banks only");
+        return -2;
+    }
+    load_taps64(p->filt.L, lo, len, padded, PAD64_FRONT);
+    load_taps64(p->filt.H, hi, len, padded, PAD64_FRONT);
+    p->hlen = (int)padded;
+    p->filt.hlen = (int)padded;
+    p->custom_len = (int)len;
+    if (name) {
+        memset(p->wname, 0, sizeof(p->wname));
+        strncpy(p->wname, name, sizeof(p->wname) - 1);
+    }
+    return PWT_OK;
+}
+extern "C" int pwt64_set_filters_inverse(pwt64_plan* p, const double* lo, const double* hi) {
+    if (!p || !lo || !hi) return fail64(PWT_ERR_ARG, "bad argument");
+    if (!p->do_separable) {
+        puts("ERROR: Wavelets.set_filters_inverse(): the double-precision plans take separable banks only");
+        return -2;
+    }
+    const unsigned padded = (unsigned)p->hlen;                      // the length given to set_filters_forward (wt.cu:587)
+    const unsigned len = p->custom_len ? (unsigned)p->custom_len : padded;
+    const int mode = p->do_swt ? PAD64_BACK : PAD64_DROP0;
+    load_taps64(p->filt.IL, lo, len, padded, mode);
+    load_taps64(p->filt.IH, hi, len, padded, mode);
     return PWT_OK;
 }
 

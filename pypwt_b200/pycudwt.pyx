@@ -112,6 +112,8 @@ cdef extern from "pwt_b200.h":
     int pwt64_timer_stop(pwt64_plan* p, float* ms) nogil
     long long pwt64_launch_count(const pwt64_plan* p) nogil
     int pwt64_lookup_filters(const char* wname, double* L, double* H, double* IL, double* IH) nogil
+    int pwt64_set_filters_forward(pwt64_plan* p, const char* name, unsigned len, const double* lo, const double* hi) nogil
+    int pwt64_set_filters_inverse(pwt64_plan* p, const double* lo, const double* hi) nogil
 
     # volumetric transform
     ctypedef struct pwt3_plan:
@@ -938,8 +940,8 @@ def lookup_filters64(str wname):
 cdef class Wavelets64:
     """Double-precision counterpart of `Wavelets`: the reference's DOUBLEPRECISION build (libpdwtd.so,
     pdwt/src/filters.h:16-30), which its Python wrapper cannot reach.  Same constructor arguments and attribute /
-    method names (pypwt.pyx:64-118); images and coefficients are float64.  Not carried over: custom filter banks,
-    add_wavelet, device-array interop."""
+    method names (pypwt.pyx:64-118); images and coefficients are float64.  Not carried over: non-separable custom
+    banks, add_wavelet, device-array interop."""
     cdef pwt64_plan* w
     cdef readonly int Nr
     cdef readonly int Nc
@@ -1110,6 +1112,26 @@ cdef class Wavelets64:
 
     def norm2sq(self):
         return self.norms()[1]
+
+    def set_wavelets_filters(self, filter_name, lowpass, highpass, i_lowpass, i_highpass):
+        """Custom separable filter bank in double precision (pypwt.pyx:487-575 -> wt.cu:558-600 with DTYPE = double);
+        re-defines the transform.  Non-separable plans are refused (the double-precision plans have no F x F stencils)."""
+        if any(len(arr) != len(lowpass) for arr in (highpass, i_lowpass, i_highpass)):
+            raise ValueError("All filters must have the same length")
+        lp = np.ascontiguousarray(lowpass, dtype=np.float64); hp = np.ascontiguousarray(highpass, dtype=np.float64)
+        ilp = np.ascontiguousarray(i_lowpass, dtype=np.float64); ihp = np.ascontiguousarray(i_highpass, dtype=np.float64)
+        name = filter_name.encode("ASCII")
+        cdef unsigned int flen = len(lowpass)
+        cdef int rc = pwt64_set_filters_forward(self.w, name, flen, <const double*> <size_t> lp.ctypes.data,
+                                                <const double*> <size_t> hp.ctypes.data)
+        if rc == 0:
+            rc = pwt64_set_filters_inverse(self.w, <const double*> <size_t> ilp.ctypes.data, <const double*> <size_t> ihp.ctypes.data)
+        if rc != 0:
+            raise ValueError("set_wavelets_filters() failed with code %d" % rc)
+        cdef pwt_info info
+        pwt64_get_info(self.w, &info)
+        self.hlen = info.hlen
+        self.wname = filter_name
 
     def sync(self):
         pwt64_sync(self.w)

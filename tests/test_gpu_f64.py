@@ -234,3 +234,55 @@ np.savez(sys.argv[1], **out)
             assert np.abs(res["1"][k] - res["0"][k]).max() <= 1e-12 * 255, k
         else:
             assert np.array_equal(res["1"][k], res["0"][k]), k
+
+
+def test_custom_banks_f64():
+    """`Wavelets64.set_wavelets_filters` (wt.cu:558-600 in the DOUBLEPRECISION build, separable banks): a built-in bank loaded as
+    a custom one is bit-identical to the built-in plan; odd-length banks (CDF 9/7, LeGall 5/3, random 7 taps: the `hlen & 1`
+    branches of separable.cu:98-102, 251-264) agree with the fp32 plans, which are pinned to the reference's CUDA build for
+    exactly these banks (test_gpu_api.py); a custom 2-tap bank is a filter bank, not the Haar butterfly; non-separable plans refuse."""
+    import pycudwt
+    import pypwt_b200
+    from test_gpu_api import BANKS
+    img = _img((97, 150), 21)
+    for wn, kw in (("db3", {}), ("sym8", {}), ("db2", dict(do_swt=1)), ("db4", dict(ndim=1))):
+        L, H, IL, IH = pypwt_b200.lookup_filters64(wn)
+        A = _W64(img, wn, 3, **kw); B = _W64(img, "db2" if wn != "db2" else "db3", 3, **kw)
+        B.set_wavelets_filters("mine", L, H, IL, IH)
+        assert B.hlen == A.hlen and B.wname == "mine"
+        if B.levels != A.levels:                             # the level count was fixed at construction (wt.cu:156-165)
+            continue
+        A.forward(); B.forward()
+        for a, b in zip(_flat(A.coeffs), _flat(B.coeffs)):
+            assert np.array_equal(a, b)
+        A.inverse(); B.inverse()
+        assert np.array_equal(A.image, B.image)
+    for bank, taps in BANKS.items():
+        for do_swt in (0, 1):
+            W = _W64(img, "db3", 2, do_swt=do_swt)
+            W.set_wavelets_filters(bank, taps["lo"], taps["hi"], taps["ilo"], taps["ihi"])
+            F = pycudwt.Wavelets(img.astype(np.float32), "db3", 2, do_swt=do_swt)
+            F.set_wavelets_filters(bank, *[np.asarray(taps[k], np.float32) for k in ("lo", "hi", "ilo", "ihi")])
+            assert W.hlen == F.hlen
+            W.forward(); F.forward()
+            for a, b in zip(_flat(W.coeffs), _flat(F.coeffs)):
+                assert a.dtype == np.float64 and np.abs(a - b).max() <= 2e-5 * max(255.0, np.abs(b).max()), (bank, do_swt)
+            W.inverse(); F.inverse()
+            assert np.abs(W.image - F.image).max() <= 2e-5 * max(255.0, np.abs(F.image).max()), (bank, do_swt)
+    s = 2.0 ** -0.5
+    W = _W64(img, "haar", 2); Hh = _W64(img, "haar", 2)
+    W.set_wavelets_filters("haar2", [s, s], [-s, s], [s, s], [s, -s])
+    W.forward(); Hh.forward()
+    for a, b in zip(_flat(W.coeffs), _flat(Hh.coeffs)):
+        close(a, b, "2-tap custom bank vs the Haar butterfly")
+    W.inverse()
+    close(W.image, img, "2-tap custom bank round trip")
+    with pytest.raises(ValueError):
+        _W64(img, "db2", 2, do_separable=0).set_wavelets_filters("x", [1, 2], [1, 2], [1, 2], [1, 2])
+
+
+def _flat(coeffs):
+    out = []
+    for c in coeffs:
+        out.extend(c if isinstance(c, (list, tuple)) else [c])
+    return out
