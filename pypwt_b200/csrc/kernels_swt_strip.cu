@@ -255,7 +255,7 @@ __device__ __forceinline__ float thr1(float v, float beta) {
 }
 
 template <int F, int SMODE, int THR, int NBUF>
-__global__ void __launch_bounds__(NT, F <= 8 ? 3 : 2)
+__global__ void __launch_bounds__(NT, F <= 8 ? (NBUF == 1 ? 4 : 3) : 2)
 k_swt_strip_inv(const float* __restrict__ A, const float* __restrict__ Hb, const float* __restrict__ V,
                 const float* __restrict__ D, float* __restrict__ out, int Nr, int Nc, int s, int TQ, int nseg,
                 long long plane, const Thr thr, const __grid_constant__ TapsDup f) {
