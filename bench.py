@@ -22,7 +22,7 @@ Keys of the JSON line (one line, rank 0):
   c3_stack     BASELINE config 3 as a measurement: a FIXED 512 x 2048 x 2048 sym8 stack (strong scaling: 512/N slices
                per rank), step = forward + global norm1/norm2sq (fused reduction + ncclAllReduce, INSIDE the CUDA-event
                region) + soft threshold + inverse; aggregate Mpixel/s, us of the collective alone
-  other_configs  (N = 1) the other BASELINE configurations in short: C2 4096^2, C4 SWT + cycle spinning + hard threshold,
+  other_configs  (N = 1) the other BASELINE configurations in short (+ the double-precision and volumetric plans): C2 4096^2, C4 SWT + cycle spinning + hard threshold,
                batched 1D DWT / SWT, two C5 filter lengths -- ms, Mpixel/s, fraction of their own HBM roofline
   host_link    pinned-memory copy bandwidth of this rank (H2D, D2H, both at once) and the NUMA placement of the rank:
                names the link that bounds `e2e`
@@ -405,9 +405,11 @@ def run_other_configs(peak):
     def den(W):
         W.forward(); W.hard_threshold(20.0); W.inverse()
 
-    def add(key, shape, wname, levels, bpp, fn=fi, **kw):
+    def add(key, shape, wname, levels, bpp, fn=fi, cls=None, dtype=None, **kw):
         img = synth(shape, 77)
-        W = pycudwt.Wavelets(img, wname, levels, **kw)
+        if dtype is not None:
+            img = img.astype(dtype)
+        W = (cls or pycudwt.Wavelets)(img, wname, levels, **kw)
         ms = t(W, fn)
         l0 = W.launch_count
         fn(W)
@@ -422,6 +424,11 @@ def run_other_configs(peak):
     add("1D 8192x8192 swt db2 L3 fwd+inv", (8192, 8192), "db2", 3, 2 * (3 + 2) * 4, ndim=1, do_swt=1)
     add("C5 8192^2 sym8 L5 fwd+inv", (8192, 8192), "sym8", 5, 16)
     add("C5 8192^2 db20 L5 fwd+inv (FMA-bound)", (8192, 8192), "db20", 5, 16)
+    # the double-precision build (32 B/px) and volumes (16 B/voxel)
+    import pypwt_b200
+    add("f64 8192^2 db2 L3 fwd+inv", (8192, 8192), "db2", 3, 32, cls=pypwt_b200.Wavelets64, dtype=np.float64)
+    add("f64 8192^2 haar L3 fwd+inv", (8192, 8192), "haar", 3, 32, cls=pypwt_b200.Wavelets64, dtype=np.float64)
+    add("3D 512^3 db2 L3 fwd+inv", (512, 512, 512), "db2", 3, 16, cls=pypwt_b200.Wavelets3D)
     return out
 
 
