@@ -79,9 +79,9 @@ k_dwt_fwd2d(const T* __restrict__ in, T* __restrict__ A, T* __restrict__ Hb,
     for (int r = warp; r < IH; r += kWarps) {
         const T* p = s_in + r * IWp + 2 * lane;
         T lo, hi;
-        if (HAAR) {
-            lo = p[0] + p[1];
-            hi = p[0] - p[1];
+        if (HAAR) {                                     // the butterfly associates down the columns first (haar.cu:27-35): keep
+            lo = p[0];                                  // the two samples of the pair, the column pass does all the arithmetic
+            hi = p[1];
         } else {
             lo = T(0), hi = T(0);
             for (int j = 0; j < F; j++) {
@@ -99,11 +99,13 @@ k_dwt_fwd2d(const T* __restrict__ in, T* __restrict__ A, T* __restrict__ Hb,
         T a, h, v, d;
         const T* pl = s_lo + (2 * y) * GTX + lane;
         const T* ph = s_hi + (2 * y) * GTX + lane;
-        if (HAAR) {
-            a = T(0.5) * (pl[0] + pl[GTX]);
-            h = T(0.5) * (pl[0] - pl[GTX]);
-            v = T(0.5) * (ph[0] + ph[GTX]);
-            d = T(0.5) * (ph[0] - ph[GTX]);
+        if (HAAR) {                                     // A = ((a + c) + (b + d)) / 2, V = ((a + c) - (b + d)) / 2,
+            const T ac = pl[0] + pl[GTX], bd = ph[0] + ph[GTX];   // H = ((a - c) + (b - d)) / 2, D = ((a - c) - (b - d)) / 2
+            const T am = pl[0] - pl[GTX], bm = ph[0] - ph[GTX];
+            a = T(0.5) * (ac + bd);
+            v = T(0.5) * (ac - bd);
+            h = T(0.5) * (am + bm);
+            d = T(0.5) * (am - bm);
         } else {
             a = h = v = d = T(0);
             for (int j = 0; j < F; j++) {

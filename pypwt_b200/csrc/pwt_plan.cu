@@ -18,6 +18,12 @@
 #include "../../include/pwt_b200.h"
 #include "pwt_internal.h"
 
+// kernels_haar2d.cu: the Haar butterfly of a 2D level for the sizes the register kernels do not take (any size; 1 launch)
+int pwt_haar2d_fwd_flat(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc, long long in_bs,
+                        long long out_bs, cudaStream_t st);
+int pwt_haar2d_inv_flat(const float* A, const float* Hb, const float* V, const float* D, float* out, int batch, int nr, int nc,
+                        int Nro, int Nco, long long in_bs, long long out_bs, cudaStream_t st);
+
 int pwt_is_haar_alias(const char* wname);
 int pwt_fill_filters(const char* wname, PwtFilters* out);
 
@@ -813,6 +819,7 @@ extern "C" int pwt_forward(pwt_plan* p) {
                     }
                     if (!n && (p->kernel_mode == 0 || p->kernel_mode == 3))
                         n = pwt_reg_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, hints, st);
+                    if (!n && haar && (p->kernel_mode == 0 || p->kernel_mode == 3)) n = pwt_haar2d_fwd_flat(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, st);
                     if (!n && p->kernel_mode != 1 && !haar && p->hlen >= p->tile_min_f && nr >= 64 && nc >= 64)
                         n = pwt_tile_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, st);
                     if (!n && p->kernel_mode != 1)
@@ -843,6 +850,7 @@ int pwt_level_fwd2d(const float* src, float* A, float* Hb, float* V, float* D, i
     if (!haar && f.hlen >= k.strip_min_f && nr >= 64 && nc >= 256)
         n = pwt_strip_dwt_fwd2d(src, A, Hb, V, D, batch, nr, nc, in_bs, out_bs, f, st);
     if (!n) n = pwt_reg_dwt_fwd2d(src, A, Hb, V, D, batch, nr, nc, in_bs, out_bs, f, haar, 0, st);
+    if (!n && haar) n = pwt_haar2d_fwd_flat(src, A, Hb, V, D, batch, nr, nc, in_bs, out_bs, st);
     if (!n && !haar && f.hlen >= k.tile_min_f && nr >= 64 && nc >= 64)
         n = pwt_tile_dwt_fwd2d(src, A, Hb, V, D, batch, nr, nc, in_bs, out_bs, f, st);
     if (!n) n = pwt_fast_dwt_fwd2d(src, A, Hb, V, D, batch, nr, nc, in_bs, out_bs, f, haar, 0, st);
@@ -856,6 +864,7 @@ int pwt_level_inv2d(const float* A, const float* Hb, const float* V, const float
     if (!haar && f.hlen >= k.strip_min_f && nr >= 32 && nc >= 128)
         n = pwt_strip_dwt_inv2d(A, Hb, V, D, dst, batch, nr, nc, Nro, Nco, in_bs, out_bs, f, st);
     if (!n) n = pwt_reg_dwt_inv2d(A, Hb, V, D, dst, batch, nr, nc, Nro, Nco, in_bs, out_bs, f, haar, 0, st);
+    if (!n && haar) n = pwt_haar2d_inv_flat(A, Hb, V, D, dst, batch, nr, nc, Nro, Nco, in_bs, out_bs, st);
     if (!n && !haar && f.hlen >= k.tile_min_f && nr >= 32 && nc >= 32)
         n = pwt_tile_dwt_inv2d(A, Hb, V, D, dst, batch, nr, nc, Nro, Nco, in_bs, out_bs, f, st);
     if (!n) n = pwt_fast_dwt_inv2d(A, Hb, V, D, dst, batch, nr, nc, Nro, Nco, in_bs, out_bs, f, haar, 0, st);
@@ -1030,6 +1039,7 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                     }
                     if (!n && (p->kernel_mode == 0 || p->kernel_mode == 3))
                         n = pwt_reg_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, hints, st);
+                    if (!n && haar && (p->kernel_mode == 0 || p->kernel_mode == 3)) n = pwt_haar2d_inv_flat(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, st);
                     if (!n && p->kernel_mode != 1 && !haar && p->hlen >= p->tile_min_f && nr >= 32 && nc >= 32)
                         n = pwt_tile_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, st);
                     if (!n && p->kernel_mode != 1)
