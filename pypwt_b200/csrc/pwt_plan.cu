@@ -30,6 +30,13 @@ static long long tail_plane_px(int hlen, long long image_px) {
     return (hlen > 4 && image_px <= (1LL << 24)) ? (1LL << 24) : (1LL << 22);
 }
 
+// Haar planes of at most this many samples take the flat butterfly kernels ahead of the register kernels (PWT_HAAR_FLAT_PX;
+// default 4096^2).  A/B, fwd+inv: 2048^2 1 level 0.0201 -> 0.0106 ms, 2 levels 0.0320 -> 0.0164; 4096^2 1 level 0.0434 -> 0.0278,
+// 2 levels 0.0710 -> 0.0394; 8192^2 2 levels 0.2189 -> 0.2060, 4 levels 0.2001 -> 0.1887; 8192^2 1 level: equal (0.172).
+static long long haar_flat_px() {
+    static const long long v = [] { const char* e = getenv("PWT_HAAR_FLAT_PX"); return e && *e ? atoll(e) : (1LL << 24); }();
+    return v;
+}
 // kernels_haar2d.cu: the Haar butterfly of a 2D level for the sizes the register kernels do not take (any size; 1 launch)
 int pwt_haar2d_fwd_flat(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc, long long in_bs,
                         long long out_bs, cudaStream_t st);
@@ -830,6 +837,8 @@ extern "C" int pwt_forward(pwt_plan* p) {
                             if (l == L) p->norm_a = 1;
                         }
                     }
+                    if (!n && haar && p->kernel_mode == 0 && (long long)nr * nc <= haar_flat_px())
+                        n = pwt_haar2d_fwd_flat(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, st);
                     if (!n && (p->kernel_mode == 0 || p->kernel_mode == 3))
                         n = pwt_reg_dwt_fwd2d(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, p->filt, haar, hints, st);
                     if (!n && haar && (p->kernel_mode == 0 || p->kernel_mode == 3)) n = pwt_haar2d_fwd_flat(src, dstA, Hb, V, D, B, nr, nc, in_bs, out_bs, st);
@@ -1051,6 +1060,8 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                         if (rc != PWT_OK) return rc;
                         strip_defer = false;
                     }
+                    if (!n && haar && p->kernel_mode == 0 && (long long)Nro * Nco <= haar_flat_px())
+                        n = pwt_haar2d_inv_flat(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, st);
                     if (!n && (p->kernel_mode == 0 || p->kernel_mode == 3))
                         n = pwt_reg_dwt_inv2d(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, p->filt, haar, hints, st);
                     if (!n && haar && (p->kernel_mode == 0 || p->kernel_mode == 3)) n = pwt_haar2d_inv_flat(cur, Hb, V, D, dst, B, nr, nc, Nro, Nco, in_bs, out_bs, st);
