@@ -18,7 +18,7 @@
 #include "../../include/pwt_b200.h"
 #include "pwt_internal.h"
 
-// Short filters outside the 3-level cascade (1- and 2-level plans): planes of at most this many samples take the strip kernels
+// Short filters outside the 3-level cascade (1- and 2-level plans): levels of at most this many samples (over the whole stack) take the strip kernels
 // instead of the register kernels.  Measured (tools/gpu_levels12.py, fwd+inv): 2048^2 db2 1 level 0.0229 -> 0.0150 ms, 2 levels
 // 0.0409 -> 0.0222; 4096^2 db2 2 levels 0.0711 -> 0.0620 but 1 level 0.0461 -> 0.0529 (F = 4: up to 2048^2); 4096^2 db3 1 level
 // 0.0593 -> 0.0528, 2 levels 0.0879 -> 0.0709 (F = 6: up to 4096^2).  PWT_TAIL_PX overrides both (A/B knob, read once).
@@ -821,7 +821,7 @@ extern "C" int pwt_forward(pwt_plan* p) {
                     // F >= 8 always; shorter filters on the small planes that follow the fused cascade (levels >= 4: the
                     // register kernels need 9-11 us per launch there, the strip kernels 3-4)
                     // ... and on widths that are not multiples of 4, where the register kernels do not apply (1001 x 777 db2: 2.4x)
-                    const bool small = l >= 4 || (p->kernel_mode == 0 && (long long)nr * nc <= tail_plane_px(p->hlen, (long long)p->Nr * p->Nc));
+                    const bool small = l >= 4 || (p->kernel_mode == 0 && (long long)B * nr * nc <= tail_plane_px(p->hlen, (long long)B * p->Nr * p->Nc));
                     const bool tail = ((small && (p->kernel_mode == 0 || p->kernel_mode == 3)) || ((nc & 3) && p->kernel_mode == 0)) &&
                                       p->hlen >= 4 && pwt_tuning().tail_strip;
                     if (!haar && ((((p->kernel_mode == 0 && p->hlen >= p->strip_min_f) || tail) && nr >= 64 && nc >= 256) || p->kernel_mode == 4)) {
@@ -1045,7 +1045,7 @@ extern "C" int pwt_inverse(pwt_plan* p) {
                 if (sep) {
                     int n = 0;
                     const int hints = (l > 1 ? PWT_HINT_OUT_FEEDS_NEXT : 0) | (l < L ? PWT_HINT_IN_FROM_PREV : 0);
-                    const bool small = l >= 4 || (p->kernel_mode == 0 && (long long)Nro * Nco <= tail_plane_px(p->hlen, (long long)p->Nr * p->Nc));
+                    const bool small = l >= 4 || (p->kernel_mode == 0 && (long long)B * Nro * Nco <= tail_plane_px(p->hlen, (long long)B * p->Nr * p->Nc));
                     const bool tail = ((small && (p->kernel_mode == 0 || p->kernel_mode == 3)) || ((Nco & 3) && p->kernel_mode == 0)) &&
                                       p->hlen >= 4 && pwt_tuning().tail_strip;
                     if (!haar && ((((p->kernel_mode == 0 && p->hlen >= p->strip_min_f) || tail) && nr >= 32 && nc >= 128) || p->kernel_mode == 4)) {
