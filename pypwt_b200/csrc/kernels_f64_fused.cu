@@ -128,31 +128,29 @@ k64_fused_fwd(const double* __restrict__ in, double* __restrict__ A, double* __r
     pwt_pdl_wait();
 #pragma unroll
     for (int c = 0; c < NST - 1; c++) stage(c);
-    {
-        for (int n0 = 0; n0 < nrows; n0 += F) {
+    for (int n0 = 0; n0 < nrows; n0 += F) {
 #pragma unroll
-            for (int u = 0; u < F; u++) {
-                const int n = n0 + u;
-                if (n < nrows) {                           // uniform over the CTA
-                    if (u % RC == 0) chunk_ready(n / RC);
-                    rowpass(smd + ((n / RC) % NST) * RC * PITCH + (u % RC) * PITCH + 2 * tid, wl[u], wh[u]);
-                    if ((u & 1) && n >= F - 1) {           // stream row n completes output k0 + (n - (F - 1)) / 2
-                        double xa = 0.0, xh = 0.0, xv = 0.0, xd = 0.0;
+        for (int u = 0; u < F; u++) {
+            const int n = n0 + u;
+            if (n < nrows) {                           // uniform over the CTA
+                if (u % RC == 0) chunk_ready(n / RC);
+                rowpass(smd + ((n / RC) % NST) * RC * PITCH + (u % RC) * PITCH + 2 * tid, wl[u], wh[u]);
+                if ((u & 1) && n >= F - 1) {           // stream row n completes output k0 + (n - (F - 1)) / 2
+                    double xa = 0.0, xh = 0.0, xv = 0.0, xd = 0.0;
 #pragma unroll
-                        for (int j = 0; j < F; j++) {
-                            const int sl = (u + 1 + j) % F;
-                            xa = fma(wl[sl], f.L[F - 1 - j], xa);
-                            xh = fma(wl[sl], f.H[F - 1 - j], xh);
-                            xv = fma(wh[sl], f.L[F - 1 - j], xv);
-                            xd = fma(wh[sl], f.H[F - 1 - j], xd);
-                        }
-                        if (colok) {
-                            const long long o = (long long)(k0 + ((n - (F - 1)) >> 1)) * Nc2;
-                            oA[o] = xa;
-                            oH[o] = xh;
-                            oV[o] = xv;
-                            oD[o] = xd;
-                        }
+                    for (int j = 0; j < F; j++) {
+                        const int sl = (u + 1 + j) % F;
+                        xa = fma(wl[sl], f.L[F - 1 - j], xa);
+                        xh = fma(wl[sl], f.H[F - 1 - j], xh);
+                        xv = fma(wh[sl], f.L[F - 1 - j], xv);
+                        xd = fma(wh[sl], f.H[F - 1 - j], xd);
+                    }
+                    if (colok) {
+                        const long long o = (long long)(k0 + ((n - (F - 1)) >> 1)) * Nc2;
+                        oA[o] = xa;
+                        oH[o] = xh;
+                        oV[o] = xv;
+                        oD[o] = xd;
                     }
                 }
             }
