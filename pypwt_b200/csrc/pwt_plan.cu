@@ -37,6 +37,9 @@ static long long haar_flat_px() {
     static const long long v = [] { const char* e = getenv("PWT_HAAR_FLAT_PX"); return e && *e ? atoll(e) : (1LL << 24); }();
     return v;
 }
+// pwt_plan64.cu: the tiled row kernels of the double-precision plans instantiated for float -- batched 1D levels with few, long rows
+int pwt_rows1d_fwd_f32(const float* in, float* A, float* D, long long rows, int Nc, const PwtFilters& f, cudaStream_t st);
+int pwt_rows1d_inv_f32(const float* A, const float* D, float* out, long long rows, int nc, int Nc_out, const PwtFilters& f, cudaStream_t st);
 // kernels_haar2d.cu: the Haar butterfly of a 2D level for the sizes the register kernels do not take (any size; 1 launch)
 int pwt_haar2d_fwd_flat(const float* in, float* A, float* Hb, float* V, float* D, int batch, int Nr, int Nc, long long in_bs,
                         long long out_bs, cudaStream_t st);
@@ -759,7 +762,9 @@ extern "C" int pwt_forward(pwt_plan* p) {
             }
             else {
                 int n = 0;
-                if (!haar && ((p->kernel_mode == 0 && p->lvNc[l - 1] >= 256) || p->kernel_mode == 4))
+                if (!haar && p->kernel_mode == 0 && rows <= 32 && p->lvNc[l - 1] >= 8192)     // few long rows: tiles along the row
+                    n = pwt_rows1d_fwd_f32(src, dstA, p->d_band[l], rows, p->lvNc[l - 1], p->filt, st);
+                if (!n && !haar && ((p->kernel_mode == 0 && p->lvNc[l - 1] >= 256) || p->kernel_mode == 4))
                     n = pwt_strip_dwt_fwd1d(src, dstA, p->d_band[l], rows, p->lvNc[l - 1], p->filt, st);
                 if (haar && p->kernel_mode != 1) n = pwt_haar_fwd1d_flat(src, dstA, p->d_band[l], rows, p->lvNc[l - 1], st);
                 if (!n) n = pwt_launch_dwt_fwd1d(src, dstA, p->d_band[l], rows, p->lvNc[l - 1], p->filt, haar, st);
@@ -935,7 +940,9 @@ extern "C" int pwt_inverse(pwt_plan* p) {
             }
             else {
                 int n = 0;
-                if (!haar && ((p->kernel_mode == 0 && p->lvNc[l] >= 128) || p->kernel_mode == 4))
+                if (!haar && p->kernel_mode == 0 && rows <= 32 && p->lvNc[l - 1] >= 8192)
+                    n = pwt_rows1d_inv_f32(cur, p->d_band[l], dst, rows, p->lvNc[l], p->lvNc[l - 1], p->filt, st);
+                if (!n && !haar && ((p->kernel_mode == 0 && p->lvNc[l] >= 128) || p->kernel_mode == 4))
                     n = pwt_strip_dwt_inv1d(cur, p->d_band[l], dst, rows, p->lvNc[l], p->lvNc[l - 1], p->filt, st);
                 if (haar && p->kernel_mode != 1) n = pwt_haar_inv1d_flat(cur, p->d_band[l], dst, rows, p->lvNc[l], p->lvNc[l - 1], st);
                 if (!n) n = pwt_launch_dwt_inv1d(cur, p->d_band[l], dst, rows, p->lvNc[l], p->lvNc[l - 1], p->filt, haar, st);

@@ -124,18 +124,18 @@ __device__ __forceinline__ int wrap_per64(int i, int N) {
 // tid, tid + 256, ... so that the stores are coalesced too.  (First version: 4 outputs per thread straight from global
 // memory -- ncu: 2x the time of the column pass for the same bytes, L1 at 67 %, DRAM at 33 %.)
 constexpr int kRowTile64 = 1024;                           // outputs per tile
-template <int F>
+template <typename T, int F>
 __global__ void __launch_bounds__(256)
-k64_rows_fwd(const double* __restrict__ in, double* __restrict__ lo, double* __restrict__ hi, long long rows, int Nc,
-             const __grid_constant__ PwtFilters64 f) {
+k64_rows_fwd(const T* __restrict__ in, T* __restrict__ lo, T* __restrict__ hi, long long rows, int Nc,
+             const __grid_constant__ PwtFiltersT<T> f) {
     constexpr int C = F / 2 - 1, TO = kRowTile64, TI = 2 * TO + F - 2;
-    __shared__ double sx[TI];
+    __shared__ T sx[TI];
     const int Nc2 = (Nc + 1) >> 1, ntile = (Nc2 + TO - 1) / TO;
     for (long long t = blockIdx.x; t < rows * ntile; t += gridDim.x) {
         const long long r = t / ntile;
         const int k0 = (int)(t - r * ntile) * TO, x0 = 2 * k0 - C;
         const int nout = min(TO, Nc2 - k0), nin = 2 * nout + F - 2;
-        const double* row = in + r * Nc;
+        const T* row = in + r * Nc;
         if (x0 >= 0 && x0 + nin <= Nc) {
             for (int i = threadIdx.x; i < nin; i += 256) sx[i] = __ldg(row + x0 + i);
         } else {
@@ -143,10 +143,10 @@ k64_rows_fwd(const double* __restrict__ in, double* __restrict__ lo, double* __r
         }
         __syncthreads();
         for (int o = threadIdx.x; o < nout; o += 256) {
-            double a = 0.0, d = 0.0;
+            T a = 0, d = 0;
 #pragma unroll
             for (int j = 0; j < F; j++) {
-                const double x = sx[2 * o + j];
+                const T x = sx[2 * o + j];
                 a = fma(x, f.L[F - 1 - j], a);
                 d = fma(x, f.H[F - 1 - j], d);
             }
@@ -158,19 +158,19 @@ k64_rows_fwd(const double* __restrict__ in, double* __restrict__ lo, double* __r
 }
 // rows, synthesis: t1, t2 [rows][nc] -> out [rows][Nc_out];  x[n] = sum_jj IL[2 jj + t0] t1[kb - jj] + IH[2 jj + t0] t2[kb - jj],
 // n = 2 j + b, t0 = (b + P) & 1, kb = j + ((b + P) >> 1), indices modulo nc (separable.cu:293-328).  Same tiling.
-template <int F>
+template <typename T, int F>
 __global__ void __launch_bounds__(256)
-k64_rows_inv(const double* __restrict__ t1, const double* __restrict__ t2, double* __restrict__ out, long long rows, int nc,
-             int Nc_out, const __grid_constant__ PwtFilters64 f) {
+k64_rows_inv(const T* __restrict__ t1, const T* __restrict__ t2, T* __restrict__ out, long long rows, int nc,
+             int Nc_out, const __grid_constant__ PwtFiltersT<T> f) {
     constexpr int P = F / 2 - 1, HALF = F / 2, TO = kRowTile64 / 2, HB = HALF - 1 - (P >> 1), TI = TO + HALF;   // HB: samples needed below j0
-    __shared__ double sa[TI], sd[TI];
+    __shared__ T sa[TI], sd[TI];
     const int ntile = (nc + TO - 1) / TO;
     for (long long t = blockIdx.x; t < rows * ntile; t += gridDim.x) {
         const long long r = t / ntile;
         const int j0 = (int)(t - r * ntile) * TO, kmin = j0 - HB;
         const int npair = min(TO, nc - j0), nin = npair + HALF;
-        const double* a = t1 + r * nc;
-        const double* d = t2 + r * nc;
+        const T* a = t1 + r * nc;
+        const T* d = t2 + r * nc;
         if (kmin >= 0 && kmin + nin <= nc) {
             for (int i = threadIdx.x; i < nin; i += 256) { sa[i] = __ldg(a + kmin + i); sd[i] = __ldg(d + kmin + i); }
         } else {
@@ -178,11 +178,11 @@ k64_rows_inv(const double* __restrict__ t1, const double* __restrict__ t2, doubl
         }
         __syncthreads();
         for (int o = threadIdx.x; o < npair; o += 256) {
-            double x[2];
+            T x[2];
 #pragma unroll
             for (int b = 0; b < 2; b++) {
                 const int t0 = (b + P) & 1, kb = o + ((b + P) >> 1) + HB;            // window index of tap jj = 0
-                double v = 0.0;
+                T v = 0;
 #pragma unroll
                 for (int jj = 0; jj < HALF; jj++) {
                     v = fma(sa[kb - jj], f.IL[2 * jj + t0], v);
@@ -191,8 +191,11 @@ k64_rows_inv(const double* __restrict__ t1, const double* __restrict__ t2, doubl
                 x[b] = v;
             }
             const int n = 2 * (j0 + o);
-            double* op = out + r * Nc_out + n;
-            if (n + 1 < Nc_out && ((((uintptr_t)op) & 15) == 0)) *reinterpret_cast<double2*>(op) = make_double2(x[0], x[1]);
+            T* op = out + r * Nc_out + n;
+            if (n + 1 < Nc_out && ((((uintptr_t)op) & (2 * sizeof(T) - 1)) == 0)) {
+                if constexpr (sizeof(T) == 8) *reinterpret_cast<double2*>(op) = make_double2(x[0], x[1]);
+                else *reinterpret_cast<float2*>(op) = make_float2(x[0], x[1]);
+            }
             else {
                 if (n < Nc_out) op[0] = x[0];
                 if (n + 1 < Nc_out) op[1] = x[1];
@@ -349,7 +352,7 @@ int level_fwd2d_2pass(const double* in, double* A, double* Hb, double* V, double
     const dim3 gc(grid64((long long)PV * ((Nr2 + KS - 1) / KS), 128), 2, batch);
     const unsigned gr = grid64(rows * ((Nc2 + kRowTile64 - 1) / kRowTile64) * 256, 256);
     switch (F) {
-#define X(FF) case FF: k64_rows_fwd<FF><<<gr, 256, 0, st>>>(in, lo, hi, rows, Nc, f); \
+#define X(FF) case FF: k64_rows_fwd<double, FF><<<gr, 256, 0, st>>>(in, lo, hi, rows, Nc, f); \
         if (vec) k64_cols_fwd<FF, 2><<<gc, 128, 0, st>>>(jb, Nr, Nc2, (long long)Nr * Nc2, out_bs, KS, f); \
         else k64_cols_fwd<FF, 1><<<gc, 128, 0, st>>>(jb, Nr, Nc2, (long long)Nr * Nc2, out_bs, KS, f); \
         return 2;
@@ -364,7 +367,7 @@ int level_fwd1d_rows(const double* in, double* A, double* D, long long rows, int
     if (F < 4 || F > 20 || (F & 1)) return 0;
     const unsigned gr = grid64(rows * ((Nc2 + kRowTile64 - 1) / kRowTile64) * 256, 256);
     switch (F) {
-#define X(FF) case FF: k64_rows_fwd<FF><<<gr, 256, 0, st>>>(in, A, D, rows, Nc, f); return 1;
+#define X(FF) case FF: k64_rows_fwd<double, FF><<<gr, 256, 0, st>>>(in, A, D, rows, Nc, f); return 1;
         PWT64_CASES(X)
 #undef X
     }
@@ -376,12 +379,38 @@ int level_inv1d_rows(const double* A, const double* D, double* out, long long ro
     if (F < 4 || F > 20 || (F & 1)) return 0;
     const unsigned gr = grid64(rows * ((nc + kRowTile64 / 2 - 1) / (kRowTile64 / 2)) * 256, 256);
     switch (F) {
-#define X(FF) case FF: k64_rows_inv<FF><<<gr, 256, 0, st>>>(A, D, out, rows, nc, Nc_out, f); return 1;
+#define X(FF) case FF: k64_rows_inv<double, FF><<<gr, 256, 0, st>>>(A, D, out, rows, nc, Nc_out, f); return 1;
         PWT64_CASES(X)
 #undef X
     }
     return 0;
 }
+}  // namespace
+// The same tiled row kernels for float: batched 1D levels with FEW, LONG rows (a single 16 M-sample signal ran the strip kernels
+// -- one 256-column strip per CTA, a one-row "walk" -- at 0.04 of the roofline).  0: not covered.
+int pwt_rows1d_fwd_f32(const float* in, float* A, float* D, long long rows, int Nc, const PwtFilters& f, cudaStream_t st) {
+    const int F = f.hlen, Nc2 = (Nc + 1) >> 1;
+    if (F < 4 || F > 20 || (F & 1)) return 0;
+    const unsigned gr = grid64(rows * ((Nc2 + kRowTile64 - 1) / kRowTile64) * 256, 256);
+    switch (F) {
+#define X(FF) case FF: k64_rows_fwd<float, FF><<<gr, 256, 0, st>>>(in, A, D, rows, Nc, f); return 1;
+        PWT64_CASES(X)
+#undef X
+    }
+    return 0;
+}
+int pwt_rows1d_inv_f32(const float* A, const float* D, float* out, long long rows, int nc, int Nc_out, const PwtFilters& f, cudaStream_t st) {
+    const int F = f.hlen;
+    if (F < 4 || F > 20 || (F & 1)) return 0;
+    const unsigned gr = grid64(rows * ((nc + kRowTile64 / 2 - 1) / (kRowTile64 / 2)) * 256, 256);
+    switch (F) {
+#define X(FF) case FF: k64_rows_inv<float, FF><<<gr, 256, 0, st>>>(A, D, out, rows, nc, Nc_out, f); return 1;
+        PWT64_CASES(X)
+#undef X
+    }
+    return 0;
+}
+namespace {
 int level_inv2d_2pass(const double* A, const double* Hb, const double* V, const double* D, double* out, double* tmp, int batch,
                       int nr, int nc, int Nro, int Nco, long long in_bs, long long out_bs, const PwtFilters64& f, cudaStream_t st) {
     const int F = f.hlen;
@@ -402,7 +431,7 @@ int level_inv2d_2pass(const double* A, const double* Hb, const double* V, const 
 #define X(FF) case FF: \
         if (vec) k64_cols_inv<FF, 2><<<gc, 128, 0, st>>>(jb, nr, Nro, nc, in_bs, (long long)Nro * nc, KS, f); \
         else k64_cols_inv<FF, 1><<<gc, 128, 0, st>>>(jb, nr, Nro, nc, in_bs, (long long)Nro * nc, KS, f); \
-        k64_rows_inv<FF><<<gr, 256, 0, st>>>(t1, t2, out, rows, nc, Nco, f); \
+        k64_rows_inv<double, FF><<<gr, 256, 0, st>>>(t1, t2, out, rows, nc, Nco, f); \
         return 2;
         PWT64_CASES(X)
 #undef X

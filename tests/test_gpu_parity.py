@@ -964,3 +964,19 @@ def test_strip_deferred_threshold_is_unobservable(wname, op, app, normalize, lev
     D.set_kernel_mode(1)
     D.inverse(); G.inverse()
     assert_close(D.image, G.image, 255.0, "deferred, then generic inverse")
+
+
+@pytest.mark.parametrize("shape", [(8192,), (10001,), (65537,), (3, 16384), (2, 20002)])
+@pytest.mark.parametrize("wname", ["db2", "db3", "sym8", "db10", "bior2.4"])
+def test_few_long_rows_1d_against_oracle(wname, shape):
+    """Batched 1D with few, long rows (a single long signal above all): per-level launches of the row kernels tiled along the row
+    (pwt_rows1d_*_f32: the double-precision plans' row kernels instantiated for float), odd lengths included, against the oracle."""
+    data = synth_image((shape[0] if len(shape) == 2 else 1, shape[-1]), seed=47)
+    data = data if len(shape) == 2 else data[0]
+    W = _W(data, wname, 4, ndim=1)
+    Wo = O.OracleWavelets(data, wname, 4, ndim=1)
+    assert W.levels == Wo.levels
+    W.forward(); Wo.forward()
+    compare_coeffs(W, Wo, SCALE, "long rows dwt " + wname)
+    W.inverse(); Wo.inverse()
+    assert_close(W.image, Wo.image, SCALE, "long rows idwt " + wname)
