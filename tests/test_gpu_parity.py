@@ -980,3 +980,31 @@ def test_few_long_rows_1d_against_oracle(wname, shape):
     compare_coeffs(W, Wo, SCALE, "long rows dwt " + wname)
     W.inverse(); Wo.inverse()
     assert_close(W.image, Wo.image, SCALE, "long rows idwt " + wname)
+
+
+@pytest.mark.parametrize("shape", [(16, 65536 + 8), (9, 131072), (40, 32768), (2, 12, 90000)])
+@pytest.mark.parametrize("wname", ["db2", "db3", "sym8"])
+def test_thin_wide_images_against_oracle(wname, shape):
+    """Fewer rows than the cascade / register kernels take but a million samples: the strip kernels walk the few rows (odd row
+    counts, a stack, levels until the rows run out), against the oracle."""
+    img = synth_image(shape, seed=51)
+    imgs = img if img.ndim == 3 else img[None]
+    try:
+        Wos = [O.OracleWavelets(x, wname, 3) for x in imgs]
+    except ValueError:
+        pytest.skip("too few rows for this filter")
+    W = _W(img, wname, 3)
+    assert W.levels == Wos[0].levels
+    W.forward()
+    c = W.coeffs
+    for k, Wo in enumerate(Wos):
+        Wo.forward()
+        pick = (lambda a: a[k]) if img.ndim == 3 else (lambda a: a)
+        assert_close(pick(c[0]), Wo.coeffs[0], SCALE, "thin A " + wname)
+        for i in range(1, len(c)):
+            for j in range(3):
+                assert_close(pick(c[i][j]), Wo.coeffs[i][j], SCALE, "thin L%d b%d %s" % (i, j, wname))
+    W.inverse()
+    for k, Wo in enumerate(Wos):
+        Wo.inverse()
+        assert_close(W.image[k] if img.ndim == 3 else W.image, Wo.image, SCALE, "thin inverse " + wname)
